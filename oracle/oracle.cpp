@@ -1,0 +1,955 @@
+// =====================================================================================
+// TEST INFRASTRUCTURE ONLY.  CPU restatement ("oracle") of the Fasim-LongTarget hot path.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this file's
+// shared object.  The product (fasim-longtarget_b200/) never links or calls it.
+//
+// Parity status: PINNED.  Every function below is checked against the compiled, unmodified
+// reference (oracle/_ref/libref_shim.so, oracle/_ref/fasim) by tests/test_oracle_vs_ref.py in
+// the build container, and against the golden fixtures under tests/golden/ (generated from the
+// reference by tests/golden/make_golden.py) everywhere else.
+//
+// Each function cites the reference lines (under /root/reference) whose behaviour it restates.
+// The restatement is scalar and deliberately literal where the reference's quirks are part of
+// the contract (Q1 pad rows, Q2 8-bit stop-recording, Q3 N/U scoring split,
+// Q4 signed lazy-F compare, Q5 float32 window schedule, Q7 banded traceback).
+// =====================================================================================
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace orc {
+
+// -------------------------------------------------------------------------------------
+// Rule tables — rules.h:6-53.  Each entry lists the images of A, T, G, C (N -> N).
+// Index: [para>=0 ? 0 : 1][strand][rule-1].
+// -------------------------------------------------------------------------------------
+static const char* kParaFwd[6] = {"TGGT", "TGCT", "TGTT", "TGGC", "TGCC", "TGTC"};            // strand 0
+static const char* kParaRev[6] = {"GTTG", "GTTC", "GTTT", "GTCG", "GTCC", "GTCT"};            // strand 1
+static const char* kAntiFwd[18] = {"GTTG", "GTTC", "GTTA", "GTCG", "GTCC", "GTCA", "GATG", "GATC", "GATA",
+                                   "GACG", "GACC", "GACA", "GCTG", "GCTC", "GCTA", "GCCG", "GCCC", "GCCA"};  // strand 1
+static const char* kAntiRev[18] = {"TGGT", "TGCT", "TGAT", "TGGC", "TGCC", "TGAC", "AGGT", "AGCT", "AGAT",
+                                   "AGGC", "AGCC", "AGAC", "CGGT", "CGCT", "CGAT", "CGGC", "CGCC", "CGAC"};  // strand 0
+
+// rules.h:94-318 transferString: returns nullptr for an invalid (para, strand, rule) (reference exits).
+static const char* rule_images(int strand, int para, int rule)
+{
+    if (para >= 0) {
+        if (rule < 1 || rule > 6) return nullptr;
+        return strand == 0 ? kParaFwd[rule - 1] : kParaRev[rule - 1];
+    }
+    if (rule < 1 || rule > 18) return nullptr;
+    return strand == 1 ? kAntiFwd[rule - 1] : kAntiRev[rule - 1];
+}
+
+static std::string transfer(const std::string& seg, int strand, int para, int rule)
+{
+    const char* img = rule_images(strand, para, rule);
+    std::string out(seg.size(), 'N');
+    if (!img) return out;
+    for (size_t i = 0; i < seg.size(); ++i) {
+        switch (seg[i]) {
+        case 'A': out[i] = img[0]; break;
+        case 'T': out[i] = img[1]; break;
+        case 'G': out[i] = img[2]; break;
+        case 'C': out[i] = img[3]; break;
+        default: out[i] = 'N'; break;      // 'N' -> 'N'; anything else -> 'N' (rules.h:308-311)
+        }
+    }
+    return out;
+}
+
+// rules.h:59-87 — characters outside ACGTN are dropped (Q13)
+static std::string complement(const std::string& s)
+{
+    std::string o;
+    o.reserve(s.size());
+    for (char ch : s) {
+        switch (ch) {
+        case 'A': o += 'T'; break;
+        case 'C': o += 'G'; break;
+        case 'G': o += 'C'; break;
+        case 'T': o += 'A'; break;
+        case 'N': o += 'N'; break;
+        default: break;
+        }
+    }
+    return o;
+}
+
+// Fasim-LongTarget.cpp:410-431, 499-522 — the (seq2, src) pair of one task
+static void task_strings(const std::string& seg, int para, int strand, int rule, std::string& seq2, std::string& src)
+{
+    if (para > 0 && strand == 0) { seq2 = transfer(seg, 0, 1, rule); src = seg; }
+    else if (para > 0) { seq2 = transfer(seg, 1, 1, rule); std::reverse(seq2.begin(), seq2.end());
+                         src = complement(seg); std::reverse(src.begin(), src.end()); }
+    else if (strand == 1) { seq2 = transfer(seg, 1, -1, rule); src = complement(seg); }
+    else { seq2 = transfer(seg, 0, -1, rule); std::reverse(seq2.begin(), seq2.end());
+           src = seg; std::reverse(src.begin(), src.end()); }
+}
+
+// -------------------------------------------------------------------------------------
+// Threshold score — stats.h:879-956 calc_score_once.  Exact affine local alignment maximum
+// under the Farrar-side scoring: cg_str (stats.h:306) maps ACGTU (any case) to themselves and
+// everything else to N; npam (stats.h:211-228): match +5 with T==U, mismatch -4, anything vs N -1.
+// gap: first 16, further 4.  The 8-bit pass re-runs in 16 bit on overflow, so the result is exact.
+// -------------------------------------------------------------------------------------
+static int stats_code(char ch)
+{
+    switch (ch) {
+    case 'A': case 'a': return 1;
+    case 'C': case 'c': return 2;
+    case 'G': case 'g': return 3;
+    case 'T': case 't': return 4;
+    case 'U': case 'u': return 5;
+    default: return 16;
+    }
+}
+static int stats_score(int a, int b)
+{
+    if (a == 16 || b == 16) return -1;
+    if (a == b) return 5;
+    if ((a == 4 && b == 5) || (a == 5 && b == 4)) return 5;
+    return -4;
+}
+
+static int threshold_score(const std::string& rna, const std::string& seq2)
+{
+    const int m = (int)rna.size(), n = (int)seq2.size();
+    if (m == 0 || n == 0) return 0;
+    std::vector<int> q(m), H(m + 1, 0), E(m + 1, 0);
+    for (int i = 0; i < m; ++i) q[i] = stats_code(rna[i]);
+    int best = 0;
+    for (int j = 0; j < n; ++j) {
+        const int d = stats_code(seq2[j]);
+        int diag = 0, F = 0;                 // H[i-1][j-1], vertical gap value entering row i
+        for (int i = 1; i <= m; ++i) {
+            int h = diag + stats_score(q[i - 1], d);
+            if (h > best) best = h;          // stats.h:678 — maximum is taken on the diagonal term
+            if (h < E[i]) h = E[i];
+            if (h < F) h = F;
+            if (h < 0) h = 0;
+            diag = H[i];
+            H[i] = h;
+            int open = h - 16;
+            E[i] = std::max(std::max(E[i] - 4, open), 0);
+            F = std::max(std::max(F - 4, open), 0);
+        }
+    }
+    return best;
+}
+
+// -------------------------------------------------------------------------------------
+// SSW-side coding — ssw_cpp.cpp:13-26 (A0 C1 G2 T3, U->0 (!), else 4) and 28-53 (5x5 matrix,
+// +5 on the ACGT diagonal, -4 elsewhere including every N cell).
+// -------------------------------------------------------------------------------------
+static int8_t ssw_code(char ch)
+{
+    switch (ch) {
+    case 'A': case 'a': case 'U': case 'u': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+    }
+}
+static inline int ssw_mat(int refc, int readc) { return (refc == readc && refc < 4) ? 5 : -4; }
+
+struct StripedResult {
+    int score = 0;        // bests[0].score (255 == overflow marker for the byte kernel)
+    int end_ref = -1;
+    int end_read = 0;
+    std::vector<int> colmax;   // maxColumn[] as recorded (0 where never recorded)
+};
+
+static inline uint8_t sat_add8(uint8_t a, uint8_t b) { int v = a + b; return (uint8_t)(v > 255 ? 255 : v); }
+static inline uint8_t sat_sub8(uint8_t a, uint8_t b) { int v = a - b; return (uint8_t)(v < 0 ? 0 : v); }
+
+// Literal lane-by-lane emulation of the 8-bit striped kernels sswNew.cpp:255-464 (sw_sse2_byte_once)
+// and :476-672 (sw_sse2_byte): 16 lanes, stripe length L = ceil(readLen/16), row(s,t) = s*L + t,
+// profile = score + bias with pad rows == bias (qP_byte :176-201), bias 4, gap open 16 / extend 4,
+// lazy-F loop with the *signed* byte compare of :369/:590 (Q4), overflow break before recording
+// (:384-396, Q2), terminate test :396/:617.
+static StripedResult striped_u8(const int8_t* ref, int ref_dir, int refLen, const int8_t* read, int readLen, int terminate)
+{
+    const int LANES = 16, bias = 4, gapO = 16, gapE = 4;
+    StripedResult out;
+    out.colmax.assign(refLen > 0 ? refLen : 0, 0);
+    const int L = (readLen + LANES - 1) / LANES;
+    out.end_read = readLen - 1;
+    if (L == 0) { out.score = 0; return out; }
+    // profile[c][t][s]
+    std::vector<uint8_t> prof((size_t)5 * L * LANES);
+    for (int c = 0; c < 5; ++c)
+        for (int t = 0; t < L; ++t)
+            for (int s = 0; s < LANES; ++s) {
+                int row = s * L + t;
+                prof[((size_t)c * L + t) * LANES + s] = (uint8_t)(row >= readLen ? bias : ssw_mat(c, read[row]) + bias);
+            }
+    std::vector<uint8_t> Hs((size_t)L * LANES, 0), Hl((size_t)L * LANES, 0), Ev((size_t)L * LANES, 0), Hmax((size_t)L * LANES, 0);
+    uint8_t vMaxScore[LANES] = {0}, vMaxMark[LANES] = {0};
+    int maxv = 0;
+    int begin = 0, end = refLen, step = 1;
+    if (ref_dir == 1) { begin = refLen - 1; end = -1; step = -1; }
+    for (int i = begin; i != end; i += step) {
+        uint8_t vF[LANES] = {0}, vMaxCol[LANES] = {0}, vH[LANES];
+        vH[0] = 0;
+        for (int s = 1; s < LANES; ++s) vH[s] = Hs[(size_t)(L - 1) * LANES + s - 1];
+        const uint8_t* vP = &prof[(size_t)ref[i] * L * LANES];
+        Hs.swap(Hl);
+        for (int t = 0; t < L; ++t) {
+            uint8_t* hs = &Hs[(size_t)t * LANES];
+            uint8_t* ev = &Ev[(size_t)t * LANES];
+            const uint8_t* hl = &Hl[(size_t)t * LANES];
+            for (int s = 0; s < LANES; ++s) {
+                uint8_t h = sat_sub8(sat_add8(vH[s], vP[(size_t)t * LANES + s]), bias);
+                uint8_t e = ev[s];
+                if (h < e) h = e;
+                if (h < vF[s]) h = vF[s];
+                if (vMaxCol[s] < h) vMaxCol[s] = h;
+                hs[s] = h;
+                uint8_t open = sat_sub8(h, gapO);
+                e = sat_sub8(e, gapE);
+                ev[s] = e > open ? e : open;
+                uint8_t f = sat_sub8(vF[s], gapE);
+                vF[s] = f > open ? f : open;
+                vH[s] = hl[s];
+            }
+        }
+        bool done = false;
+        for (int k = 0; k < LANES && !done; ++k) {
+            for (int s = LANES - 1; s >= 1; --s) vF[s] = vF[s - 1];
+            vF[0] = 0;
+            for (int t = 0; t < L; ++t) {
+                uint8_t* hs = &Hs[(size_t)t * LANES];
+                bool any = false;
+                for (int s = 0; s < LANES; ++s) {
+                    uint8_t h = hs[s];
+                    if (h < vF[s]) h = vF[s];
+                    if (vMaxCol[s] < h) vMaxCol[s] = h;
+                    hs[s] = h;
+                    uint8_t open = sat_sub8(h, gapO);
+                    vF[s] = sat_sub8(vF[s], gapE);
+                    if ((int8_t)vF[s] > (int8_t)open) any = true;      // signed compare — Q4
+                }
+                if (!any) { done = true; break; }
+            }
+        }
+        bool changed = false;
+        for (int s = 0; s < LANES; ++s) {
+            if (vMaxScore[s] < vMaxCol[s]) vMaxScore[s] = vMaxCol[s];
+            if (vMaxScore[s] != vMaxMark[s]) changed = true;
+        }
+        if (changed) {
+            int temp = 0;
+            for (int s = 0; s < LANES; ++s) { vMaxMark[s] = vMaxScore[s]; if (vMaxScore[s] > temp) temp = vMaxScore[s]; }
+            if (temp > maxv) {
+                maxv = temp;
+                if (maxv + bias >= 255) break;                          // overflow: column i is NOT recorded
+                out.end_ref = i;
+                Hmax = Hs;
+            }
+        }
+        int cm = 0;
+        for (int s = 0; s < LANES; ++s) if (vMaxCol[s] > cm) cm = vMaxCol[s];
+        out.colmax[i] = cm;
+        if (cm == terminate) break;
+    }
+    for (int t = 0; t < L; ++t)
+        for (int s = 0; s < LANES; ++s)
+            if (Hmax[(size_t)t * LANES + s] == maxv) { int row = t + s * L; if (row < out.end_read) out.end_read = row; }
+    out.score = (maxv + bias >= 255) ? 255 : maxv;
+    return out;
+}
+
+static inline int16_t sat_adds16(int16_t a, int16_t b) { int v = (int)a + b; return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
+static inline int16_t sat_subu16(int16_t a, int16_t b) { int v = (int)(uint16_t)a - (int)(uint16_t)b; return (int16_t)(uint16_t)(v < 0 ? 0 : v); }
+
+// Literal emulation of the 16-bit striped kernel sswNew.cpp:893-1069 (sw_sse2_word): 8 lanes, no bias,
+// pad rows score 0 (qP_word :674-696), end_ref initialised to 0 (:910).
+static StripedResult striped_i16(const int8_t* ref, int ref_dir, int refLen, const int8_t* read, int readLen, int terminate)
+{
+    const int LANES = 8, gapO = 16, gapE = 4;
+    StripedResult out;
+    out.colmax.assign(refLen > 0 ? refLen : 0, 0);
+    out.end_ref = 0;
+    out.end_read = readLen - 1;
+    const int L = (readLen + LANES - 1) / LANES;
+    if (L == 0) return out;
+    std::vector<int16_t> prof((size_t)5 * L * LANES);
+    for (int c = 0; c < 5; ++c)
+        for (int t = 0; t < L; ++t)
+            for (int s = 0; s < LANES; ++s) {
+                int row = s * L + t;
+                prof[((size_t)c * L + t) * LANES + s] = (int16_t)(row >= readLen ? 0 : ssw_mat(c, read[row]));
+            }
+    std::vector<int16_t> Hs((size_t)L * LANES, 0), Hl((size_t)L * LANES, 0), Ev((size_t)L * LANES, 0), Hmax((size_t)L * LANES, 0);
+    int16_t vMaxScore[LANES] = {0}, vMaxMark[LANES] = {0};
+    int maxv = 0;
+    int begin = 0, end = refLen, step = 1;
+    if (ref_dir == 1) { begin = refLen - 1; end = -1; step = -1; }
+    for (int i = begin; i != end; i += step) {
+        int16_t vF[LANES] = {0}, vMaxCol[LANES] = {0}, vH[LANES];
+        vH[0] = 0;
+        for (int s = 1; s < LANES; ++s) vH[s] = Hs[(size_t)(L - 1) * LANES + s - 1];
+        const int16_t* vP = &prof[(size_t)ref[i] * L * LANES];
+        Hs.swap(Hl);
+        for (int t = 0; t < L; ++t) {
+            int16_t* hs = &Hs[(size_t)t * LANES];
+            int16_t* ev = &Ev[(size_t)t * LANES];
+            const int16_t* hl = &Hl[(size_t)t * LANES];
+            for (int s = 0; s < LANES; ++s) {
+                int16_t h = sat_adds16(vH[s], vP[(size_t)t * LANES + s]);
+                int16_t e = ev[s];
+                if (h < e) h = e;
+                if (h < vF[s]) h = vF[s];
+                if (vMaxCol[s] < h) vMaxCol[s] = h;
+                hs[s] = h;
+                int16_t open = sat_subu16(h, gapO);
+                e = sat_subu16(e, gapE);
+                ev[s] = e > open ? e : open;
+                int16_t f = sat_subu16(vF[s], gapE);
+                vF[s] = f > open ? f : open;
+                vH[s] = hl[s];
+            }
+        }
+        bool done = false;
+        for (int k = 0; k < LANES && !done; ++k) {
+            for (int s = LANES - 1; s >= 1; --s) vF[s] = vF[s - 1];
+            vF[0] = 0;
+            for (int t = 0; t < L; ++t) {
+                int16_t* hs = &Hs[(size_t)t * LANES];
+                bool any = false;
+                for (int s = 0; s < LANES; ++s) {
+                    int16_t h = hs[s];
+                    if (h < vF[s]) h = vF[s];
+                    if (vMaxCol[s] < h) vMaxCol[s] = h;
+                    hs[s] = h;
+                    int16_t open = sat_subu16(h, gapO);
+                    vF[s] = sat_subu16(vF[s], gapE);
+                    if (vF[s] > open) any = true;
+                }
+                if (!any) { done = true; break; }
+            }
+        }
+        bool changed = false;
+        for (int s = 0; s < LANES; ++s) {
+            if (vMaxScore[s] < vMaxCol[s]) vMaxScore[s] = vMaxCol[s];
+            if (vMaxScore[s] != vMaxMark[s]) changed = true;
+        }
+        if (changed) {
+            int temp = vMaxScore[0];
+            for (int s = 0; s < LANES; ++s) { vMaxMark[s] = vMaxScore[s]; if (vMaxScore[s] > temp) temp = vMaxScore[s]; }
+            if ((uint16_t)temp > (uint16_t)maxv) {
+                maxv = (uint16_t)temp;
+                out.end_ref = i;
+                Hmax = Hs;
+            }
+        }
+        int cm = vMaxCol[0];
+        for (int s = 0; s < LANES; ++s) if (vMaxCol[s] > cm) cm = vMaxCol[s];
+        out.colmax[i] = (uint16_t)cm;
+        if ((uint16_t)cm == (uint16_t)terminate) break;
+    }
+    for (int t = 0; t < L; ++t)
+        for (int s = 0; s < LANES; ++s)
+            if ((uint16_t)Hmax[(size_t)t * LANES + s] == (uint16_t)maxv) { int row = t + s * L; if (row < out.end_read) out.end_read = row; }
+    out.score = maxv;
+    return out;
+}
+
+// Per-column maxima as Aligner::preAlign sees them — ssw_cpp.cpp:397-440 + sswNew.cpp:1309-1390.
+// (the 16-bit re-run at sswNew.cpp:1348 needs a recorded value >= 255, which the byte kernel can
+// never produce — Q2 — so it is restated as unreachable.)
+static std::vector<int> colmax_literal(const std::string& rna, const std::string& seq2)
+{
+    const int m = (int)rna.size(), n = (int)seq2.size();
+    std::vector<int8_t> q(m), r(n);
+    for (int i = 0; i < m; ++i) q[i] = ssw_code(rna[i]);
+    for (int i = 0; i < n; ++i) r[i] = ssw_code(seq2[i]);
+    StripedResult s = striped_u8(r.data(), 0, n, q.data(), m, 255);
+    return s.colmax;
+}
+
+// "Exact model" of the same array: exact affine SW over m16 = 16*ceil(m/16) rows
+// (pad rows score 0), per-column maximum, zeroed from the first column whose maximum is >= 251.
+// Equals colmax_literal unless Q4 fires.  *true_max receives the untruncated matrix maximum.
+static std::vector<int> colmax_model(const std::string& rna, const std::string& seq2, int* true_max)
+{
+    const int m = (int)rna.size(), n = (int)seq2.size();
+    const int m16 = 16 * ((m + 15) / 16);
+    std::vector<int8_t> q(m);
+    for (int i = 0; i < m; ++i) q[i] = ssw_code(rna[i]);
+    std::vector<int> H(m16 + 1, 0), E(m16 + 1, 0), cm(n, 0);
+    int best = 0;
+    for (int j = 0; j < n; ++j) {
+        const int d = ssw_code(seq2[j]);
+        int diag = 0, F = 0, colbest = 0;
+        for (int i = 1; i <= m16; ++i) {
+            int s = (i <= m) ? ssw_mat(d, q[i - 1]) : 0;
+            int h = std::max(std::max(diag + s, E[i]), std::max(F, 0));
+            diag = H[i];
+            H[i] = h;
+            if (h > colbest) colbest = h;
+            int open = h - 16;
+            E[i] = std::max(std::max(E[i] - 4, open), 0);
+            F = std::max(std::max(F - 4, open), 0);
+        }
+        cm[j] = colbest;
+        if (colbest > best) best = colbest;
+    }
+    if (true_max) *true_max = best;
+    int jstar = n;
+    for (int j = 0; j < n; ++j) if (cm[j] >= 251) { jstar = j; break; }
+    for (int j = jstar; j < n; ++j) cm[j] = 0;
+    return cm;
+}
+
+// Peak picking — ssw_cpp.cpp:442-572 (hit filter :446-457, run merge :470-572).
+struct Peak { int score, pos; };
+static std::vector<Peak> pick_peaks(const std::vector<int>& cm, int threshold)
+{
+    std::vector<Peak> hits, out;
+    for (int j = 0; j < (int)cm.size(); ++j) if (cm[j] > threshold) hits.push_back({cm[j], j});
+    size_t k = 0;
+    const size_t nh = hits.size();
+    while (k < nh) {
+        if (k == nh - 1) { out.push_back(hits[k]); break; }
+        int gap = hits[k + 1].pos - hits[k].pos;
+        if (gap > 0 && gap < 5) {
+            size_t first = k, bestk = k;
+            while (k + 1 < nh) {                                   // extend the run
+                int g = hits[k + 1].pos - hits[k].pos;
+                if (!(g > 0 && g < 5)) break;
+                ++k;
+                if (hits[k].score > hits[bestk].score) bestk = k;  // first maximum of the run
+            }
+            (void)first;
+            out.push_back(hits[bestk]);
+            ++k;
+        } else {
+            out.push_back(hits[k]);
+            ++k;
+        }
+    }
+    return out;
+}
+
+// -------------------------------------------------------------------------------------
+// banded_sw — sswNew.cpp:1071-1259.  Literal restatement of the band indexing (set_u/set_d at
+// :105/:108), tie rules (:1132-1149) and traceback (:1159-1238).  Returns false on the
+// reference's "Trace back error" path.
+// -------------------------------------------------------------------------------------
+static inline int band_u(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x + 1; }
+static inline int band_d(int w, int i, int j, int plane) { int x = i - w; if (x < 0) x = 0; return (j - x) * 3 + plane; }
+
+static bool banded_traceback(const int8_t* ref, const int8_t* read, int refLen, int readLen, int score, int band_width,
+                             std::vector<uint32_t>& cigar)
+{
+    const int gapO = 16, gapE = 4;
+    std::vector<int> h_b, e_b, h_c;
+    std::vector<int8_t> dir;
+    int maxv = 0, width_d = 0;
+    do {
+        const int width = band_width * 2 + 3;
+        width_d = band_width * 2 + 1;
+        h_b.assign(width + 2, 0); e_b.resize(width + 2); h_c.resize(width + 2);
+        if (dir.size() < (size_t)width_d * readLen * 3 + 8) dir.resize((size_t)width_d * readLen * 3 + 8, 0);
+        // NOTE: the reference keeps e_b / h_c contents across band doublings (realloc); values that are
+        // read before being written in a pass are only the explicitly zeroed edge cells (:1119).
+        for (int j = 1; j < width - 1; ++j) h_b[j] = 0;
+        for (int i = 0; i < readLen; ++i) {
+            int beg = std::max(0, i - band_width), end = std::min(refLen - 1, i + band_width);
+            int edge = std::min(end + 1, width - 1);
+            int f = 0, u = 0;
+            h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
+            int8_t* line = &dir[(size_t)width_d * i * 3];
+            for (int j = beg; j <= end; ++j) {
+                u = band_u(band_width, i, j);
+                const int e = band_u(band_width, i - 1, j), b = band_u(band_width, i, j - 1), d = band_u(band_width, i - 1, j - 1);
+                const int de = band_d(band_width, i, j, 0), df = band_d(band_width, i, j, 1), dh = band_d(band_width, i, j, 2);
+                int t1 = (i == 0) ? -gapO : h_b[e] - gapO;
+                int t2 = (i == 0) ? -gapE : e_b[e] - gapE;
+                e_b[u] = t1 > t2 ? t1 : t2;
+                line[de] = t1 > t2 ? 3 : 2;
+                t1 = h_c[b] - gapO;
+                t2 = f - gapE;
+                f = t1 > t2 ? t1 : t2;
+                line[df] = t1 > t2 ? 5 : 4;
+                const int e1 = e_b[u] > 0 ? e_b[u] : 0, f1 = f > 0 ? f : 0;
+                t1 = e1 > f1 ? e1 : f1;
+                t2 = h_b[d] + ssw_mat(ref[j], read[i]);
+                h_c[u] = t1 > t2 ? t1 : t2;
+                if (h_c[u] > maxv) maxv = h_c[u];
+                if (t1 <= t2) line[dh] = 1;
+                else line[dh] = e1 > f1 ? line[de] : line[df];
+            }
+            for (int j = 1; j <= u; ++j) h_b[j] = h_c[j];
+        }
+        band_width *= 2;
+    } while (maxv < score);
+    band_width /= 2;
+
+    int i = readLen - 1, j = refLen - 1, run = 0, plane = 2;
+    char op = 'M', prev = 'M';
+    std::vector<uint32_t> rev;
+    auto enc = [](int len, char o) { return (uint32_t)(len << 4) | (o == 'M' ? 0u : (o == 'I' ? 1u : 2u)); };
+    long line_off = (long)width_d * (readLen - 1) * 3;      // direction_line after the fill loop points at the last row
+    while (i > 0) {
+        long idx = line_off + band_d(band_width, i, j, plane);
+        if (idx < 0 || idx >= (long)dir.size()) return false;
+        switch (dir[idx]) {
+        case 1: --i; --j; plane = 2; line_off -= (long)width_d * 3; op = 'M'; break;
+        case 2: --i; plane = 0; line_off -= (long)width_d * 3; op = 'I'; break;
+        case 3: --i; plane = 2; line_off -= (long)width_d * 3; op = 'I'; break;
+        case 4: --j; plane = 1; op = 'D'; break;
+        case 5: --j; plane = 2; op = 'D'; break;
+        default: return false;
+        }
+        if (op == prev) ++run;
+        else { rev.push_back(enc(run, prev)); prev = op; run = 1; }
+    }
+    if (op == 'M') rev.push_back(enc(run + 1, op));
+    else { rev.push_back(enc(run, op)); rev.push_back(enc(1, 'M')); }
+    cigar.assign(rev.rbegin(), rev.rend());
+    return true;
+}
+
+struct Alignment {
+    int sw_score = 0, ref_begin = 0, ref_end = 0, query_begin = 0, query_end = 0;
+    std::vector<uint32_t> cigar;
+};
+
+// Aligner::Align -> ssw_align — ssw_cpp.cpp:599-643, sswNew.cpp:1446-1547 (flag 0x0f, filters 0/32767).
+static Alignment align_window(const std::vector<int8_t>& read, const int8_t* ref, int refLen)
+{
+    Alignment al;
+    const int readLen = (int)read.size();
+    bool word = false;
+    StripedResult fwd = striped_u8(ref, 0, refLen, read.data(), readLen, 255);
+    if (fwd.score == 255) { fwd = striped_i16(ref, 0, refLen, read.data(), readLen, 65535); word = true; }
+    int score1 = fwd.score, ref_end1 = fwd.end_ref, read_end1 = fwd.end_read;
+    // reverse pass (:1508-1520)
+    std::vector<int8_t> rr(read.begin(), read.begin() + (read_end1 + 1));
+    std::reverse(rr.begin(), rr.end());
+    StripedResult rev = word ? striped_i16(ref, 1, ref_end1 + 1, rr.data(), read_end1 + 1, score1)
+                             : striped_u8(ref, 1, ref_end1 + 1, rr.data(), read_end1 + 1, score1 & 0xff);
+    score1 = std::min(rev.score, score1);
+    const int ref_begin1 = rev.end_ref, read_begin1 = read_end1 - rev.end_read;
+    const int rl = ref_end1 - ref_begin1 + 1, ql = read_end1 - read_begin1 + 1;
+    const int bw = std::abs(rl - ql) + 1;
+    al.sw_score = score1; al.ref_begin = ref_begin1; al.ref_end = ref_end1; al.query_begin = read_begin1; al.query_end = read_end1;
+    if (ref_begin1 < 0 || read_begin1 < 0 || !banded_traceback(ref + ref_begin1, read.data() + read_begin1, rl, ql, score1, bw, al.cigar)) {
+        al = Alignment();          // ssw_cpp.cpp:631-633: failed traceback -> sw_score 0
+    }
+    return al;
+}
+
+// -------------------------------------------------------------------------------------
+// Triplex record — sim.h:20-45, 72-97; fastsim.h:291-414 (convertMyTriplex), 416-560 (getAlignment)
+// -------------------------------------------------------------------------------------
+struct Triplex {
+    int stari = 0, endi = 0, starj = 0, endj = 0, reverse = 0, strand = 0, rule = 0, nt = 0;
+    float score = 0, identity = 0, tri_score = 0;
+    std::string stri_align, strj_align;
+    int middle = 0, center = 0, motif = 0, neartriplex = 0;
+    long genomestart = 0, genomeend = 0;
+    std::string chr;
+};
+
+static float triplex_score(char c1, char c2, int para)     // sim.h:72-97
+{
+    if (para > 0) {
+        if (c1 == 'A' && c2 == 'T') return 3.7;
+        if (c1 == 'T' && c2 == 'G') return 2.8;
+        if (c1 == 'G' && c2 == 'G') return 2.2;
+        if (c1 == 'G' && c2 == 'T') return 2.4;
+        if (c1 == 'G' && c2 == 'C') return 4.5;
+        if (c1 == 'C' && c2 == 'T') return 2.6;
+        if (c1 == 'C' && c2 == 'C') return 2.4;
+    } else {
+        if (c1 == 'A' && c2 == 'A') return 3.0;
+        if (c1 == 'A' && c2 == 'T') return 3.5;
+        if (c1 == 'A' && c2 == 'C') return 1.0;
+        if (c1 == 'T' && c2 == 'G') return 1.0;
+        if (c1 == 'G' && c2 == 'A') return 1.0;
+        if (c1 == 'G' && c2 == 'G') return 3.0;
+        if (c1 == 'G' && c2 == 'C') return 3.0;
+        if (c1 == 'C' && c2 == 'T') return 2.0;
+        if (c1 == 'C' && c2 == 'C') return 1.0;
+    }
+    return 0;
+}
+
+struct Params {
+    int rule = 0, cutLength = 5000, strand = 0, overlap = 100, ntMin = 20, ntMax = 100000;
+    float minIdentity = 60, minStability = 1;
+    int penaltyT = -1000, penaltyC = 0, cDistance = 15, cLength = 50;
+};
+
+static void convert_triplex(const Alignment& al, std::vector<Triplex>& list, const std::string& rna, const std::string& seq2,
+                            const std::string& src, long dnaStart, int rule, int strand, int para, const Params& P)
+{
+    // CIGAR expansion (fastsim.h:416-560; the 60-column chunking there only wraps printing)
+    std::string ref_align, read_align, src_align;
+    int q = al.ref_begin, p = al.query_begin;
+    for (uint32_t c : al.cigar) {
+        const uint32_t len = c >> 4, op = c & 15u;
+        for (uint32_t k = 0; k < len; ++k) {
+            if (op == 1) { ref_align += '-'; src_align += '-'; read_align += rna[p++]; }             // I
+            else if (op == 2) { ref_align += seq2[q]; src_align += src[q]; ++q; read_align += '-'; }    // D
+            else { ref_align += seq2[q]; src_align += src[q]; ++q; read_align += rna[p++]; }            // M
+        }
+    }
+    const int nt = (int)ref_align.size();
+    int match = 0, mismatch = 0;
+    for (int i = 0; i < nt; ++i) (ref_align[i] == read_align[i]) ? ++match : ++mismatch;
+    float identity = (float)(100 * match) / (float)(match + mismatch);
+    float tri = 0.0f, prescore = 0.0f, hv = 0.0f;
+    char prechar = 0, cur = 0;
+    if (nt >= P.ntMin && nt <= P.ntMax) {
+        for (int i = 0; i < nt; ++i) {
+            cur = (ref_align[i] == '-') ? '-' : src_align[i];
+            hv = triplex_score(cur, read_align[i], para);
+            if (cur == prechar && cur == 'T') { tri = tri - prescore + P.penaltyT; hv = P.penaltyT; }
+            if (cur == prechar && cur == 'C') { tri = tri - prescore + P.penaltyC; hv = P.penaltyC; }
+            prescore = hv;
+            if (ref_align[i] != '-') prechar = cur;
+            tri += hv;
+        }
+        tri = tri / nt;
+    }
+    int refStart, refEnd;
+    if ((para > 0 && strand == 1) || (para < 0 && strand == 0)) {
+        refStart = (int)seq2.size() - al.ref_end - 1;
+        refEnd = (int)seq2.size() - al.ref_begin - 1;
+    } else { refStart = al.ref_begin + 1; refEnd = al.ref_end + 1; }
+    if (nt >= P.ntMin) {
+        Triplex t;
+        t.stari = al.query_begin + 1; t.endi = al.query_end + 1;
+        t.starj = (int)(refStart + dnaStart); t.endj = (int)(refEnd + dnaStart);
+        t.strand = strand; t.reverse = para; t.rule = rule; t.nt = nt;
+        t.score = (float)al.sw_score; t.identity = identity; t.tri_score = tri;
+        t.stri_align = read_align; t.strj_align = src_align;
+        list.push_back(t);
+    }
+}
+
+// comparators — fastsim.h:92-156
+static bool cmp_multi(const Triplex& a, const Triplex& b)
+{
+    if (a.stari == b.stari) { if (a.starj == b.starj) return a.score > b.score; return a.starj > b.starj; }
+    return a.starj > b.starj;
+}
+static bool cmp_multi2(const Triplex& a, const Triplex& b)
+{
+    if (a.endi == b.endi) { if (a.starj == b.starj) return a.score > b.score; return a.starj < b.starj; }
+    return a.starj < b.starj;
+}
+static bool cmp_score(const Triplex& a, const Triplex& b) { return a.score > b.score; }
+static bool same_triplex(const Triplex& a, const Triplex& b)
+{
+    if (a.stari == b.stari && a.starj == b.starj && a.endi == b.endi && a.endj == b.endj && a.score == b.score) return true;
+    if (b.stari >= a.stari && b.starj >= a.starj && b.endi <= a.endi && b.endj <= a.endj && b.score < a.score) return true;
+    return false;
+}
+
+struct WindowTrace { int peak_score, peak_pos, cut, sw, rb, re, qb, qe; };
+
+// One task — fastsim.h:158-289 (fastSIM) with the threshold of Fasim-LongTarget.cpp:413.
+static void run_task(const std::string& rna, const std::string& seg, long dnaStart, int para, int strand, int rule,
+                     const Params& P, std::vector<Triplex>& out, int* minscore_out, std::vector<Peak>* peaks_out,
+                     std::vector<WindowTrace>* trace)
+{
+    std::string seq2, src;
+    task_strings(seg, para, strand, rule, seq2, src);
+    const int minscore = (int)(threshold_score(rna, seq2) * 0.8);
+    if (minscore_out) *minscore_out = minscore;
+    std::vector<int> cm = colmax_literal(rna, seq2);
+    std::vector<Peak> peaks = pick_peaks(cm, minscore);
+    if (peaks_out) *peaks_out = peaks;
+    std::vector<int8_t> read(rna.size()), refc(seq2.size());
+    for (size_t i = 0; i < rna.size(); ++i) read[i] = ssw_code(rna[i]);
+    for (size_t i = 0; i < seq2.size(); ++i) refc[i] = ssw_code(seq2[i]);
+    std::vector<Triplex> mine;
+    for (const Peak& pk : peaks) {
+        float Iden = 0.6;
+        int cut = 0, bestcut = 0, flag = 0;
+        Alignment al, best;
+        best.sw_score = 0;
+        while (Iden <= 1) {                                   // fastsim.h:209-237 (4 iterations, Q5)
+            cut = (int)(pk.score + 24) / (9 * Iden - 4) + 1;
+            cut = pk.pos - cut + 1 > 0 ? cut : pk.pos + 1;
+            al = align_window(read, refc.data() + (pk.pos - cut + 1), cut);
+            if (trace) trace->push_back({pk.score, pk.pos, cut, al.sw_score, al.ref_begin, al.ref_end, al.query_begin, al.query_end});
+            if (al.sw_score >= pk.score) { flag = 1; break; }
+            if (al.sw_score > best.sw_score && al.ref_end == cut - 1) { best = al; bestcut = cut; flag = 2; }
+            Iden += 0.1;
+        }
+        if (flag == 2) { al = best; cut = bestcut; }
+        if (al.sw_score != 0) {
+            al.ref_begin += pk.pos - cut + 1;
+            al.ref_end += pk.pos - cut + 1;
+            convert_triplex(al, mine, rna, seq2, src, dnaStart, rule, strand, para, P);
+        }
+    }
+    std::sort(mine.begin(), mine.end(), cmp_multi);
+    mine.erase(std::unique(mine.begin(), mine.end(), same_triplex), mine.end());
+    std::sort(mine.begin(), mine.end(), cmp_multi2);
+    mine.erase(std::unique(mine.begin(), mine.end(), same_triplex), mine.end());
+    std::sort(mine.begin(), mine.end(), cmp_score);
+    const size_t lim = mine.size() > 50 ? 50 : mine.size();
+    for (size_t i = 0; i < lim; ++i) {
+        const Triplex& t = mine[i];
+        if (t.identity >= P.minIdentity && t.tri_score >= P.minStability && t.nt >= P.ntMin) out.push_back(t);
+    }
+}
+
+// Fasim-LongTarget.cpp:873-933
+static bool same_seq(const std::string& s)
+{
+    size_t a = 0, c = 0, g = 0, t = 0, u = 0, n = 0;
+    for (char ch : s) { a += ch == 'A'; c += ch == 'C'; g += ch == 'G'; t += ch == 'T'; u += ch == 'U'; n += ch == 'N'; }
+    const size_t z = s.size();
+    return a == z || c == z || g == z || t == z || u == z || n == z;
+}
+
+struct TaskId { int para, strand, rule; };
+// task order of Fasim-LongTarget.cpp:404-585
+static std::vector<TaskId> task_order(const Params& P)
+{
+    std::vector<TaskId> v;
+    if (P.strand >= 0) {
+        if (P.rule == 0) for (int r = 1; r <= 6; ++r) { v.push_back({1, 0, r}); v.push_back({1, 1, r}); }
+        if (P.rule > 0 && P.rule < 7) { v.push_back({1, 0, P.rule}); v.push_back({1, 1, P.rule}); }
+    }
+    if (P.strand <= 0) {
+        if (P.rule == 0) for (int r = 1; r <= 18; ++r) { v.push_back({-1, 1, r}); v.push_back({-1, 0, r}); }
+        else { v.push_back({-1, 1, P.rule}); v.push_back({-1, 0, P.rule}); }
+    }
+    return v;
+}
+
+// One DNA record — Fasim-LongTarget.cpp:379-598 (LongTarget) incl. cutSequence fastsim.h:71-90.
+static void run_record(const std::string& rna, const std::string& dna, const Params& P, std::vector<Triplex>& out)
+{
+    std::vector<Triplex> all;
+    const std::vector<TaskId> order = task_order(P);
+    unsigned pos = 0;
+    while (pos < dna.size()) {
+        std::string seg = dna.substr(pos, P.cutLength);
+        long start = pos;
+        pos += P.cutLength; pos -= P.overlap;
+        if (same_seq(seg)) continue;
+        for (const TaskId& t : order) run_task(rna, seg, start, t.para, t.strand, t.rule, P, all, nullptr, nullptr, nullptr);
+    }
+    for (const Triplex& t : all)
+        if (t.score >= 0.0f && t.identity >= P.minIdentity && t.tri_score >= P.minStability && t.nt >= P.cLength) out.push_back(t);
+}
+
+// cluster_triplex — Fasim-LongTarget.cpp:600-691 (Class / MidPoint / Center only).
+// Keys are kept as signed 64-bit; with any negative key the reference never terminates (Q11) — here
+// such keys simply take part in the ordered scan.
+static void cluster(std::vector<Triplex>& v, int dd, int length)
+{
+    std::map<long, long> W;
+    long best = 0, center = 0;
+    bool found = false;
+    for (Triplex& t : v) {
+        if (t.nt > length) {
+            const int mid = (t.stari + t.endi) / 2;
+            t.middle = mid; t.motif = 0;
+            W[mid];
+            for (int i = -dd; i <= dd; ++i) {
+                if (i > 0) W[mid + i] += dd - i;
+                else if (i < 0) W[mid + i] += dd + i;
+                if (W[mid + i] > best) { best = W[mid + i]; center = mid + i; found = true; }
+            }
+            t.neartriplex = (int)W[mid];
+        }
+    }
+    int cls = 1;
+    while (found) {
+        for (long p = center - dd; p <= center + dd; ++p) {
+            for (Triplex& t : v) if (t.middle == p && t.motif == 0) { t.motif = cls; t.center = (int)center; }
+            W.erase(p);
+        }
+        best = 0; found = false;
+        for (auto& kv : W) if (kv.second > best) { best = kv.second; center = kv.first; found = true; }
+        ++cls;
+    }
+}
+
+static const char* strand_name(int reverse, int strand)   // Fasim-LongTarget.cpp:851-871
+{
+    if (reverse == 1 && strand == 0) return "ParaPlus";
+    if (reverse == 1 && strand == 1) return "ParaMinus";
+    if (reverse == -1 && strand == 1) return "AntiMinus";
+    if (reverse == -1 && strand == 0) return "AntiPlus";
+    return "";
+}
+static bool cmp_motif(const Triplex& a, const Triplex& b) { return a.motif < b.motif; }
+
+// printResult — Fasim-LongTarget.cpp:797-828: cluster, unstable sort by class, 19 columns.
+static std::string format_sorted(std::vector<Triplex>& v, const Params& P)
+{
+    std::string o = "QueryStart\tQueryEnd\tStartInSeq\tEndInSeq\tDirection\tChr\tStartInGenome\tEndInGenome\tMeanStability\t"
+                    "MeanIdentity(%)\tStrand\tRule\tScore\tNt(bp)\tClass\tMidPoint\tCenter\tTFO sequence\tTTS sequence\n";
+    cluster(v, P.cDistance, P.cLength);
+    std::sort(v.begin(), v.end(), cmp_motif);
+    char buf[512];
+    for (const Triplex& t : v) {
+        if (t.motif == 0) continue;
+        snprintf(buf, sizeof buf, "%d\t%d\t%d\t%d\t%s\t%s\t%ld\t%ld\t%g\t%g\t%s\t%d\t%g\t%d\t%d\t%d\t%d\t", t.stari, t.endi, t.starj,
+                 t.endj, t.starj < t.endj ? "R" : "L", t.chr.c_str(), t.genomestart, t.genomeend, (double)t.tri_score,
+                 (double)t.identity, strand_name(t.reverse, t.strand), t.rule, (double)t.score, t.nt, t.motif, t.middle, t.center);
+        o += buf; o += t.stri_align; o += '\t'; o += t.strj_align; o += '\n';
+    }
+    return o;
+}
+
+static unsigned fbits(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static void append_text(std::string& out, const Triplex& t)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%08x\t%08x\t%08x\t%d\t%d\t%d\t%d\t%ld\t%ld\t", t.stari, t.endi, t.starj,
+             t.endj, t.strand, t.reverse, t.rule, t.nt, fbits(t.score), fbits(t.identity), fbits(t.tri_score), t.middle, t.center,
+             t.motif, t.neartriplex, t.genomestart, t.genomeend);
+    out += buf; out += t.stri_align; out += '\t'; out += t.strj_align; out += '\t'; out += t.chr; out += '\n';
+}
+static int emit(const std::string& s, char* out, long cap)
+{
+    if ((long)s.size() + 1 > cap) return -(int)(s.size() + 1);
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+static Params params_from(const int* p)
+{
+    Params P;
+    P.rule = p[0]; P.cutLength = p[1]; P.strand = p[2]; P.overlap = p[3]; P.ntMin = p[4]; P.ntMax = p[5];
+    P.minIdentity = (float)p[6]; P.minStability = (float)p[7]; P.penaltyT = p[8]; P.penaltyC = p[9]; P.cDistance = p[10]; P.cLength = p[11];
+    return P;
+}
+
+}  // namespace orc
+
+// =====================================================================================
+// C ABI for ctypes (same shapes as oracle/ref_shim.cpp so tests can swap one for the other)
+// =====================================================================================
+extern "C" {
+
+int orc_task_strings(const char* seg, int para, int strand, int rule, char* seq2_out, char* src_out)
+{
+    std::string s2, sr;
+    orc::task_strings(seg, para, strand, rule, s2, sr);
+    memcpy(seq2_out, s2.c_str(), s2.size() + 1);
+    memcpy(src_out, sr.c_str(), sr.size() + 1);
+    return (int)s2.size();
+}
+
+int orc_calc_score_once(const char* rna, const char* seq2) { return orc::threshold_score(rna, seq2); }
+
+int orc_colmax(const char* rna, const char* seq2, int n, int* out)
+{
+    std::vector<int> cm = orc::colmax_literal(rna, std::string(seq2, n));
+    for (int i = 0; i < n; ++i) out[i] = cm[i];
+    return n;
+}
+
+int orc_colmax_model(const char* rna, const char* seq2, int n, int* out, int* true_max)
+{
+    std::vector<int> cm = orc::colmax_model(rna, std::string(seq2, n), true_max);
+    for (int i = 0; i < n; ++i) out[i] = cm[i];
+    return n;
+}
+
+int orc_prealign(const char* rna, const char* seq2, int n, int threshold, int* scores, int* positions, int cap)
+{
+    std::vector<int> cm = orc::colmax_literal(rna, std::string(seq2, n));
+    std::vector<orc::Peak> pk = orc::pick_peaks(cm, threshold);
+    for (size_t i = 0; i < pk.size() && (int)i < cap; ++i) { scores[i] = pk[i].score; positions[i] = pk[i].pos; }
+    return (int)pk.size();
+}
+
+int orc_peaks_from_colmax(const int* cm, int n, int threshold, int* scores, int* positions, int cap)
+{
+    std::vector<int> v(cm, cm + n);
+    std::vector<orc::Peak> pk = orc::pick_peaks(v, threshold);
+    for (size_t i = 0; i < pk.size() && (int)i < cap; ++i) { scores[i] = pk[i].score; positions[i] = pk[i].pos; }
+    return (int)pk.size();
+}
+
+int orc_align(const char* rna, const char* win, int wlen, int* out6, unsigned* cigar, int cap)
+{
+    const int m = (int)strlen(rna);
+    std::vector<int8_t> read(m), ref(wlen);
+    for (int i = 0; i < m; ++i) read[i] = orc::ssw_code(rna[i]);
+    for (int i = 0; i < wlen; ++i) ref[i] = orc::ssw_code(win[i]);
+    orc::Alignment al = orc::align_window(read, ref.data(), wlen);
+    out6[0] = al.sw_score; out6[1] = al.ref_begin; out6[2] = al.ref_end; out6[3] = al.query_begin; out6[4] = al.query_end;
+    out6[5] = (int)al.cigar.size();
+    for (size_t i = 0; i < al.cigar.size() && (int)i < cap; ++i) cigar[i] = al.cigar[i];
+    return 0;
+}
+
+int orc_task(const char* rna, const char* seg, long dna_start, int para, int strand, int rule, const int* params,
+             int* minscore_out, char* out, long cap)
+{
+    orc::Params P = orc::params_from(params);
+    std::vector<orc::Triplex> list;
+    orc::run_task(rna, seg, dna_start, para, strand, rule, P, list, minscore_out, nullptr, nullptr);
+    std::string txt;
+    for (auto& t : list) orc::append_text(txt, t);
+    return orc::emit(txt, out, cap);
+}
+
+// window trace of one task: rows of 8 ints (peak_score, peak_pos, cut, sw, rb, re, qb, qe); returns row count
+int orc_task_trace(const char* rna, const char* seg, int para, int strand, int rule, const int* params, int* rows, int cap_rows)
+{
+    orc::Params P = orc::params_from(params);
+    std::vector<orc::Triplex> list;
+    std::vector<orc::WindowTrace> tr;
+    orc::run_task(rna, seg, 0, para, strand, rule, P, list, nullptr, nullptr, &tr);
+    for (size_t i = 0; i < tr.size() && (int)i < cap_rows; ++i) memcpy(rows + 8 * i, &tr[i], 8 * sizeof(int));
+    return (int)tr.size();
+}
+
+int orc_longtarget(const char* rna, const char* dna, const int* params, char* out, long cap)
+{
+    orc::Params P = orc::params_from(params);
+    std::vector<orc::Triplex> list;
+    orc::run_record(rna, dna, P, list);
+    std::string txt;
+    for (auto& t : list) orc::append_text(txt, t);
+    return orc::emit(txt, out, cap);
+}
+
+int orc_cluster(int n, const int* stari, const int* endi, const int* nt, int dd, int length, int* middle, int* center, int* motif)
+{
+    std::vector<orc::Triplex> v(n);
+    for (int i = 0; i < n; ++i) { v[i].stari = stari[i]; v[i].endi = endi[i]; v[i].nt = nt[i]; }
+    orc::cluster(v, dd, length);
+    for (int i = 0; i < n; ++i) { middle[i] = v[i].middle; center[i] = v[i].center; motif[i] = v[i].motif; }
+    return 0;
+}
+
+// Whole single-record run: returns the bytes of the -TFOsorted file (Fasim-LongTarget.cpp:78-172, 797-828).
+int orc_run_tfosorted(const char* rna, const char* dna, const char* chr, long record_start, const int* params, char* out, long cap)
+{
+    orc::Params P = orc::params_from(params);
+    std::vector<orc::Triplex> list;
+    orc::run_record(rna, dna, P, list);
+    for (auto& t : list) {                                   // Fasim-LongTarget.cpp:141-149
+        t.chr = chr;
+        t.genomestart = t.starj + record_start - 1;
+        t.genomeend = t.endj + record_start - 1;
+    }
+    std::string txt = orc::format_sorted(list, P);
+    return orc::emit(txt, out, cap);
+}
+
+}  // extern "C"
