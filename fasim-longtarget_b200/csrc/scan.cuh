@@ -1,0 +1,377 @@
+// Scan stage: translation (rules.h) fused into a packed 16-bit x2 affine-gap Smith-Waterman that
+// yields, per DNA column, the maximum score over all (padded) RNA rows — the device counterpart of
+// calc_score_once (stats.h:879) + ssw_pre_align / sw_sse2_byte_once (sswNew.cpp:1309, 255) — and the
+// threshold-hit compaction + run merge of Aligner::preAlign (ssw_cpp.cpp:442-572).
+//
+// Work unit ("item") = one DNA segment x one *pair* of tasks that read the segment in the same
+// direction; the two tasks live in the two 16-bit halves of every register (same RNA, same DNA,
+// different 5-letter rule image), so the halves are independent cells with identical control flow.
+//
+// One warp owns one item.  Lanes own R consecutive RNA rows each (a strip of 32*R rows); DNA columns
+// stream through the lanes as an anti-diagonal wavefront (lane l works on column s-l at step s), the
+// hand-off of (H, F, running column max) to the next lane is a warp shuffle.  RNAs longer than one
+// strip are strip-mined; the strip boundary row (H, F, column max per column) round-trips through an
+// L2-resident buffer.  Query profiles (score of every RNA row against each of the 5 DNA base codes,
+// already packed for the two tasks) sit in shared memory; the segment's base codes are staged there too.
+//
+// Per cell pair (two tasks) the recurrence is 6 instructions:
+//   t = VIADDMNMX.RELU(Hdiag, s, E)     t  = max(Hdiag + s, E, 0)
+//   u = VIADD.16x2(t, -16)              (FMA pipe)
+//   E = VIADDMNMX(E, -4, u)
+//   H = VIMNMX(t, F)
+//   F = VIADDMNMX(F, -4, u)
+//   cm = VIMNMX3(cm, t, t')             (one per two rows)
+// Dropping the F->E and E->F openings is exact for these penalties (a gap directly followed by a gap
+// of the other kind is always dominated by a diagonal step: 2*16 > 4+16).
+#pragma once
+#include "common.cuh"
+
+namespace ltg {
+
+struct SegDesc {
+    int64_t start;    // offset of the segment in the record
+    int32_t len;
+    int32_t flags;    // bit0: skip (homopolymer, same_seq Fasim-LongTarget.cpp:873), bit1: contains a non-ACGT byte
+};
+constexpr int kSegSkip = 1, kSegNonACGT = 2;
+
+struct ScanItem {
+    int32_t seg;
+    int32_t pair;
+};
+
+__constant__ TaskDef c_tasks[kMaxTasks];
+__constant__ PairDef c_pairs[kMaxPairs];
+
+// ---------------------------------------------------------------------------------------------
+// ASCII -> base codes
+__global__ void k_encode(const unsigned char* __restrict__ dna, uint8_t* __restrict__ codes, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) codes[i] = (uint8_t)dna_code(dna[i]);
+}
+
+// per-segment flags: homopolymer test of same_seq (all bytes equal and one of A C G T U N) and
+// "has a byte outside ACGT" (needs the second, N-aware threshold scoring — SURVEY App. B Q3)
+__global__ void k_seg_flags(const unsigned char* __restrict__ dna, SegDesc* __restrict__ segs, int n_segs)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_segs) return;
+    const SegDesc sd = segs[warp];
+    const unsigned char* p = dna + sd.start;
+    const unsigned char c0 = p[0];
+    bool same = true, clean = true;
+    for (int i = lane; i < sd.len; i += 32) {
+        const unsigned char c = p[i];
+        same &= (c == c0);
+        clean &= (c == 'A' || c == 'C' || c == 'G' || c == 'T');
+    }
+    same = __all_sync(0xffffffffu, same);
+    clean = __all_sync(0xffffffffu, clean);
+    if (lane == 0) {
+        const bool letter = (c0 == 'A' || c0 == 'C' || c0 == 'G' || c0 == 'T' || c0 == 'U' || c0 == 'N');
+        segs[warp].flags = ((same && letter) ? kSegSkip : 0) | (clean ? 0 : kSegNonACGT);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Query profiles.  Layout per (pair, strip): [x = 0..4][k = 0..R/4-1][lane = 0..31][e = 0..3] uint32,
+// entry = packed scores of RNA row (strip*32R + lane*R + 4k + e) against base code x under the two
+// tasks' rule images.  kind 0: SSW scoring (ssw_cpp.cpp:28-53; pad rows up to 16*ceil(m/16) score 0 as
+// in qP_byte sswNew.cpp:195); kind 1: Farrar-side scoring of calc_score_once (stats.h:211-228: N -1, U==T).
+template <int R>
+__global__ void k_build_profiles(const uint8_t* __restrict__ rna_ssw, const uint8_t* __restrict__ rna_stats, int m,
+                                 int n_pairs, int n_strips, int kind, uint32_t* __restrict__ out)
+{
+    const int per_block = 5 * 32 * R;
+    const int64_t total = (int64_t)n_pairs * n_strips * per_block;
+    const int m16 = 16 * ((m + 15) / 16);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int rem = (int)(idx % per_block);
+        const int64_t blk = idx / per_block;
+        const int strip = (int)(blk % n_strips), pair = (int)(blk / n_strips);
+        const int x = rem / (32 * R);
+        rem -= x * 32 * R;
+        const int k = rem / 128, lane = (rem % 128) / 4, e = rem & 3;
+        const int row = strip * 32 * R + lane * R + 4 * k + e;
+        int sc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const TaskDef& t = c_tasks[c_pairs[pair].task[h]];
+            const int d = t.img[x];                 // translated base, SSW code 0..3 / 4 = N
+            int s;
+            if (row >= m16) s = kGhost;
+            else if (row >= m) s = 0;
+            else if (kind == 0) {
+                const int q = rna_ssw[row];
+                s = (q == d && d < 4) ? kMatch : kMismatch;
+            } else {
+                const int q = rna_stats[row];       // 0 A,1 C,2 G,3 T,4 U,5 N
+                if (q == 5 || d == 4) s = -1;
+                else if (q == d || (q == 4 && d == 3)) s = kMatch;
+                else s = kMismatch;
+            }
+            sc[h] = s;
+        }
+        out[idx] = pack16(sc[0], sc[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ScanArgs {
+    const uint8_t* codes;       // base codes of the record
+    const SegDesc* segs;
+    const ScanItem* items;
+    int n_items;
+    const uint32_t* profiles;   // [pair][strip][5*32*R]
+    int n_strips;
+    int max_len;                // row pitch of colmax / bnd (>= longest segment)
+    uint32_t* colmax;           // [item][max_len] packed column maxima of the two tasks
+    uint4* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F, cm, -)
+    int* counter;               // work queue head
+};
+
+template <int R>
+__host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
+{
+    return 5 * 32 * R * 4 + 32 * 16 + ((max_len + 64 + 15) / 16) * 16;
+}
+
+#define LTG_CELL(SV, RR)                                          \
+    {                                                             \
+        const uint32_t t_ = __viaddmax_s16x2_relu(d, (SV), E[RR]); \
+        const uint32_t u_ = __vadd2(t_, kNegOpen);                \
+        E[RR] = __viaddmax_s16x2(E[RR], kNegExt, u_);             \
+        const uint32_t h_ = __vmaxs2(t_, f);                      \
+        f = __viaddmax_s16x2(f, kNegExt, u_);                     \
+        d = Hd[RR];                                               \
+        Hd[RR] = h_;                                              \
+        tv[(RR) & 1] = t_;                                        \
+        if ((RR) & 1) cm = __vimax3_s16x2(cm, tv[0], tv[1]);      \
+        hlast = h_;                                               \
+    }
+
+template <int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
+{
+    static_assert(R % 4 == 0, "R must be a multiple of 4");
+    extern __shared__ uint4 smem_u4[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp_bytes = scan_warp_smem_bytes<R>(a.max_len);
+    uint4* s_prof = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(smem_u4) + (size_t)wib * warp_bytes);
+    uint4* s_ring = s_prof + 5 * (R / 4) * 32;
+    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_ring + 32);
+    uint4* bnd = a.bnd + (size_t)(blockIdx.x * WARPS + wib) * a.max_len;
+    const uint32_t kNegOpen = 0xFFF0FFF0u, kNegExt = 0xFFFCFFFCu;
+    constexpr int PLANE = (R / 4) * 32;     // uint4 per base-code plane
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= a.n_items) break;
+        const ScanItem it = a.items[item];
+        const SegDesc sd = a.segs[it.seg];
+        const int n = sd.len;
+        const bool rev = c_pairs[it.pair].reversed != 0;
+        const uint8_t* gcodes = a.codes + sd.start;
+        __syncwarp();
+        // stage base codes with 32 neutral ('N' plane) columns on both sides
+        for (int i = lane; i < n + 64; i += 32) {
+            const int j = i - 32;
+            s_codes[i] = (j < 0 || j >= n) ? (uint8_t)kBaseOther : gcodes[rev ? (n - 1 - j) : j];
+        }
+        uint32_t* cm_out = a.colmax + (size_t)item * a.max_len;
+
+        for (int strip = 0; strip < a.n_strips; ++strip) {
+            const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
+            __syncwarp();
+            for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
+            __syncwarp();
+            const bool first = (strip == 0), last = (strip == a.n_strips - 1);
+            uint32_t Hd[R], E[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
+            uint32_t hout = 0, fout = 0, cmout = 0, hdiag = 0;
+            const int steps = n + 31;
+            for (int s = 0; s < steps; ++s) {
+                if (!first && (s & 31) == 0) {
+                    __syncwarp();
+                    const int j = s + lane;
+                    uint4 pk = make_uint4(0, 0, 0, 0);
+                    if (j < n) pk = bnd[j];
+                    s_ring[lane] = pk;
+                    __syncwarp();
+                }
+                uint32_t hin = __shfl_up_sync(0xffffffffu, hout, 1);
+                uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);
+                uint32_t cmin = __shfl_up_sync(0xffffffffu, cmout, 1);
+                if (lane == 0) {
+                    if (first) { hin = 0; fin = 0; cmin = 0; }
+                    else { const uint4 pk = s_ring[s & 31]; hin = pk.x; fin = pk.y; cmin = pk.z; }
+                }
+                const int x = s_codes[s - lane + 32];
+                const uint4* pp = s_prof + x * PLANE + lane;
+                uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;
+                uint32_t tv[2];
+#pragma unroll
+                for (int k = 0; k < R / 4; ++k) {
+                    const uint4 sc = pp[k * 32];
+                    LTG_CELL(sc.x, 4 * k + 0)
+                    LTG_CELL(sc.y, 4 * k + 1)
+                    LTG_CELL(sc.z, 4 * k + 2)
+                    LTG_CELL(sc.w, 4 * k + 3)
+                }
+                hdiag = hin;
+                hout = hlast; fout = f; cmout = cm;
+                if (lane == 31) {
+                    const int j = s - 31;
+                    if (j >= 0) {
+                        if (last) cm_out[j] = cm;
+                        else bnd[j] = make_uint4(hout, fout, cmout, 0u);
+                    }
+                }
+            }
+        }
+    }
+}
+#undef LTG_CELL
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue: per task the exact maximum, the threshold (int)(max*0.8) (Fasim-LongTarget.cpp:413), the
+// 8-bit "stop recording" truncation (Q2), threshold-hit compaction and run merge to peaks
+// (ssw_cpp.cpp:446-572).  One warp per item; hits are found with __ballot_sync and consumed in column
+// order; peaks are buffered one per lane and appended to the global pool with ONE atomicAdd per flush.
+struct EpiArgs {
+    const uint32_t* colmax;
+    const ScanItem* items;
+    const SegDesc* segs;
+    int n_items;
+    int max_len;
+    int tasks_per_seg;
+    const int* stats_max;    // [seg*T + task] exact calc_score_once maxima from the N-aware pass, or nullptr
+    int mode;                // 0: first pass over all items; 1: second pass (literal colmax present) — only halves flagged literal
+    int* task_max;           // [seg*T + task]
+    int* task_thr;
+    int* task_npeaks;
+    int* task_flags;         // bit0 overflow(>=251) seen, bit1 literal re-run required (Q4 guard), bit2 int16 range exceeded
+    int* pk_count;
+    int pk_cap;
+    int* pk_task;
+    int* pk_pos;
+    int* pk_score;
+};
+constexpr int kTaskOverflow = 1, kTaskLiteral = 2, kTaskRange = 4;
+
+__device__ inline void epi_flush(const EpiArgs& a, int lane, int& nbuf, int task, int bpos, int bscore)
+{
+    // lanes [0, nbuf) each hold one buffered peak
+    int base = 0;
+    if (lane == 0) base = atomicAdd(a.pk_count, nbuf);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < nbuf && base + lane < a.pk_cap) {
+        a.pk_task[base + lane] = task;
+        a.pk_pos[base + lane] = bpos;
+        a.pk_score[base + lane] = bscore;
+    }
+    nbuf = 0;
+}
+
+__global__ void k_epilogue(const EpiArgs a)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.n_items) return;
+    const ScanItem it = a.items[warp];
+    const SegDesc sd = a.segs[it.seg];
+    const int n = sd.len;
+    const uint32_t* cm = a.colmax + (size_t)warp * a.max_len;
+    const PairDef pd = c_pairs[it.pair];
+    for (int h = 0; h < 2; ++h) {
+        if (h == 1 && pd.task[1] == pd.task[0]) break;
+        const int task = it.seg * a.tasks_per_seg + pd.task[h];
+        int thr, jstar = n;
+        if (a.mode == 0) {
+            int mx = 0;
+            for (int j = lane; j < n; j += 32) {
+                const uint32_t v = cm[j];
+                const int s = h ? hi16(v) : lo16(v);
+                mx = max(mx, s);
+                if (s >= kOverflowU8) jstar = min(jstar, j);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                jstar = min(jstar, __shfl_xor_sync(0xffffffffu, jstar, o));
+            }
+            const int score = a.stats_max ? a.stats_max[task] : mx;
+            thr = (int)((double)score * 0.8);
+            int flags = (jstar < n ? kTaskOverflow : 0) | (mx >= kQ4Guard ? kTaskLiteral : 0) | (mx >= 32000 ? kTaskRange : 0);
+            if (lane == 0) { a.task_max[task] = score; a.task_thr[task] = thr; a.task_flags[task] = flags; a.task_npeaks[task] = 0; }
+            if (flags & kTaskLiteral) continue;      // peaks come from the literal re-run
+        } else {
+            if (!(a.task_flags[task] & kTaskLiteral)) continue;
+            thr = a.task_thr[task];
+            // the literal column maxima already carry the stop-recording zeros
+        }
+        // hits in column order, run merge (ssw_cpp.cpp:470-572): consecutive hits < 5 apart form a run,
+        // a run reports its first maximum
+        bool have = false;
+        int last_pos = 0, best_pos = 0, best_score = 0, npk = 0;
+        int nbuf = 0, bpos = 0, bscore = 0;
+        for (int j0 = 0; j0 < jstar; j0 += 32) {
+            const int j = j0 + lane;
+            int s = 0;
+            if (j < jstar) { const uint32_t v = cm[j]; s = h ? hi16(v) : lo16(v); }
+            unsigned mask = __ballot_sync(0xffffffffu, j < jstar && s > thr);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int pos = j0 + b;
+                const int sc = __shfl_sync(0xffffffffu, s, b);
+                if (have && pos - last_pos < 5) {
+                    if (sc > best_score) { best_score = sc; best_pos = pos; }
+                } else {
+                    if (have) {
+                        if (lane == nbuf) { bpos = best_pos; bscore = best_score; }
+                        ++nbuf; ++npk;
+                        if (nbuf == 32) epi_flush(a, lane, nbuf, task, bpos, bscore);
+                    }
+                    have = true; best_score = sc; best_pos = pos;
+                }
+                last_pos = pos;
+            }
+        }
+        if (have) {
+            if (lane == nbuf) { bpos = best_pos; bscore = best_score; }
+            ++nbuf; ++npk;
+        }
+        if (nbuf) epi_flush(a, lane, nbuf, task, bpos, bscore);
+        if (lane == 0) a.task_npeaks[task] = npk;
+    }
+}
+
+// maximum of each half of a packed colmax row (used for the N-aware threshold pass)
+__global__ void k_rowmax(const uint32_t* __restrict__ colmax, const ScanItem* __restrict__ items, const SegDesc* __restrict__ segs,
+                         int n_items, int max_len, int tasks_per_seg, int* __restrict__ stats_max)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_items) return;
+    const ScanItem it = items[warp];
+    const int n = segs[it.seg].len;
+    const uint32_t* cm = colmax + (size_t)warp * max_len;
+    int m0 = 0, m1 = 0;
+    for (int j = lane; j < n; j += 32) { const uint32_t v = cm[j]; m0 = max(m0, lo16(v)); m1 = max(m1, hi16(v)); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    if (lane == 0) {
+        const PairDef pd = c_pairs[it.pair];
+        stats_max[it.seg * tasks_per_seg + pd.task[0]] = m0;
+        stats_max[it.seg * tasks_per_seg + pd.task[1]] = m1;
+    }
+}
+
+}  // namespace ltg

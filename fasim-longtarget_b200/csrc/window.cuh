@@ -1,0 +1,410 @@
+// Window stage: the device counterpart of fastSIM's per-peak loop (fastsim.h:202-272) around
+// Aligner::Align -> ssw_align (ssw_cpp.cpp:599, sswNew.cpp:1446): forward Smith-Waterman of the whole
+// lncRNA against a short DNA window ending at the peak, reverse pass to locate the beginning, banded
+// traceback to a CIGAR, expansion to the aligned TFO / TTS strings.
+//
+// Layout is transposed with respect to the scan: lanes own window COLUMNS (R per lane) and the RNA
+// streams through them, so a 55-column window keeps ~m/(m+g) of its lanes busy instead of ~60 %.
+// Windows are right-aligned in groups of g = 4/8/16/32 lanes (pad columns on the left stay identically
+// zero); a warp carries 32/g groups in each 16-bit half.  Scores are computed on the fly
+// (XNOR of scaled base codes, then max(~e + 6, -4)), so every group may stream its own RNA slice —
+// the forward pass streams rows 0..m-1, the reverse pass rows qe..0.
+// Result tracking costs one VIMNMX3 per two cells plus a rarely taken slow path: forward keeps the
+// maximum with the reference's tie rules (first column, then first row: sswNew.cpp:605-629), reverse keeps
+// the first column (then first row) whose value equals the forward score (terminate test :617).
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace ltg {
+
+constexpr int kWinR = 8;            // window columns per lane
+constexpr int kWinClasses = 4;      // groups of 4, 8, 16, 32 lanes  (32, 64, 128, 256 columns)
+constexpr int kMaxWindow = 32 * kWinR;
+
+struct WinState {
+    // peak pool
+    int n_peaks;
+    const int* pk_task;
+    const int* pk_pos;
+    const int* pk_score;
+    // per peak
+    int* w_len;        // columns of the window in flight (cut, or re+1 in the reverse pass)
+    int* w_done;       // 1: final alignment chosen
+    int* best_sw; int* best_cut; int* best_re; int* best_qe;
+    int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb;
+    // class lists
+    int* cls_count;    // [4]
+    int* cls_list;     // [4][cap]
+    int cap;
+    // dp result per peak: (best value, column, row)
+    int4* res;
+    int* bin_counter;
+    // geometry
+    const uint8_t* codes; const SegDesc* segs; int tasks_per_seg;
+    const uint8_t* rna_ssw; int m;
+    const int* cut_table;   // [256][4]  cut length per (peak score, round) — fastsim.h:210 evaluated in float32 on the host
+    long long* cell_counter;
+    const int* forced_cut;  // probe path: explicit window length per peak (nullptr in the product path)
+};
+
+__device__ inline int win_class(int len) { return len <= 4 * kWinR ? 0 : (len <= 8 * kWinR ? 1 : (len <= 16 * kWinR ? 2 : 3)); }
+
+// round >= 0: forward plan for round `round`; round < 0: reverse plan over the chosen alignments
+__global__ void k_win_plan(const WinState w, int round)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n_peaks) return;
+    int len;
+    if (round >= 0) {
+        if (round == 0) { w.w_done[i] = 0; w.best_sw[i] = 0; w.fin_sw[i] = 0; }
+        else if (w.w_done[i]) return;
+        const int sc = w.pk_score[i], pos = w.pk_pos[i];
+        int cut = w.forced_cut ? w.forced_cut[i] : w.cut_table[min(sc, 255) * 4 + round];
+        if (pos - cut + 1 <= 0) cut = pos + 1;                 // fastsim.h:211
+        len = cut;
+    } else {
+        if (w.fin_sw[i] <= 0) return;
+        len = w.fin_re[i] + 1;
+    }
+    w.w_len[i] = len;
+    const int c = win_class(len);
+    const int slot = atomicAdd(&w.cls_count[c], 1);
+    w.cls_list[(size_t)c * w.cap + slot] = i;
+    if (round >= 0 && w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, (unsigned long long)len * (unsigned long long)w.m);
+}
+
+__device__ inline int bins_of_class(int count, int c) { const int wpw = 2 * (32 / (4 << c)); return (count + wpw - 1) / wpw; }
+
+template <bool REV>
+__global__ void __launch_bounds__(128) k_win_dp(const WinState w)
+{
+    constexpr int R = kWinR;
+    const int lane = threadIdx.x & 31;
+    const uint32_t kNegOpen = 0xFFF0FFF0u, kNegExt = 0xFFFCFFFCu, kSix = 0x00060006u, kMis = 0xFFFCFFFCu;
+    int nb[kWinClasses], total = 0;
+#pragma unroll
+    for (int c = 0; c < kWinClasses; ++c) { nb[c] = bins_of_class(w.cls_count[c], c); total += nb[c]; }
+
+    for (;;) {
+        int bin = 0;
+        if (lane == 0) bin = atomicAdd(w.bin_counter, 1);
+        bin = __shfl_sync(0xffffffffu, bin, 0);
+        if (bin >= total) break;
+        int c = 0, b = bin;
+        while (b >= nb[c]) { b -= nb[c]; ++c; }
+        const int g = 4 << c, gpw = 32 / g;            // lanes per group, groups per half-warp
+        const int lig = lane & (g - 1), grp = lane / g;
+        const bool leader = (lig == 0);
+
+        // per-half window description for this lane's group
+        int wi[2], len[2], slen[2], sbase[2], sdir[2];
+        uint32_t dq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) dq[r] = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int slot = (b * 2 + h) * gpw + grp;
+            wi[h] = (slot < w.cls_count[c]) ? w.cls_list[(size_t)c * w.cap + slot] : -1;
+            len[h] = 0; slen[h] = 0; sbase[h] = 0; sdir[h] = 1;
+            int colcode[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) colcode[r] = 80;
+            if (wi[h] >= 0) {
+                const int i = wi[h];
+                const int task = w.pk_task[i];
+                const SegDesc sd = w.segs[task / w.tasks_per_seg];
+                const TaskDef td = c_tasks[task % w.tasks_per_seg];
+                const int L = w.w_len[i];
+                len[h] = L;
+                const int cutw = REV ? w.fin_cut[i] : L;
+                const int ws = w.pk_pos[i] - cutw + 1;                    // window start in seq2 coordinates
+                if (REV) { slen[h] = w.fin_qe[i] + 1; sbase[h] = w.fin_qe[i]; sdir[h] = -1; }
+                else { slen[h] = w.m; sbase[h] = 0; sdir[h] = 1; }
+                const int off = g * R - L;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int cc = lig * R + r - off;
+                    if (cc >= 0) {
+                        const int q = REV ? (ws + w.fin_re[i] - cc) : (ws + cc);
+                        const int x = w.codes[sd.start + (td.reversed ? (sd.len - 1 - q) : q)];
+                        const int d = td.img[x];
+                        colcode[r] = d < 4 ? d * 16 : 80;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) dq[r] |= (uint32_t)colcode[r] << (16 * h);
+        }
+        int nsteps = max(slen[0], slen[1]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+        nsteps += g - 1;
+
+        int best[2], bcol[2], brow[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            best[h] = (REV && wi[h] >= 0) ? w.fin_sw[wi[h]] - 1 : 0;
+            bcol[h] = 0x7fffffff; brow[h] = 0;
+        }
+        uint32_t trigm1 = pack16(max(best[0], 0), max(best[1], 0));
+        const uint32_t keep = leader ? 0u : 0xffffffffu;
+
+        uint32_t Hd[R], E[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
+        uint32_t hout = 0, fout = 0, xout = pack16(64, 64), hdiag = 0;
+        // leader prefetch of the stream symbol
+        auto fetch = [&](int s) -> uint32_t {
+            int c0 = 64, c1 = 64;
+            if (leader) {
+                if (s < slen[0]) { const int q = w.rna_ssw[sbase[0] + sdir[0] * s]; c0 = q < 4 ? q * 16 : 64; }
+                if (s < slen[1]) { const int q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = q < 4 ? q * 16 : 64; }
+            }
+            return pack16(c0, c1);
+        };
+        uint32_t xnext = fetch(0);
+        for (int s = 0; s < nsteps; ++s) {
+            const uint32_t myx = xnext;
+            xnext = fetch(s + 1);
+            uint32_t hin = __shfl_up_sync(0xffffffffu, hout, 1) & keep;
+            uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1) & keep;
+            uint32_t xin = __shfl_up_sync(0xffffffffu, xout, 1);
+            xin = leader ? myx : xin;
+            uint32_t d = hdiag, f = fin, hlast = 0;
+            uint32_t t[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t y = ~(xin ^ dq[r]);
+                const uint32_t sc = __viaddmax_s16x2(y, kSix, kMis);          // +5 on equal codes, -4 otherwise
+                t[r] = __viaddmax_s16x2_relu(d, sc, E[r]);
+                const uint32_t u = __vadd2(t[r], kNegOpen);
+                E[r] = __viaddmax_s16x2(E[r], kNegExt, u);
+                const uint32_t hh = __vmaxs2(t[r], f);
+                f = __viaddmax_s16x2(f, kNegExt, u);
+                d = Hd[r];
+                Hd[r] = hh;
+                hlast = hh;
+            }
+            uint32_t ms = __vimax3_s16x2(t[0], t[1], t[2]);
+            ms = __vimax3_s16x2(ms, t[3], t[4]);
+            ms = __vimax3_s16x2(ms, t[5], t[6]);
+            ms = __vmaxs2(ms, t[7]);
+            if (__vmaxs2(trigm1, ms) != trigm1) {
+                const int row = s - lig;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (wi[h] < 0 || row < 0 || row >= slen[h]) continue;
+                    const int off = g * R - len[h];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int cc = lig * R + r - off;
+                        const int v = h ? hi16(t[r]) : lo16(t[r]);
+                        if (cc >= 0 && (v > best[h] || (v == best[h] && cc < bcol[h]))) { best[h] = v; bcol[h] = cc; brow[h] = row; }
+                    }
+                }
+                if (!REV) trigm1 = pack16(max(best[0] - 1, 0), max(best[1] - 1, 0));
+            }
+            hdiag = hin;
+            hout = hlast; fout = f; xout = xin;
+        }
+        // group reduction: highest value, then smallest column (lower lanes own smaller columns)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            for (int o = 1; o < g; o <<= 1) {
+                const int ob = __shfl_down_sync(0xffffffffu, best[h], o);
+                const int oc = __shfl_down_sync(0xffffffffu, bcol[h], o);
+                const int orow = __shfl_down_sync(0xffffffffu, brow[h], o);
+                if (lig + o < g && (ob > best[h] || (ob == best[h] && oc < bcol[h]))) { best[h] = ob; bcol[h] = oc; brow[h] = orow; }
+            }
+            if (leader && wi[h] >= 0) w.res[wi[h]] = make_int4(best[h], bcol[h], brow[h], 0);
+        }
+    }
+}
+
+// forward decision of fastSIM's loop (fastsim.h:216-250) for round `round` (0..3)
+__global__ void k_win_decide(const WinState w, int round)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n_peaks || w.w_done[i]) return;
+    const int cut = w.w_len[i];
+    const int4 v = w.res[i];
+    int sw = 0, re = 0, qe = 0;
+    if (v.x > 0) { sw = v.x; re = v.y; qe = v.z; }
+    const int S = w.pk_score[i];
+    if (sw >= S) {
+        w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.w_done[i] = 1;
+        return;
+    }
+    if (sw > w.best_sw[i] && re == cut - 1) { w.best_sw[i] = sw; w.best_cut[i] = cut; w.best_re[i] = re; w.best_qe[i] = qe; }
+    if (round == 3) {
+        if (w.best_sw[i] > 0) { w.fin_sw[i] = w.best_sw[i]; w.fin_cut[i] = w.best_cut[i]; w.fin_re[i] = w.best_re[i]; w.fin_qe[i] = w.best_qe[i]; }
+        else { w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; }
+        w.w_done[i] = 1;
+    }
+}
+
+// reverse result: beginning of the alignment (sswNew.cpp:1518-1520)
+__global__ void k_win_finish(const WinState w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n_peaks || w.fin_sw[i] <= 0) return;
+    const int S = w.fin_sw[i];
+    const int4 v = w.res[i];
+    int col = -1, row = 0;
+    if (v.x == S) { col = v.y; row = v.z; }
+    if (col < 0) {
+        // cannot happen for an exact forward score; a literal (Q4) forward score is resolved by the literal reverse pass
+        if (S < kQ4Guard) w.fin_sw[i] = 0;
+        w.fin_rb[i] = 0; w.fin_qb[i] = 0;
+        return;
+    }
+    w.fin_rb[i] = w.fin_re[i] - col;
+    w.fin_qb[i] = w.fin_qe[i] - row;
+}
+
+// ---------------------------------------------------------------------------------------------
+// banded_sw (sswNew.cpp:1071-1259) + getAlignment expansion (fastsim.h:416-560), one thread per chosen
+// alignment.  Per-thread scratch: three int rows of (2*bw+5), the direction bytes 3*(2*bw+1)*readLen, and
+// the op / string staging area.  Alignments whose band outgrows the scratch are flagged (status 2) and
+// re-run by a second launch with a large scratch.
+struct TraceArgs {
+    WinState w;
+    const unsigned char* dna;      // raw record bytes (for the TTS string)
+    const unsigned char* rna_raw;  // raw lncRNA bytes (for the TFO string)
+    unsigned char* scratch; long long scratch_per_thread;
+    int only_overflow;             // second launch: only alignments flagged status 2
+    // outputs per peak
+    int* al_status;                // 0 none, 1 ok, 2 needs a larger scratch / pool, 3 traceback left the band (sw_score -> 0)
+    int* al_nt; int* al_match; long long* al_stroff;
+    char* strpool; long long strcap; long long* str_count;
+};
+
+__device__ inline int band_u(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x + 1; }
+__device__ inline int band_d(int w, int i, int j, int p) { int x = i - w; if (x < 0) x = 0; return (j - x) * 3 + p; }
+
+__device__ inline char comp_char(unsigned char c)
+{
+    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
+}
+
+__global__ void k_traceback(const TraceArgs a)
+{
+    const WinState& w = a.w;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    unsigned char* sc = a.scratch + (size_t)tid * a.scratch_per_thread;
+    for (int i = tid; i < w.n_peaks; i += nthreads) {
+        if (!a.only_overflow) a.al_status[i] = 0;
+        if (w.fin_sw[i] <= 0) continue;
+        if (a.only_overflow && a.al_status[i] != 2) continue;
+
+        const int task = w.pk_task[i];
+        const SegDesc sd = w.segs[task / w.tasks_per_seg];
+        const TaskDef td = c_tasks[task % w.tasks_per_seg];
+        const int ws = w.pk_pos[i] - w.fin_cut[i] + 1;
+        const int rb = w.fin_rb[i], re = w.fin_re[i], qb = w.fin_qb[i], qe = w.fin_qe[i];
+        const int refLen = re - rb + 1, readLen = qe - qb + 1, score = w.fin_sw[i];
+        const uint8_t* gc = w.codes + sd.start;
+        auto gidx = [&](int q) -> int { return td.reversed ? (sd.len - 1 - q) : q; };     // seq2 index -> segment index
+        const int ntmax = refLen + readLen;
+
+        int bw = abs(refLen - readLen) + 1, maxv = 0, width_d = 0;
+        int8_t* dir = nullptr;
+        bool fits = true;
+        for (;;) {
+            const int width = bw * 2 + 3;
+            width_d = bw * 2 + 1;
+            const long long need = 3LL * (width + 2) * 4 + 3LL * width_d * readLen + 3LL * (ntmax + 4) + 32;
+            if (need > a.scratch_per_thread) { fits = false; break; }
+            int* h_b = reinterpret_cast<int*>(sc);
+            int* e_b = h_b + width + 2;
+            int* h_c = e_b + width + 2;
+            dir = reinterpret_cast<int8_t*>(h_c + width + 2);
+            for (int j = 0; j < width + 2; ++j) { h_b[j] = 0; e_b[j] = 0; h_c[j] = 0; }
+            for (int ii = 0; ii < readLen; ++ii) {
+                const int beg = max(0, ii - bw), end = min(refLen - 1, ii + bw);
+                const int edge = min(end + 1, width - 1);
+                int f = 0, u = 0;
+                h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
+                int8_t* line = dir + (size_t)width_d * ii * 3;
+                const int rc = w.rna_ssw[qb + ii];
+                for (int j = beg; j <= end; ++j) {
+                    u = band_u(bw, ii, j);
+                    const int e = band_u(bw, ii - 1, j), b = band_u(bw, ii, j - 1), dd = band_u(bw, ii - 1, j - 1);
+                    const int de = band_d(bw, ii, j, 0), df = band_d(bw, ii, j, 1), dh = band_d(bw, ii, j, 2);
+                    int t1 = (ii == 0) ? -kGapOpen : h_b[e] - kGapOpen;
+                    int t2 = (ii == 0) ? -kGapExt : e_b[e] - kGapExt;
+                    e_b[u] = t1 > t2 ? t1 : t2;
+                    line[de] = t1 > t2 ? 3 : 2;
+                    t1 = h_c[b] - kGapOpen;
+                    t2 = f - kGapExt;
+                    f = t1 > t2 ? t1 : t2;
+                    line[df] = t1 > t2 ? 5 : 4;
+                    const int e1 = e_b[u] > 0 ? e_b[u] : 0, f1 = f > 0 ? f : 0;
+                    t1 = e1 > f1 ? e1 : f1;
+                    const int rf = td.img[gc[gidx(ws + rb + j)]];
+                    t2 = h_b[dd] + ((rf == rc && rf < 4) ? kMatch : kMismatch);
+                    h_c[u] = t1 > t2 ? t1 : t2;
+                    if (h_c[u] > maxv) maxv = h_c[u];
+                    if (t1 <= t2) line[dh] = 1;
+                    else line[dh] = e1 > f1 ? line[de] : line[df];
+                }
+                for (int j = 1; j <= u; ++j) h_b[j] = h_c[j];
+            }
+            if (maxv >= score) break;
+            bw *= 2;
+        }
+        if (!fits) { a.al_status[i] = 2; continue; }
+
+        // traceback (sswNew.cpp:1159-1238): ops come out end -> start; written backwards into `ops`
+        unsigned char* ops = reinterpret_cast<unsigned char*>(dir) + 3LL * width_d * readLen;
+        char* tfo = reinterpret_cast<char*>(ops + ntmax + 4);
+        char* tts = tfo + ntmax + 4;
+        int wp = ntmax + 2;
+        int ii = readLen - 1, j = refLen - 1, plane = 2;
+        long long line_off = (long long)width_d * (readLen - 1) * 3;
+        bool bad = false;
+        while (ii > 0) {
+            const long long idx = line_off + band_d(bw, ii, j, plane);
+            if (j < 0 || idx < 0 || idx >= 3LL * width_d * readLen) { bad = true; break; }
+            const int dv = dir[idx];
+            if (dv == 1) { --ii; --j; plane = 2; line_off -= (long long)width_d * 3; ops[--wp] = 0; }
+            else if (dv == 2) { --ii; plane = 0; line_off -= (long long)width_d * 3; ops[--wp] = 1; }
+            else if (dv == 3) { --ii; plane = 2; line_off -= (long long)width_d * 3; ops[--wp] = 1; }
+            else if (dv == 4) { --j; plane = 1; ops[--wp] = 2; }
+            else if (dv == 5) { --j; plane = 2; ops[--wp] = 2; }
+            else { bad = true; break; }
+            if (wp <= 1) { bad = true; break; }
+        }
+        if (bad) { a.al_status[i] = 3; continue; }
+        ops[--wp] = 0;      // closing rule (:1220-1238): the alignment always starts with one more M column
+        const int nt = ntmax + 2 - wp;
+        // expansion from the front exactly like getAlignment: q walks the translated DNA from ref_begin, p the RNA
+        int q = ws + rb, p = qb, match = 0;
+        for (int k = 0; k < nt; ++k) {
+            const int op = ops[wp + k];
+            char rch = '-', sch = '-', tch = '-';
+            if (op != 2) rch = (char)a.rna_raw[p++];
+            if (op != 1) {
+                const int gi = gidx(q++);
+                const unsigned char raw = a.dna[sd.start + gi];
+                sch = td.comp_src ? comp_char(raw) : (char)raw;
+                const int dcode = td.img[gc[gi]];
+                tch = dcode < 4 ? "ACGT"[dcode] : 'N';
+            }
+            tfo[k] = rch; tts[k] = sch;
+            if (tch == rch) ++match;
+        }
+        const long long so = (long long)atomicAdd((unsigned long long*)a.str_count, (unsigned long long)(2 * (nt + 1)));
+        if (so + 2 * (nt + 1) > a.strcap) { a.al_status[i] = 2; continue; }
+        char* o = a.strpool + so;
+        for (int k = 0; k < nt; ++k) o[k] = tfo[k];
+        o[nt] = 0;
+        for (int k = 0; k < nt; ++k) o[nt + 1 + k] = tts[k];
+        o[2 * nt + 1] = 0;
+        a.al_nt[i] = nt; a.al_match[i] = match; a.al_stroff[i] = so;
+        a.al_status[i] = 1;
+    }
+}
+
+}  // namespace ltg

@@ -1,0 +1,247 @@
+// Drop-in process surface of the reference `fasim` (Fasim-LongTarget.cpp:78-172 main, :269-377 initEnv,
+// :174-267 FASTA readers, :797-845 printResult, :694-795 print_cluster) on top of the C ABI above.
+// Included at the end of engine.cu (same translation unit: it uses the anonymous-namespace helpers).
+#include <fstream>
+#include <getopt.h>
+#include <time.h>
+
+namespace {
+
+struct FastaRecord { std::string species, chr; long start = 0; std::string header, seq; };
+
+// readDna — Fasim-LongTarget.cpp:202-267.  Header ">species|chr|start-end".  Unlike the canonical variant
+// (which never resets its accumulator) every record is parsed on its own, like
+// fasim-LongTarget.cpp:215-263 does.
+bool read_dna_fasta(const std::string& path, std::vector<FastaRecord>& out)
+{
+    std::ifstream in(path.c_str());
+    if (!in) return false;
+    std::string line;
+    FastaRecord cur;
+    bool have = false;
+    auto flush = [&]() { if (have) out.push_back(cur); };
+    while (std::getline(in, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
+        if (!line.empty() && line[0] == '>') {
+            flush();
+            cur = FastaRecord();
+            have = true;
+            cur.header = line.substr(1);
+            std::string field, startstr;
+            int bars = 0;
+            for (size_t i = 1; i < line.size(); ++i) {
+                const char ch = line[i];
+                if (ch == '|' && bars == 0) { cur.species = field; field.clear(); ++bars; continue; }
+                if (ch == '|' && bars == 1) { cur.chr = field; field.clear(); ++bars; continue; }
+                if (ch == '-' && bars == 2) { startstr = field; field.clear(); continue; }
+                field += ch;
+            }
+            cur.start = atoi(startstr.c_str());
+        } else if (have) {
+            cur.seq += line;
+        }
+    }
+    flush();
+    return true;
+}
+
+// readRna — Fasim-LongTarget.cpp:174-200: first line is the name (every '>' removed), all other lines are
+// concatenated.
+bool read_rna_fasta(const std::string& path, std::string& name, std::string& seq)
+{
+    std::ifstream in(path.c_str());
+    if (!in) return false;
+    std::string line;
+    name.clear(); seq.clear();
+    if (!std::getline(in, line)) return true;
+    for (char ch : line) if (ch != '>' && ch != '\r' && ch != '\n') name += ch;
+    while (std::getline(in, line)) {
+        for (char ch : line) if (ch != '\r' && ch != '\n') seq += ch;
+    }
+    return true;
+}
+
+void usage()
+{
+    printf("fasim (B200 build) — genome-wide lncRNA:DNA triplex scan\n"
+           "  -f1 <dna.fa>   DNA FASTA, header >species|chr|start-end\n"
+           "  -f2 <rna.fa>   lncRNA FASTA\n"
+           "  -O  <dir/>     output directory (must exist)\n"
+           "  -r N  rule (0 = all)          -t N  strand (0 both, >0 parallel, <0 anti-parallel)\n"
+           "  -c N  segment length (5000)   -o N  segment overlap (100)\n"
+           "  -i N  min identity (60)       -S N  min stability (1)\n"
+           "  -ni N min triplex nt (20)     -na N max triplex nt (100000)\n"
+           "  -pc N penalty C (0)           -pt N penalty T (-1000)\n"
+           "  -ds N cluster distance (15)   -lg N min length for clustering (50)\n"
+           "  --device N  CUDA device (default 0)\n");
+}
+
+}  // namespace
+
+extern "C" {
+
+int ltg_write_tfosorted(const ltg_result* r, const char* path)
+{
+    if (!r || !path) { set_error("null argument"); return LTG_ERR_ARG; }
+    FILE* f = fopen(path, "w");
+    if (!f) { set_error("cannot write %s", path); return LTG_ERR_IO; }
+    fputs("QueryStart\tQueryEnd\tStartInSeq\tEndInSeq\tDirection\tChr\tStartInGenome\tEndInGenome\tMeanStability\t"
+          "MeanIdentity(%)\tStrand\tRule\tScore\tNt(bp)\tClass\tMidPoint\tCenter\tTFO sequence\tTTS sequence\n", f);
+    const char* chr = r->text + (r->n_triplex ? 0 : 0);
+    (void)chr;
+    for (int64_t i = 0; i < r->n_triplex; ++i) {
+        const ltg_triplex& t = r->triplex[i];
+        if (t.motif == 0) continue;                             // Fasim-LongTarget.cpp:819-822
+        const char* chrname = r->text + t.chr_off;
+        fprintf(f, "%d\t%d\t%d\t%d\t%s\t%s\t%ld\t%ld\t%g\t%g\t%s\t%d\t%g\t%d\t%d\t%d\t%d\t%s\t%s\n", t.stari, t.endi, t.starj, t.endj,
+                t.starj < t.endj ? "R" : "L", chrname, (long)t.genomestart, (long)t.genomeend, (double)t.tri_score, (double)t.identity,
+                ltg_host::strand_name(t.reverse, t.strand), t.rule, (double)t.score, t.nt, t.motif, t.middle, t.center,
+                r->text + t.tfo_off, r->text + t.tts_off);
+    }
+    fclose(f);
+    return LTG_OK;
+}
+
+// print_cluster — Fasim-LongTarget.cpp:694-795 for class levels 1 and 2 (called from printResult :831-836
+// with start_genome - 1).  Restated from the coverage map semantics; see the line comments.
+int ltg_write_tfoclass(const ltg_result* r, const ltg_params* p, const char* sorted_path, const char* chr, int64_t record_start,
+                       int64_t dna_size, const char* rna_name)
+{
+    if (!r || !p || !sorted_path) { set_error("null argument"); return LTG_ERR_ARG; }
+    // rebuild the per-class coverage maps exactly as cluster_triplex fills class1[] (:661-672)
+    std::map<size_t, size_t> cov[6];
+    for (int64_t i = 0; i < r->n_triplex; ++i) {
+        const ltg_triplex& t = r->triplex[i];
+        if (t.motif < 1 || t.motif > 5) continue;
+        if (t.endj > t.starj) for (int j = t.starj; j < t.endj; ++j) cov[t.motif][(size_t)j]++;
+        else for (int j = t.endj; j < t.starj; ++j) cov[t.motif][(size_t)j]++;
+    }
+    const std::string base(sorted_path);
+    const long start_genome = (long)record_start - 1;
+    for (int level = 1; level <= 2; ++level) {
+        char name[64];
+        snprintf(name, sizeof name, "-TFOclass%d-%d-%d", level, p->c_distance, p->c_length);
+        const std::string path = base.substr(0, base.size() >= 10 ? base.size() - 10 : 0) + name;     // strips "-TFOsorted" (:706)
+        FILE* f = fopen(path.c_str(), "w");
+        if (!f) { set_error("cannot write %s", path.c_str()); return LTG_ERR_IO; }
+        fprintf(f, "browser position %s:%ld-%ld\n", chr, start_genome, start_genome + (long)dna_size);
+        fputs("browser hide all\nbrowser pack refGene encodeRegions\nbrowser full altGraph\n"
+              "# 300 base wide bar graph, ausoScale is on by default == graphing\n"
+              "# limits will dynamically change to always show full range of data\n"
+              "# in viewing window, priority = 20 position this as the second graph\n"
+              "# Note, zero-relative, half-open coordinate system in use for bedGraph format\n", f);
+        fprintf(f, "track type=bedGraph name='%s TTS (%d)' description='%d-%d' visibility=full color=200,100,0 altColor=0,100,200 priority=20\n",
+                rna_name, level, p->c_distance, p->c_length);
+        const std::map<size_t, size_t>& m = cov[level];
+        struct Row { long a, b, v; };
+        std::vector<Row> rows;
+        long final_genome = 0;
+        for (auto& kv : m) final_genome = (long)kv.first + start_genome;                              // :723-726
+        int count = 0;
+        for (auto it = m.begin(); it != m.end();) {                                                   // :727-766
+            const long first0 = (long)it->first;
+            long tmp1 = (long)it->first, tmp2 = (long)it->second;
+            if (tmp1 + start_genome == final_genome) { rows.push_back({first0 + start_genome - 1, tmp1 + start_genome, tmp2}); break; }
+            ++it;
+            while (it != m.end() && labs((long)it->first - tmp1) == 1 && (long)it->second == tmp2) {
+                if ((long)it->first + start_genome == final_genome) break;
+                tmp1 = (long)it->first; tmp2 = (long)it->second;
+                ++it;
+            }
+            rows.push_back({first0 + start_genome - (count == 0 ? 2 : 1), tmp1 + start_genome, tmp2});
+            ++count;
+            if (it != m.end() && labs((long)it->first - tmp1) != 1) rows.push_back({tmp1 + start_genome, (long)it->first + start_genome - 1, 0});
+        }
+        for (const Row& rw : rows) fprintf(f, "%s\t%ld\t%ld\t%ld\n", chr, rw.a, rw.b, rw.v);
+        fclose(f);
+    }
+    return LTG_OK;
+}
+
+int ltg_main(int argc, char* const* argv)
+{
+    ltg_params P;
+    ltg_default_params(&P);
+    std::string f1 = "./", f2 = "./", outdir = "./";
+    int device = 0;
+    // same option table as initEnv (Fasim-LongTarget.cpp:271-283); -m, -d, -cn, -F are accepted and ignored
+    // (-F selects the SIM path, which this build does not provide: it is reported as an error)
+    const char* optstring = "f:s:r:O:c:m:t:i:S:z:Y:Z:h:C:D:E:o:y:Fd";
+    static const struct option long_options[] = {
+        {"f1", required_argument, nullptr, 'f'}, {"f2", required_argument, nullptr, 's'}, {"ni", required_argument, nullptr, 'y'},
+        {"na", required_argument, nullptr, 'z'}, {"pc", required_argument, nullptr, 'Y'}, {"pt", required_argument, nullptr, 'Z'},
+        {"cn", required_argument, nullptr, 'C'}, {"ds", required_argument, nullptr, 'D'}, {"lg", required_argument, nullptr, 'E'},
+        {"device", required_argument, nullptr, 1000}, {nullptr, 0, nullptr, 0}};
+    if (argc <= 1) { usage(); return 1; }
+    optind = 1;
+    int opt;
+    bool want_sim = false;
+    while ((opt = getopt_long_only(argc, argv, optstring, long_options, nullptr)) != -1) {
+        switch (opt) {
+        case 'f': f1 = optarg; break;
+        case 's': f2 = optarg; break;
+        case 'r': P.rule = atoi(optarg); break;
+        case 'O': outdir = optarg; break;
+        case 'c': P.cut_length = atoi(optarg); break;
+        case 't': P.strand = atoi(optarg); break;
+        case 'i': P.min_identity = atoi(optarg); break;
+        case 'S': P.min_stability = atoi(optarg); break;
+        case 'y': P.nt_min = atoi(optarg); break;
+        case 'z': P.nt_max = atoi(optarg); break;
+        case 'Y': P.penalty_c = atoi(optarg); break;
+        case 'Z': P.penalty_t = atoi(optarg); break;
+        case 'o': P.overlap = atoi(optarg); break;
+        case 'D': P.c_distance = atoi(optarg); break;
+        case 'E': P.c_length = atoi(optarg); break;
+        case 'F': want_sim = true; break;
+        case 'h': usage(); return 1;
+        case 1000: device = atoi(optarg); break;
+        default: break;
+        }
+    }
+    if (want_sim) { fprintf(stderr, "fasim: -F (SIM mode) is not available in the B200 build\n"); return 2; }
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    printf("Searching triplexes using Fasim\n");
+    std::vector<FastaRecord> recs;
+    if (!read_dna_fasta(f1, recs) || recs.empty()) { fprintf(stderr, "fasim: cannot read DNA file %s\n", f1.c_str()); return 2; }
+    std::string lnc_name, lnc;
+    if (!read_rna_fasta(f2, lnc_name, lnc) || lnc.empty()) { fprintf(stderr, "fasim: cannot read RNA file %s\n", f2.c_str()); return 2; }
+    printf("%s\n", lnc_name.c_str());
+
+    ltg_context* ctx = nullptr;
+    if (ltg_create(device, &ctx) != LTG_OK) { fprintf(stderr, "fasim: %s\n", ltg_last_error()); return 3; }
+    int rc = ltg_set_params(ctx, &P);
+    if (rc == LTG_OK) rc = ltg_set_query(ctx, lnc_name.c_str(), lnc.c_str(), (int64_t)lnc.size());
+    ltg_result* all = nullptr;
+    if (rc == LTG_OK) rc = ltg_result_new(&all);
+    for (size_t i = 0; rc == LTG_OK && i < recs.size(); ++i) {
+        ltg_result* one = nullptr;
+        rc = ltg_scan_record(ctx, recs[i].seq.data(), (int64_t)recs[i].seq.size(), recs[i].chr.c_str(), recs[i].start, &one);
+        if (rc == LTG_OK) { rc = ltg_result_append(all, one); ltg_result_free(one); }
+    }
+    if (rc != LTG_OK) { fprintf(stderr, "fasim: %s\n", ltg_last_error()); ltg_result_free(all); ltg_destroy(ctx); return 3; }
+    ltg_cluster(all, &P);
+    // output name: <O>/<species>-<lncName>-<f1 minus last 3 chars>-TFOsorted (Fasim-LongTarget.cpp:123, 800-802); the
+    // directory part of -f1 is dropped (the reference embeds it and then silently fails to open the file, Q14)
+    std::string base = f1;
+    const size_t slash = base.find_last_of('/');
+    if (slash != std::string::npos) base = base.substr(slash + 1);
+    base = base.substr(0, base.size() >= 3 ? base.size() - 3 : 0);
+    const std::string out_path = outdir + "/" + recs[0].species + "-" + lnc_name + "-" + base + "-TFOsorted";
+    rc = ltg_write_tfosorted(all, out_path.c_str());
+    if (rc == LTG_OK) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, (int64_t)recs[0].seq.size(), lnc_name.c_str());
+    if (rc != LTG_OK) fprintf(stderr, "fasim: %s\n", ltg_last_error());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    printf("finished normally\nRunning time is %g\n", secs);
+    if (all->scan_cells > 0 && secs > 0)
+        printf("[b200] segments=%ld tasks=%ld peaks=%ld scan_cells=%.3e gpu_scan_ms=%.2f gpu_window_ms=%.2f literal_tasks=%ld literal_windows=%ld\n",
+               (long)all->n_segments, (long)all->n_tasks, (long)all->n_peaks, (double)all->scan_cells, all->gpu_ms_scan, all->gpu_ms_window,
+               (long)all->n_literal_tasks, (long)all->n_literal_windows);
+    ltg_result_free(all);
+    ltg_destroy(ctx);
+    return rc == LTG_OK ? 0 : 3;
+}
+
+}  // extern "C"
