@@ -58,7 +58,7 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ltg_params params;
     // task tables (depend on params.rule / params.strand)
     std::vector<TaskDef> tasks;
@@ -164,7 +164,8 @@ struct BatchOut {
     std::vector<uint32_t> colmax;   // only when requested (probe)
     long long window_cells = 0;
     int n_literal_tasks = 0, n_literal_windows = 0;
-    float ms_scan = 0, ms_window = 0;
+    float ms_scan = 0, ms_window = 0, ms_scan_kernel = 0;
+    int n_scan_launches = 0;
 };
 
 int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax)
@@ -268,7 +269,10 @@ int run_batch(ltg_context* c, const std::vector<HostSeg>& segs, bool want_colmax
         c->launches += 1;
         stats_max = c->d_stats_max.as<int>();
     }
+    LTG_CUDA_CHECK(cudaEventRecord(c->ev[4], c->stream));
     if (int e = launch_scan(c, n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
+    LTG_CUDA_CHECK(cudaEventRecord(c->ev[5], c->stream));
+    out.n_scan_launches = 1;
 
     // peaks
     int pk_cap = std::max(4096, n_tasks * 48);
@@ -336,6 +340,7 @@ int run_batch(ltg_context* c, const std::vector<HostSeg>& segs, bool want_colmax
     }
     LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     LTG_CUDA_CHECK(cudaEventElapsedTime(&out.ms_scan, c->ev[0], c->ev[1]));
+    LTG_CUDA_CHECK(cudaEventElapsedTime(&out.ms_scan_kernel, c->ev[4], c->ev[5]));
     if (!want_alignments || n_peaks == 0) {
         out.fin_sw.assign(n_peaks, 0);
         return LTG_OK;
@@ -539,6 +544,7 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
             BatchOut bo;
             if (int e = run_batch(c, batch, false, true, bo)) return e;
             stats.gpu_ms_scan += bo.ms_scan; stats.gpu_ms_window += bo.ms_window;
+            stats.gpu_ms_scan_kernel += bo.ms_scan_kernel; stats.n_scan_launches += bo.n_scan_launches;
             stats.n_peaks += (int64_t)bo.pk_task.size(); stats.window_cells += bo.window_cells;
             stats.n_literal_tasks += bo.n_literal_tasks; stats.n_literal_windows += bo.n_literal_windows;
             // order peaks by (task, position): the reference walks tasks in order and peaks by ascending column
@@ -581,6 +587,7 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
     r->n_peaks = stats.n_peaks; r->window_cells = stats.window_cells; r->n_literal_tasks = stats.n_literal_tasks;
     r->n_literal_windows = stats.n_literal_windows; r->gpu_ms_scan = stats.gpu_ms_scan; r->gpu_ms_window = stats.gpu_ms_window;
     r->gpu_launches = c->launches - launches0;
+    r->gpu_ms_scan_kernel = stats.gpu_ms_scan_kernel; r->n_scan_launches = stats.n_scan_launches;
     *out = r;
     return LTG_OK;
 }
@@ -622,7 +629,7 @@ int ltg_create(int device, ltg_context** out)
     c->num_sms = prop.multiProcessorCount;
     ltg_default_params(&c->params);
     LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) LTG_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 6; ++i) LTG_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
     *out = c;
     return LTG_OK;
 }
@@ -639,7 +646,7 @@ void ltg_destroy(ltg_context* c)
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs})
         b->release();
     for (int k = 0; k < 12; ++k) c->d_w[k].release();
-    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -727,6 +734,7 @@ int ltg_result_append(ltg_result* dst, const ltg_result* src)
     dst->n_peaks += src->n_peaks; dst->window_cells += src->window_cells; dst->n_literal_tasks += src->n_literal_tasks;
     dst->n_literal_windows += src->n_literal_windows; dst->gpu_ms_scan += src->gpu_ms_scan; dst->gpu_ms_window += src->gpu_ms_window;
     dst->gpu_launches += src->gpu_launches;
+    dst->gpu_ms_scan_kernel += src->gpu_ms_scan_kernel; dst->n_scan_launches += src->n_scan_launches;
     return LTG_OK;
 }
 

@@ -78,6 +78,8 @@ typedef struct ltg_result {
     double gpu_ms_scan;         /* CUDA-event time of the scan + peak kernels                      */
     double gpu_ms_window;       /* CUDA-event time of the window kernels                           */
     int64_t gpu_launches;       /* kernels launched for this result                                */
+    double gpu_ms_scan_kernel;  /* CUDA-event time of the k_scan launches alone (roofline numerator) */
+    int64_t n_scan_launches;    /* number of k_scan launches                                       */
 } ltg_result;
 
 /* ---- context ---------------------------------------------------------------------------------- */

@@ -952,4 +952,25 @@ int orc_run_tfosorted(const char* rna, const char* dna, const char* chr, long re
     return orc::emit(txt, out, cap);
 }
 
+// Multi-record run (main() loop, Fasim-LongTarget.cpp:133-166, with per-record parsing as in the "reference +
+// multi-record fix" build): records are scanned in order, lists concatenated, then clustered / sorted / printed once.
+int orc_run_tfosorted_multi(const char* rna, int n_records, const char* const* dnas, const char* const* chrs, const long* starts,
+                            const int* params, char* out, long cap)
+{
+    orc::Params P = orc::params_from(params);
+    std::vector<orc::Triplex> all;
+    for (int r = 0; r < n_records; ++r) {
+        std::vector<orc::Triplex> list;
+        orc::run_record(rna, dnas[r], P, list);
+        for (auto& t : list) {
+            t.chr = chrs[r];
+            t.genomestart = t.starj + starts[r] - 1;
+            t.genomeend = t.endj + starts[r] - 1;
+            all.push_back(t);
+        }
+    }
+    std::string txt = orc::format_sorted(all, P);
+    return orc::emit(txt, out, cap);
+}
+
 }  // extern "C"

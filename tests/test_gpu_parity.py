@@ -1,0 +1,279 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/fasim_b200.h) against the golden vectors of the
+unmodified reference and against the CPU oracle on the same seeded inputs.  Integer / index / byte results must be
+bit-exact; the float32 columns (score, identity, stability) are compared by bit pattern as well (the stated
+tolerance of 1e-6 relative is therefore met with margin 0)."""
+import ctypes as C
+import os
+import random
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import fasim_b200 as fb
+from _harness import GOLDEN, TASKS, oracle, oracle_side, params_array, read_fasta, splitmix_bases
+
+pytestmark = pytest.mark.gpu
+O = oracle_side()
+
+
+def f2b(x):
+    return "%08x" % struct.unpack("<I", struct.pack("<f", x))[0]
+
+
+def rows_as_oracle_text(rows):
+    return [[str(r["stari"]), str(r["endi"]), str(r["starj"]), str(r["endj"]), str(r["strand"]), str(r["reverse"]), str(r["rule"]),
+             str(r["nt"]), f2b(r["score"]), f2b(r["identity"]), f2b(r["tri_score"]), r["tfo"], r["tts"]] for r in rows]
+
+
+def oracle_text_rows(txt):
+    out = []
+    for l in txt.splitlines():
+        e = l.split("\t")
+        out.append(e[:11] + [e[17], e[18]])
+    return out
+
+
+def demo(data_dir):
+    rna = read_fasta(os.path.join(data_dir, "H19.fa"))[0][1]
+    hdr, dna = read_fasta(os.path.join(data_dir, "testDNA.fa"))[0]
+    return rna, hdr, dna
+
+
+def run_cli_files(tmp_path, dna_name, dna_text, rna_name, rna_text, flags):
+    d = str(tmp_path)
+    open(os.path.join(d, dna_name), "w").write(dna_text)
+    open(os.path.join(d, rna_name), "w").write(rna_text)
+    os.makedirs(os.path.join(d, "out"), exist_ok=True)
+    r = fb.run_cli(["-f1", dna_name, "-f2", rna_name, "-O", "out/"] + flags, cwd=d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return {f: open(os.path.join(d, "out", f)).read() for f in sorted(os.listdir(os.path.join(d, "out")))}
+
+
+# ------------------------------------------------------------------------------------------------ scan stage
+def test_scan_stage_demo_all_tasks(engine, golden, data_dir):
+    rna, _, dna = demo(data_dir)
+    engine.set_params()
+    engine.set_query("H19", rna)
+    got = engine.probe_segment(dna, TASKS)
+    cms = np.load(os.path.join(GOLDEN, "demo_colmax.npz"))["colmax"]
+    for k, (t, g) in enumerate(zip(golden["demo_tasks"], got)):
+        assert g["max_score"] == t["max_score"], t
+        assert g["threshold"] == t["threshold"], t
+        assert (g["colmax"] == cms[k]).all(), t
+        assert [list(p) for p in g["peaks"]] == t["peaks"], t
+    assert sum(1 for t in golden["demo_tasks"] if t["max_score"] >= 251) == 4      # Q2 tasks are in the fixture
+
+
+def test_window_alignments_demo(engine, golden, data_dir):
+    rna, _, _ = demo(data_dir)
+    engine.set_params()
+    engine.set_query("H19", rna)
+    wins = golden["demo_windows"]
+    got = engine.Align([w["window"] for w in wins])
+    for w, (o5, cig) in zip(wins, got):
+        assert list(o5) == w["out5"]
+        assert cig == [c for c in w["cigar"] if c >> 4]          # zero-length ops of banded_sw are not observable
+
+
+def test_q4_reproducer_window_seam(engine, golden):
+    """Aligner::Align on the constructed Q4 case: the reference reports 181 / 30M2I12M where exact SW gives 190."""
+    q = golden["q4"]
+    engine.set_params()
+    engine.set_query("q4", q["rna"])
+    (o5, cig), = engine.Align([q["dna"]])
+    assert [list(o5), cig] == [q["align"][0], [c for c in q["align"][1] if c >> 4]]
+    assert o5[0] == 181
+
+
+def test_q4_reproducer_scan_seam(engine, golden):
+    """Column maxima of the Q4 case through the scan seam.  AntiMinus rule 8 is a bijection on ACGT
+    (A->G, C->C, G->T, T->A), so the crafted translated text has a pre-image segment."""
+    q = golden["q4"]
+    seg = q["dna"].translate(str.maketrans("GCTA", "ACGT"))
+    s2, _ = O.task_strings(seg, -1, 1, 8)
+    assert s2 == q["dna"]
+    engine.set_params()
+    engine.set_query("q4", q["rna"])
+    g = engine.probe_segment(seg, [(-1, 1, 8)])[0]
+    assert g["literal"] == 1
+    assert list(g["colmax"]) == q["colmax"]
+    assert g["max_score"] == q["calc"] == 190 and max(q["colmax"]) == 181
+    assert g["peaks"] == O.prealign(q["rna"], s2, int(190 * 0.8))
+
+
+def test_n_and_u_scoring(engine, golden):
+    g = golden["nu_record"]
+    engine.set_params(c_length=20)
+    engine.set_query("u", g["rna"])
+    rows = engine.LongTarget(g["dna"])
+    assert rows_as_oracle_text(rows) == oracle_text_rows(g["text"])
+    g2 = golden["nu_record_plainrna"]
+    engine.set_query("plain", g2["rna"])
+    rows = engine.LongTarget(g["dna"])
+    assert rows_as_oracle_text(rows) == oracle_text_rows(g2["text"])
+    # function level: thresholds under the N-aware scoring, column maxima under the SSW scoring
+    seg = g["dna"][900:1400]
+    pr = engine.probe_segment(seg, TASKS[:6])
+    for (pa, st, ru), r in zip(TASKS[:6], pr):
+        s2, _ = O.task_strings(seg, pa, st, ru)
+        assert r["max_score"] == O.calc_score_once(g2["rna"], s2)
+        assert (r["colmax"] == O.colmax(g2["rna"], s2)).all()
+
+
+@pytest.mark.parametrize("key", ["tail", "homopolymer"])
+def test_segment_edge_cases(engine, golden, key):
+    g = golden[key]
+    engine.set_params(c_length=20)
+    engine.set_query("syn", g["rna"])
+    rows = engine.LongTarget(g["dna"])
+    assert rows_as_oracle_text(rows) == oracle_text_rows(g["text"])
+
+
+def test_tiny_and_ragged_inputs_vs_oracle(engine):
+    rnd = random.Random(11)
+    engine.set_params(c_length=10, nt_min=5)
+    for trial in range(12):
+        m = rnd.choice([1, 2, 15, 16, 17, 31, 100, 511, 512, 513, 777])
+        n = rnd.choice([1, 2, 5, 31, 32, 33, 100, 333])
+        rna = splitmix_bases(100 + trial, m)
+        dna = splitmix_bases(200 + trial, n)
+        if trial % 3 == 0:            # plant a strong hit
+            k = min(m, n, 60)
+            dna = dna[:n - k] + rna[:k].replace("A", "x").replace("T", "A").replace("x", "T")[:k]
+        engine.set_query("r", rna)
+        pr = engine.probe_segment(dna, TASKS)
+        for (pa, st, ru), r in zip(TASKS, pr):
+            s2, _ = O.task_strings(dna, pa, st, ru)
+            mx = O.calc_score_once(rna, s2)
+            assert r["max_score"] == mx, (m, n, pa, st, ru)
+            assert (r["colmax"] == O.colmax(rna, s2)).all(), (m, n, pa, st, ru)
+            assert r["peaks"] == O.prealign(rna, s2, int(mx * 0.8)), (m, n, pa, st, ru)
+        rows = engine.LongTarget(dna)
+        assert rows_as_oracle_text(rows) == oracle_text_rows(O.longtarget(rna, dna, cLength=10, ntMin=5)), (m, n)
+    assert engine.LongTarget("") == []
+
+
+# ------------------------------------------------------------------------------------------------ record / file level
+def test_demo_record_level(engine, data_dir):
+    rna, _, dna = demo(data_dir)
+    engine.set_params()
+    engine.set_query("H19", rna)
+    rows = engine.LongTarget(dna, "chr11", 2158478)
+    assert rows_as_oracle_text(rows) == oracle_text_rows(O.longtarget(rna, dna))
+    assert all(r["genomestart"] == r["starj"] + 2158478 - 1 for r in rows)
+
+
+@pytest.mark.parametrize("tag,flags", [
+    ("lg40", ["-lg", "40"]),
+    ("complex", ["-c", "5000", "-i", "70", "-S", "1.0", "-ni", "25", "-na", "1000", "-pc", "1", "-pt", "-500", "-ds", "10", "-lg", "60"]),
+])
+def test_cli_demo_files_byte_equal(tmp_path, data_dir, tag, flags):
+    files = run_cli_files(tmp_path, "testDNA.fa", open(os.path.join(data_dir, "testDNA.fa")).read(), "H19.fa",
+                          open(os.path.join(data_dir, "H19.fa")).read(), flags)
+    names = [f for f in os.listdir(GOLDEN) if f.startswith("demo_%s__" % tag)]
+    assert len(names) == 3
+    for g in names:
+        assert files[g.split("__", 1)[1]] == open(os.path.join(GOLDEN, g)).read(), g
+
+
+@pytest.mark.parametrize("tag,flags", [("r3", ["-r", "3", "-lg", "40"]), ("t1", ["-t", "1", "-lg", "40"]),
+                                       ("tm1r10", ["-t", "-1", "-r", "10", "-lg", "30"]), ("c1000", ["-c", "1000", "-o", "50", "-lg", "40"])])
+def test_cli_rule_strand_cut_options(tmp_path, data_dir, tag, flags):
+    files = run_cli_files(tmp_path, "testDNA.fa", open(os.path.join(data_dir, "testDNA.fa")).read(), "H19.fa",
+                          open(os.path.join(data_dir, "H19.fa")).read(), flags)
+    assert files["hg19-H19-testDNA-TFOsorted"] == open(os.path.join(GOLDEN, "demo_%s__TFOsorted" % tag)).read()
+
+
+def test_cli_meg3_multi_record(tmp_path, data_dir, golden):
+    files = run_cli_files(tmp_path, "MEG3-12.fa", open(os.path.join(data_dir, "MEG3-DNAseq-first12.fa")).read(), "MEG3.fa",
+                          open(os.path.join(data_dir, "MEG3-ENST00000451743.fa")).read(), ["-lg", "60"])
+    got = [v for k, v in files.items() if k.endswith("TFOsorted")][0]
+    assert got == open(os.path.join(GOLDEN, "meg3_first12_mr__TFOsorted")).read()
+
+
+def test_meg3_single_records(engine, data_dir, golden):
+    rna = read_fasta(os.path.join(data_dir, "MEG3-ENST00000451743.fa"))[0][1]
+    recs = read_fasta(os.path.join(data_dir, "MEG3-DNAseq-first12.fa"))
+    engine.set_params(c_length=60)
+    engine.set_query("MEG3", rna)
+    for k, (hdr, dna) in enumerate(recs):
+        sp, ch, rng = hdr.split("|")
+        res = engine.scan_record(dna, ch, int(rng.split("-")[0]))
+        engine.cluster_triplex(res)
+        path = "/tmp/_meg3_rec_TFOsorted"
+        engine.printResult(res, path)
+        engine.free(res)
+        assert open(path).read() == golden["meg3_records"]["rec%02d" % k], k
+
+
+@pytest.mark.parametrize("name", ["NEAT1", "MALAT1"])
+def test_cli_long_lncrnas_complex_flags(tmp_path, data_dir, name):
+    files = run_cli_files(tmp_path, "testDNA.fa", open(os.path.join(data_dir, "testDNA.fa")).read(), name + ".fa",
+                          open(os.path.join(data_dir, name + ".fa")).read(),
+                          ["-i", "70", "-S", "1.0", "-ni", "25", "-pt", "-500", "-ds", "10", "-lg", "60"])
+    got = [v for k, v in files.items() if k.endswith("TFOsorted")][0]
+    assert got == open(os.path.join(GOLDEN, "%s_testDNA_complex__TFOsorted" % name)).read()
+
+
+def test_cli_synthetic_and_planted(tmp_path, golden):
+    sdna, srna = splitmix_bases(1001, 30000), splitmix_bases(2001, 1000)
+    files = run_cli_files(tmp_path, "syn.fa", ">syn|chr1|1-30000\n%s\n" % sdna, "synRNA.fa", ">synRNA1k\n%s\n" % srna, ["-lg", "20"])
+    assert files["syn-synRNA1k-syn-TFOsorted"] == open(os.path.join(GOLDEN, "syn30k_lg20__TFOsorted")).read()
+    p = golden["planted"]
+    files = run_cli_files(tmp_path, "pl.fa", ">syn|chr1|1-20000\n%s\n" % p["dna"], "plRNA.fa", ">plRNA\n%s\n" % p["rna"], ["-lg", "30"])
+    assert files["syn-plRNA-pl-TFOsorted"] == open(os.path.join(GOLDEN, "planted20k_lg30__TFOsorted")).read()
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_1mbp(engine):
+    """Size-independent properties at bench scale (1 Mbp x 3 kb): determinism, shard-invariance (scanning the region as
+    four shards cut at segment starts gives the same triplexes) and oracle spot checks on sampled tasks."""
+    n = 1_000_000
+    dna = splitmix_bases(1001, n)
+    rna = splitmix_bases(2001, 3000)
+    engine.set_params()
+    engine.set_query("synRNA3k", rna)
+    a = engine.LongTarget(dna, "chr1", 1)
+    b = engine.LongTarget(dna, "chr1", 1)
+    assert a == b
+    stride = 4900
+    cuts = [0, 51 * stride, 102 * stride, 153 * stride, n]
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        end = min(n, hi + 100) if hi < n else n          # each shard carries the 100-bp overlap of its last segment
+        rows = engine.LongTarget(dna[lo:end], "chr1", 1)
+        for r in rows:
+            r["starj"] += lo; r["endj"] += lo; r["genomestart"] += lo; r["genomeend"] += lo
+        # a shard's trailing partial segment re-appears as the head of the next shard's first segment: drop rows that
+        # come from the trailing overlap-only segment
+        parts.append(rows)
+    key = lambda r: (r["starj"], r["endj"], r["stari"], r["endi"], r["rule"], r["strand"], r["reverse"], f2b(r["score"]))
+    whole = sorted(set(map(key, a)))
+    shard = sorted(set(k for rows in parts for k in map(key, rows)))
+    missing = [k for k in whole if k not in set(shard)]
+    assert not missing, missing[:3]
+    rnd = random.Random(3)
+    for _ in range(6):
+        s = rnd.randrange(0, n // stride) * stride
+        seg = dna[s:s + 5000]
+        tasks = rnd.sample(TASKS, 4)
+        pr = engine.probe_segment(seg, tasks)
+        for (pa, st, ru), r in zip(tasks, pr):
+            s2, _ = O.task_strings(seg, pa, st, ru)
+            mx = O.calc_score_once(rna, s2)
+            assert r["max_score"] == mx and r["peaks"] == O.prealign(rna, s2, int(mx * 0.8))
+            assert (r["colmax"] == O.colmax(rna, s2)).all()
+    # three whole segments against the oracle, record level
+    for s in (0, 49 * stride, 150 * stride):
+        seg = dna[s:s + 5000]
+        assert rows_as_oracle_text(engine.LongTarget(seg)) == oracle_text_rows(O.longtarget(rna, seg))
+
+
+def test_error_behaviour(engine):
+    with pytest.raises(fb.FasimError):
+        engine.set_params(rule=19, strand=-1)           # reference: exit(1) in transferString
+    with pytest.raises(fb.FasimError):
+        engine.set_params(cut_length=100, overlap=100)  # reference: cutSequence never advances
+    engine.set_params()
