@@ -225,7 +225,7 @@ def bench_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def run(device_resident, steps):
-        stats = dict(cells=0, bases=0, rows=0, launches=0, scan_ms=0.0, scan_launches=0, win_ms=0.0, win_cells=0, peaks=0, d2h=0,
+        stats = dict(cells=0, bases=0, rows=0, launches=0, scan_ms=0.0, scan_launches=0, win_ms=0.0, win_cells=0, peaks=0, d2h=0, h2d=0,
                      lit_tasks=0, lit_windows=0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -244,7 +244,7 @@ def bench_gpu(args, rank, world, local_rank):
             stats["launches"] += r.gpu_launches; stats["scan_ms"] += r.gpu_ms_scan_kernel; stats["scan_launches"] += r.n_scan_launches
             stats["win_ms"] += r.gpu_ms_window; stats["win_cells"] += r.window_cells; stats["peaks"] += r.n_peaks
             stats["lit_tasks"] += r.n_literal_tasks; stats["lit_windows"] += r.n_literal_windows
-            stats["d2h"] += r.n_triplex * C.sizeof(fb.Triplex) + r.text_bytes + r.n_peaks * 60
+            stats["d2h"] += r.d2h_bytes; stats["h2d"] += r.h2d_bytes
             fb.lib().ltg_result_free(res)
         e1.record(stream)
         torch.cuda.synchronize()
@@ -298,7 +298,7 @@ def bench_gpu(args, rank, world, local_rank):
             "literal_tasks_per_step": st["lit_tasks"] / args.steps,
             "gpu_launches": int(st["launches"]),
             "stage_ms_per_step": {"scan_kernel": st["scan_ms"] / args.steps, "window": st["win_ms"] / args.steps},
-            "e2e": {"value": gcups_e, "unit": "GCUPS", "h2d_bytes_per_step": int(st_e["bases"] / args.steps),
+            "e2e": {"value": gcups_e, "unit": "GCUPS", "h2d_bytes_per_step": int(st_e["h2d"] / args.steps),
                     "d2h_bytes_per_step": int(st_e["d2h"] / args.steps), "ms_per_step": ms_e / args.steps,
                     "mbp_per_s": st_e["bases"] / (ms_e * 1e-3) / 1e6},
             "roofline": {"bound": "int_simd", "kernel": "k_scan<16,4>", "achieved": scan_gcups, "peak": peak, "unit": "GCUPS",

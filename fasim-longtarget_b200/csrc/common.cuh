@@ -55,7 +55,8 @@ struct TaskDef {
     int8_t reversed;  // 1: seq2 is the reversed translated segment (ParaMinus, AntiPlus)
     int8_t img[5];    // translated SSW code for base code 0..4 (A,C,G,T,N)
     int8_t comp_src;  // 1: source strand string is complemented (ParaMinus, AntiMinus)
-    int8_t pad_[2];
+    int8_t pair;      // scan pair that carries this task ...
+    int8_t half;      // ... and the 16-bit half of the packed registers it lives in
 };
 constexpr int kMaxTasks = 48;
 constexpr int kMaxPairs = 48;

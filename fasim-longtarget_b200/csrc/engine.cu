@@ -1,12 +1,20 @@
 // libfasim_b200.so — context, device memory model, pipeline orchestration and the C ABI of
 // include/fasim_b200.h.  One context = one GPU = one stream.  No CPU compute fallback: every DP cell is
 // computed by the kernels in scan.cuh / window.cuh / literal.cuh.
+//
+// Pipeline per DNA record:  H2D -> k_encode / k_seg_flags -> batches of segments, each
+//   device phase  k_scan (strip maxima) -> k_epilogue x3 (+ literal re-runs) -> window rounds -> traceback pass 1
+//                 -> asynchronous D2H of one plain record per peak into a pinned batch slot
+//   host phase    (worker threads, overlapped with the device phase of the next batch) per-task
+//                 de-duplication / ranking / filters of fastSIM's tail (fastsim.h:273-288)
+// -> record filter -> traceback pass 2 (strings of the surviving rows only) -> result.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/fasim_b200.h"
@@ -45,10 +53,53 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-constexpr int kScanR = 16;          // RNA rows per lane in the scan kernel (strip = 512 rows)
-constexpr int kScanWarps = 4;       // warps per CTA
-constexpr int kScanCtasPerSm = 3;
-constexpr int kBatchSegments = 2048;
+// page-locked host memory (asynchronous D2H at full PCIe rate)
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return LTG_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        LTG_CUDA_CHECK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+        return LTG_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+#ifndef LTG_SCAN_R
+#define LTG_SCAN_R 16
+#endif
+#ifndef LTG_SCAN_WARPS
+#define LTG_SCAN_WARPS 4
+#endif
+#ifndef LTG_SCAN_CTAS
+#define LTG_SCAN_CTAS 3
+#endif
+constexpr int kScanR = LTG_SCAN_R;          // RNA rows per lane in the scan kernel (strip = 32 * kScanR rows)
+constexpr int kScanWarps = LTG_SCAN_WARPS;  // warps per CTA
+constexpr int kScanCtasPerSm = LTG_SCAN_CTAS;
+constexpr int kBatchSegments = 1024;
+constexpr size_t kStripBytesPerBatch = 8ull << 30;      // cap of the strip-maxima buffer of one batch
+
+struct HostSeg { int64_t start; int32_t len; int32_t flags; };
+
+// what one batch leaves on the host: pinned copies filled by asynchronous D2H, consumed by the host phase
+struct HostBatch {
+    std::vector<HostSeg> segs;
+    int n_tasks = 0, n_peaks = 0;
+    PinBuf task_off, jobs, tout, task_info, scalars;
+    cudaEvent_t ready = nullptr, ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timed = false, timed_windows = false, has_stats_pass = false;
+    int n_literal_tasks = 0;
+    std::vector<ltg_host::Triplex> rows;        // output of the host phase, task order
+    std::string error;
+    std::thread worker;
+};
 
 }  // namespace ltg
 
@@ -57,8 +108,9 @@ using namespace ltg;
 struct ltg_context {
     int device = 0;
     int num_sms = 0;
+    int host_threads = 1;
+    bool prune = true;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ltg_params params;
     // task tables (depend on params.rule / params.strand)
     std::vector<TaskDef> tasks;
@@ -72,15 +124,24 @@ struct ltg_context {
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_colmax, d_bnd, d_counters;
-    DevBuf d_task_max, d_task_thr, d_task_npk, d_task_flags, d_stats_max;
+    DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
-    DevBuf d_w[12], d_cls_list, d_res;
-    DevBuf d_al_status, d_al_nt, d_al_match, d_al_stroff, d_strpool, d_scratch, d_scratch_big;
+    DevBuf d_w[16], d_cls_list, d_res;
+    DevBuf d_jobs, d_tout, d_strpool, d_scratch, d_scratch_big;
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
-    int64_t launches = 0;
+    HostBatch hb[2];
+    int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
 namespace {
+
+// per-task scalars of the scan stage, one row of 5 ints per array: [max | thr | npeaks | flags | jstar][n_tasks]
+struct TaskInfo {
+    int* max; int* thr; int* npk; int* flags; int* jstar;
+    TaskInfo(int* base, int n) : max(base), thr(base + n), npk(base + 2 * (size_t)n), flags(base + 3 * (size_t)n), jstar(base + 4 * (size_t)n) {}
+};
+
+enum { kCntScan = 0, kCntPeaks = 1, kCntBin = 2, kCntCls = 8, kCntCells = 16, kCntLit = 24, kCntLitTotal = 26, kCntTotal = 32 };
 
 int upload_tables(ltg_context* c)
 {
@@ -98,6 +159,7 @@ int upload_tables(ltg_context* c)
             p.task[0] = (int16_t)idx[k];
             p.task[1] = (int16_t)(k + 1 < idx.size() ? idx[k + 1] : idx[k]);
             p.reversed = (int16_t)dir; p.pad_ = 0;
+            for (int h = 1; h >= 0; --h) { c->tasks[p.task[h]].pair = (int8_t)c->pairs.size(); c->tasks[p.task[h]].half = (int8_t)h; }
             c->pairs.push_back(p);
         }
     }
@@ -148,24 +210,18 @@ int prepare(ltg_context* c)
     LTG_CUDA_CHECK(cudaSetDevice(c->device));
     if (c->tables_dirty) if (int e = upload_tables(c)) return e;
     if (c->profiles_dirty) if (int e = build_profiles(c)) return e;
+    if (int e = c->d_counters.ensure(sizeof(int) * kCntTotal)) return e;
     return LTG_OK;
 }
 
-struct HostSeg { int64_t start; int32_t len; int32_t flags; };
-
-// One batch of segments through scan -> peaks -> windows -> traceback.  Everything device-side is
-// asynchronous on the context stream; the host syncs where it needs counts.
-struct BatchOut {
-    std::vector<int> task_max, task_thr, task_npk, task_flags;
-    std::vector<int> pk_task, pk_pos, pk_score;
-    std::vector<int> fin_sw, fin_cut, fin_rb, fin_re, fin_qb, fin_qe, al_status, al_nt, al_match;
-    std::vector<long long> al_stroff;
-    std::vector<char> strpool;
-    std::vector<uint32_t> colmax;   // only when requested (probe)
-    long long window_cells = 0;
-    int n_literal_tasks = 0, n_literal_windows = 0;
-    float ms_scan = 0, ms_window = 0, ms_scan_kernel = 0;
-    int n_scan_launches = 0;
+// what the function-level probes want back from a batch (everything host-side, synchronous)
+struct ProbeOut {
+    std::vector<int> task_max, task_thr, task_npk, task_flags, task_off;
+    std::vector<int> pk_pos, pk_score;
+    std::vector<uint32_t> colmax;           // [item][strip][max_len]
+    std::vector<uint16_t> lit_colmax;       // [literal row][max_len]
+    std::vector<int> task_litrow;
+    int max_len = 0;
 };
 
 int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax)
@@ -174,32 +230,33 @@ int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, 
     const size_t smem = (size_t)kScanWarps * scan_warp_smem_bytes<kScanR>(max_len);
     if (smem > 227 * 1024) { set_error("segment length %d needs %zu bytes of shared memory per CTA", max_len, smem); return LTG_ERR_LIMIT; }
     LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<kScanR, kScanWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (int e = c->d_bnd.ensure((size_t)blocks * kScanWarps * max_len * sizeof(uint4))) return e;
+    if (int e = c->d_bnd.ensure((size_t)blocks * kScanWarps * max_len * sizeof(uint2))) return e;
     int* counters = c->d_counters.as<int>();
-    LTG_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(int), c->stream));
+    LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntScan, 0, sizeof(int), c->stream));
     ScanArgs a;
     a.codes = c->d_codes.as<uint8_t>(); a.segs = c->d_segs.as<SegDesc>(); a.items = c->d_items.as<ScanItem>();
     a.n_items = n_items; a.profiles = prof; a.n_strips = c->n_strips; a.max_len = max_len;
-    a.colmax = colmax; a.bnd = c->d_bnd.as<uint4>(); a.counter = counters;
+    a.colmax = colmax; a.bnd = c->d_bnd.as<uint2>(); a.counter = counters + kCntScan;
     k_scan<kScanR, kScanWarps><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
     c->launches += 1;
     LTG_CUDA_CHECK(cudaGetLastError());
     return LTG_OK;
 }
 
-
 // ---- literal (Q4) slow path launchers ---------------------------------------------------------
-int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, int max_read_len, const WinState* w, int max_len)
+// n_jobs < 0: the job count lives on the device (n_jobs_dev); the grid is sized for the worst case and idles when
+// the list is empty, so no host round trip is needed to decide whether to launch.
+int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const int* n_jobs_dev, int max_read_len, const WinState* w, int max_len)
 {
     const int L = (max_read_len + 15) / 16;
     const long long per_slot = (long long)L * 16 * 4 + 64;
-    const int blocks = std::min((n_jobs + 7) / 8, c->num_sms * 8);        // 128 threads = 8 half-warp slots per block
+    const int blocks = n_jobs >= 0 ? std::max(1, std::min((n_jobs + 7) / 8, c->num_sms * 8)) : c->num_sms * 2;   // 128 threads = 8 half-warp slots per block
     const int nslots = blocks * 8;
     if (int e = c->d_lit_work.ensure((size_t)nslots * per_slot)) return e;
     LiteralArgs la;
-    la.jobs = d_jobs; la.n_jobs = n_jobs; la.codes = c->d_codes.as<uint8_t>(); la.segs = c->d_segs.as<SegDesc>();
+    la.jobs = d_jobs; la.n_jobs = n_jobs; la.n_jobs_dev = n_jobs_dev; la.codes = c->d_codes.as<uint8_t>(); la.segs = c->d_segs.as<SegDesc>();
     la.rna_ssw = c->d_rna_ssw.as<uint8_t>(); la.work = c->d_lit_work.as<unsigned char>(); la.work_per_slot = per_slot;
-    la.colmax16 = c->d_colmax.as<uint16_t>(); la.max_len = max_len;
+    la.lit_colmax = c->d_lit_colmax.as<uint16_t>(); la.max_len = max_len; la.task_litrow = c->d_task_litrow.as<int>();
     if (w) la.w = *w; else memset(&la.w, 0, sizeof la.w);
     k_literal<<<blocks, 128, 0, c->stream>>>(la);
     c->launches += 1;
@@ -207,152 +264,21 @@ int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, int max
     return LTG_OK;
 }
 
-int run_literal_scan(ltg_context* c, const std::vector<LiteralJob>& jobs, int max_len)
-{
-    if (int e = c->d_lit_jobs.ensure(sizeof(LiteralJob) * jobs.size())) return e;
-    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_lit_jobs.p, jobs.data(), sizeof(LiteralJob) * jobs.size(), cudaMemcpyHostToDevice, c->stream));
-    if (int e = launch_literal(c, c->d_lit_jobs.as<LiteralJob>(), (int)jobs.size(), c->m, nullptr, max_len)) return e;
-    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // `jobs` is host memory owned by the caller
-    return LTG_OK;
-}
-
-int literal_windows(ltg_context* c, const WinState& w, bool reverse, int* total)
+int literal_windows(ltg_context* c, const WinState& w, bool reverse)
 {
     if (int e = c->d_lit_jobs.ensure(sizeof(LiteralJob) * (size_t)w.n_peaks)) return e;
-    int* cnt = c->d_counters.as<int>() + 24;
+    int* cnt = c->d_counters.as<int>() + kCntLit + (reverse ? 1 : 0);
     LTG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
-    k_lit_collect<<<(w.n_peaks + 255) / 256, 256, 0, c->stream>>>(w, reverse ? 1 : 0, c->d_lit_jobs.as<LiteralJob>(), cnt);
+    k_lit_collect<<<(w.n_peaks + 255) / 256, 256, 0, c->stream>>>(w, reverse ? 1 : 0, c->d_lit_jobs.as<LiteralJob>(), cnt,
+                                                                 c->d_counters.as<int>() + kCntLitTotal);
     c->launches += 1;
-    int n = 0;
-    LTG_CUDA_CHECK(cudaMemcpyAsync(&n, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (n == 0) return LTG_OK;
-    *total += n;
-    return launch_literal(c, c->d_lit_jobs.as<LiteralJob>(), n, c->m, &w, 0);
+    return launch_literal(c, c->d_lit_jobs.as<LiteralJob>(), -1, cnt, c->m, &w, 0);
 }
 
-int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, BatchOut& out);
-
-int run_batch(ltg_context* c, const std::vector<HostSeg>& segs, bool want_colmax, bool want_alignments, BatchOut& out)
+// ---------------- window stage: peaks (device-resident pool) -> chosen alignments -> traceback pass 1 ----------------
+int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* strip_colmax, int max_len, HostBatch* hb)
 {
-    const int T = (int)c->tasks.size(), P = (int)c->pairs.size();
-    const int S = (int)segs.size();
-    int max_len = 1;
-    bool any_stats = !c->rna_plain;
-    for (const HostSeg& s : segs) { max_len = std::max(max_len, s.len); if (s.flags & kSegNonACGT) any_stats = true; }
-    max_len = (max_len + 3) & ~3;
-    const int n_items = S * P, n_tasks = S * T;
-
-    if (int e = c->d_segs.ensure(sizeof(SegDesc) * S)) return e;
-    if (int e = c->d_items.ensure(sizeof(ScanItem) * n_items)) return e;
-    if (int e = c->d_colmax.ensure((size_t)n_items * max_len * 4)) return e;
-    if (int e = c->d_counters.ensure(256)) return e;
-    for (DevBuf* b : {&c->d_task_max, &c->d_task_thr, &c->d_task_npk, &c->d_task_flags, &c->d_stats_max})
-        if (int e = b->ensure(sizeof(int) * n_tasks)) return e;
-
-    std::vector<SegDesc> hs(S);
-    std::vector<ScanItem> items(n_items);
-    for (int s = 0; s < S; ++s) {
-        hs[s].start = segs[s].start; hs[s].len = segs[s].len; hs[s].flags = segs[s].flags;
-        for (int p = 0; p < P; ++p) { items[(size_t)s * P + p].seg = s; items[(size_t)s * P + p].pair = p; }
-    }
-    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_segs.p, hs.data(), sizeof(SegDesc) * S, cudaMemcpyHostToDevice, c->stream));
-    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_items.p, items.data(), sizeof(ScanItem) * n_items, cudaMemcpyHostToDevice, c->stream));
-
-    LTG_CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
-    // optional N/U-aware threshold pass (Q3): exact maxima under the Farrar-side scoring
-    const int* stats_max = nullptr;
-    if (any_stats) {
-        if (int e = launch_scan(c, n_items, max_len, c->d_prof_stats.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
-        k_rowmax<<<(n_items * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_colmax.as<uint32_t>(), c->d_items.as<ScanItem>(), c->d_segs.as<SegDesc>(),
-                                                                   n_items, max_len, T, c->d_stats_max.as<int>());
-        c->launches += 1;
-        stats_max = c->d_stats_max.as<int>();
-    }
-    LTG_CUDA_CHECK(cudaEventRecord(c->ev[4], c->stream));
-    if (int e = launch_scan(c, n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
-    LTG_CUDA_CHECK(cudaEventRecord(c->ev[5], c->stream));
-    out.n_scan_launches = 1;
-
-    // peaks
-    int pk_cap = std::max(4096, n_tasks * 48);
-    int n_peaks = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        for (DevBuf* b : {&c->d_pk_task, &c->d_pk_pos, &c->d_pk_score}) if (int e = b->ensure(sizeof(int) * (size_t)pk_cap)) return e;
-        int* counters = c->d_counters.as<int>();
-        LTG_CUDA_CHECK(cudaMemsetAsync(counters + 1, 0, sizeof(int), c->stream));
-        EpiArgs ea;
-        ea.colmax = c->d_colmax.as<uint32_t>(); ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
-        ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.mode = 0;
-        ea.task_max = c->d_task_max.as<int>(); ea.task_thr = c->d_task_thr.as<int>(); ea.task_npeaks = c->d_task_npk.as<int>();
-        ea.task_flags = c->d_task_flags.as<int>(); ea.pk_count = counters + 1; ea.pk_cap = pk_cap;
-        ea.pk_task = c->d_pk_task.as<int>(); ea.pk_pos = c->d_pk_pos.as<int>(); ea.pk_score = c->d_pk_score.as<int>();
-        k_epilogue<<<(n_items * 32 + 127) / 128, 128, 0, c->stream>>>(ea);
-        c->launches += 1;
-        LTG_CUDA_CHECK(cudaGetLastError());
-
-        // Q4 guard: tasks whose exact maximum could carry F >= 132 across a stripe boundary are re-run through
-        // the literal striped emulation, their peaks come from the literal column maxima
-        out.task_flags.resize(n_tasks);
-        LTG_CUDA_CHECK(cudaMemcpyAsync(out.task_flags.data(), c->d_task_flags.p, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        std::vector<LiteralJob> jobs;
-        for (int t = 0; t < n_tasks; ++t) {
-            if (out.task_flags[t] & kTaskRange) { set_error("alignment score exceeds the 16-bit range (segment too long for this build)"); return LTG_ERR_LIMIT; }
-            if (out.task_flags[t] & kTaskLiteral) {
-                LiteralJob j; j.kind = 0; j.task = t; j.seg = t / T; j.tdef = t % T; j.ref_start = 0; j.ref_len = segs[t / T].len;
-                j.read_start = 0; j.read_len = c->m; j.read_dir = 1; j.ref_dir = 0; j.terminate = 255; j.peak = -1;
-                j.out_item = 0; j.out_half = 0;
-                for (int p = 0; p < P; ++p) for (int h = 1; h >= 0; --h) if (c->pairs[p].task[h] == j.tdef) { j.out_item = j.seg * P + p; j.out_half = h; }
-                jobs.push_back(j);
-            }
-        }
-        out.n_literal_tasks = (int)jobs.size();
-        if (!jobs.empty()) {
-            if (int e = run_literal_scan(c, jobs, max_len)) return e;
-            ea.mode = 1;
-            k_epilogue<<<(n_items * 32 + 127) / 128, 128, 0, c->stream>>>(ea);
-            c->launches += 1;
-            LTG_CUDA_CHECK(cudaGetLastError());
-        }
-        LTG_CUDA_CHECK(cudaMemcpyAsync(&n_peaks, counters + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        if (n_peaks <= pk_cap) break;
-        pk_cap = n_peaks + 1024;      // pool too small: grow and redo the (cheap) epilogue
-        if (attempt == 1) { set_error("peak pool overflow"); return LTG_ERR_LIMIT; }
-    }
-    LTG_CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
-
-    out.task_max.resize(n_tasks); out.task_thr.resize(n_tasks); out.task_npk.resize(n_tasks);
-    LTG_CUDA_CHECK(cudaMemcpyAsync(out.task_max.data(), c->d_task_max.p, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
-    LTG_CUDA_CHECK(cudaMemcpyAsync(out.task_thr.data(), c->d_task_thr.p, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
-    LTG_CUDA_CHECK(cudaMemcpyAsync(out.task_npk.data(), c->d_task_npk.p, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
-    LTG_CUDA_CHECK(cudaMemcpyAsync(out.task_flags.data(), c->d_task_flags.p, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
-    out.pk_task.resize(n_peaks); out.pk_pos.resize(n_peaks); out.pk_score.resize(n_peaks);
-    if (n_peaks) {
-        LTG_CUDA_CHECK(cudaMemcpyAsync(out.pk_task.data(), c->d_pk_task.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(out.pk_pos.data(), c->d_pk_pos.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(out.pk_score.data(), c->d_pk_score.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
-    }
-    if (want_colmax) {
-        out.colmax.resize((size_t)n_items * max_len);
-        LTG_CUDA_CHECK(cudaMemcpyAsync(out.colmax.data(), c->d_colmax.p, out.colmax.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    }
-    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    LTG_CUDA_CHECK(cudaEventElapsedTime(&out.ms_scan, c->ev[0], c->ev[1]));
-    LTG_CUDA_CHECK(cudaEventElapsedTime(&out.ms_scan_kernel, c->ev[4], c->ev[5]));
-    if (!want_alignments || n_peaks == 0) {
-        out.fin_sw.assign(n_peaks, 0);
-        return LTG_OK;
-    }
-    return run_windows(c, n_peaks, T, nullptr, out);
-}
-
-// ---------------- window stage: peaks (device-resident pool) -> chosen alignments + strings ----------------
-int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, BatchOut& out)
-{
-    LTG_CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
-    for (int k = 0; k < 12; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
+    for (int k = 0; k < 16; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
     if (int e = c->d_cls_list.ensure(sizeof(int) * (size_t)n_peaks * kWinClasses)) return e;
     if (int e = c->d_res.ensure(sizeof(int4) * (size_t)n_peaks)) return e;
     int* counters = c->d_counters.as<int>();
@@ -363,100 +289,281 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, Batch
     w.best_sw = c->d_w[2].as<int>(); w.best_cut = c->d_w[3].as<int>(); w.best_re = c->d_w[4].as<int>(); w.best_qe = c->d_w[5].as<int>();
     w.fin_sw = c->d_w[6].as<int>(); w.fin_cut = c->d_w[7].as<int>(); w.fin_re = c->d_w[8].as<int>(); w.fin_qe = c->d_w[9].as<int>();
     w.fin_rb = c->d_w[10].as<int>(); w.fin_qb = c->d_w[11].as<int>();
-    w.cls_count = counters + 8; w.cls_list = c->d_cls_list.as<int>(); w.cap = n_peaks;
-    w.res = c->d_res.as<int4>(); w.bin_counter = counters + 2;
+    w.w_lo = c->d_w[12].as<int>(); w.w_rows = c->d_w[13].as<int>(); w.w_bound = c->d_w[14].as<int>();
+    w.cls_count = counters + kCntCls; w.cls_list = c->d_cls_list.as<int>(); w.cap = n_peaks;
+    w.res = c->d_res.as<int4>(); w.bin_counter = counters + kCntBin;
     w.codes = c->d_codes.as<uint8_t>(); w.segs = c->d_segs.as<SegDesc>(); w.tasks_per_seg = T;
     w.rna_ssw = c->d_rna_ssw.as<uint8_t>(); w.m = c->m; w.cut_table = c->d_cut.as<int>();
-    w.cell_counter = reinterpret_cast<long long*>(counters + 16);
+    w.cell_counter = reinterpret_cast<long long*>(counters + kCntCells);
     w.forced_cut = forced_cut;
-    LTG_CUDA_CHECK(cudaMemsetAsync(counters + 16, 0, 8, c->stream));
-    const int pb = (n_peaks + 255) / 256;
+    w.strip_colmax = c->prune ? strip_colmax : nullptr; w.n_strips = c->n_strips; w.strip_rows = 32 * kScanR; w.max_len = max_len;
+    w.n_pairs = (int)c->pairs.size();
+    LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCells, 0, 8, c->stream));
+    LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntLitTotal, 0, sizeof(int), c->stream));
+    const int pb = (n_peaks + 255) / 256, plan_blocks = (n_peaks * 8 + 255) / 256;
     const int dp_blocks = c->num_sms * 4;
-    std::vector<int> h_sw(n_peaks), h_done(n_peaks);
+    auto reset_bins = [&]() -> int {
+        LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntBin, 0, sizeof(int), c->stream));
+        LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCls, 0, sizeof(int) * kWinClasses, c->stream));
+        return LTG_OK;
+    };
     for (int round = 0; round < 4; ++round) {
-        LTG_CUDA_CHECK(cudaMemsetAsync(counters + 2, 0, sizeof(int), c->stream));
-        LTG_CUDA_CHECK(cudaMemsetAsync(counters + 8, 0, sizeof(int) * kWinClasses, c->stream));
-        k_win_plan<<<pb, 256, 0, c->stream>>>(w, round);
-        k_win_dp<false><<<dp_blocks, 128, 0, c->stream>>>(w);
-        c->launches += 2;
+        for (int retry = 0; retry < (w.strip_colmax ? 2 : 1); ++retry) {
+            if (int e = reset_bins()) return e;
+            k_win_plan<<<plan_blocks, 256, 0, c->stream>>>(w, round, retry);
+            k_win_dp<false><<<dp_blocks, 128, 0, c->stream>>>(w);
+            c->launches += 2;
+        }
         // Q4 guard for windows: exact forward scores >= 148 are recomputed by the literal emulation
-        if (int e = literal_windows(c, w, /*reverse=*/false, &out.n_literal_windows)) return e;
+        if (int e = literal_windows(c, w, /*reverse=*/false)) return e;
         k_win_decide<<<pb, 256, 0, c->stream>>>(w, round);
         c->launches += 1;
         LTG_CUDA_CHECK(cudaGetLastError());
     }
     // reverse pass over the chosen alignments
-    LTG_CUDA_CHECK(cudaMemsetAsync(counters + 2, 0, sizeof(int), c->stream));
-    LTG_CUDA_CHECK(cudaMemsetAsync(counters + 8, 0, sizeof(int) * kWinClasses, c->stream));
-    k_win_plan<<<pb, 256, 0, c->stream>>>(w, -1);
+    if (int e = reset_bins()) return e;
+    k_win_plan<<<plan_blocks, 256, 0, c->stream>>>(w, -1, 0);
     k_win_dp<true><<<dp_blocks, 128, 0, c->stream>>>(w);
     k_win_finish<<<pb, 256, 0, c->stream>>>(w);
     c->launches += 3;
-    if (int e = literal_windows(c, w, /*reverse=*/true, &out.n_literal_windows)) return e;
+    if (int e = literal_windows(c, w, /*reverse=*/true)) return e;
     LTG_CUDA_CHECK(cudaGetLastError());
 
-    // traceback + string expansion
+    // traceback pass 1: nt / identity / stability of every chosen alignment
+    if (int e = c->d_jobs.ensure(sizeof(TraceJob) * (size_t)n_peaks)) return e;
+    if (int e = c->d_tout.ensure(sizeof(TraceOut) * (size_t)n_peaks)) return e;
+    k_make_trace_jobs<<<pb, 256, 0, c->stream>>>(w, c->d_jobs.as<TraceJob>());
+    c->launches += 1;
+    (void)hb;
+    return LTG_OK;
+}
+
+// both traceback launches (regular scratch, then the rare alignments whose band outgrew it) over a job list
+int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* d_out, char* strpool)
+{
     const int tb_threads = c->num_sms * 256;
     const long long scratch_small = 24 * 1024, scratch_big = 8LL << 20;
+    const int big_threads = 128;
     if (int e = c->d_scratch.ensure((size_t)tb_threads * scratch_small)) return e;
-    for (DevBuf* b : {&c->d_al_status, &c->d_al_nt, &c->d_al_match}) if (int e = b->ensure(sizeof(int) * (size_t)n_peaks)) return e;
-    if (int e = c->d_al_stroff.ensure(sizeof(long long) * (size_t)n_peaks)) return e;
-    long long strcap = std::max<long long>(1 << 20, (long long)n_peaks * 512);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        if (int e = c->d_strpool.ensure((size_t)strcap)) return e;
-        LTG_CUDA_CHECK(cudaMemsetAsync(counters + 20, 0, 8, c->stream));
-        TraceArgs ta;
-        ta.w = w; ta.dna = c->d_dna.as<unsigned char>(); ta.rna_raw = c->d_rna_raw.as<unsigned char>();
-        ta.scratch = c->d_scratch.as<unsigned char>(); ta.scratch_per_thread = scratch_small; ta.only_overflow = 0;
-        ta.al_status = c->d_al_status.as<int>(); ta.al_nt = c->d_al_nt.as<int>(); ta.al_match = c->d_al_match.as<int>();
-        ta.al_stroff = c->d_al_stroff.as<long long>(); ta.strpool = c->d_strpool.as<char>(); ta.strcap = strcap;
-        ta.str_count = reinterpret_cast<long long*>(counters + 20);
-        k_traceback<<<tb_threads / 64, 64, 0, c->stream>>>(ta);
-        c->launches += 1;
-        out.al_status.resize(n_peaks);
-        long long used = 0;
-        LTG_CUDA_CHECK(cudaMemcpyAsync(out.al_status.data(), c->d_al_status.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(&used, counters + 20, 8, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        if (used > strcap) { strcap = used + (1 << 20); continue; }      // string pool too small: redo
-        int n_over = 0;
-        for (int s : out.al_status) n_over += (s == 2);
-        if (n_over) {
-            const int big_threads = 256;
-            if (int e = c->d_scratch_big.ensure((size_t)big_threads * scratch_big)) return e;
-            ta.scratch = c->d_scratch_big.as<unsigned char>(); ta.scratch_per_thread = scratch_big; ta.only_overflow = 1;
-            k_traceback<<<big_threads / 64, 64, 0, c->stream>>>(ta);
-            c->launches += 1;
-            LTG_CUDA_CHECK(cudaMemcpyAsync(out.al_status.data(), c->d_al_status.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
-            LTG_CUDA_CHECK(cudaMemcpyAsync(&used, counters + 20, 8, cudaMemcpyDeviceToHost, c->stream));
-            LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            if (used > strcap) { strcap = used + (1 << 20); continue; }
-            for (int s : out.al_status) if (s == 2) { set_error("traceback band exceeds the device scratch"); return LTG_ERR_LIMIT; }
-        }
-        out.strpool.resize((size_t)used);
-        if (used) LTG_CUDA_CHECK(cudaMemcpyAsync(out.strpool.data(), c->d_strpool.p, (size_t)used, cudaMemcpyDeviceToHost, c->stream));
-        break;
-    }
-    LTG_CUDA_CHECK(cudaEventRecord(c->ev[3], c->stream));
-    auto fetch = [&](std::vector<int>& v, const int* d) -> int {
-        v.resize(n_peaks);
-        LTG_CUDA_CHECK(cudaMemcpyAsync(v.data(), d, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
-        return LTG_OK;
-    };
-    if (int e = fetch(out.fin_sw, w.fin_sw)) return e;
-    if (int e = fetch(out.fin_cut, w.fin_cut)) return e;
-    if (int e = fetch(out.fin_rb, w.fin_rb)) return e;
-    if (int e = fetch(out.fin_re, w.fin_re)) return e;
-    if (int e = fetch(out.fin_qb, w.fin_qb)) return e;
-    if (int e = fetch(out.fin_qe, w.fin_qe)) return e;
-    if (int e = fetch(out.al_nt, c->d_al_nt.as<int>())) return e;
-    if (int e = fetch(out.al_match, c->d_al_match.as<int>())) return e;
-    out.al_stroff.resize(n_peaks);
-    LTG_CUDA_CHECK(cudaMemcpyAsync(out.al_stroff.data(), c->d_al_stroff.p, sizeof(long long) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
-    LTG_CUDA_CHECK(cudaMemcpyAsync(&out.window_cells, counters + 16, 8, cudaMemcpyDeviceToHost, c->stream));
-    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    LTG_CUDA_CHECK(cudaEventElapsedTime(&out.ms_window, c->ev[2], c->ev[3]));
+    if (int e = c->d_scratch_big.ensure((size_t)big_threads * scratch_big)) return e;
+    TraceArgs ta;
+    ta.jobs = d_jobs; ta.n_jobs = n_jobs; ta.codes = c->d_codes.as<uint8_t>(); ta.dna = c->d_dna.as<unsigned char>();
+    ta.rna_ssw = c->d_rna_ssw.as<uint8_t>(); ta.rna_raw = c->d_rna_raw.as<unsigned char>();
+    ta.nt_min = c->params.nt_min; ta.nt_max = c->params.nt_max; ta.penalty_t = c->params.penalty_t; ta.penalty_c = c->params.penalty_c;
+    ta.out = d_out; ta.strpool = strpool;
+    ta.scratch = c->d_scratch.as<unsigned char>(); ta.scratch_per_thread = scratch_small; ta.only_overflow = 0;
+    const int blocks = std::max(1, std::min(tb_threads / 64, (n_jobs + 63) / 64));
+    k_traceback<<<blocks, 64, 0, c->stream>>>(ta);
+    ta.scratch = c->d_scratch_big.as<unsigned char>(); ta.scratch_per_thread = scratch_big; ta.only_overflow = 1;
+    k_traceback<<<big_threads / 64, 64, 0, c->stream>>>(ta);
+    c->launches += 2;
+    LTG_CUDA_CHECK(cudaGetLastError());
     return LTG_OK;
+}
+
+// Device phase of one batch of segments: scan -> peaks -> windows -> traceback pass 1 -> async D2H into `hb`.
+// The host only synchronises where it needs a count (literal tasks, number of peaks).
+int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch& hb, bool want_alignments, ProbeOut* probe)
+{
+    const int T = (int)c->tasks.size(), P = (int)c->pairs.size();
+    const int S = (int)segs.size();
+    int max_len = 1;
+    bool any_stats = !c->rna_plain;
+    for (const HostSeg& s : segs) { max_len = std::max(max_len, s.len); if (s.flags & kSegNonACGT) any_stats = true; }
+    max_len = (max_len + 3) & ~3;
+    const int n_items = S * P, n_tasks = S * T;
+    hb.segs = segs; hb.n_tasks = n_tasks; hb.n_peaks = 0; hb.rows.clear(); hb.error.clear();
+    hb.timed = true; hb.timed_windows = false; hb.has_stats_pass = any_stats; hb.n_literal_tasks = 0;
+
+    if (int e = c->d_segs.ensure(sizeof(SegDesc) * S)) return e;
+    if (int e = c->d_items.ensure(sizeof(ScanItem) * n_items)) return e;
+    if (int e = c->d_colmax.ensure((size_t)n_items * c->n_strips * max_len * 4)) return e;
+    if (int e = c->d_task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
+    if (int e = c->d_task_off.ensure(sizeof(int) * ((size_t)n_tasks + 1))) return e;
+    if (int e = c->d_stats_max.ensure(sizeof(int) * (size_t)n_tasks)) return e;
+    if (int e = c->d_task_litrow.ensure(sizeof(int) * (size_t)n_tasks)) return e;
+    if (int e = hb.task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
+    if (int e = hb.task_off.ensure(sizeof(int) * ((size_t)n_tasks + 1))) return e;
+    if (int e = hb.scalars.ensure(64)) return e;
+    TaskInfo ti(c->d_task_info.as<int>(), n_tasks), hti(hb.task_info.as<int>(), n_tasks);
+    int* counters = c->d_counters.as<int>();
+
+    std::vector<SegDesc> hs(S);
+    std::vector<ScanItem> items(n_items);
+    for (int s = 0; s < S; ++s) {
+        hs[s].start = segs[s].start; hs[s].len = segs[s].len; hs[s].flags = segs[s].flags;
+        for (int p = 0; p < P; ++p) { items[(size_t)s * P + p].seg = s; items[(size_t)s * P + p].pair = p; }
+    }
+    // (pageable sources: these copies return once the data is staged, so the vectors may die at scope exit)
+    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_segs.p, hs.data(), sizeof(SegDesc) * S, cudaMemcpyHostToDevice, c->stream));
+    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_items.p, items.data(), sizeof(ScanItem) * n_items, cudaMemcpyHostToDevice, c->stream));
+
+    LTG_CUDA_CHECK(cudaEventRecord(hb.ev[0], c->stream));
+    // optional N/U-aware threshold pass (Q3): exact maxima under the Farrar-side scoring
+    const int* stats_max = nullptr;
+    if (any_stats) {
+        if (int e = launch_scan(c, n_items, max_len, c->d_prof_stats.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
+        k_rowmax<<<(n_items * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_colmax.as<uint32_t>(), c->d_items.as<ScanItem>(), c->d_segs.as<SegDesc>(),
+                                                                   n_items, c->n_strips, max_len, T, c->d_stats_max.as<int>());
+        c->launches += 1;
+        stats_max = c->d_stats_max.as<int>();
+    }
+    LTG_CUDA_CHECK(cudaEventRecord(hb.ev[4], c->stream));
+    if (int e = launch_scan(c, n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
+    LTG_CUDA_CHECK(cudaEventRecord(hb.ev[5], c->stream));
+
+    // peaks: statistics + count, literal re-runs, count of those, exclusive scan, write
+    EpiArgs ea;
+    ea.colmax = c->d_colmax.as<uint32_t>(); ea.n_strips = c->n_strips; ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
+    ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
+    ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.mode = 0;
+    ea.task_max = ti.max; ea.task_thr = ti.thr; ea.task_npeaks = ti.npk; ea.task_flags = ti.flags; ea.task_jstar = ti.jstar;
+    ea.task_off = c->d_task_off.as<int>(); ea.pk_task = nullptr; ea.pk_pos = nullptr; ea.pk_score = nullptr;
+    const int epi_blocks = (n_items * 32 + 127) / 128;
+    k_epilogue<<<epi_blocks, 128, 0, c->stream>>>(ea);
+    c->launches += 1;
+    LTG_CUDA_CHECK(cudaGetLastError());
+
+    // Q4 guard: tasks whose exact maximum could carry F >= 132 across a stripe boundary are re-run through
+    // the literal striped emulation, their peaks come from the literal column maxima
+    LTG_CUDA_CHECK(cudaMemcpyAsync(hti.flags, ti.flags, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
+    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
+    std::vector<LiteralJob> jobs;
+    for (int t = 0; t < n_tasks; ++t) {
+        if (hti.flags[t] & kTaskRange) { set_error("alignment score exceeds the 16-bit range (segment too long for this build)"); return LTG_ERR_LIMIT; }
+        if (hti.flags[t] & kTaskLiteral) {
+            LiteralJob j; memset(&j, 0, sizeof j);
+            j.kind = 0; j.task = t; j.seg = t / T; j.tdef = t % T; j.ref_start = 0; j.ref_len = segs[t / T].len;
+            j.read_start = 0; j.read_len = c->m; j.read_dir = 1; j.ref_dir = 0; j.terminate = 255; j.peak = -1;
+            jobs.push_back(j);
+        }
+    }
+    hb.n_literal_tasks = (int)jobs.size();
+    if (!jobs.empty()) {
+        if (int e = c->d_lit_jobs.ensure(sizeof(LiteralJob) * jobs.size())) return e;
+        if (int e = c->d_lit_colmax.ensure(sizeof(uint16_t) * jobs.size() * (size_t)max_len)) return e;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_lit_jobs.p, jobs.data(), sizeof(LiteralJob) * jobs.size(), cudaMemcpyHostToDevice, c->stream));
+        if (int e = launch_literal(c, c->d_lit_jobs.as<LiteralJob>(), (int)jobs.size(), nullptr, c->m, nullptr, max_len)) return e;
+        ea.lit_colmax = c->d_lit_colmax.as<uint16_t>();
+        ea.mode = 1;
+        k_epilogue<<<epi_blocks, 128, 0, c->stream>>>(ea);
+        c->launches += 1;
+        LTG_CUDA_CHECK(cudaGetLastError());
+    }
+    k_exclusive_scan<<<1, 1024, 0, c->stream>>>(ti.npk, c->d_task_off.as<int>(), n_tasks, counters + kCntPeaks);
+    c->launches += 1;
+    int n_peaks = 0;
+    LTG_CUDA_CHECK(cudaMemcpyAsync(&n_peaks, counters + kCntPeaks, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // (also: `jobs` is host memory of this scope)
+    hb.n_peaks = n_peaks;
+    if (n_peaks > 0) {
+        for (DevBuf* b : {&c->d_pk_task, &c->d_pk_pos, &c->d_pk_score}) if (int e = b->ensure(sizeof(int) * (size_t)n_peaks)) return e;
+        ea.pk_task = c->d_pk_task.as<int>(); ea.pk_pos = c->d_pk_pos.as<int>(); ea.pk_score = c->d_pk_score.as<int>();
+        ea.mode = 2;
+        k_epilogue<<<epi_blocks, 128, 0, c->stream>>>(ea);
+        c->launches += 1;
+        LTG_CUDA_CHECK(cudaGetLastError());
+    }
+    LTG_CUDA_CHECK(cudaEventRecord(hb.ev[1], c->stream));
+
+    LTG_CUDA_CHECK(cudaMemcpyAsync(hb.task_info.p, c->d_task_info.p, sizeof(int) * 5 * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
+    LTG_CUDA_CHECK(cudaMemcpyAsync(hb.task_off.p, c->d_task_off.p, sizeof(int) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += sizeof(int) * 6 * (int64_t)n_tasks;
+    if (probe) {
+        probe->max_len = max_len;
+        probe->pk_pos.resize(n_peaks); probe->pk_score.resize(n_peaks);
+        if (n_peaks) {
+            LTG_CUDA_CHECK(cudaMemcpyAsync(probe->pk_pos.data(), c->d_pk_pos.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
+            LTG_CUDA_CHECK(cudaMemcpyAsync(probe->pk_score.data(), c->d_pk_score.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
+        }
+        probe->colmax.resize((size_t)n_items * c->n_strips * max_len);
+        LTG_CUDA_CHECK(cudaMemcpyAsync(probe->colmax.data(), c->d_colmax.p, probe->colmax.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        probe->lit_colmax.resize(jobs.size() * (size_t)max_len);
+        probe->task_litrow.assign(n_tasks, -1);
+        if (!jobs.empty()) {
+            LTG_CUDA_CHECK(cudaMemcpyAsync(probe->lit_colmax.data(), c->d_lit_colmax.p, probe->lit_colmax.size() * 2, cudaMemcpyDeviceToHost, c->stream));
+            LTG_CUDA_CHECK(cudaMemcpyAsync(probe->task_litrow.data(), c->d_task_litrow.p, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
+        }
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        probe->task_max.assign(hti.max, hti.max + n_tasks); probe->task_thr.assign(hti.thr, hti.thr + n_tasks);
+        probe->task_npk.assign(hti.npk, hti.npk + n_tasks); probe->task_flags.assign(hti.flags, hti.flags + n_tasks);
+        probe->task_off.assign(hb.task_off.as<int>(), hb.task_off.as<int>() + n_tasks);
+    }
+    if (want_alignments && n_peaks > 0) {
+        LTG_CUDA_CHECK(cudaEventRecord(hb.ev[2], c->stream));
+        if (int e = run_windows(c, n_peaks, T, nullptr, c->d_colmax.as<uint32_t>(), max_len, &hb)) return e;
+        if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), n_peaks, c->d_tout.as<TraceOut>(), nullptr)) return e;
+        LTG_CUDA_CHECK(cudaEventRecord(hb.ev[3], c->stream));
+        hb.timed_windows = true;
+        if (int e = hb.jobs.ensure(sizeof(TraceJob) * (size_t)n_peaks)) return e;
+        if (int e = hb.tout.ensure(sizeof(TraceOut) * (size_t)n_peaks)) return e;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.jobs.p, c->d_jobs.p, sizeof(TraceJob) * (size_t)n_peaks, cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.tout.p, c->d_tout.p, sizeof(TraceOut) * (size_t)n_peaks, cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.p, counters + kCntCells, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        c->d2h_bytes += (int64_t)(sizeof(TraceJob) + sizeof(TraceOut)) * n_peaks + 64;
+    } else {
+        hb.n_peaks = want_alignments ? n_peaks : 0;
+        memset(hb.scalars.p, 0, 64);
+    }
+    LTG_CUDA_CHECK(cudaEventRecord(hb.ready, c->stream));
+    return LTG_OK;
+}
+
+// Host phase of one batch (fastSIM's tail, fastsim.h:253-288, per task in the reference's task order): runs on
+// `threads` worker threads over contiguous task ranges; the per-thread outputs are concatenated in order.
+void host_phase(const ltg_context* c, HostBatch& hb, int threads)
+{
+    const int T = (int)c->tasks.size();
+    const int n_tasks = hb.n_tasks, n_peaks = hb.n_peaks;
+    hb.rows.clear();
+    if (n_peaks == 0) return;
+    const int* off = hb.task_off.as<int>();
+    const TraceJob* jobs = hb.jobs.as<TraceJob>();
+    const TraceOut* tout = hb.tout.as<TraceOut>();
+    threads = std::max(1, std::min(threads, n_tasks / 256 + 1));
+    std::vector<std::vector<ltg_host::Triplex>> part(threads);
+    std::vector<std::string> errs(threads);
+    auto work = [&](int k) {
+        // balance by peak count: thread k takes the tasks whose first peak falls into its slice of the peak pool
+        const long long p0 = (long long)n_peaks * k / threads, p1 = (long long)n_peaks * (k + 1) / threads;
+        int t0 = (int)(std::lower_bound(off, off + n_tasks, (int)p0) - off);
+        int t1 = (k + 1 == threads) ? n_tasks : (int)(std::lower_bound(off, off + n_tasks, (int)p1) - off);
+        if (k == 0) t0 = 0;
+        std::vector<ltg_host::Triplex> mine;
+        for (int task = t0; task < t1; ++task) {
+            const int b = off[task], e = (task + 1 < n_tasks) ? off[task + 1] : n_peaks;
+            if (b == e) continue;
+            mine.clear();
+            const HostSeg& sg = hb.segs[task / T];
+            const TaskDef& td = c->tasks[task % T];
+            for (int i = b; i < e; ++i) {                       // peaks of a task come in ascending column order
+                const TraceJob& J = jobs[i];
+                if (J.score <= 0) continue;                     // fastsim.h:253 (sw_score == 0 -> skipped)
+                if (tout[i].status == 2) { errs[k] = "traceback band exceeds the device scratch"; continue; }
+                if (tout[i].status != 1) continue;              // banded_sw failed -> sw_score 0 (ssw_cpp.cpp:627-633)
+                ltg_host::DeviceAlignment al;
+                al.sw_score = J.score; al.ws = J.ws; al.rb = J.rb; al.re = J.re; al.query_begin = J.qb; al.query_end = J.qe;
+                al.nt = tout[i].nt; al.identity = tout[i].identity; al.tri_score = tout[i].tri;
+                ltg_host::make_triplex(al, task % T, sg.len, (long)sg.start, td.para, td.strand, td.rule, c->params, mine);
+            }
+            if (!mine.empty()) ltg_host::finish_task(mine, c->params, part[k]);
+        }
+    };
+    if (threads == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int k = 1; k < threads; ++k) pool.emplace_back(work, k);
+        work(0);
+        for (std::thread& t : pool) t.join();
+    }
+    size_t total = 0;
+    for (auto& v : part) total += v.size();
+    hb.rows.reserve(total);
+    for (int k = 0; k < threads; ++k) {
+        hb.rows.insert(hb.rows.end(), part[k].begin(), part[k].end());
+        if (!errs[k].empty()) hb.error = errs[k];
+    }
 }
 
 // cutSequence — fastsim.h:71-90
@@ -475,7 +582,7 @@ struct ResultBuilder {
     std::vector<ltg_triplex> tri;
     std::string text;
     int64_t chr_off = -1;
-    void add(const ltg_host::Triplex& t, const char* chr, int64_t record_start, int record)
+    void add(const ltg_host::Triplex& t, const char* tfo, const char* tts, const char* chr, int64_t record_start, int record)
     {
         if (chr_off < 0) { chr_off = (int64_t)text.size(); text += (chr ? chr : ""); text += '\0'; }
         ltg_triplex o;
@@ -484,8 +591,8 @@ struct ResultBuilder {
         o.rule = t.rule; o.nt = t.nt; o.score = t.score; o.identity = t.identity; o.tri_score = t.tri_score;
         o.genomestart = t.starj + record_start - 1;         // Fasim-LongTarget.cpp:146-147
         o.genomeend = t.endj + record_start - 1;
-        o.tfo_off = (int64_t)text.size(); text += t.tfo; text += '\0';
-        o.tts_off = (int64_t)text.size(); text += t.tts; text += '\0';
+        o.tfo_off = (int64_t)text.size(); text.append(tfo, (size_t)t.nt); text += '\0';
+        o.tts_off = (int64_t)text.size(); text.append(tts, (size_t)t.nt); text += '\0';
         o.chr_off = chr_off;
         o.record = record;
         tri.push_back(o);
@@ -504,25 +611,91 @@ ltg_result* finish_result(ResultBuilder& rb)
     return r;
 }
 
+// traceback pass 2: TFO / TTS strings of `rows` (alignments of the record resident in d_dna / d_codes)
+int fetch_strings(ltg_context* c, const std::vector<ltg_host::Triplex>& rows, std::vector<char>& pool, std::vector<int64_t>& offs)
+{
+    const size_t n = rows.size();
+    offs.resize(n);
+    pool.clear();
+    if (n == 0) return LTG_OK;
+    std::vector<TraceJob> jobs(n);
+    int64_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const ltg_host::Triplex& t = rows[i];
+        TraceJob& J = jobs[i];
+        J.seg_start = t.seg_start; J.seg_len = t.seg_len; J.tdef = t.tdef; J.ws = t.ws; J.rb = t.rb; J.re = t.re; J.qb = t.qb; J.qe = t.qe;
+        J.score = (int)t.score; J.out_off = total;
+        offs[i] = total;
+        total += 2 * ((int64_t)t.nt + 1);
+    }
+    if (int e = c->d_jobs.ensure(sizeof(TraceJob) * n)) return e;
+    if (int e = c->d_tout.ensure(sizeof(TraceOut) * n)) return e;
+    if (int e = c->d_strpool.ensure((size_t)total)) return e;
+    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_jobs.p, jobs.data(), sizeof(TraceJob) * n, cudaMemcpyHostToDevice, c->stream));
+    if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), (int)n, c->d_tout.as<TraceOut>(), c->d_strpool.as<char>())) return e;
+    pool.resize((size_t)total);
+    std::vector<TraceOut> tout(n);
+    LTG_CUDA_CHECK(cudaMemcpyAsync(pool.data(), c->d_strpool.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    LTG_CUDA_CHECK(cudaMemcpyAsync(tout.data(), c->d_tout.p, sizeof(TraceOut) * n, cudaMemcpyDeviceToHost, c->stream));
+    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->h2d_bytes += (int64_t)(sizeof(TraceJob) * n);
+    c->d2h_bytes += total + (int64_t)(sizeof(TraceOut) * n);
+    for (size_t i = 0; i < n; ++i)
+        if (tout[i].status != 1 || tout[i].nt != rows[i].nt) { set_error("string pass disagrees with the first traceback pass (row %zu)", i); return LTG_ERR_STATE; }
+    return LTG_OK;
+}
+
+struct RecordStats {
+    int64_t n_segments = 0, n_tasks = 0, scan_cells = 0, n_peaks = 0, window_cells = 0, n_literal_tasks = 0, n_literal_windows = 0;
+    double ms_scan = 0, ms_window = 0, ms_scan_kernel = 0;
+    int64_t n_scan_launches = 0;
+};
+
+// closes a batch slot: waits for its host phase, collects timings / counters / rows
+int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg_host::Triplex>& record_list)
+{
+    if (hb.worker.joinable()) hb.worker.join();
+    if (!hb.timed) return LTG_OK;
+    hb.timed = false;
+    if (!hb.error.empty()) { set_error("%s", hb.error.c_str()); return LTG_ERR_LIMIT; }
+    float ms = 0;
+    LTG_CUDA_CHECK(cudaEventSynchronize(hb.ready));
+    LTG_CUDA_CHECK(cudaEventElapsedTime(&ms, hb.ev[0], hb.ev[1])); st.ms_scan += ms;
+    LTG_CUDA_CHECK(cudaEventElapsedTime(&ms, hb.ev[4], hb.ev[5])); st.ms_scan_kernel += ms;
+    if (hb.timed_windows) { LTG_CUDA_CHECK(cudaEventElapsedTime(&ms, hb.ev[2], hb.ev[3])); st.ms_window += ms; }
+    st.n_scan_launches += 1;
+    const int T = (int)c->tasks.size();
+    st.n_segments += (int64_t)hb.segs.size();
+    st.n_tasks += (int64_t)hb.segs.size() * T;
+    for (const HostSeg& sg : hb.segs) st.scan_cells += (int64_t)sg.len * c->m * T;
+    st.n_peaks += hb.n_peaks;
+    st.n_literal_tasks += hb.n_literal_tasks;
+    const int* sc = hb.scalars.as<int>();
+    long long cells = 0; memcpy(&cells, sc, 8);
+    st.window_cells += cells;
+    st.n_literal_windows += sc[kCntLitTotal - kCntCells];
+    record_list.insert(record_list.end(), hb.rows.begin(), hb.rows.end());
+    hb.rows.clear();
+    return LTG_OK;
+}
+
 int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char* h_dna, int64_t len, const char* chr,
                      int64_t record_start, ltg_result** out)
 {
-    (void)chr;
     if (!c || !out) { set_error("null argument"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
-    const int64_t launches0 = c->launches;
+    const int64_t launches0 = c->launches, h2d0 = c->h2d_bytes, d2h0 = c->d2h_bytes;
     std::vector<HostSeg> segs;
     if (int e = cut_segments(len, c->params, segs)) return e;
     ResultBuilder rb;
-    ltg_result stats;
-    memset(&stats, 0, sizeof stats);
+    RecordStats st;
     if (len > 0) {
         // the record lives in d_dna (either copied from the host or device-to-device from the user's buffer)
         if (int e = c->d_dna.ensure((size_t)len)) return e;
         if (int e = c->d_codes.ensure((size_t)len)) return e;
-        if (h_dna) LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_dna.p, h_dna, (size_t)len, cudaMemcpyHostToDevice, c->stream));
+        if (h_dna) { LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_dna.p, h_dna, (size_t)len, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += len; }
         else LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_dna.p, d_dna_user, (size_t)len, cudaMemcpyDeviceToDevice, c->stream));
-        k_encode<<<std::min<int64_t>((len + 255) / 256, 148 * 16), 256, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_codes.as<uint8_t>(), len);
+        k_encode<<<(int)std::min<int64_t>((len + 255) / 256, 148 * 16), 256, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_codes.as<uint8_t>(), len);
         c->launches += 1;
         // segment flags (same_seq + non-ACGT) for the whole record
         const int NS = (int)segs.size();
@@ -534,60 +707,54 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
         c->launches += 1;
         LTG_CUDA_CHECK(cudaMemcpyAsync(hs.data(), c->d_segs.p, sizeof(SegDesc) * NS, cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->h2d_bytes += (int64_t)sizeof(SegDesc) * NS; c->d2h_bytes += (int64_t)sizeof(SegDesc) * NS;
         std::vector<HostSeg> active;
         for (int s = 0; s < NS; ++s) { segs[s].flags = hs[s].flags; if (!(hs[s].flags & kSegSkip)) active.push_back(segs[s]); }
 
-        const int T = (int)c->tasks.size();
+        // batch size: bounded by the strip-maxima buffer; at least two batches when there is enough work so that the
+        // host phase of one overlaps the device phase of the next
+        const size_t per_seg = (size_t)c->pairs.size() * c->n_strips * (size_t)((c->params.cut_length + 3) & ~3) * 4;
+        size_t bs = std::max<size_t>(16, std::min<size_t>(kBatchSegments, kStripBytesPerBatch / std::max<size_t>(1, per_seg)));
+        if (active.size() > 256 && active.size() < 2 * bs) bs = (active.size() + 1) / 2;
         std::vector<ltg_host::Triplex> record_list;
-        for (size_t b0 = 0; b0 < active.size(); b0 += kBatchSegments) {
-            std::vector<HostSeg> batch(active.begin() + b0, active.begin() + std::min(active.size(), b0 + (size_t)kBatchSegments));
-            BatchOut bo;
-            if (int e = run_batch(c, batch, false, true, bo)) return e;
-            stats.gpu_ms_scan += bo.ms_scan; stats.gpu_ms_window += bo.ms_window;
-            stats.gpu_ms_scan_kernel += bo.ms_scan_kernel; stats.n_scan_launches += bo.n_scan_launches;
-            stats.n_peaks += (int64_t)bo.pk_task.size(); stats.window_cells += bo.window_cells;
-            stats.n_literal_tasks += bo.n_literal_tasks; stats.n_literal_windows += bo.n_literal_windows;
-            // order peaks by (task, position): the reference walks tasks in order and peaks by ascending column
-            const int np = (int)bo.pk_task.size();
-            std::vector<int> order(np);
-            std::iota(order.begin(), order.end(), 0);
-            std::sort(order.begin(), order.end(), [&](int x, int y) {
-                if (bo.pk_task[x] != bo.pk_task[y]) return bo.pk_task[x] < bo.pk_task[y];
-                return bo.pk_pos[x] < bo.pk_pos[y];
+        int rc = LTG_OK;
+        size_t nb = 0;
+        for (size_t b0 = 0; b0 < active.size() && rc == LTG_OK; b0 += bs, ++nb) {
+            HostBatch& hb = c->hb[nb & 1];
+            if ((rc = retire_batch(c, hb, st, record_list)) != LTG_OK) break;       // batch nb-2: slot free again
+            std::vector<HostSeg> batch(active.begin() + b0, active.begin() + std::min(active.size(), b0 + bs));
+            if ((rc = run_batch_device(c, batch, hb, true, nullptr)) != LTG_OK) { hb.timed = false; break; }
+            ltg_context* ctx = c;
+            HostBatch* slot = &hb;
+            hb.worker = std::thread([ctx, slot]() {
+                cudaSetDevice(ctx->device);
+                if (cudaEventSynchronize(slot->ready) != cudaSuccess) { slot->error = "device phase failed"; return; }
+                host_phase(ctx, *slot, ctx->host_threads);
             });
-            size_t k = 0;
-            std::vector<ltg_host::Triplex> mine;
-            for (int task = 0; task < (int)batch.size() * T; ++task) {
-                mine.clear();
-                const HostSeg& sg = batch[task / T];
-                const TaskDef& td = c->tasks[task % T];
-                while (k < order.size() && bo.pk_task[order[k]] == task) {
-                    const int i = order[k++];
-                    if (bo.fin_sw[i] <= 0 || bo.al_status[i] != 1) continue;     // fastsim.h:253 (sw_score == 0 -> skipped)
-                    ltg_host::DeviceAlignment al;
-                    const int ws = bo.pk_pos[i] - bo.fin_cut[i] + 1;
-                    al.sw_score = bo.fin_sw[i]; al.ref_begin = ws + bo.fin_rb[i]; al.ref_end = ws + bo.fin_re[i];
-                    al.query_begin = bo.fin_qb[i]; al.query_end = bo.fin_qe[i];
-                    al.nt = bo.al_nt[i]; al.match = bo.al_match[i];
-                    al.tfo = bo.strpool.data() + bo.al_stroff[i];
-                    al.tts = al.tfo + al.nt + 1;
-                    ltg_host::make_triplex(al, sg.len, (long)sg.start, td.para, td.strand, td.rule, c->params, mine);
-                }
-                if (!mine.empty()) ltg_host::finish_task(mine, c->params, record_list);
-            }
-            stats.n_segments += (int64_t)batch.size();
-            stats.n_tasks += (int64_t)batch.size() * T;
-            for (const HostSeg& sg : batch) stats.scan_cells += (int64_t)sg.len * c->m * T;
         }
+        // retire in batch order: the older slot first
+        for (size_t k = 0; k < 2; ++k) {
+            HostBatch& hb = c->hb[(nb + k) & 1];
+            const int e = retire_batch(c, hb, st, record_list);
+            if (rc == LTG_OK) rc = e;
+        }
+        if (rc != LTG_OK) { cudaStreamSynchronize(c->stream); return rc; }
+        std::vector<ltg_host::Triplex> keep;
         for (const ltg_host::Triplex& t : record_list)
-            if (ltg_host::passes_record_filter(t, c->params)) rb.add(t, chr, record_start, 0);
+            if (ltg_host::passes_record_filter(t, c->params)) keep.push_back(t);
+        std::vector<char> pool;
+        std::vector<int64_t> offs;
+        if (int e = fetch_strings(c, keep, pool, offs)) return e;
+        for (size_t i = 0; i < keep.size(); ++i)
+            rb.add(keep[i], pool.data() + offs[i], pool.data() + offs[i] + keep[i].nt + 1, chr, record_start, 0);
     }
     ltg_result* r = finish_result(rb);
-    r->n_segments = stats.n_segments; r->n_tasks = stats.n_tasks; r->scan_cells = stats.scan_cells; r->dna_bases = len;
-    r->n_peaks = stats.n_peaks; r->window_cells = stats.window_cells; r->n_literal_tasks = stats.n_literal_tasks;
-    r->n_literal_windows = stats.n_literal_windows; r->gpu_ms_scan = stats.gpu_ms_scan; r->gpu_ms_window = stats.gpu_ms_window;
+    r->n_segments = st.n_segments; r->n_tasks = st.n_tasks; r->scan_cells = st.scan_cells; r->dna_bases = len;
+    r->n_peaks = st.n_peaks; r->window_cells = st.window_cells; r->n_literal_tasks = st.n_literal_tasks;
+    r->n_literal_windows = st.n_literal_windows; r->gpu_ms_scan = st.ms_scan; r->gpu_ms_window = st.ms_window;
     r->gpu_launches = c->launches - launches0;
-    r->gpu_ms_scan_kernel = stats.gpu_ms_scan_kernel; r->n_scan_launches = stats.n_scan_launches;
+    r->gpu_ms_scan_kernel = st.ms_scan_kernel; r->n_scan_launches = st.n_scan_launches;
+    r->h2d_bytes = c->h2d_bytes - h2d0; r->d2h_bytes = c->d2h_bytes - d2h0;
     *out = r;
     return LTG_OK;
 }
@@ -629,7 +796,18 @@ int ltg_create(int device, ltg_context** out)
     c->num_sms = prop.multiProcessorCount;
     ltg_default_params(&c->params);
     LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 6; ++i) LTG_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+    for (HostBatch& hb : c->hb) {
+        LTG_CUDA_CHECK(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
+        for (int i = 0; i < 6; ++i) LTG_CUDA_CHECK(cudaEventCreate(&hb.ev[i]));
+    }
+    // host-phase worker threads: LTG_HOST_THREADS, else the host cores divided among the visible GPUs (one process
+    // per GPU is the deployment model), capped at 16
+    int threads = 0;
+    if (const char* e = getenv("LTG_HOST_THREADS")) threads = atoi(e);
+    if (threads <= 0) threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, n)));
+    c->host_threads = threads;
+    // LTG_NO_PRUNE=1 makes every window sweep the whole lncRNA (the reference's amount of work); results are identical
+    if (const char* e = getenv("LTG_NO_PRUNE")) c->prune = atoi(e) == 0;
     *out = c;
     return LTG_OK;
 }
@@ -639,14 +817,19 @@ void ltg_destroy(ltg_context* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (HostBatch& hb : c->hb) {
+        if (hb.worker.joinable()) hb.worker.join();
+        for (PinBuf* b : {&hb.task_off, &hb.jobs, &hb.tout, &hb.task_info, &hb.scalars}) b->release();
+        if (hb.ready) cudaEventDestroy(hb.ready);
+        for (int i = 0; i < 6; ++i) if (hb.ev[i]) cudaEventDestroy(hb.ev[i]);
+    }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
-                      &c->d_segs, &c->d_items, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_max, &c->d_task_thr, &c->d_task_npk,
-                      &c->d_task_flags, &c->d_stats_max, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_cls_list, &c->d_res,
-                      &c->d_al_status, &c->d_al_nt, &c->d_al_match, &c->d_al_stroff, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
+                      &c->d_segs, &c->d_items, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
+                      &c->d_stats_max, &c->d_task_litrow, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_cls_list, &c->d_res,
+                      &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs})
         b->release();
-    for (int k = 0; k < 12; ++k) c->d_w[k].release();
-    for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int k = 0; k < 16; ++k) c->d_w[k].release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -735,6 +918,7 @@ int ltg_result_append(ltg_result* dst, const ltg_result* src)
     dst->n_literal_windows += src->n_literal_windows; dst->gpu_ms_scan += src->gpu_ms_scan; dst->gpu_ms_window += src->gpu_ms_window;
     dst->gpu_launches += src->gpu_launches;
     dst->gpu_ms_scan_kernel += src->gpu_ms_scan_kernel; dst->n_scan_launches += src->n_scan_launches;
+    dst->h2d_bytes += src->h2d_bytes; dst->d2h_bytes += src->d2h_bytes;
     return LTG_OK;
 }
 
@@ -762,32 +946,41 @@ int ltg_probe_segment(ltg_context* c, const char* seg, int32_t seg_len, ltg_task
     std::vector<HostSeg> segs(1);
     segs[0].start = 0; segs[0].len = seg_len; segs[0].flags = 0;
     for (int i = 0; i < seg_len; ++i) { const char ch = seg[i]; if (!(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T')) segs[0].flags |= kSegNonACGT; }
-    BatchOut bo;
-    if (int e = run_batch(c, segs, colmax != nullptr, false, bo)) return e;
-    const int T = (int)c->tasks.size(), P = (int)c->pairs.size();
-    const int max_len = (seg_len + 3) & ~3;
+    ProbeOut po;
+    HostBatch& hb = c->hb[0];
+    const int rc = run_batch_device(c, segs, hb, false, &po);
+    hb.timed = false;
+    if (rc != LTG_OK) return rc;
+    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const int T = (int)c->tasks.size();
+    const int max_len = po.max_len;
     for (int q = 0; q < n_tasks; ++q) {
         int t = -1;
         for (int k = 0; k < T; ++k) if (c->tasks[k].para == tasks[q].para && c->tasks[k].strand == tasks[q].strand && c->tasks[k].rule == tasks[q].rule) t = k;
         if (t < 0) { set_error("task (%d,%d,%d) is not part of the configured rule/strand selection", tasks[q].para, tasks[q].strand, tasks[q].rule); return LTG_ERR_ARG; }
-        tasks[q].max_score = bo.task_max[t]; tasks[q].threshold = bo.task_thr[t]; tasks[q].n_peaks = bo.task_npk[t];
-        tasks[q].literal = (bo.task_flags[t] & kTaskLiteral) ? 1 : 0;
+        tasks[q].max_score = po.task_max[t]; tasks[q].threshold = po.task_thr[t]; tasks[q].n_peaks = po.task_npk[t];
+        const bool literal = (po.task_flags[t] & kTaskLiteral) != 0;
+        tasks[q].literal = literal ? 1 : 0;
         if (colmax) {
-            int item = -1, half = 0;
-            for (int p = 0; p < P; ++p) for (int h = 0; h < 2; ++h) if (c->pairs[p].task[h] == t && item < 0) { item = p; half = h; }
-            const uint32_t* row = bo.colmax.data() + (size_t)item * max_len;
-            bool cut = false;
-            for (int j = 0; j < seg_len; ++j) {
-                int v = half ? hi16(row[j]) : lo16(row[j]);
-                if (v >= kOverflowU8) cut = true;          // Q2: nothing is recorded from the first >= 251 column on
-                colmax[(size_t)q * seg_len + j] = cut ? 0 : v;
+            if (literal) {
+                // the literal emulation reports exactly what the reference's 8-bit kernel records
+                const uint16_t* row = po.lit_colmax.data() + (size_t)po.task_litrow[t] * max_len;
+                for (int j = 0; j < seg_len; ++j) colmax[(size_t)q * seg_len + j] = row[j];
+            } else {
+                const int item = c->tasks[t].pair, half = c->tasks[t].half;
+                const uint32_t* rows = po.colmax.data() + (size_t)item * c->n_strips * max_len;
+                bool cut = false;
+                for (int j = 0; j < seg_len; ++j) {
+                    int v = 0;
+                    for (int k = 0; k < c->n_strips; ++k) { const uint32_t x = rows[(size_t)k * max_len + j]; v = std::max(v, half ? hi16(x) : lo16(x)); }
+                    if (v >= kOverflowU8) cut = true;          // Q2: nothing is recorded from the first >= 251 column on
+                    colmax[(size_t)q * seg_len + j] = cut ? 0 : v;
+                }
             }
         }
         if (peak_score && peak_pos) {
-            std::vector<std::pair<int, int>> pk;
-            for (size_t i = 0; i < bo.pk_task.size(); ++i) if (bo.pk_task[i] == t) pk.push_back({bo.pk_pos[i], bo.pk_score[i]});
-            std::sort(pk.begin(), pk.end());
-            for (size_t i = 0; i < pk.size() && (int)i < peak_cap; ++i) { peak_pos[(size_t)q * peak_cap + i] = pk[i].first; peak_score[(size_t)q * peak_cap + i] = pk[i].second; }
+            const int b = po.task_off[t], e = b + po.task_npk[t];
+            for (int i = b; i < e && i - b < peak_cap; ++i) { peak_pos[(size_t)q * peak_cap + (i - b)] = po.pk_pos[i]; peak_score[(size_t)q * peak_cap + (i - b)] = po.pk_score[i]; }
         }
     }
     return LTG_OK;
@@ -806,6 +999,7 @@ int ltg_probe_align(ltg_context* c, const char* const* windows, const int32_t* w
     id.para = 1; id.strand = 0; id.rule = 1; id.reversed = 0; id.comp_src = 0;
     for (int k = 0; k < 5; ++k) id.img[k] = (int8_t)k;
     PairDef pd; pd.task[0] = pd.task[1] = 0; pd.reversed = 0; pd.pad_ = 0;
+    id.pair = 0; id.half = 0;
     LTG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tasks, &id, sizeof id, 0, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pairs, &pd, sizeof pd, 0, cudaMemcpyHostToDevice, c->stream));
     c->tables_dirty = true;
@@ -832,19 +1026,38 @@ int ltg_probe_align(ltg_context* c, const char* const* windows, const int32_t* w
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_pk_pos.p, pk_pos.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_pk_score.p, pk_score.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_stats_max.p, fcut.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    BatchOut bo;
-    bo.pk_task = pk_task; bo.pk_pos = pk_pos; bo.pk_score = pk_score;
-    if (int e = run_windows(c, n, 1, c->d_stats_max.as<int>(), bo)) return e;
+    if (int e = run_windows(c, n, 1, c->d_stats_max.as<int>(), nullptr, 0, nullptr)) return e;
+    if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), n, c->d_tout.as<TraceOut>(), nullptr)) return e;
+    std::vector<TraceJob> jobs(n);
+    std::vector<TraceOut> tout(n);
+    LTG_CUDA_CHECK(cudaMemcpyAsync(jobs.data(), c->d_jobs.p, sizeof(TraceJob) * n, cudaMemcpyDeviceToHost, c->stream));
+    LTG_CUDA_CHECK(cudaMemcpyAsync(tout.data(), c->d_tout.p, sizeof(TraceOut) * n, cudaMemcpyDeviceToHost, c->stream));
+    LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    // strings of every successful window through the second traceback pass (the product's own string path)
+    std::vector<ltg_host::Triplex> rows;
+    std::vector<int> row_of(n, -1);
+    for (int i = 0; i < n; ++i) {
+        if (jobs[i].score <= 0 || tout[i].status != 1) continue;
+        ltg_host::Triplex t;
+        t.nt = tout[i].nt; t.score = (float)jobs[i].score; t.tdef = 0; t.seg_len = jobs[i].seg_len; t.seg_start = (long)jobs[i].seg_start;
+        t.ws = jobs[i].ws; t.rb = jobs[i].rb; t.re = jobs[i].re; t.qb = jobs[i].qb; t.qe = jobs[i].qe;
+        row_of[i] = (int)rows.size();
+        rows.push_back(t);
+    }
+    std::vector<char> pool;
+    std::vector<int64_t> offs;
+    if (int e = fetch_strings(c, rows, pool, offs)) return e;
     for (int i = 0; i < n; ++i) {
         int32_t* o = out6 + (size_t)i * 6;
-        if (bo.fin_sw[i] <= 0 || bo.al_status[i] != 1) { for (int k = 0; k < 6; ++k) o[k] = 0; continue; }
-        o[0] = bo.fin_sw[i]; o[1] = bo.fin_rb[i]; o[2] = bo.fin_re[i]; o[3] = bo.fin_qb[i]; o[4] = bo.fin_qe[i];
+        if (row_of[i] < 0) { for (int k = 0; k < 6; ++k) o[k] = 0; continue; }
+        o[0] = jobs[i].score; o[1] = jobs[i].rb; o[2] = jobs[i].re; o[3] = jobs[i].qb; o[4] = jobs[i].qe;
         // run-length CIGAR from the aligned strings (M: both present, I: gap on the DNA side, D: gap on the RNA side)
-        const char* tfo = bo.strpool.data() + bo.al_stroff[i];
-        const char* tts = tfo + bo.al_nt[i] + 1;
+        const int nt = tout[i].nt;
+        const char* tfo = pool.data() + offs[row_of[i]];
+        const char* tts = tfo + nt + 1;
         int nc = 0, run = 0, prev = -1;
-        for (int k = 0; k <= bo.al_nt[i]; ++k) {
-            const int op = k == bo.al_nt[i] ? -2 : (tts[k] == '-' ? 1 : (tfo[k] == '-' ? 2 : 0));
+        for (int k = 0; k <= nt; ++k) {
+            const int op = k == nt ? -2 : (tts[k] == '-' ? 1 : (tfo[k] == '-' ? 2 : 0));
             if (op == prev) { ++run; continue; }
             if (prev >= 0) { if (cigar && nc < cigar_cap) cigar[(size_t)i * cigar_cap + nc] = ((uint32_t)run << 4) | (uint32_t)prev; ++nc; }
             prev = op; run = 1;

@@ -25,14 +25,15 @@ struct LiteralJob {
     int read_start, read_len, read_dir;     // rows: rna[read_start + read_dir * k], k in [0, read_len)
     int terminate;
     int peak;          // window jobs: peak index
-    int out_item, out_half;                 // scan jobs: destination row / half of the packed colmax buffer
 };
 
 struct LiteralArgs {
     const LiteralJob* jobs; int n_jobs;
+    const int* n_jobs_dev;                              // used when n_jobs < 0: the count was produced on the device
     const uint8_t* codes; const SegDesc* segs; const uint8_t* rna_ssw;
     unsigned char* work; long long work_per_slot;       // 4 * L * 16 bytes per half-warp slot
-    uint16_t* colmax16; int max_len;                    // packed colmax buffer viewed as 16-bit halves
+    uint16_t* lit_colmax; int max_len;                  // scan jobs: row `job index` receives the literal column maxima
+    int* task_litrow;                                   // scan jobs: [task] -> that row
     WinState w;
 };
 
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
     const int slot = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2 + halfw;
     const int nslots = ((gridDim.x * blockDim.x) >> 5) * 2;
     const int bias = 4;
-    for (int jb = slot; jb < a.n_jobs; jb += nslots) {
+    const int n_jobs = a.n_jobs >= 0 ? a.n_jobs : *a.n_jobs_dev;
+    for (int jb = slot; jb < n_jobs; jb += nslots) {
         const LiteralJob J = a.jobs[jb];
         const SegDesc sd = a.segs[J.seg];
         const TaskDef td = c_tasks[J.tdef];
@@ -57,8 +59,9 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
         for (int t = 0; t < L; ++t) { Hs[t * 16 + s] = 0; Hl[t * 16 + s] = 0; Ev[t * 16 + s] = 0; Hm[t * 16 + s] = 0; }
         uint16_t* cmrow = nullptr;
         if (J.kind == 0) {
-            cmrow = a.colmax16 + ((size_t)J.out_item * a.max_len) * 2 + J.out_half;
-            for (int j = s; j < J.ref_len; j += 16) cmrow[(size_t)j * 2] = 0;
+            cmrow = a.lit_colmax + (size_t)jb * a.max_len;
+            for (int j = s; j < J.ref_len; j += 16) cmrow[j] = 0;
+            if (s == 0) a.task_litrow[J.task] = jb;
         }
         __syncwarp(hmask);
         int vMaxScore = 0, vMaxMark = 0, maxv = 0, end_ref = -1;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
             int cm = vMaxCol;
 #pragma unroll
             for (int o = 8; o; o >>= 1) cm = max(cm, __shfl_xor_sync(hmask, cm, o, 16));
-            if (cmrow && s == 0) cmrow[(size_t)i * 2] = (uint16_t)cm;
+            if (cmrow && s == 0) cmrow[i] = (uint16_t)cm;
             if (cm == J.terminate) break;
         }
         if (J.kind == 0) continue;
@@ -142,13 +145,13 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
 }
 
 // collect the windows whose exact score reaches the Q4 guard
-__global__ void k_lit_collect(const WinState w, int reverse, LiteralJob* jobs, int* count)
+__global__ void k_lit_collect(const WinState w, int reverse, LiteralJob* jobs, int* count, int* count_total)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.n_peaks) return;
     LiteralJob J;
     const int task = w.pk_task[i];
-    J.task = task; J.seg = task / w.tasks_per_seg; J.tdef = task % w.tasks_per_seg; J.peak = i; J.out_item = 0; J.out_half = 0;
+    J.task = task; J.seg = task / w.tasks_per_seg; J.tdef = task % w.tasks_per_seg; J.peak = i;
     if (!reverse) {
         if (w.w_done[i]) return;
         const int4 v = w.res[i];
@@ -163,6 +166,7 @@ __global__ void k_lit_collect(const WinState w, int reverse, LiteralJob* jobs, i
         J.read_start = w.fin_qe[i]; J.read_len = w.fin_qe[i] + 1; J.read_dir = -1; J.terminate = sw & 0xff;
     }
     jobs[atomicAdd(count, 1)] = J;
+    atomicAdd(count_total, 1);
 }
 
 }  // namespace ltg

@@ -127,22 +127,30 @@ struct ScanArgs {
     const uint32_t* profiles;   // [pair][strip][5*32*R]
     int n_strips;
     int max_len;                // row pitch of colmax / bnd (>= longest segment)
-    uint32_t* colmax;           // [item][max_len] packed column maxima of the two tasks
-    uint4* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F, cm, -)
+    uint32_t* colmax;           // [item][strip][max_len] packed column maxima of the two tasks, one row per RNA strip
+    uint2* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F)
     int* counter;               // work queue head
 };
 
 template <int R>
 __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
 {
-    return 5 * 32 * R * 4 + 32 * 16 + ((max_len + 64 + 15) / 16) * 16;
+    return 5 * 32 * R * 4 + 32 * 8 + ((max_len + 64 + 15) / 16) * 16;
 }
+
+// E update: fused VIADDMNMX (2 ALU-pipe slots) or VIADD on the FMA pipe + VIMNMX (1 ALU-pipe slot); the split form
+// trades one issue slot for one ALU-pipe slot (measured rates: profiles/int_simd_peak.json)
+#ifdef LTG_SCAN_SPLIT_E
+#define LTG_E_UPDATE(EV, U) EV = __vmaxs2(__vadd2(EV, kNegExt), (U))
+#else
+#define LTG_E_UPDATE(EV, U) EV = __viaddmax_s16x2(EV, kNegExt, (U))
+#endif
 
 #define LTG_CELL(SV, RR)                                          \
     {                                                             \
         const uint32_t t_ = __viaddmax_s16x2_relu(d, (SV), E[RR]); \
         const uint32_t u_ = __vadd2(t_, kNegOpen);                \
-        E[RR] = __viaddmax_s16x2(E[RR], kNegExt, u_);             \
+        LTG_E_UPDATE(E[RR], u_);                                  \
         const uint32_t h_ = __vmaxs2(t_, f);                      \
         f = __viaddmax_s16x2(f, kNegExt, u_);                     \
         d = Hd[RR];                                               \
@@ -152,6 +160,9 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
         hlast = h_;                                               \
     }
 
+// The column maxima are kept PER STRIP (32*R RNA rows): the epilogue combines them into the reference's
+// per-column maximum, and the window stage uses them as upper bounds to skip RNA rows that cannot hold a
+// window's best cell (window.cuh, "row pruning").
 template <int R, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 {
@@ -160,9 +171,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_bytes = scan_warp_smem_bytes<R>(a.max_len);
     uint4* s_prof = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(smem_u4) + (size_t)wib * warp_bytes);
-    uint4* s_ring = s_prof + 5 * (R / 4) * 32;
+    uint2* s_ring = reinterpret_cast<uint2*>(s_prof + 5 * (R / 4) * 32);
     uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_ring + 32);
-    uint4* bnd = a.bnd + (size_t)(blockIdx.x * WARPS + wib) * a.max_len;
+    uint2* bnd = a.bnd + (size_t)(blockIdx.x * WARPS + wib) * a.max_len;
     const uint32_t kNegOpen = 0xFFF0FFF0u, kNegExt = 0xFFFCFFFCu;
     constexpr int PLANE = (R / 4) * 32;     // uint4 per base-code plane
 
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             const int j = i - 32;
             s_codes[i] = (j < 0 || j >= n) ? (uint8_t)kBaseOther : gcodes[rev ? (n - 1 - j) : j];
         }
-        uint32_t* cm_out = a.colmax + (size_t)item * a.max_len;
+        uint32_t* cm_item = a.colmax + (size_t)item * a.n_strips * a.max_len;
 
         for (int strip = 0; strip < a.n_strips; ++strip) {
             const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
@@ -190,46 +201,62 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
             __syncwarp();
             const bool first = (strip == 0), last = (strip == a.n_strips - 1);
+            uint32_t* cm_out = cm_item + (size_t)strip * a.max_len;
             uint32_t Hd[R], E[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
             uint32_t hout = 0, fout = 0, cmout = 0, hdiag = 0;
             const int steps = n + 31;
+            // software pipeline: the packed scores of step s+1 are loaded while step s computes, and the base code
+            // two steps ahead is fetched, so no step starts by waiting on a shared-memory round trip
+            const uint8_t* cp = s_codes + (32 - lane);
+            uint4 sc[R / 4];
+            {
+                const uint4* pp0 = s_prof + (int)cp[0] * PLANE + lane;
+#pragma unroll
+                for (int k = 0; k < R / 4; ++k) sc[k] = pp0[k * 32];
+            }
+            int xn = cp[1];
             for (int s = 0; s < steps; ++s) {
                 if (!first && (s & 31) == 0) {
                     __syncwarp();
                     const int j = s + lane;
-                    uint4 pk = make_uint4(0, 0, 0, 0);
+                    uint2 pk = make_uint2(0, 0);
                     if (j < n) pk = bnd[j];
                     s_ring[lane] = pk;
                     __syncwarp();
                 }
+                const uint4* ppn = s_prof + xn * PLANE + lane;
+                uint4 scn[R / 4];
+#pragma unroll
+                for (int k = 0; k < R / 4; ++k) scn[k] = ppn[k * 32];
+                xn = cp[min(s + 2, steps)];
                 uint32_t hin = __shfl_up_sync(0xffffffffu, hout, 1);
                 uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);
                 uint32_t cmin = __shfl_up_sync(0xffffffffu, cmout, 1);
                 if (lane == 0) {
-                    if (first) { hin = 0; fin = 0; cmin = 0; }
-                    else { const uint4 pk = s_ring[s & 31]; hin = pk.x; fin = pk.y; cmin = pk.z; }
+                    cmin = 0;
+                    if (first) { hin = 0; fin = 0; }
+                    else { const uint2 pk = s_ring[s & 31]; hin = pk.x; fin = pk.y; }
                 }
-                const int x = s_codes[s - lane + 32];
-                const uint4* pp = s_prof + x * PLANE + lane;
                 uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;
                 uint32_t tv[2];
 #pragma unroll
                 for (int k = 0; k < R / 4; ++k) {
-                    const uint4 sc = pp[k * 32];
-                    LTG_CELL(sc.x, 4 * k + 0)
-                    LTG_CELL(sc.y, 4 * k + 1)
-                    LTG_CELL(sc.z, 4 * k + 2)
-                    LTG_CELL(sc.w, 4 * k + 3)
+                    LTG_CELL(sc[k].x, 4 * k + 0)
+                    LTG_CELL(sc[k].y, 4 * k + 1)
+                    LTG_CELL(sc[k].z, 4 * k + 2)
+                    LTG_CELL(sc[k].w, 4 * k + 3)
                 }
+#pragma unroll
+                for (int k = 0; k < R / 4; ++k) sc[k] = scn[k];
                 hdiag = hin;
                 hout = hlast; fout = f; cmout = cm;
                 if (lane == 31) {
                     const int j = s - 31;
                     if (j >= 0) {
-                        if (last) cm_out[j] = cm;
-                        else bnd[j] = make_uint4(hout, fout, cmout, 0u);
+                        cm_out[j] = cm;
+                        if (!last) bnd[j] = make_uint2(hout, fout);
                     }
                 }
             }
@@ -237,40 +264,45 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
     }
 }
 #undef LTG_CELL
+#undef LTG_E_UPDATE
 
 // ---------------------------------------------------------------------------------------------
 // Epilogue: per task the exact maximum, the threshold (int)(max*0.8) (Fasim-LongTarget.cpp:413), the
 // 8-bit "stop recording" truncation (Q2), threshold-hit compaction and run merge to peaks
 // (ssw_cpp.cpp:446-572).  One warp per item; hits are found with __ballot_sync and consumed in column
-// order; peaks are buffered one per lane and appended to the global pool with ONE atomicAdd per flush.
+// order.  Three passes over the (L2/HBM-resident) strip maxima:
+//   mode 0  statistics of every task + peak COUNT of the tasks that stay on the exact path
+//   mode 1  peak count of the tasks re-run by the literal emulation (Q4 guard)
+//   (exclusive scan of the counts -> one contiguous, position-ordered slice of the peak pool per task)
+//   mode 2  peaks written, 32 at a time, one lane per peak
 struct EpiArgs {
-    const uint32_t* colmax;
+    const uint32_t* colmax;      // [item][strip][max_len]
+    int n_strips;
+    const uint16_t* lit_colmax;  // [literal row][max_len] column maxima of the literal re-runs
+    const int* task_litrow;      // [task] row in lit_colmax (valid when the task carries kTaskLiteral)
     const ScanItem* items;
     const SegDesc* segs;
     int n_items;
     int max_len;
     int tasks_per_seg;
     const int* stats_max;    // [seg*T + task] exact calc_score_once maxima from the N-aware pass, or nullptr
-    int mode;                // 0: first pass over all items; 1: second pass (literal colmax present) — only halves flagged literal
+    int mode;
     int* task_max;           // [seg*T + task]
     int* task_thr;
     int* task_npeaks;
     int* task_flags;         // bit0 overflow(>=251) seen, bit1 literal re-run required (Q4 guard), bit2 int16 range exceeded
-    int* pk_count;
-    int pk_cap;
+    int* task_jstar;         // first column >= 251 (or n): nothing is recorded from there on (Q2)
+    const int* task_off;     // mode 2: first peak slot of every task
     int* pk_task;
     int* pk_pos;
     int* pk_score;
 };
 constexpr int kTaskOverflow = 1, kTaskLiteral = 2, kTaskRange = 4;
 
-__device__ inline void epi_flush(const EpiArgs& a, int lane, int& nbuf, int task, int bpos, int bscore)
+__device__ inline void epi_flush(const EpiArgs& a, int lane, int& nbuf, int base, int task, int bpos, int bscore)
 {
-    // lanes [0, nbuf) each hold one buffered peak
-    int base = 0;
-    if (lane == 0) base = atomicAdd(a.pk_count, nbuf);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (lane < nbuf && base + lane < a.pk_cap) {
+    // lanes [0, nbuf) each hold one buffered peak; `base` = slot of the first of them
+    if (lane < nbuf) {
         a.pk_task[base + lane] = task;
         a.pk_pos[base + lane] = bpos;
         a.pk_score[base + lane] = bscore;
@@ -285,17 +317,23 @@ __global__ void k_epilogue(const EpiArgs a)
     const ScanItem it = a.items[warp];
     const SegDesc sd = a.segs[it.seg];
     const int n = sd.len;
-    const uint32_t* cm = a.colmax + (size_t)warp * a.max_len;
+    const uint32_t* cm = a.colmax + (size_t)warp * a.n_strips * a.max_len;
     const PairDef pd = c_pairs[it.pair];
     for (int h = 0; h < 2; ++h) {
         if (h == 1 && pd.task[1] == pd.task[0]) break;
         const int task = it.seg * a.tasks_per_seg + pd.task[h];
+        // column maximum over all strips, as the reference's scan reports it
+        auto exact_at = [&](int j) -> int {
+            uint32_t v = cm[j];
+            for (int k = 1; k < a.n_strips; ++k) v = __vmaxs2(v, cm[(size_t)k * a.max_len + j]);
+            return h ? hi16(v) : lo16(v);
+        };
         int thr, jstar = n;
+        const uint16_t* lit = nullptr;
         if (a.mode == 0) {
             int mx = 0;
             for (int j = lane; j < n; j += 32) {
-                const uint32_t v = cm[j];
-                const int s = h ? hi16(v) : lo16(v);
+                const int s = exact_at(j);
                 mx = max(mx, s);
                 if (s >= kOverflowU8) jstar = min(jstar, j);
             }
@@ -306,14 +344,21 @@ __global__ void k_epilogue(const EpiArgs a)
             }
             const int score = a.stats_max ? a.stats_max[task] : mx;
             thr = (int)((double)score * 0.8);
-            int flags = (jstar < n ? kTaskOverflow : 0) | (mx >= kQ4Guard ? kTaskLiteral : 0) | (mx >= 32000 ? kTaskRange : 0);
-            if (lane == 0) { a.task_max[task] = score; a.task_thr[task] = thr; a.task_flags[task] = flags; a.task_npeaks[task] = 0; }
-            if (flags & kTaskLiteral) continue;      // peaks come from the literal re-run
+            const int flags = (jstar < n ? kTaskOverflow : 0) | (mx >= kQ4Guard ? kTaskLiteral : 0) | (mx >= 32000 ? kTaskRange : 0);
+            if (lane == 0) {
+                a.task_max[task] = score; a.task_thr[task] = thr; a.task_flags[task] = flags; a.task_npeaks[task] = 0;
+                a.task_jstar[task] = (flags & kTaskLiteral) ? n : jstar;     // literal maxima already carry the stop-recording zeros
+            }
+            if (flags & kTaskLiteral) continue;      // counted in mode 1, from the literal re-run
         } else {
-            if (!(a.task_flags[task] & kTaskLiteral)) continue;
+            const bool is_lit = (a.task_flags[task] & kTaskLiteral) != 0;
+            if (a.mode == 1 && !is_lit) continue;
             thr = a.task_thr[task];
-            // the literal column maxima already carry the stop-recording zeros
+            jstar = a.task_jstar[task];
+            if (is_lit) lit = a.lit_colmax + (size_t)a.task_litrow[task] * a.max_len;
         }
+        const bool write = (a.mode == 2);
+        const int base = write ? a.task_off[task] : 0;
         // hits in column order, run merge (ssw_cpp.cpp:470-572): consecutive hits < 5 apart form a run,
         // a run reports its first maximum
         bool have = false;
@@ -322,7 +367,7 @@ __global__ void k_epilogue(const EpiArgs a)
         for (int j0 = 0; j0 < jstar; j0 += 32) {
             const int j = j0 + lane;
             int s = 0;
-            if (j < jstar) { const uint32_t v = cm[j]; s = h ? hi16(v) : lo16(v); }
+            if (j < jstar) s = lit ? (int)lit[j] : exact_at(j);
             unsigned mask = __ballot_sync(0xffffffffu, j < jstar && s > thr);
             while (mask) {
                 const int b = __ffs(mask) - 1;
@@ -335,7 +380,7 @@ __global__ void k_epilogue(const EpiArgs a)
                     if (have) {
                         if (lane == nbuf) { bpos = best_pos; bscore = best_score; }
                         ++nbuf; ++npk;
-                        if (nbuf == 32) epi_flush(a, lane, nbuf, task, bpos, bscore);
+                        if (nbuf == 32) { if (write) epi_flush(a, lane, nbuf, base + npk - 32, task, bpos, bscore); else nbuf = 0; }
                     }
                     have = true; best_score = sc; best_pos = pos;
                 }
@@ -346,31 +391,62 @@ __global__ void k_epilogue(const EpiArgs a)
             if (lane == nbuf) { bpos = best_pos; bscore = best_score; }
             ++nbuf; ++npk;
         }
-        if (nbuf) epi_flush(a, lane, nbuf, task, bpos, bscore);
-        if (lane == 0) a.task_npeaks[task] = npk;
+        if (write) { if (nbuf) epi_flush(a, lane, nbuf, base + npk - nbuf, task, bpos, bscore); }
+        else if (lane == 0) a.task_npeaks[task] = npk;
     }
 }
 
-// maximum of each half of a packed colmax row (used for the N-aware threshold pass)
+// exclusive prefix sum of the per-task peak counts (one block; n is a few 10^4..10^5)
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ total)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? in[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            const int t = s_warp[lane];
+            int y = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int z = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += z; }
+            s_warp[lane] = y - t;            // exclusive offset of every warp
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < n) out[i] = carry + s_warp[w] + x - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[w] + x;
+        __syncthreads();
+    }
+    if (tid == 0) *total = s_carry;
+}
+
+// maximum of each half of an item's packed strip maxima (used for the N-aware threshold pass)
 __global__ void k_rowmax(const uint32_t* __restrict__ colmax, const ScanItem* __restrict__ items, const SegDesc* __restrict__ segs,
-                         int n_items, int max_len, int tasks_per_seg, int* __restrict__ stats_max)
+                         int n_items, int n_strips, int max_len, int tasks_per_seg, int* __restrict__ stats_max)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_items) return;
     const ScanItem it = items[warp];
     const int n = segs[it.seg].len;
-    const uint32_t* cm = colmax + (size_t)warp * max_len;
-    int m0 = 0, m1 = 0;
-    for (int j = lane; j < n; j += 32) { const uint32_t v = cm[j]; m0 = max(m0, lo16(v)); m1 = max(m1, hi16(v)); }
+    const uint32_t* cm = colmax + (size_t)warp * n_strips * max_len;
+    uint32_t v = 0;
+    for (int k = 0; k < n_strips; ++k)
+        for (int j = lane; j < n; j += 32) v = __vmaxs2(v, cm[(size_t)k * max_len + j]);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-        m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-    }
+    for (int o = 16; o; o >>= 1) v = __vmaxs2(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) {
         const PairDef pd = c_pairs[it.pair];
-        stats_max[it.seg * tasks_per_seg + pd.task[0]] = m0;
-        stats_max[it.seg * tasks_per_seg + pd.task[1]] = m1;
+        stats_max[it.seg * tasks_per_seg + pd.task[0]] = lo16(v);
+        stats_max[it.seg * tasks_per_seg + pd.task[1]] = hi16(v);
     }
 }
 

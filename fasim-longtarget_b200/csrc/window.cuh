@@ -1,5 +1,5 @@
 // Window stage: the device counterpart of fastSIM's per-peak loop (fastsim.h:202-272) around
-// Aligner::Align -> ssw_align (ssw_cpp.cpp:599, sswNew.cpp:1446): forward Smith-Waterman of the whole
+// Aligner::Align -> ssw_align (ssw_cpp.cpp:599, sswNew.cpp:1446): forward Smith-Waterman of the
 // lncRNA against a short DNA window ending at the peak, reverse pass to locate the beginning, banded
 // traceback to a CIGAR, expansion to the aligned TFO / TTS strings.
 //
@@ -7,11 +7,25 @@
 // streams through them, so a 55-column window keeps ~m/(m+g) of its lanes busy instead of ~60 %.
 // Windows are right-aligned in groups of g = 4/8/16/32 lanes (pad columns on the left stay identically
 // zero); a warp carries 32/g groups in each 16-bit half.  Scores are computed on the fly
-// (XNOR of scaled base codes, then max(~e + 6, -4)), so every group may stream its own RNA slice —
-// the forward pass streams rows 0..m-1, the reverse pass rows qe..0.
+// (XNOR of scaled base codes, then max(~e + 6, -4)), so every group may stream its own RNA slice.
 // Result tracking costs one VIMNMX3 per two cells plus a rarely taken slow path: forward keeps the
 // maximum with the reference's tie rules (first column, then first row: sswNew.cpp:605-629), reverse keeps
 // the first column (then first row) whose value equals the forward score (terminate test :617).
+//
+// Row pruning (exact, not a heuristic).  The reference sweeps all m RNA rows for every window.  Two facts
+// let this stage sweep far fewer rows and still return the identical (score, end column, end row):
+//  (1) a local alignment that spans c columns and has a positive score spans fewer than 2.25*c + 1 rows
+//      (every inserted row costs >= 4, every column yields <= 5), so the value of a cell only depends on
+//      the win_margin(c) rows above it;
+//  (2) a window cell can never exceed the same cell of the whole-segment matrix, and the scan stage kept,
+//      per strip of 32*R_scan RNA rows, the column maxima of that matrix (scan.cuh).
+// For a lower bound L of the window's best score, only strips whose maximum over the window's columns
+// reaches L can hold the best cell (or a tie that matters for the tie rules); the stream covers those strips
+// plus the margin above them.  Values computed on a sub-range of rows are lower bounds of the true values, so
+// if the result r of a pruned sweep satisfies r >= L it is exact; otherwise the window is swept again with
+// L = r (a proven lower bound), which is exact by the same argument.  First try: L = peak score.
+// The reverse pass only needs win_margin(re+1) rows: every cell equal to the forward score belongs to an
+// alignment that starts at the forward end cell (tie rules of the forward pass), see DESIGN.md.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -19,7 +33,9 @@
 namespace ltg {
 
 constexpr int kWinR = 8;            // window columns per lane
-constexpr int kWinClasses = 4;      // groups of 4, 8, 16, 32 lanes  (32, 64, 128, 256 columns)
+constexpr int kWinColClasses = 4;   // groups of 4, 8, 16, 32 lanes  (32, 64, 128, 256 columns)
+constexpr int kWinClasses = 8;      // x 2 stream-length classes (<= / > kWinLongRows rows)
+constexpr int kWinLongRows = 1024;
 constexpr int kMaxWindow = 32 * kWinR;
 
 struct WinState {
@@ -30,14 +46,17 @@ struct WinState {
     const int* pk_score;
     // per peak
     int* w_len;        // columns of the window in flight (cut, or re+1 in the reverse pass)
+    int* w_lo;         // first RNA row of the forward stream in flight
+    int* w_rows;       // number of RNA rows streamed
+    int* w_bound;      // the lower bound L the row range was derived from (0: all rows, result exact by construction)
     int* w_done;       // 1: final alignment chosen
     int* best_sw; int* best_cut; int* best_re; int* best_qe;
     int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb;
     // class lists
-    int* cls_count;    // [4]
-    int* cls_list;     // [4][cap]
+    int* cls_count;    // [kWinClasses]
+    int* cls_list;     // [kWinClasses][cap]
     int cap;
-    // dp result per peak: (best value, column, row)
+    // dp result per peak: (best value, column, row, 1 if written by the literal emulation)
     int4* res;
     int* bin_counter;
     // geometry
@@ -46,35 +65,89 @@ struct WinState {
     const int* cut_table;   // [256][4]  cut length per (peak score, round) — fastsim.h:210 evaluated in float32 on the host
     long long* cell_counter;
     const int* forced_cut;  // probe path: explicit window length per peak (nullptr in the product path)
+    // strip maxima of the scan stage (nullptr: no pruning, every window streams the whole lncRNA)
+    const uint32_t* strip_colmax; int n_strips; int strip_rows; int max_len; int n_pairs;
 };
 
-__device__ inline int win_class(int len) { return len <= 4 * kWinR ? 0 : (len <= 8 * kWinR ? 1 : (len <= 16 * kWinR ? 2 : 3)); }
+__device__ inline int win_col_class(int len) { return len <= 4 * kWinR ? 0 : (len <= 8 * kWinR ? 1 : (len <= 16 * kWinR ? 2 : 3)); }
+__device__ inline int win_class(int len, int rows) { return win_col_class(len) + (rows > kWinLongRows ? kWinColClasses : 0); }
+// rows spanned by a positive-score local alignment over `cols` columns: < 2.25 * cols + 1
+__host__ __device__ inline int win_margin(int cols) { return (9 * cols) / 4 + 2; }
 
-// round >= 0: forward plan for round `round`; round < 0: reverse plan over the chosen alignments
-__global__ void k_win_plan(const WinState w, int round)
+// round >= 0, retry 0: forward plan for round `round` (row range from the bound L = peak score);
+// round >= 0, retry 1: windows whose pruned result fell short of the bound they were planned with, re-planned with
+//                      L = that result; round < 0: reverse plan over the chosen alignments.
+// 8 threads cooperate on one peak (the strip-bound scan reads n_strips * cut column maxima).
+__global__ void k_win_plan(const WinState w, int round, int retry)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.n_peaks) return;
-    int len;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 3, sub = gt & 7;
+    bool active = i < w.n_peaks;
+    int len = 0, lo = 0, rows = 0, bound = 0;
+    if (active) {
+        if (round >= 0) {
+            const int sc = w.pk_score[i], pos = w.pk_pos[i];
+            if (!retry) {
+                if (round == 0) { if (sub == 0) { w.w_done[i] = 0; w.best_sw[i] = 0; w.fin_sw[i] = 0; } }
+                else if (w.w_done[i]) active = false;
+                int cut = w.forced_cut ? w.forced_cut[i] : w.cut_table[min(sc, 255) * 4 + round];
+                if (pos - cut + 1 <= 0) cut = pos + 1;                 // fastsim.h:211
+                len = cut;
+                bound = sc;
+            } else {
+                const int4 v = w.res[i];
+                if (w.w_done[i] || v.x >= w.w_bound[i]) active = false;      // exact already
+                len = w.w_len[i];
+                bound = max(v.x, 0);
+            }
+        } else {
+            if (w.fin_sw[i] <= 0) active = false;
+            len = w.fin_re[i] + 1;
+        }
+    }
+    // strip bound scan (forward plans only): which strips can hold a cell >= bound inside the window's columns
+    int klo = 0x7fffffff, khi = -1;
+    if (round >= 0 && w.strip_colmax != nullptr) {
+        const bool scan = active && bound > 0;
+        int task = 0, pos = 0;
+        if (scan) { task = w.pk_task[i]; pos = w.pk_pos[i]; }
+        const TaskDef td = c_tasks[task % w.tasks_per_seg];
+        const uint32_t* base = w.strip_colmax + ((size_t)(task / w.tasks_per_seg) * w.n_pairs + td.pair) * w.n_strips * w.max_len;
+        for (int k = 0; k < w.n_strips; ++k) {
+            int b = -32768;
+            if (scan) {
+                const uint32_t* row = base + (size_t)k * w.max_len;
+                uint32_t v = 0x80008000u;
+                for (int j = pos - len + 1 + sub; j <= pos; j += 8) v = __vmaxs2(v, row[j]);
+                b = td.half ? hi16(v) : lo16(v);
+            }
+            b = max(b, __shfl_xor_sync(0xffffffffu, b, 1));
+            b = max(b, __shfl_xor_sync(0xffffffffu, b, 2));
+            b = max(b, __shfl_xor_sync(0xffffffffu, b, 4));
+            if (scan && b >= bound) { klo = min(klo, k); khi = k; }
+        }
+    }
+    if (!active || sub != 0) return;
     if (round >= 0) {
-        if (round == 0) { w.w_done[i] = 0; w.best_sw[i] = 0; w.fin_sw[i] = 0; }
-        else if (w.w_done[i]) return;
-        const int sc = w.pk_score[i], pos = w.pk_pos[i];
-        int cut = w.forced_cut ? w.forced_cut[i] : w.cut_table[min(sc, 255) * 4 + round];
-        if (pos - cut + 1 <= 0) cut = pos + 1;                 // fastsim.h:211
-        len = cut;
+        lo = 0; rows = w.m;
+        if (khi >= 0) {
+            lo = max(0, klo * w.strip_rows - win_margin(len));
+            const int hi = min(w.m - 1, (khi + 1) * w.strip_rows - 1);
+            rows = hi - lo + 1;
+        }
+        if (rows >= w.m) { lo = 0; rows = w.m; bound = 0; }      // whole lncRNA: exact whatever the result
+        w.w_lo[i] = lo; w.w_rows[i] = rows; w.w_bound[i] = bound;
+        if (w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, (unsigned long long)len * (unsigned long long)rows);
     } else {
-        if (w.fin_sw[i] <= 0) return;
-        len = w.fin_re[i] + 1;
+        rows = min(w.fin_qe[i] + 1, win_margin(len));
     }
     w.w_len[i] = len;
-    const int c = win_class(len);
+    const int c = win_class(len, rows);
     const int slot = atomicAdd(&w.cls_count[c], 1);
     w.cls_list[(size_t)c * w.cap + slot] = i;
-    if (round >= 0 && w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, (unsigned long long)len * (unsigned long long)w.m);
 }
 
-__device__ inline int bins_of_class(int count, int c) { const int wpw = 2 * (32 / (4 << c)); return (count + wpw - 1) / wpw; }
+__device__ inline int bins_of_class(int count, int c) { const int wpw = 2 * (32 / (4 << (c & 3))); return (count + wpw - 1) / wpw; }
 
 template <bool REV>
 __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
@@ -93,7 +166,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
         if (bin >= total) break;
         int c = 0, b = bin;
         while (b >= nb[c]) { b -= nb[c]; ++c; }
-        const int g = 4 << c, gpw = 32 / g;            // lanes per group, groups per half-warp
+        const int g = 4 << (c & 3), gpw = 32 / g;      // lanes per group, groups per half-warp
         const int lig = lane & (g - 1), grp = lane / g;
         const bool leader = (lig == 0);
 
@@ -119,8 +192,8 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                 len[h] = L;
                 const int cutw = REV ? w.fin_cut[i] : L;
                 const int ws = w.pk_pos[i] - cutw + 1;                    // window start in seq2 coordinates
-                if (REV) { slen[h] = w.fin_qe[i] + 1; sbase[h] = w.fin_qe[i]; sdir[h] = -1; }
-                else { slen[h] = w.m; sbase[h] = 0; sdir[h] = 1; }
+                if (REV) { slen[h] = min(w.fin_qe[i] + 1, win_margin(L)); sbase[h] = w.fin_qe[i]; sdir[h] = -1; }
+                else { slen[h] = w.w_rows[i]; sbase[h] = w.w_lo[i]; sdir[h] = 1; }
                 const int off = g * R - L;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -217,7 +290,8 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                 const int orow = __shfl_down_sync(0xffffffffu, brow[h], o);
                 if (lig + o < g && (ob > best[h] || (ob == best[h] && oc < bcol[h]))) { best[h] = ob; bcol[h] = oc; brow[h] = orow; }
             }
-            if (leader && wi[h] >= 0) w.res[wi[h]] = make_int4(best[h], bcol[h], brow[h], 0);
+            // forward: absolute RNA row; reverse: index into the reversed stream (k_win_finish subtracts it from qe)
+            if (leader && wi[h] >= 0) w.res[wi[h]] = make_int4(best[h], bcol[h], REV ? brow[h] : sbase[h] + brow[h], 0);
         }
     }
 }
@@ -264,21 +338,59 @@ __global__ void k_win_finish(const WinState w)
 }
 
 // ---------------------------------------------------------------------------------------------
-// banded_sw (sswNew.cpp:1071-1259) + getAlignment expansion (fastsim.h:416-560), one thread per chosen
-// alignment.  Per-thread scratch: three int rows of (2*bw+5), the direction bytes 3*(2*bw+1)*readLen, and
-// the op / string staging area.  Alignments whose band outgrows the scratch are flagged (status 2) and
-// re-run by a second launch with a large scratch.
+// banded_sw (sswNew.cpp:1071-1259) + getAlignment expansion (fastsim.h:416-560) + the identity / stability
+// arithmetic of convertMyTriplex (fastsim.h:323-383), one thread per alignment.  An alignment is described by a
+// self-contained TraceJob, so the same kernel serves two passes:
+//   pass 1  every chosen alignment of a batch: nt, identity, stability only (what the host needs to de-duplicate,
+//           rank and filter — fastsim.h:273-288, Fasim-LongTarget.cpp:589-597);
+//   pass 2  the few alignments that survive those filters: the TFO / TTS strings, written at host-assigned offsets.
+// Per-thread scratch: three int rows of (2*bw+5), the direction bytes 3*(2*bw+1)*readLen, and the op / string
+// staging area.  Alignments whose band outgrows the scratch are flagged (status 2) and re-run by a second launch
+// with a large scratch.
+struct TraceJob {
+    long long seg_start;       // segment offset in the record
+    int seg_len, tdef;         // segment length, index into the task table
+    int ws;                    // window start in seq2 (translated-segment) coordinates
+    int rb, re, qb, qe;        // alignment box: window-relative columns, lncRNA rows
+    int score;                 // sw_score (<= 0: nothing to do)
+    long long out_off;         // pass 2: offset of the string pair in the pool
+};
+
+struct TraceOut {
+    int status;                // 0 none, 1 ok, 2 needs a larger scratch, 3 traceback left the band (sw_score -> 0)
+    int nt;                    // alignment columns
+    float identity, tri;       // MeanIdentity(%) / MeanStability, float32 evaluated exactly as fastsim.h:323-383
+};
+
 struct TraceArgs {
-    WinState w;
+    const TraceJob* jobs; int n_jobs;
+    const uint8_t* codes;          // base codes of the record
     const unsigned char* dna;      // raw record bytes (for the TTS string)
+    const uint8_t* rna_ssw;        // lncRNA, SSW codes
     const unsigned char* rna_raw;  // raw lncRNA bytes (for the TFO string)
     unsigned char* scratch; long long scratch_per_thread;
     int only_overflow;             // second launch: only alignments flagged status 2
-    // outputs per peak
-    int* al_status;                // 0 none, 1 ok, 2 needs a larger scratch / pool, 3 traceback left the band (sw_score -> 0)
-    int* al_nt; int* al_match; long long* al_stroff;
-    char* strpool; long long strcap; long long* str_count;
+    int nt_min, nt_max, penalty_t, penalty_c;
+    TraceOut* out;                 // per job
+    char* strpool;                 // pass 2 only (nullptr in pass 1): tfo at out_off, tts at out_off + nt + 1, both NUL-terminated
 };
+
+__global__ void k_make_trace_jobs(const WinState w, TraceJob* jobs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n_peaks) return;
+    TraceJob J;
+    const int task = w.pk_task[i];
+    const SegDesc sd = w.segs[task / w.tasks_per_seg];
+    J.seg_start = sd.start; J.seg_len = sd.len; J.tdef = task % w.tasks_per_seg;
+    J.score = w.fin_sw[i];
+    J.ws = 0; J.rb = J.re = J.qb = J.qe = 0; J.out_off = 0;
+    if (J.score > 0) {
+        J.ws = w.pk_pos[i] - w.fin_cut[i] + 1;
+        J.rb = w.fin_rb[i]; J.re = w.fin_re[i]; J.qb = w.fin_qb[i]; J.qe = w.fin_qe[i];
+    }
+    jobs[i] = J;
+}
 
 __device__ inline int band_u(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x + 1; }
 __device__ inline int band_d(int w, int i, int j, int p) { int x = i - w; if (x < 0) x = 0; return (j - x) * 3 + p; }
@@ -288,24 +400,38 @@ __device__ inline char comp_char(unsigned char c)
     switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
 }
 
+// Hoogsteen / reverse-Hoogsteen stability of one (DNA base, RNA base) column — sim.h:72-97
+__device__ inline float stability_dev(char dna, char rna, int para)
+{
+    if (para > 0) {
+        if (dna == 'A' && rna == 'T') return 3.7f;
+        if (dna == 'T' && rna == 'G') return 2.8f;
+        if (dna == 'G') { if (rna == 'G') return 2.2f; if (rna == 'T') return 2.4f; if (rna == 'C') return 4.5f; }
+        if (dna == 'C') { if (rna == 'T') return 2.6f; if (rna == 'C') return 2.4f; }
+    } else {
+        if (dna == 'A') { if (rna == 'A') return 3.0f; if (rna == 'T') return 3.5f; if (rna == 'C') return 1.0f; }
+        if (dna == 'T' && rna == 'G') return 1.0f;
+        if (dna == 'G') { if (rna == 'A') return 1.0f; if (rna == 'G') return 3.0f; if (rna == 'C') return 3.0f; }
+        if (dna == 'C') { if (rna == 'T') return 2.0f; if (rna == 'C') return 1.0f; }
+    }
+    return 0.0f;
+}
+
 __global__ void k_traceback(const TraceArgs a)
 {
-    const WinState& w = a.w;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     unsigned char* sc = a.scratch + (size_t)tid * a.scratch_per_thread;
-    for (int i = tid; i < w.n_peaks; i += nthreads) {
-        if (!a.only_overflow) a.al_status[i] = 0;
-        if (w.fin_sw[i] <= 0) continue;
-        if (a.only_overflow && a.al_status[i] != 2) continue;
+    for (int i = tid; i < a.n_jobs; i += nthreads) {
+        if (!a.only_overflow) a.out[i].status = 0;
+        const TraceJob J = a.jobs[i];
+        if (J.score <= 0) continue;
+        if (a.only_overflow && a.out[i].status != 2) continue;
 
-        const int task = w.pk_task[i];
-        const SegDesc sd = w.segs[task / w.tasks_per_seg];
-        const TaskDef td = c_tasks[task % w.tasks_per_seg];
-        const int ws = w.pk_pos[i] - w.fin_cut[i] + 1;
-        const int rb = w.fin_rb[i], re = w.fin_re[i], qb = w.fin_qb[i], qe = w.fin_qe[i];
-        const int refLen = re - rb + 1, readLen = qe - qb + 1, score = w.fin_sw[i];
-        const uint8_t* gc = w.codes + sd.start;
-        auto gidx = [&](int q) -> int { return td.reversed ? (sd.len - 1 - q) : q; };     // seq2 index -> segment index
+        const TaskDef td = c_tasks[J.tdef];
+        const int ws = J.ws, rb = J.rb, re = J.re, qb = J.qb, qe = J.qe;
+        const int refLen = re - rb + 1, readLen = qe - qb + 1, score = J.score;
+        const uint8_t* gc = a.codes + J.seg_start;
+        auto gidx = [&](int q) -> int { return td.reversed ? (J.seg_len - 1 - q) : q; };     // seq2 index -> segment index
         const int ntmax = refLen + readLen;
 
         int bw = abs(refLen - readLen) + 1, maxv = 0, width_d = 0;
@@ -327,7 +453,7 @@ __global__ void k_traceback(const TraceArgs a)
                 int f = 0, u = 0;
                 h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
                 int8_t* line = dir + (size_t)width_d * ii * 3;
-                const int rc = w.rna_ssw[qb + ii];
+                const int rc = a.rna_ssw[qb + ii];
                 for (int j = beg; j <= end; ++j) {
                     u = band_u(bw, ii, j);
                     const int e = band_u(bw, ii - 1, j), b = band_u(bw, ii, j - 1), dd = band_u(bw, ii - 1, j - 1);
@@ -354,7 +480,7 @@ __global__ void k_traceback(const TraceArgs a)
             if (maxv >= score) break;
             bw *= 2;
         }
-        if (!fits) { a.al_status[i] = 2; continue; }
+        if (!fits) { a.out[i].status = 2; continue; }
 
         // traceback (sswNew.cpp:1159-1238): ops come out end -> start; written backwards into `ops`
         unsigned char* ops = reinterpret_cast<unsigned char*>(dir) + 3LL * width_d * readLen;
@@ -376,7 +502,7 @@ __global__ void k_traceback(const TraceArgs a)
             else { bad = true; break; }
             if (wp <= 1) { bad = true; break; }
         }
-        if (bad) { a.al_status[i] = 3; continue; }
+        if (bad) { a.out[i].status = 3; continue; }
         ops[--wp] = 0;      // closing rule (:1220-1238): the alignment always starts with one more M column
         const int nt = ntmax + 2 - wp;
         // expansion from the front exactly like getAlignment: q walks the translated DNA from ref_begin, p the RNA
@@ -387,7 +513,7 @@ __global__ void k_traceback(const TraceArgs a)
             if (op != 2) rch = (char)a.rna_raw[p++];
             if (op != 1) {
                 const int gi = gidx(q++);
-                const unsigned char raw = a.dna[sd.start + gi];
+                const unsigned char raw = a.dna[J.seg_start + gi];
                 sch = td.comp_src ? comp_char(raw) : (char)raw;
                 const int dcode = td.img[gc[gi]];
                 tch = dcode < 4 ? "ACGT"[dcode] : 'N';
@@ -395,15 +521,34 @@ __global__ void k_traceback(const TraceArgs a)
             tfo[k] = rch; tts[k] = sch;
             if (tch == rch) ++match;
         }
-        const long long so = (long long)atomicAdd((unsigned long long*)a.str_count, (unsigned long long)(2 * (nt + 1)));
-        if (so + 2 * (nt + 1) > a.strcap) { a.al_status[i] = 2; continue; }
-        char* o = a.strpool + so;
-        for (int k = 0; k < nt; ++k) o[k] = tfo[k];
-        o[nt] = 0;
-        for (int k = 0; k < nt; ++k) o[nt + 1 + k] = tts[k];
-        o[2 * nt + 1] = 0;
-        a.al_nt[i] = nt; a.al_match[i] = match; a.al_stroff[i] = so;
-        a.al_status[i] = 1;
+        // identity and mean stability in float32, same operation order as convertMyTriplex (fastsim.h:335, 342-383);
+        // explicit round-to-nearest intrinsics keep the compiler from contracting or re-associating anything
+        const float identity = __fdiv_rn(__int2float_rn(100 * match), __int2float_rn(nt));
+        float tri = 0.0f;
+        if (nt >= a.nt_min && nt <= a.nt_max) {
+            float prev_val = 0.0f;
+            char prev_ch = 0;
+            const float pt = __int2float_rn(a.penalty_t), pc = __int2float_rn(a.penalty_c);
+            for (int k = 0; k < nt; ++k) {
+                const char ch = tts[k];
+                float val = stability_dev(ch, tfo[k], td.para);
+                if (ch == prev_ch && ch == 'T') { tri = __fadd_rn(__fsub_rn(tri, prev_val), pt); val = pt; }
+                if (ch == prev_ch && ch == 'C') { tri = __fadd_rn(__fsub_rn(tri, prev_val), pc); val = pc; }
+                prev_val = val;
+                if (ch != '-') prev_ch = ch;
+                tri = __fadd_rn(tri, val);
+            }
+            tri = __fdiv_rn(tri, __int2float_rn(nt));
+        }
+                if (a.strpool) {
+            char* o = a.strpool + J.out_off;
+            for (int k = 0; k < nt; ++k) o[k] = tfo[k];
+            o[nt] = 0;
+            for (int k = 0; k < nt; ++k) o[nt + 1 + k] = tts[k];
+            o[2 * nt + 1] = 0;
+        }
+        TraceOut o1; o1.status = 1; o1.nt = nt; o1.identity = identity; o1.tri = tri;
+        a.out[i] = o1;
     }
 }
 

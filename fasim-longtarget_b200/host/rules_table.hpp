@@ -41,7 +41,7 @@ inline bool make_task(int para, int strand, int rule, ltg::TaskDef& t)
     t.comp_src = (int8_t)(strand == 1);
     t.img[0] = (int8_t)letter_code(im->a); t.img[1] = (int8_t)letter_code(im->c);
     t.img[2] = (int8_t)letter_code(im->g); t.img[3] = (int8_t)letter_code(im->t); t.img[4] = 4;
-    t.pad_[0] = t.pad_[1] = 0;
+    t.pair = 0; t.half = 0;
     return true;
 }
 

@@ -1,6 +1,8 @@
 // Host side of the hot path that stays scalar C++: turning device alignments
-// into triplex records, the per-task de-duplication, clustering and the -TFOsorted / -TFOclass writers.
-// Everything here is cheap string / list work; all DP runs on the GPU.
+// into triplex records, the per-task de-duplication (std::sort / std::unique with the reference's comparators,
+// whose outcome depends on libstdc++'s permutation — SURVEY App. B Q8), clustering and the -TFOsorted /
+// -TFOclass writers.  Everything here is cheap list work on plain records; all DP, the traceback, the identity
+// and stability arithmetic and the string expansion run on the GPU.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -14,77 +16,39 @@
 
 namespace ltg_host {
 
+// One candidate triplex while it travels through the per-task de-duplication and the filters.  Plain data: the
+// TFO / TTS strings are only produced (by the second traceback pass on the GPU) for the rows that survive.
 struct Triplex {
     int stari = 0, endi = 0, starj = 0, endj = 0, reverse = 0, strand = 0, rule = 0, nt = 0;
     float score = 0, identity = 0, tri_score = 0;
-    std::string tfo, tts;               // stri_align / strj_align of sim.h:36-37
-    int middle = 0, center = 0, motif = 0;
-    long genomestart = 0, genomeend = 0;
-    int record = 0;
+    // where the alignment lives: input of the string pass (window.cuh TraceJob)
+    int tdef = 0, seg_len = 0, ws = 0, rb = 0, re = 0, qb = 0, qe = 0;
+    long seg_start = 0;
 };
 
-// Hoogsteen / reverse-Hoogsteen stability table — sim.h:72-97
-inline float stability(char dna, char rna, int para)
-{
-    if (para > 0) {
-        switch (dna) {
-        case 'A': if (rna == 'T') return 3.7; break;
-        case 'T': if (rna == 'G') return 2.8; break;
-        case 'G': if (rna == 'G') return 2.2; if (rna == 'T') return 2.4; if (rna == 'C') return 4.5; break;
-        case 'C': if (rna == 'T') return 2.6; if (rna == 'C') return 2.4; break;
-        default: break;
-        }
-    } else {
-        switch (dna) {
-        case 'A': if (rna == 'A') return 3.0; if (rna == 'T') return 3.5; if (rna == 'C') return 1.0; break;
-        case 'T': if (rna == 'G') return 1.0; break;
-        case 'G': if (rna == 'A') return 1.0; if (rna == 'G') return 3.0; if (rna == 'C') return 3.0; break;
-        case 'C': if (rna == 'T') return 2.0; if (rna == 'C') return 1.0; break;
-        default: break;
-        }
-    }
-    return 0;
-}
-
-struct DeviceAlignment {        // one chosen alignment as it comes back from the GPU
-    int sw_score, ref_begin, ref_end, query_begin, query_end;   // ref_* in translated-segment coordinates
-    int nt, match;
-    const char* tfo;            // lncRNA side, '-' in D columns
-    const char* tts;            // DNA source-strand side, '-' in I columns
+struct DeviceAlignment {        // one chosen alignment as it comes back from the GPU (pass 1 of the traceback)
+    int sw_score, ws, rb, re, query_begin, query_end;   // ws + rb / ws + re = ref_begin / ref_end in translated-segment coordinates
+    int nt;
+    float identity, tri_score;  // evaluated on the device exactly as fastsim.h:323-383 does (float32, same order)
 };
 
-// convertMyTriplex — fastsim.h:291-414 (identity :323-335, stability with TT/CC penalties :342-383,
-// orientation-dependent coordinates :389-396).  float32 throughout, same evaluation order.
-inline void make_triplex(const DeviceAlignment& al, int seg_len, long seg_start, int para, int strand, int rule,
+// tail of convertMyTriplex — fastsim.h:385-405: orientation-dependent coordinates (:389-396), nt >= ntMin gate (:397)
+inline void make_triplex(const DeviceAlignment& al, int tdef, int seg_len, long seg_start, int para, int strand, int rule,
                          const ltg_params& P, std::vector<Triplex>& out)
 {
-    const int nt = al.nt;
-    const float identity = (float)(100 * al.match) / (float)(nt);
-    float sum = 0.0f, prev_val = 0.0f, val = 0.0f;
-    char prev_ch = 0, ch = 0;
-    if (nt >= P.nt_min && nt <= P.nt_max) {
-        for (int i = 0; i < nt; ++i) {
-            ch = al.tts[i];
-            val = stability(ch, al.tfo[i], para);
-            if (ch == prev_ch && ch == 'T') { sum = sum - prev_val + P.penalty_t; val = P.penalty_t; }
-            if (ch == prev_ch && ch == 'C') { sum = sum - prev_val + P.penalty_c; val = P.penalty_c; }
-            prev_val = val;
-            if (ch != '-') prev_ch = ch;
-            sum += val;
-        }
-        sum = sum / nt;
-    }
+    if (al.nt < P.nt_min) return;
+    const int ref_begin = al.ws + al.rb, ref_end = al.ws + al.re;
     int a, b;
-    if ((para > 0 && strand == 1) || (para < 0 && strand == 0)) { a = seg_len - al.ref_end - 1; b = seg_len - al.ref_begin - 1; }
-    else { a = al.ref_begin + 1; b = al.ref_end + 1; }
-    if (nt < P.nt_min) return;
+    if ((para > 0 && strand == 1) || (para < 0 && strand == 0)) { a = seg_len - ref_end - 1; b = seg_len - ref_begin - 1; }
+    else { a = ref_begin + 1; b = ref_end + 1; }
     Triplex t;
     t.stari = al.query_begin + 1; t.endi = al.query_end + 1;
     t.starj = (int)(a + seg_start); t.endj = (int)(b + seg_start);
-    t.strand = strand; t.reverse = para; t.rule = rule; t.nt = nt;
-    t.score = (float)al.sw_score; t.identity = identity; t.tri_score = sum;
-    t.tfo.assign(al.tfo, nt); t.tts.assign(al.tts, nt);
-    out.push_back(std::move(t));
+    t.strand = strand; t.reverse = para; t.rule = rule; t.nt = al.nt;
+    t.score = (float)al.sw_score; t.identity = al.identity; t.tri_score = al.tri_score;
+    t.tdef = tdef; t.seg_len = seg_len; t.seg_start = seg_start;
+    t.ws = al.ws; t.rb = al.rb; t.re = al.re; t.qb = al.query_begin; t.qe = al.query_end;
+    out.push_back(t);
 }
 
 // comparators of fastsim.h:92-156 (not strict weak orders — kept verbatim in meaning, Q8)

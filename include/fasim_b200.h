@@ -80,6 +80,8 @@ typedef struct ltg_result {
     int64_t gpu_launches;       /* kernels launched for this result                                */
     double gpu_ms_scan_kernel;  /* CUDA-event time of the k_scan launches alone (roofline numerator) */
     int64_t n_scan_launches;    /* number of k_scan launches                                       */
+    int64_t h2d_bytes;          /* bytes copied host -> device for this result (DNA, descriptors)   */
+    int64_t d2h_bytes;          /* bytes copied device -> host (per-peak records, strings, counters) */
 } ltg_result;
 
 /* ---- context ---------------------------------------------------------------------------------- */

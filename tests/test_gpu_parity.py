@@ -271,6 +271,39 @@ def test_full_size_properties_1mbp(engine):
         assert rows_as_oracle_text(engine.LongTarget(seg)) == oracle_text_rows(O.longtarget(rna, seg))
 
 
+def test_row_pruning_is_exact(data_dir):
+    """The window stage skips RNA rows that provably cannot hold a window's best cell (window.cuh).  With LTG_NO_PRUNE=1
+    every window sweeps the whole lncRNA like the reference does: both modes must give identical rows, on random DNA
+    (few strips survive) and on the repeat-rich demo (many ties, overflow and literal windows)."""
+    dna = splitmix_bases(1001, 300_000)
+    rna = splitmix_bases(2001, 3000)
+    drna, _, ddna = demo(data_dir)
+    os.environ["LTG_NO_PRUNE"] = "1"
+    try:
+        full = fb.Engine(0)
+    finally:
+        del os.environ["LTG_NO_PRUNE"]
+    pruned = fb.Engine(0)
+    try:
+        for eng in (full, pruned):
+            eng.set_params(c_length=20)
+        outs = []
+        for eng in (full, pruned):
+            eng.set_query("synRNA3k", rna)
+            res = eng.scan_record(dna, "chr1", 1)
+            rows, cells = fb.result_rows(res), res.contents.window_cells
+            eng.free(res)
+            eng.set_query("H19", drna)
+            rows2 = eng.LongTarget(ddna, "chr11", 1)
+            outs.append((rows, rows2, cells))
+        assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 0
+        assert outs[0][1] == outs[1][1] and len(outs[0][1]) > 0
+        assert outs[1][2] * 2 < outs[0][2]          # and it actually prunes: fewer than half of the window cells
+    finally:
+        full.close()
+        pruned.close()
+
+
 def test_error_behaviour(engine):
     with pytest.raises(fb.FasimError):
         engine.set_params(rule=19, strand=-1)           # reference: exit(1) in transferString
