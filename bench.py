@@ -316,6 +316,8 @@ def bench_gpu(args, rank, world, local_rank):
         elif world == 1:
             line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "reference", "sample": "reference binary not built"}
         print(json.dumps(line))
+        if args.debug_stats:
+            print(json.dumps({"window_stage_stats": eng.debug_stats()}), file=sys.stderr)
     eng.close()
     if dist:
         dist.barrier()
@@ -331,6 +333,7 @@ def main():
     ap.add_argument("--region-mbp", type=float, default=REGION_BP / 1e6)
     ap.add_argument("--ref-chunk-bp", type=int, default=49100)        # 10 full segments + tail per core and step
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-stats", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -84,7 +84,7 @@ constexpr int kScanR = LTG_SCAN_R;          // RNA rows per lane in the scan ker
 constexpr int kScanWarps = LTG_SCAN_WARPS;  // warps per CTA
 constexpr int kScanCtasPerSm = LTG_SCAN_CTAS;
 constexpr int kBatchSegments = 1024;
-constexpr size_t kStripBytesPerBatch = 8ull << 30;      // cap of the strip-maxima buffer of one batch
+constexpr size_t kStripBytesPerBatch = 16ull << 30;     // cap of the granule-maxima buffer of one batch
 
 struct HostSeg { int64_t start; int32_t len; int32_t flags; };
 
@@ -126,11 +126,12 @@ struct ltg_context {
     DevBuf d_dna, d_codes, d_segs, d_items, d_colmax, d_bnd, d_counters;
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
-    DevBuf d_w[16], d_cls_list, d_res;
+    DevBuf d_w[18], d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
     DevBuf d_jobs, d_tout, d_strpool, d_scratch, d_scratch_big;
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
     HostBatch hb[2];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    unsigned long long win_stats[20] = {0};     // windows / cells planned per (round, retry) + reverse (ltg_debug_stats)
 };
 
 namespace {
@@ -141,7 +142,7 @@ struct TaskInfo {
     TaskInfo(int* base, int n) : max(base), thr(base + n), npk(base + 2 * (size_t)n), flags(base + 3 * (size_t)n), jstar(base + 4 * (size_t)n) {}
 };
 
-enum { kCntScan = 0, kCntPeaks = 1, kCntBin = 2, kCntCls = 8, kCntCells = 16, kCntLit = 24, kCntLitTotal = 26, kCntTotal = 32 };
+enum { kCntScan = 0, kCntPeaks = 1, kCntOvf = 2 /* and 3 */, kCntCells = 16, kCntLit = 24, kCntLitTotal = 26, kCntTotal = 32 };
 
 int upload_tables(ltg_context* c)
 {
@@ -218,7 +219,7 @@ int prepare(ltg_context* c)
 struct ProbeOut {
     std::vector<int> task_max, task_thr, task_npk, task_flags, task_off;
     std::vector<int> pk_pos, pk_score;
-    std::vector<uint32_t> colmax;           // [item][strip][max_len]
+    std::vector<uint32_t> colmax;           // [item][max_len] maximum over the granules
     std::vector<uint16_t> lit_colmax;       // [literal row][max_len]
     std::vector<int> task_litrow;
     int max_len = 0;
@@ -276,10 +277,11 @@ int literal_windows(ltg_context* c, const WinState& w, bool reverse)
 }
 
 // ---------------- window stage: peaks (device-resident pool) -> chosen alignments -> traceback pass 1 ----------------
-int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* strip_colmax, int max_len, HostBatch* hb)
+int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* gran_colmax, int max_len, HostBatch* hb)
 {
-    for (int k = 0; k < 16; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
-    if (int e = c->d_cls_list.ensure(sizeof(int) * (size_t)n_peaks * kWinClasses)) return e;
+    for (int k = 0; k < 18; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
+    if (int e = c->d_win_list.ensure(sizeof(int) * (size_t)n_peaks)) return e;
+    if (int e = c->d_win_sched.ensure(sizeof(WinSched))) return e;
     if (int e = c->d_res.ensure(sizeof(int4) * (size_t)n_peaks)) return e;
     int* counters = c->d_counters.as<int>();
     WinState w;
@@ -289,30 +291,33 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.best_sw = c->d_w[2].as<int>(); w.best_cut = c->d_w[3].as<int>(); w.best_re = c->d_w[4].as<int>(); w.best_qe = c->d_w[5].as<int>();
     w.fin_sw = c->d_w[6].as<int>(); w.fin_cut = c->d_w[7].as<int>(); w.fin_re = c->d_w[8].as<int>(); w.fin_qe = c->d_w[9].as<int>();
     w.fin_rb = c->d_w[10].as<int>(); w.fin_qb = c->d_w[11].as<int>();
-    w.w_lo = c->d_w[12].as<int>(); w.w_rows = c->d_w[13].as<int>(); w.w_bound = c->d_w[14].as<int>();
-    w.cls_count = counters + kCntCls; w.cls_list = c->d_cls_list.as<int>(); w.cap = n_peaks;
-    w.res = c->d_res.as<int4>(); w.bin_counter = counters + kCntBin;
+    w.w_lo = c->d_w[12].as<int>(); w.w_rows = c->d_w[13].as<int>(); w.w_bound = c->d_w[14].as<int>(); w.w_key = c->d_w[15].as<int>(); w.w_floor = c->d_w[16].as<int>();
+    w.sched = c->d_win_sched.as<WinSched>(); w.list = c->d_win_list.as<int>();
+    w.res = c->d_res.as<int4>();
     w.codes = c->d_codes.as<uint8_t>(); w.segs = c->d_segs.as<SegDesc>(); w.tasks_per_seg = T;
     w.rna_ssw = c->d_rna_ssw.as<uint8_t>(); w.m = c->m; w.cut_table = c->d_cut.as<int>();
     w.cell_counter = reinterpret_cast<long long*>(counters + kCntCells);
     w.forced_cut = forced_cut;
-    w.strip_colmax = c->prune ? strip_colmax : nullptr; w.n_strips = c->n_strips; w.strip_rows = 32 * kScanR; w.max_len = max_len;
+    w.gran_colmax = c->prune ? gran_colmax : nullptr; w.n_gran = c->n_strips * kGranPerStrip; w.gran_rows = kGranLanes * kScanR; w.max_len = max_len;
     w.n_pairs = (int)c->pairs.size();
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCells, 0, 8, c->stream));
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntLitTotal, 0, sizeof(int), c->stream));
+    LTG_CUDA_CHECK(cudaMemsetAsync(w.sched, 0, sizeof(WinSched), c->stream));
+    LTG_CUDA_CHECK(cudaMemsetAsync(w.w_key, 0xff, sizeof(int) * (size_t)n_peaks, c->stream));
     const int pb = (n_peaks + 255) / 256, plan_blocks = (n_peaks * 8 + 255) / 256;
     const int dp_blocks = c->num_sms * 4;
-    auto reset_bins = [&]() -> int {
-        LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntBin, 0, sizeof(int), c->stream));
-        LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCls, 0, sizeof(int) * kWinClasses, c->stream));
-        return LTG_OK;
+    // plan -> key offsets -> placement: the sorted work list of the next k_win_dp launch
+    auto schedule = [&](int round, int retry) {
+        k_win_plan<<<plan_blocks, 256, 0, c->stream>>>(w, round, retry);
+        k_win_offsets<<<1, 1024, 0, c->stream>>>(w.sched);
+        k_win_place<<<pb, 256, 0, c->stream>>>(w);
+        c->launches += 3;
     };
     for (int round = 0; round < 4; ++round) {
-        for (int retry = 0; retry < (w.strip_colmax ? 2 : 1); ++retry) {
-            if (int e = reset_bins()) return e;
-            k_win_plan<<<plan_blocks, 256, 0, c->stream>>>(w, round, retry);
+        for (int retry = 0; retry < (w.gran_colmax ? 2 : 1); ++retry) {
+            schedule(round, retry);
             k_win_dp<false><<<dp_blocks, 128, 0, c->stream>>>(w);
-            c->launches += 2;
+            c->launches += 1;
         }
         // Q4 guard for windows: exact forward scores >= 148 are recomputed by the literal emulation
         if (int e = literal_windows(c, w, /*reverse=*/false)) return e;
@@ -321,11 +326,10 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
         LTG_CUDA_CHECK(cudaGetLastError());
     }
     // reverse pass over the chosen alignments
-    if (int e = reset_bins()) return e;
-    k_win_plan<<<plan_blocks, 256, 0, c->stream>>>(w, -1, 0);
+    schedule(-1, 0);
     k_win_dp<true><<<dp_blocks, 128, 0, c->stream>>>(w);
     k_win_finish<<<pb, 256, 0, c->stream>>>(w);
-    c->launches += 3;
+    c->launches += 2;
     if (int e = literal_windows(c, w, /*reverse=*/true)) return e;
     LTG_CUDA_CHECK(cudaGetLastError());
 
@@ -338,25 +342,40 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     return LTG_OK;
 }
 
-// both traceback launches (regular scratch, then the rare alignments whose band outgrew it) over a job list
+// the three tiers of the traceback over a job list: shared-memory fast path for everything, then the generic kernel
+// with a 24 KB global scratch for what the fast path handed over, then an 8 MB scratch for the rare huge bands
+constexpr int kTraceTpb = 128, kTraceBytes = 896;
 int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* d_out, char* strpool)
 {
-    const int tb_threads = c->num_sms * 256;
+    const int tb_threads = c->num_sms * 64;
     const long long scratch_small = 24 * 1024, scratch_big = 8LL << 20;
     const int big_threads = 128;
     if (int e = c->d_scratch.ensure((size_t)tb_threads * scratch_small)) return e;
     if (int e = c->d_scratch_big.ensure((size_t)big_threads * scratch_big)) return e;
+    if (int e = c->d_ovf_list.ensure(sizeof(int) * 2 * (size_t)n_jobs)) return e;
+    int* cnt = c->d_counters.as<int>() + kCntOvf;
+    int* list1 = c->d_ovf_list.as<int>(), * list2 = list1 + n_jobs;
+    LTG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 2 * sizeof(int), c->stream));
     TraceArgs ta;
     ta.jobs = d_jobs; ta.n_jobs = n_jobs; ta.codes = c->d_codes.as<uint8_t>(); ta.dna = c->d_dna.as<unsigned char>();
     ta.rna_ssw = c->d_rna_ssw.as<uint8_t>(); ta.rna_raw = c->d_rna_raw.as<unsigned char>();
     ta.nt_min = c->params.nt_min; ta.nt_max = c->params.nt_max; ta.penalty_t = c->params.penalty_t; ta.penalty_c = c->params.penalty_c;
     ta.out = d_out; ta.strpool = strpool;
-    ta.scratch = c->d_scratch.as<unsigned char>(); ta.scratch_per_thread = scratch_small; ta.only_overflow = 0;
-    const int blocks = std::max(1, std::min(tb_threads / 64, (n_jobs + 63) / 64));
-    k_traceback<<<blocks, 64, 0, c->stream>>>(ta);
-    ta.scratch = c->d_scratch_big.as<unsigned char>(); ta.scratch_per_thread = scratch_big; ta.only_overflow = 1;
+    // tier 1
+    ta.scratch = nullptr; ta.scratch_per_thread = 0; ta.in_list = nullptr; ta.in_count = nullptr; ta.out_list = list1; ta.out_count = cnt;
+    const int smem = kTraceTpb * kTraceBytes;
+    LTG_CUDA_CHECK(cudaFuncSetAttribute(k_traceback_fast<kTraceTpb, kTraceBytes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int fast_blocks = std::max(1, std::min(c->num_sms * 2, (n_jobs + kTraceTpb - 1) / kTraceTpb));
+    k_traceback_fast<kTraceTpb, kTraceBytes><<<fast_blocks, kTraceTpb, smem, c->stream>>>(ta);
+    // tier 2
+    ta.scratch = c->d_scratch.as<unsigned char>(); ta.scratch_per_thread = scratch_small;
+    ta.in_list = list1; ta.in_count = cnt; ta.out_list = list2; ta.out_count = cnt + 1;
+    k_traceback<<<tb_threads / 64, 64, 0, c->stream>>>(ta);
+    // tier 3
+    ta.scratch = c->d_scratch_big.as<unsigned char>(); ta.scratch_per_thread = scratch_big;
+    ta.in_list = list2; ta.in_count = cnt + 1; ta.out_list = nullptr; ta.out_count = nullptr;
     k_traceback<<<big_threads / 64, 64, 0, c->stream>>>(ta);
-    c->launches += 2;
+    c->launches += 3;
     LTG_CUDA_CHECK(cudaGetLastError());
     return LTG_OK;
 }
@@ -377,14 +396,16 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
 
     if (int e = c->d_segs.ensure(sizeof(SegDesc) * S)) return e;
     if (int e = c->d_items.ensure(sizeof(ScanItem) * n_items)) return e;
-    if (int e = c->d_colmax.ensure((size_t)n_items * c->n_strips * max_len * 4)) return e;
+    const int n_gran = c->n_strips * kGranPerStrip;
+    if (int e = c->d_colmax.ensure((size_t)n_items * n_gran * max_len * 4)) return e;
+    if (int e = c->d_colmax_all.ensure((size_t)n_items * max_len * 4)) return e;
     if (int e = c->d_task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
     if (int e = c->d_task_off.ensure(sizeof(int) * ((size_t)n_tasks + 1))) return e;
     if (int e = c->d_stats_max.ensure(sizeof(int) * (size_t)n_tasks)) return e;
     if (int e = c->d_task_litrow.ensure(sizeof(int) * (size_t)n_tasks)) return e;
     if (int e = hb.task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
     if (int e = hb.task_off.ensure(sizeof(int) * ((size_t)n_tasks + 1))) return e;
-    if (int e = hb.scalars.ensure(64)) return e;
+    if (int e = hb.scalars.ensure(256)) return e;
     TaskInfo ti(c->d_task_info.as<int>(), n_tasks), hti(hb.task_info.as<int>(), n_tasks);
     int* counters = c->d_counters.as<int>();
 
@@ -404,7 +425,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     if (any_stats) {
         if (int e = launch_scan(c, n_items, max_len, c->d_prof_stats.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
         k_rowmax<<<(n_items * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_colmax.as<uint32_t>(), c->d_items.as<ScanItem>(), c->d_segs.as<SegDesc>(),
-                                                                   n_items, c->n_strips, max_len, T, c->d_stats_max.as<int>());
+                                                                   n_items, n_gran, max_len, T, c->d_stats_max.as<int>());
         c->launches += 1;
         stats_max = c->d_stats_max.as<int>();
     }
@@ -414,7 +435,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
 
     // peaks: statistics + count, literal re-runs, count of those, exclusive scan, write
     EpiArgs ea;
-    ea.colmax = c->d_colmax.as<uint32_t>(); ea.n_strips = c->n_strips; ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
+    ea.colmax = c->d_colmax.as<uint32_t>(); ea.n_gran = n_gran; ea.colmax_all = c->d_colmax_all.as<uint32_t>(); ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
     ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
     ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.mode = 0;
     ea.task_max = ti.max; ea.task_thr = ti.thr; ea.task_npeaks = ti.npk; ea.task_flags = ti.flags; ea.task_jstar = ti.jstar;
@@ -477,8 +498,8 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
             LTG_CUDA_CHECK(cudaMemcpyAsync(probe->pk_pos.data(), c->d_pk_pos.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
             LTG_CUDA_CHECK(cudaMemcpyAsync(probe->pk_score.data(), c->d_pk_score.p, sizeof(int) * n_peaks, cudaMemcpyDeviceToHost, c->stream));
         }
-        probe->colmax.resize((size_t)n_items * c->n_strips * max_len);
-        LTG_CUDA_CHECK(cudaMemcpyAsync(probe->colmax.data(), c->d_colmax.p, probe->colmax.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        probe->colmax.resize((size_t)n_items * max_len);
+        LTG_CUDA_CHECK(cudaMemcpyAsync(probe->colmax.data(), c->d_colmax_all.p, probe->colmax.size() * 4, cudaMemcpyDeviceToHost, c->stream));
         probe->lit_colmax.resize(jobs.size() * (size_t)max_len);
         probe->task_litrow.assign(n_tasks, -1);
         if (!jobs.empty()) {
@@ -501,10 +522,12 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.jobs.p, c->d_jobs.p, sizeof(TraceJob) * (size_t)n_peaks, cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.tout.p, c->d_tout.p, sizeof(TraceOut) * (size_t)n_peaks, cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.p, counters + kCntCells, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 64, &c->d_win_sched.as<WinSched>()->st_windows[0], 20 * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, c->stream));
         c->d2h_bytes += (int64_t)(sizeof(TraceJob) + sizeof(TraceOut)) * n_peaks + 64;
     } else {
         hb.n_peaks = want_alignments ? n_peaks : 0;
-        memset(hb.scalars.p, 0, 64);
+        memset(hb.scalars.p, 0, 256);
     }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ready, c->stream));
     return LTG_OK;
@@ -674,6 +697,7 @@ int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg
     long long cells = 0; memcpy(&cells, sc, 8);
     st.window_cells += cells;
     st.n_literal_windows += sc[kCntLitTotal - kCntCells];
+    for (int k = 0; k < 20; ++k) c->win_stats[k] += reinterpret_cast<const unsigned long long*>(hb.scalars.as<char>() + 64)[k];
     record_list.insert(record_list.end(), hb.rows.begin(), hb.rows.end());
     hb.rows.clear();
     return LTG_OK;
@@ -713,7 +737,7 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
 
         // batch size: bounded by the strip-maxima buffer; at least two batches when there is enough work so that the
         // host phase of one overlaps the device phase of the next
-        const size_t per_seg = (size_t)c->pairs.size() * c->n_strips * (size_t)((c->params.cut_length + 3) & ~3) * 4;
+        const size_t per_seg = (size_t)c->pairs.size() * c->n_strips * kGranPerStrip * (size_t)((c->params.cut_length + 3) & ~3) * 4;
         size_t bs = std::max<size_t>(16, std::min<size_t>(kBatchSegments, kStripBytesPerBatch / std::max<size_t>(1, per_seg)));
         if (active.size() > 256 && active.size() < 2 * bs) bs = (active.size() + 1) / 2;
         std::vector<ltg_host::Triplex> record_list;
@@ -825,16 +849,22 @@ void ltg_destroy(ltg_context* c)
     }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
                       &c->d_segs, &c->d_items, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
-                      &c->d_stats_max, &c->d_task_litrow, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_cls_list, &c->d_res,
+                      &c->d_stats_max, &c->d_task_litrow, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs})
         b->release();
-    for (int k = 0; k < 16; ++k) c->d_w[k].release();
+    for (int k = 0; k < 18; ++k) c->d_w[k].release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 void* ltg_stream(ltg_context* c) { return c ? (void*)c->stream : nullptr; }
+
+void ltg_debug_stats(ltg_context* c, int64_t* out20, int reset)
+{
+    if (!c || !out20) return;
+    for (int k = 0; k < 20; ++k) { out20[k] = (int64_t)c->win_stats[k]; if (reset) c->win_stats[k] = 0; }
+}
 
 int ltg_set_params(ltg_context* c, const ltg_params* p)
 {
@@ -968,11 +998,10 @@ int ltg_probe_segment(ltg_context* c, const char* seg, int32_t seg_len, ltg_task
                 for (int j = 0; j < seg_len; ++j) colmax[(size_t)q * seg_len + j] = row[j];
             } else {
                 const int item = c->tasks[t].pair, half = c->tasks[t].half;
-                const uint32_t* rows = po.colmax.data() + (size_t)item * c->n_strips * max_len;
+                const uint32_t* row = po.colmax.data() + (size_t)item * max_len;
                 bool cut = false;
                 for (int j = 0; j < seg_len; ++j) {
-                    int v = 0;
-                    for (int k = 0; k < c->n_strips; ++k) { const uint32_t x = rows[(size_t)k * max_len + j]; v = std::max(v, half ? hi16(x) : lo16(x)); }
+                    const int v = half ? hi16(row[j]) : lo16(row[j]);
                     if (v >= kOverflowU8) cut = true;          // Q2: nothing is recorded from the first >= 251 column on
                     colmax[(size_t)q * seg_len + j] = cut ? 0 : v;
                 }

@@ -127,7 +127,8 @@ struct ScanArgs {
     const uint32_t* profiles;   // [pair][strip][5*32*R]
     int n_strips;
     int max_len;                // row pitch of colmax / bnd (>= longest segment)
-    uint32_t* colmax;           // [item][strip][max_len] packed column maxima of the two tasks, one row per RNA strip
+    uint32_t* colmax;           // [item][granule][max_len] packed column maxima of the two tasks, one row per granule of
+                                // kGranLanes*R RNA rows (n_strips * 32/kGranLanes granules per item)
     uint2* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F)
     int* counter;               // work queue head
 };
@@ -160,9 +161,13 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
         hlast = h_;                                               \
     }
 
-// The column maxima are kept PER STRIP (32*R RNA rows): the epilogue combines them into the reference's
-// per-column maximum, and the window stage uses them as upper bounds to skip RNA rows that cannot hold a
-// window's best cell (window.cuh, "row pruning").
+// The column maxima are kept PER GRANULE of kGranLanes lanes (kGranLanes*R RNA rows; the running maximum that
+// travels along the lanes restarts at every granule head and the granule's last lane stores it): the epilogue
+// combines them into the reference's per-column maximum, and the window stage uses them as upper bounds to
+// skip RNA rows that cannot hold a window's best cell (window.cuh, "row pruning").
+constexpr int kGranLanes = 8;                    // lanes per granule
+constexpr int kGranPerStrip = 32 / kGranLanes;   // granules per strip
+
 template <int R, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 {
@@ -193,7 +198,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             const int j = i - 32;
             s_codes[i] = (j < 0 || j >= n) ? (uint8_t)kBaseOther : gcodes[rev ? (n - 1 - j) : j];
         }
-        uint32_t* cm_item = a.colmax + (size_t)item * a.n_strips * a.max_len;
+        uint32_t* cm_item = a.colmax + (size_t)item * a.n_strips * kGranPerStrip * a.max_len;
+        const bool gran_head = (lane & (kGranLanes - 1)) == 0, gran_tail = (lane & (kGranLanes - 1)) == kGranLanes - 1;
 
         for (int strip = 0; strip < a.n_strips; ++strip) {
             const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
@@ -201,7 +207,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
             __syncwarp();
             const bool first = (strip == 0), last = (strip == a.n_strips - 1);
-            uint32_t* cm_out = cm_item + (size_t)strip * a.max_len;
+            // this lane's granule row, biased so that cm_lane[s] is the slot of the column it finishes at step s
+            uint32_t* cm_lane = cm_item + ((size_t)strip * kGranPerStrip + (lane / kGranLanes)) * a.max_len - lane;
             uint32_t Hd[R], E[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
@@ -234,8 +241,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 uint32_t hin = __shfl_up_sync(0xffffffffu, hout, 1);
                 uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);
                 uint32_t cmin = __shfl_up_sync(0xffffffffu, cmout, 1);
+                if (gran_head) cmin = 0;
                 if (lane == 0) {
-                    cmin = 0;
                     if (first) { hin = 0; fin = 0; }
                     else { const uint2 pk = s_ring[s & 31]; hin = pk.x; fin = pk.y; }
                 }
@@ -252,13 +259,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 for (int k = 0; k < R / 4; ++k) sc[k] = scn[k];
                 hdiag = hin;
                 hout = hlast; fout = f; cmout = cm;
-                if (lane == 31) {
-                    const int j = s - 31;
-                    if (j >= 0) {
-                        cm_out[j] = cm;
-                        if (!last) bnd[j] = make_uint2(hout, fout);
-                    }
-                }
+                if (gran_tail && s >= lane && s - lane < n) cm_lane[s] = cm;
+                if (lane == 31 && !last && s >= 31) bnd[s - 31] = make_uint2(hout, fout);
             }
         }
     }
@@ -270,14 +272,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 // Epilogue: per task the exact maximum, the threshold (int)(max*0.8) (Fasim-LongTarget.cpp:413), the
 // 8-bit "stop recording" truncation (Q2), threshold-hit compaction and run merge to peaks
 // (ssw_cpp.cpp:446-572).  One warp per item; hits are found with __ballot_sync and consumed in column
-// order.  Three passes over the (L2/HBM-resident) strip maxima:
-//   mode 0  statistics of every task + peak COUNT of the tasks that stay on the exact path
+// order.  Three passes:
+//   mode 0  granule maxima -> per-column maximum (one compact row per item), statistics of every task + peak COUNT of
+//           the tasks that stay on the exact path
 //   mode 1  peak count of the tasks re-run by the literal emulation (Q4 guard)
 //   (exclusive scan of the counts -> one contiguous, position-ordered slice of the peak pool per task)
 //   mode 2  peaks written, 32 at a time, one lane per peak
 struct EpiArgs {
-    const uint32_t* colmax;      // [item][strip][max_len]
-    int n_strips;
+    const uint32_t* colmax;      // [item][granule][max_len]
+    int n_gran;                  // granule rows per item
+    uint32_t* colmax_all;        // [item][max_len] maximum over the granules (written by mode 0, read by modes 1 and 2)
     const uint16_t* lit_colmax;  // [literal row][max_len] column maxima of the literal re-runs
     const int* task_litrow;      // [task] row in lit_colmax (valid when the task carries kTaskLiteral)
     const ScanItem* items;
@@ -317,17 +321,22 @@ __global__ void k_epilogue(const EpiArgs a)
     const ScanItem it = a.items[warp];
     const SegDesc sd = a.segs[it.seg];
     const int n = sd.len;
-    const uint32_t* cm = a.colmax + (size_t)warp * a.n_strips * a.max_len;
+    const uint32_t* cm = a.colmax + (size_t)warp * a.n_gran * a.max_len;
+    uint32_t* cm_all = a.colmax_all + (size_t)warp * a.max_len;
     const PairDef pd = c_pairs[it.pair];
+    if (a.mode == 0) {
+        // column maximum over all granules, as the reference's scan reports it
+        for (int j = lane; j < n; j += 32) {
+            uint32_t v = cm[j];
+            for (int k = 1; k < a.n_gran; ++k) v = __vmaxs2(v, cm[(size_t)k * a.max_len + j]);
+            cm_all[j] = v;
+        }
+        __syncwarp();
+    }
     for (int h = 0; h < 2; ++h) {
         if (h == 1 && pd.task[1] == pd.task[0]) break;
         const int task = it.seg * a.tasks_per_seg + pd.task[h];
-        // column maximum over all strips, as the reference's scan reports it
-        auto exact_at = [&](int j) -> int {
-            uint32_t v = cm[j];
-            for (int k = 1; k < a.n_strips; ++k) v = __vmaxs2(v, cm[(size_t)k * a.max_len + j]);
-            return h ? hi16(v) : lo16(v);
-        };
+        auto exact_at = [&](int j) -> int { const uint32_t v = cm_all[j]; return h ? hi16(v) : lo16(v); };
         int thr, jstar = n;
         const uint16_t* lit = nullptr;
         if (a.mode == 0) {
@@ -429,17 +438,17 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const int* __restrict__
     if (tid == 0) *total = s_carry;
 }
 
-// maximum of each half of an item's packed strip maxima (used for the N-aware threshold pass)
+// maximum of each half of an item's packed granule maxima (used for the N-aware threshold pass)
 __global__ void k_rowmax(const uint32_t* __restrict__ colmax, const ScanItem* __restrict__ items, const SegDesc* __restrict__ segs,
-                         int n_items, int n_strips, int max_len, int tasks_per_seg, int* __restrict__ stats_max)
+                         int n_items, int n_gran, int max_len, int tasks_per_seg, int* __restrict__ stats_max)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_items) return;
     const ScanItem it = items[warp];
     const int n = segs[it.seg].len;
-    const uint32_t* cm = colmax + (size_t)warp * n_strips * max_len;
+    const uint32_t* cm = colmax + (size_t)warp * n_gran * max_len;
     uint32_t v = 0;
-    for (int k = 0; k < n_strips; ++k)
+    for (int k = 0; k < n_gran; ++k)
         for (int j = lane; j < n; j += 32) v = __vmaxs2(v, cm[(size_t)k * max_len + j]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = __vmaxs2(v, __shfl_xor_sync(0xffffffffu, v, o));

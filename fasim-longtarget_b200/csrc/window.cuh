@@ -18,12 +18,13 @@
 //      (every inserted row costs >= 4, every column yields <= 5), so the value of a cell only depends on
 //      the win_margin(c) rows above it;
 //  (2) a window cell can never exceed the same cell of the whole-segment matrix, and the scan stage kept,
-//      per strip of 32*R_scan RNA rows, the column maxima of that matrix (scan.cuh).
-// For a lower bound L of the window's best score, only strips whose maximum over the window's columns
-// reaches L can hold the best cell (or a tie that matters for the tie rules); the stream covers those strips
-// plus the margin above them.  Values computed on a sub-range of rows are lower bounds of the true values, so
-// if the result r of a pruned sweep satisfies r >= L it is exact; otherwise the window is swept again with
-// L = r (a proven lower bound), which is exact by the same argument.  First try: L = peak score.
+//      per granule of kGranLanes*R_scan RNA rows, the column maxima of that matrix (scan.cuh).
+// For a guess L of the window's best score, the stream covers the granules whose maximum over the window's
+// columns reaches L, the granules between them, and the margin above the first.  Let B be the largest such
+// maximum among the granules left out.  Values computed on a sub-range of rows are lower bounds of the true
+// values and every left-out cell is <= B, so a result r > B is exact (value, and every tie that matters for the
+// tie rules); otherwise the window is swept again with L = r (a proven lower bound), and that second result is
+// exact by the same argument.  First guess: L = peak score.
 // The reverse pass only needs win_margin(re+1) rows: every cell equal to the forward score belongs to an
 // alignment that starts at the forward end cell (tie rules of the forward pass), see DESIGN.md.
 #pragma once
@@ -33,10 +34,27 @@
 namespace ltg {
 
 constexpr int kWinR = 8;            // window columns per lane
-constexpr int kWinColClasses = 4;   // groups of 4, 8, 16, 32 lanes  (32, 64, 128, 256 columns)
-constexpr int kWinClasses = 8;      // x 2 stream-length classes (<= / > kWinLongRows rows)
-constexpr int kWinLongRows = 1024;
 constexpr int kMaxWindow = 32 * kWinR;
+constexpr int kWinRowBuckets = 64;  // stream-length buckets of 64 rows (the last one takes everything longer)
+constexpr int kWinKeys = 32 * kWinRowBuckets;
+
+// Work list of one k_win_dp launch.  A window of `len` columns is carried by a group of g = ceil(len / kWinR) lanes
+// (class c = g - 1); a warp carries floor(32 / g) groups in each 16-bit half.  Windows are counting-sorted by
+// (g, stream length descending), so the windows that share a warp stream about the same number of RNA rows and the
+// short bins come last in the queue.
+struct WinSched {
+    int hist[kWinKeys];        // windows per key
+    int off[kWinKeys];         // exclusive prefix of hist
+    int fill[kWinKeys];
+    int cls_count[32];         // windows per class
+    int cls_off[32];           // first list slot of the class
+    int bin_start[32];         // first bin (warp work unit) of the class
+    int total_bins;
+    int bin_counter;
+    // statistics (LTG_STATS): windows / cells planned per (round, retry); [8] = reverse pass
+    unsigned long long st_windows[10];
+    unsigned long long st_cells[10];
+};
 
 struct WinState {
     // peak pool
@@ -48,42 +66,46 @@ struct WinState {
     int* w_len;        // columns of the window in flight (cut, or re+1 in the reverse pass)
     int* w_lo;         // first RNA row of the forward stream in flight
     int* w_rows;       // number of RNA rows streamed
-    int* w_bound;      // the lower bound L the row range was derived from (0: all rows, result exact by construction)
+    int* w_bound;      // a result >= w_bound is exact (row pruning, see the header comment); 0: all rows were streamed
+    int* w_floor;      // cells <= w_floor cannot matter for this sweep (they neither prove exactness nor beat a proven
+                       // lower bound), so the per-lane result tracker starts there
+    int* w_key;        // sort key of the window in flight, -1: not in flight
     int* w_done;       // 1: final alignment chosen
     int* best_sw; int* best_cut; int* best_re; int* best_qe;
     int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb;
-    // class lists
-    int* cls_count;    // [kWinClasses]
-    int* cls_list;     // [kWinClasses][cap]
-    int cap;
+    WinSched* sched;
+    int* list;         // [n_peaks] window indices in key order
     // dp result per peak: (best value, column, row, 1 if written by the literal emulation)
     int4* res;
-    int* bin_counter;
     // geometry
     const uint8_t* codes; const SegDesc* segs; int tasks_per_seg;
     const uint8_t* rna_ssw; int m;
     const int* cut_table;   // [256][4]  cut length per (peak score, round) — fastsim.h:210 evaluated in float32 on the host
     long long* cell_counter;
     const int* forced_cut;  // probe path: explicit window length per peak (nullptr in the product path)
-    // strip maxima of the scan stage (nullptr: no pruning, every window streams the whole lncRNA)
-    const uint32_t* strip_colmax; int n_strips; int strip_rows; int max_len; int n_pairs;
+    // granule maxima of the scan stage (nullptr: no pruning, every window streams the whole lncRNA)
+    const uint32_t* gran_colmax; int n_gran; int gran_rows; int max_len; int n_pairs;
 };
 
-__device__ inline int win_col_class(int len) { return len <= 4 * kWinR ? 0 : (len <= 8 * kWinR ? 1 : (len <= 16 * kWinR ? 2 : 3)); }
-__device__ inline int win_class(int len, int rows) { return win_col_class(len) + (rows > kWinLongRows ? kWinColClasses : 0); }
 // rows spanned by a positive-score local alignment over `cols` columns: < 2.25 * cols + 1
 __host__ __device__ inline int win_margin(int cols) { return (9 * cols) / 4 + 2; }
+__device__ inline int win_key(int len, int rows)
+{
+    const int g = (len + kWinR - 1) / kWinR;
+    const int rb = min(kWinRowBuckets - 1, (rows + 63) >> 6);
+    return (g - 1) * kWinRowBuckets + (kWinRowBuckets - 1 - rb);
+}
 
 // round >= 0, retry 0: forward plan for round `round` (row range from the bound L = peak score);
-// round >= 0, retry 1: windows whose pruned result fell short of the bound they were planned with, re-planned with
+// round >= 0, retry 1: windows whose pruned result fell short of the value that proves it exact, re-planned with
 //                      L = that result; round < 0: reverse plan over the chosen alignments.
-// 8 threads cooperate on one peak (the strip-bound scan reads n_strips * cut column maxima).
+// 8 threads cooperate on one peak (the granule-bound scan reads n_gran * cut column maxima).
 __global__ void k_win_plan(const WinState w, int round, int retry)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 3, sub = gt & 7;
     bool active = i < w.n_peaks;
-    int len = 0, lo = 0, rows = 0, bound = 0;
+    int len = 0, rows = 0, bound = 0, proven = 0;
     if (active) {
         if (round >= 0) {
             const int sc = w.pk_score[i], pos = w.pk_pos[i];
@@ -99,55 +121,115 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
                 if (w.w_done[i] || v.x >= w.w_bound[i]) active = false;      // exact already
                 len = w.w_len[i];
                 bound = max(v.x, 0);
+                proven = bound;              // a cell with this value exists: anything below it is irrelevant now
             }
         } else {
             if (w.fin_sw[i] <= 0) active = false;
             len = w.fin_re[i] + 1;
         }
     }
-    // strip bound scan (forward plans only): which strips can hold a cell >= bound inside the window's columns
-    int klo = 0x7fffffff, khi = -1;
-    if (round >= 0 && w.strip_colmax != nullptr) {
+    // granule bound scan (forward plans only): granules klo..khi can hold a cell >= bound inside the window's columns;
+    // `outside` = the largest bound of any granule left out (a result above it is exact)
+    int klo = -1, khi = -1, outside = 0;
+    if (round >= 0 && w.gran_colmax != nullptr) {
         const bool scan = active && bound > 0;
         int task = 0, pos = 0;
         if (scan) { task = w.pk_task[i]; pos = w.pk_pos[i]; }
         const TaskDef td = c_tasks[task % w.tasks_per_seg];
-        const uint32_t* base = w.strip_colmax + ((size_t)(task / w.tasks_per_seg) * w.n_pairs + td.pair) * w.n_strips * w.max_len;
-        for (int k = 0; k < w.n_strips; ++k) {
-            int b = -32768;
+        const uint32_t* base = w.gran_colmax + ((size_t)(task / w.tasks_per_seg) * w.n_pairs + td.pair) * w.n_gran * w.max_len;
+        int pending = 0;        // largest bound among the non-qualifying granules after the last qualifying one
+        for (int k = 0; k < w.n_gran; ++k) {
+            int b = 0;
             if (scan) {
                 const uint32_t* row = base + (size_t)k * w.max_len;
-                uint32_t v = 0x80008000u;
+                uint32_t v = 0;
                 for (int j = pos - len + 1 + sub; j <= pos; j += 8) v = __vmaxs2(v, row[j]);
                 b = td.half ? hi16(v) : lo16(v);
             }
             b = max(b, __shfl_xor_sync(0xffffffffu, b, 1));
             b = max(b, __shfl_xor_sync(0xffffffffu, b, 2));
             b = max(b, __shfl_xor_sync(0xffffffffu, b, 4));
-            if (scan && b >= bound) { klo = min(klo, k); khi = k; }
+            if (scan && b >= bound) {
+                if (klo < 0) { klo = k; outside = pending; }      // everything before the first qualifying granule is left out
+                khi = k;
+                pending = 0;                                       // granules between two qualifying ones are streamed too
+            } else pending = max(pending, b);
         }
+        outside = max(outside, pending);
     }
     if (!active || sub != 0) return;
     if (round >= 0) {
-        lo = 0; rows = w.m;
+        int lo = 0, floor_v = max(proven - 1, 0);
+        rows = w.m; bound = 0;
         if (khi >= 0) {
-            lo = max(0, klo * w.strip_rows - win_margin(len));
-            const int hi = min(w.m - 1, (khi + 1) * w.strip_rows - 1);
-            rows = hi - lo + 1;
+            lo = max(0, klo * w.gran_rows - win_margin(len));
+            const int hi = min(w.m - 1, (khi + 1) * w.gran_rows - 1);
+            if (hi - lo + 1 < w.m) { rows = hi - lo + 1; bound = outside + 1; floor_v = max(floor_v, outside); } else lo = 0;
         }
-        if (rows >= w.m) { lo = 0; rows = w.m; bound = 0; }      // whole lncRNA: exact whatever the result
-        w.w_lo[i] = lo; w.w_rows[i] = rows; w.w_bound[i] = bound;
+        w.w_lo[i] = lo; w.w_rows[i] = rows; w.w_bound[i] = bound; w.w_floor[i] = floor_v;
         if (w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, (unsigned long long)len * (unsigned long long)rows);
+        atomicAdd(&w.sched->st_windows[round * 2 + retry], 1ull);
+        atomicAdd(&w.sched->st_cells[round * 2 + retry], (unsigned long long)len * (unsigned long long)rows);
     } else {
         rows = min(w.fin_qe[i] + 1, win_margin(len));
+        atomicAdd(&w.sched->st_windows[8], 1ull);
+        atomicAdd(&w.sched->st_cells[8], (unsigned long long)len * (unsigned long long)rows);
     }
     w.w_len[i] = len;
-    const int c = win_class(len, rows);
-    const int slot = atomicAdd(&w.cls_count[c], 1);
-    w.cls_list[(size_t)c * w.cap + slot] = i;
+    const int key = win_key(len, rows);
+    w.w_key[i] = key;
+    atomicAdd(&w.sched->hist[key], 1);
 }
 
-__device__ inline int bins_of_class(int count, int c) { const int wpw = 2 * (32 / (4 << (c & 3))); return (count + wpw - 1) / wpw; }
+// exclusive prefix of the key histogram, per-class counts / list offsets / bin ranges (one block of 1024 threads)
+__global__ void __launch_bounds__(1024) k_win_offsets(WinSched* sc)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_cls[32];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int v0 = sc->hist[2 * tid], v1 = sc->hist[2 * tid + 1];
+    int x = v0 + v1;
+    const int mine = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[wp] = x;
+    __syncthreads();
+    if (wp == 0) {
+        const int t = s_warp[lane];
+        int y = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int z = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += z; }
+        s_warp[lane] = y - t;
+        s_cls[lane] = t;                 // one warp of this block covers exactly one class (64 keys = 32 threads x 2)
+    }
+    __syncthreads();
+    const int excl = s_warp[wp] + x - mine;
+    sc->off[2 * tid] = excl; sc->off[2 * tid + 1] = excl + v0;
+    sc->fill[2 * tid] = 0; sc->fill[2 * tid + 1] = 0;
+    sc->hist[2 * tid] = 0; sc->hist[2 * tid + 1] = 0;       // ready for the next plan
+    if (wp == 0) {
+        const int cnt = s_cls[lane];
+        const int g = lane + 1, wpw = 2 * (32 / g);
+        const int bins = (cnt + wpw - 1) / wpw;
+        int y = bins;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int z = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += z; }
+        sc->cls_count[lane] = cnt;
+        sc->cls_off[lane] = s_warp[lane];
+        sc->bin_start[lane] = y - bins;
+        if (lane == 31) { sc->total_bins = y; sc->bin_counter = 0; }
+    }
+}
+
+__global__ void k_win_place(const WinState w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n_peaks) return;
+    const int key = w.w_key[i];
+    if (key < 0) return;
+    w.w_key[i] = -1;
+    w.list[w.sched->off[key] + atomicAdd(&w.sched->fill[key], 1)] = i;
+}
 
 template <bool REV>
 __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
@@ -155,19 +237,24 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
     constexpr int R = kWinR;
     const int lane = threadIdx.x & 31;
     const uint32_t kNegOpen = 0xFFF0FFF0u, kNegExt = 0xFFFCFFFCu, kSix = 0x00060006u, kMis = 0xFFFCFFFCu;
-    int nb[kWinClasses], total = 0;
-#pragma unroll
-    for (int c = 0; c < kWinClasses; ++c) { nb[c] = bins_of_class(w.cls_count[c], c); total += nb[c]; }
+    const WinSched* sc = w.sched;
+    const int total = sc->total_bins;
+    const int my_bin_start = sc->bin_start[lane];
+    const bool my_cls_used = sc->cls_count[lane] > 0;
 
     for (;;) {
         int bin = 0;
-        if (lane == 0) bin = atomicAdd(w.bin_counter, 1);
+        if (lane == 0) bin = atomicAdd(&w.sched->bin_counter, 1);
         bin = __shfl_sync(0xffffffffu, bin, 0);
         if (bin >= total) break;
-        int c = 0, b = bin;
-        while (b >= nb[c]) { b -= nb[c]; ++c; }
-        const int g = 4 << (c & 3), gpw = 32 / g;      // lanes per group, groups per half-warp
-        const int lig = lane & (g - 1), grp = lane / g;
+        // class of the bin: the last class whose first bin is <= bin and that is not empty (empty classes share their start
+        // with the next one, so the highest qualifying lane is the right one)
+        const int c = 31 - __clz(__ballot_sync(0xffffffffu, my_bin_start <= bin && my_cls_used));
+        const int b = bin - __shfl_sync(0xffffffffu, my_bin_start, c);
+        const int g = c + 1, gpw = 32 / g;             // lanes per group, groups per half-warp
+        const int cls_count = sc->cls_count[c], cls_off = sc->cls_off[c];
+        const bool idle = lane >= gpw * g;             // lanes beyond the last whole group carry nothing
+        const int grp = idle ? gpw : lane / g, lig = idle ? lane - gpw * g : lane - grp * g;
         const bool leader = (lig == 0);
 
         // per-half window description for this lane's group
@@ -178,7 +265,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int slot = (b * 2 + h) * gpw + grp;
-            wi[h] = (slot < w.cls_count[c]) ? w.cls_list[(size_t)c * w.cap + slot] : -1;
+            wi[h] = (!idle && slot < cls_count) ? w.list[cls_off + slot] : -1;
             len[h] = 0; slen[h] = 0; sbase[h] = 0; sdir[h] = 1;
             int colcode[R];
 #pragma unroll
@@ -214,13 +301,16 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
         for (int o = 16; o; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
         nsteps += g - 1;
 
+        // result tracker: starts at the floor below which nothing matters (reverse: forward score - 1; forward: w_floor);
+        // `runmax` (one instruction per step) keeps the plain maximum, the proven lower bound a re-plan starts from
         int best[2], bcol[2], brow[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            best[h] = (REV && wi[h] >= 0) ? w.fin_sw[wi[h]] - 1 : 0;
+            best[h] = wi[h] >= 0 ? (REV ? w.fin_sw[wi[h]] - 1 : w.w_floor[wi[h]]) : 0;
             bcol[h] = 0x7fffffff; brow[h] = 0;
         }
         uint32_t trigm1 = pack16(max(best[0], 0), max(best[1], 0));
+        uint32_t runmax = 0;
         const uint32_t keep = leader ? 0u : 0xffffffffu;
 
         uint32_t Hd[R], E[R];
@@ -249,8 +339,8 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const uint32_t y = ~(xin ^ dq[r]);
-                const uint32_t sc = __viaddmax_s16x2(y, kSix, kMis);          // +5 on equal codes, -4 otherwise
-                t[r] = __viaddmax_s16x2_relu(d, sc, E[r]);
+                const uint32_t sc2 = __viaddmax_s16x2(y, kSix, kMis);         // +5 on equal codes, -4 otherwise
+                t[r] = __viaddmax_s16x2_relu(d, sc2, E[r]);
                 const uint32_t u = __vadd2(t[r], kNegOpen);
                 E[r] = __viaddmax_s16x2(E[r], kNegExt, u);
                 const uint32_t hh = __vmaxs2(t[r], f);
@@ -263,6 +353,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
             ms = __vimax3_s16x2(ms, t[3], t[4]);
             ms = __vimax3_s16x2(ms, t[5], t[6]);
             ms = __vmaxs2(ms, t[7]);
+            if (!REV) runmax = __vmaxs2(runmax, ms);
             if (__vmaxs2(trigm1, ms) != trigm1) {
                 const int row = s - lig;
 #pragma unroll
@@ -276,7 +367,8 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                         if (cc >= 0 && (v > best[h] || (v == best[h] && cc < bcol[h]))) { best[h] = v; bcol[h] = cc; brow[h] = row; }
                     }
                 }
-                if (!REV) trigm1 = pack16(max(best[0] - 1, 0), max(best[1] - 1, 0));
+                // ties with an ACHIEVED best matter (smaller column wins); an unreached floor only needs strictly larger cells
+                if (!REV) trigm1 = pack16(max(best[0] - (bcol[0] != 0x7fffffff), 0), max(best[1] - (bcol[1] != 0x7fffffff), 0));
             }
             hdiag = hin;
             hout = hlast; fout = f; xout = xin;
@@ -284,14 +376,24 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
         // group reduction: highest value, then smallest column (lower lanes own smaller columns)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            int rmx = h ? hi16(runmax) : lo16(runmax);
             for (int o = 1; o < g; o <<= 1) {
                 const int ob = __shfl_down_sync(0xffffffffu, best[h], o);
                 const int oc = __shfl_down_sync(0xffffffffu, bcol[h], o);
                 const int orow = __shfl_down_sync(0xffffffffu, brow[h], o);
-                if (lig + o < g && (ob > best[h] || (ob == best[h] && oc < bcol[h]))) { best[h] = ob; bcol[h] = oc; brow[h] = orow; }
+                const int orm = __shfl_down_sync(0xffffffffu, rmx, o);
+                if (lig + o < g) {
+                    rmx = max(rmx, orm);
+                    if (ob > best[h] || (ob == best[h] && oc < bcol[h])) { best[h] = ob; bcol[h] = oc; brow[h] = orow; }
+                }
             }
-            // forward: absolute RNA row; reverse: index into the reversed stream (k_win_finish subtracts it from qe)
-            if (leader && wi[h] >= 0) w.res[wi[h]] = make_int4(best[h], bcol[h], REV ? brow[h] : sbase[h] + brow[h], 0);
+            // forward: absolute RNA row; reverse: index into the reversed stream (k_win_finish subtracts it from qe).
+            // A forward sweep in which no cell rose above the floor reports its plain maximum (position unknown, never used:
+            // such a result is below w_bound, so the window is re-planned from it).
+            if (leader && wi[h] >= 0) {
+                if (!REV && bcol[h] == 0x7fffffff) w.res[wi[h]] = make_int4(rmx, 0, 0, 0);
+                else w.res[wi[h]] = make_int4(best[h], bcol[h], REV ? brow[h] : sbase[h] + brow[h], 0);
+            }
         }
     }
 }
@@ -310,7 +412,17 @@ __global__ void k_win_decide(const WinState w, int round)
         w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.w_done[i] = 1;
         return;
     }
-    if (sw > w.best_sw[i] && re == cut - 1) { w.best_sw[i] = sw; w.best_cut[i] = cut; w.best_re[i] = re; w.best_qe[i] = qe; }
+    if (sw > w.best_sw[i] && re == cut - 1) {
+        w.best_sw[i] = sw; w.best_cut[i] = cut; w.best_re[i] = re; w.best_qe[i] = qe;
+        // The later rounds look at nested, shorter windows with the same right end, so their exact scores cannot exceed
+        // this one: they can neither reach S (> sw) nor replace this candidate (needs a strictly larger score), and the
+        // loop ends with this candidate (fastsim.h:236-249).  Only when this score came from the literal emulation (which may
+        // report less than exact SW, res.w = 1) a later round could still overtake it, so those keep going.
+        if (v.w == 0) {
+            w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.w_done[i] = 1;
+            return;
+        }
+    }
     if (round == 3) {
         if (w.best_sw[i] > 0) { w.fin_sw[i] = w.best_sw[i]; w.fin_cut[i] = w.best_cut[i]; w.fin_re[i] = w.best_re[i]; w.fin_qe[i] = w.best_qe[i]; }
         else { w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; }
@@ -369,7 +481,8 @@ struct TraceArgs {
     const uint8_t* rna_ssw;        // lncRNA, SSW codes
     const unsigned char* rna_raw;  // raw lncRNA bytes (for the TFO string)
     unsigned char* scratch; long long scratch_per_thread;
-    int only_overflow;             // second launch: only alignments flagged status 2
+    const int* in_list; const int* in_count;   // work list (nullptr: all jobs)
+    int* out_list; int* out_count;             // jobs this launch could not finish (status 2) — input of the next tier
     int nt_min, nt_max, penalty_t, penalty_c;
     TraceOut* out;                 // per job
     char* strpool;                 // pass 2 only (nullptr in pass 1): tfo at out_off, tts at out_off + nt + 1, both NUL-terminated
@@ -421,11 +534,12 @@ __global__ void k_traceback(const TraceArgs a)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     unsigned char* sc = a.scratch + (size_t)tid * a.scratch_per_thread;
-    for (int i = tid; i < a.n_jobs; i += nthreads) {
-        if (!a.only_overflow) a.out[i].status = 0;
+    const int n_todo = a.in_list ? min(*a.in_count, a.n_jobs) : a.n_jobs;
+    for (int k0 = tid; k0 < n_todo; k0 += nthreads) {
+        const int i = a.in_list ? a.in_list[k0] : k0;
+        if (!a.in_list) a.out[i].status = 0;
         const TraceJob J = a.jobs[i];
         if (J.score <= 0) continue;
-        if (a.only_overflow && a.out[i].status != 2) continue;
 
         const TaskDef td = c_tasks[J.tdef];
         const int ws = J.ws, rb = J.rb, re = J.re, qb = J.qb, qe = J.qe;
@@ -480,7 +594,7 @@ __global__ void k_traceback(const TraceArgs a)
             if (maxv >= score) break;
             bw *= 2;
         }
-        if (!fits) { a.out[i].status = 2; continue; }
+        if (!fits) { a.out[i].status = 2; if (a.out_list) a.out_list[atomicAdd(a.out_count, 1)] = i; continue; }
 
         // traceback (sswNew.cpp:1159-1238): ops come out end -> start; written backwards into `ops`
         unsigned char* ops = reinterpret_cast<unsigned char*>(dir) + 3LL * width_d * readLen;
@@ -548,6 +662,138 @@ __global__ void k_traceback(const TraceArgs a)
             o[2 * nt + 1] = 0;
         }
         TraceOut o1; o1.status = 1; o1.nt = nt; o1.identity = identity; o1.tri = tri;
+        a.out[i] = o1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast tier of the traceback: the same banded_sw + expansion, with the whole working set of an alignment in shared
+// memory (typical need: ~400 bytes).  The per-thread region is interleaved word-wise across the block
+// (word k of thread t at [k][t]), so every access of a warp is bank-conflict free whatever the threads index.
+// Differences to k_traceback are representational only: int16 score rows, the three direction planes of a band cell
+// packed into one byte (bit0: E opened, bit1: F opened, bits 2..4: H code), no staging of the expanded strings.
+// Anything that does not fit, and any traceback step that would leave the band of its row (where the reference reads
+// whatever lies next to it in memory), is handed to k_traceback through out_list.
+template <int TPB, int BYTES>
+__global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
+{
+    extern __shared__ uint32_t tb_words[];
+    unsigned char* const sbase = reinterpret_cast<unsigned char*>(tb_words) + threadIdx.x * 4;
+    auto at = [&](int b) -> unsigned char* { return sbase + (size_t)(b >> 2) * (TPB * 4) + (b & 3); };
+    auto ld16 = [&](int off, int k) -> int { return *reinterpret_cast<const int16_t*>(at(off + 2 * k)); };
+    auto st16 = [&](int off, int k, int v) { *reinterpret_cast<int16_t*>(at(off + 2 * k)) = (int16_t)v; };
+    const int tid = blockIdx.x * TPB + threadIdx.x, nthreads = gridDim.x * TPB;
+    for (int i = tid; i < a.n_jobs; i += nthreads) {
+        a.out[i].status = 0;
+        const TraceJob J = a.jobs[i];
+        if (J.score <= 0) continue;
+        const TaskDef td = c_tasks[J.tdef];
+        const int ws = J.ws, rb = J.rb, qb = J.qb;
+        const int refLen = J.re - rb + 1, readLen = J.qe - qb + 1, score = J.score;
+        const uint8_t* gc = a.codes + J.seg_start;
+        auto gidx = [&](int q) -> int { return td.reversed ? (J.seg_len - 1 - q) : q; };     // seq2 index -> segment index
+        const int ntmax = refLen + readLen;
+
+        int bw = abs(refLen - readLen) + 1, maxv = 0, width_d = 0, o_dir = 0, o_ops = 0;
+        bool fits = true;
+        for (;;) {
+            const int width = bw * 2 + 3;
+            width_d = bw * 2 + 1;
+            const int rowb = ((width + 2) * 2 + 3) & ~3;
+            o_dir = 3 * rowb;
+            o_ops = o_dir + ((width_d * readLen + 3) & ~3);
+            if ((long long)o_ops + ntmax + 4 > BYTES || (long long)width_d * readLen > BYTES) { fits = false; break; }
+            const int HB = 0, EB = rowb, HC = 2 * rowb;
+            for (int j = 0; j < width + 2; ++j) { st16(HB, j, 0); st16(EB, j, 0); st16(HC, j, 0); }
+            for (int ii = 0; ii < readLen; ++ii) {
+                const int beg = max(0, ii - bw), end = min(refLen - 1, ii + bw);
+                const int edge = min(end + 1, width - 1);
+                int f = 0, u = 0;
+                st16(HB, 0, 0); st16(EB, 0, 0); st16(HB, edge, 0); st16(EB, edge, 0); st16(HC, 0, 0);
+                const int line = o_dir + width_d * ii;
+                const int rc = a.rna_ssw[qb + ii];
+                for (int j = beg; j <= end; ++j) {
+                    u = band_u(bw, ii, j);
+                    const int e = band_u(bw, ii - 1, j), b = band_u(bw, ii, j - 1), dd = band_u(bw, ii - 1, j - 1);
+                    int t1 = (ii == 0) ? -kGapOpen : ld16(HB, e) - kGapOpen;
+                    int t2 = (ii == 0) ? -kGapExt : ld16(EB, e) - kGapExt;
+                    const int ev = t1 > t2 ? t1 : t2;
+                    const int de = t1 > t2 ? 3 : 2;
+                    st16(EB, u, ev);
+                    t1 = ld16(HC, b) - kGapOpen;
+                    t2 = f - kGapExt;
+                    f = t1 > t2 ? t1 : t2;
+                    const int df = t1 > t2 ? 5 : 4;
+                    const int e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;
+                    t1 = e1 > f1 ? e1 : f1;
+                    const int rf = td.img[gc[gidx(ws + rb + j)]];
+                    t2 = ld16(HB, dd) + ((rf == rc && rf < 4) ? kMatch : kMismatch);
+                    const int hv = t1 > t2 ? t1 : t2;
+                    st16(HC, u, hv);
+                    if (hv > maxv) maxv = hv;
+                    const int dh = (t1 <= t2) ? 1 : (e1 > f1 ? de : df);
+                    *at(line + (j - beg)) = (unsigned char)((de & 1) | ((df & 1) << 1) | (dh << 2));
+                }
+                for (int j = 1; j <= u; ++j) st16(HB, j, ld16(HC, j));
+            }
+            if (maxv >= score) break;
+            bw *= 2;
+        }
+        // traceback (sswNew.cpp:1159-1238): ops come out end -> start; written backwards into `ops`
+        int wp = ntmax + 2;
+        if (fits) {
+            int ii = readLen - 1, j = refLen - 1, plane = 2;
+            while (ii > 0) {
+                const int c = j - max(0, ii - bw);
+                if (j < 0 || c < 0 || c >= width_d || wp <= 2) { fits = false; break; }     // off the band: the generic tier decides
+                const int byte = *at(o_dir + width_d * ii + c);
+                const int dv = plane == 0 ? 2 + (byte & 1) : (plane == 1 ? 4 + ((byte >> 1) & 1) : (byte >> 2));
+                --wp;
+                if (dv == 1) { --ii; --j; plane = 2; *at(o_ops + wp) = 0; }
+                else if (dv == 2) { --ii; plane = 0; *at(o_ops + wp) = 1; }
+                else if (dv == 3) { --ii; plane = 2; *at(o_ops + wp) = 1; }
+                else if (dv == 4) { --j; plane = 1; *at(o_ops + wp) = 2; }
+                else { --j; plane = 2; *at(o_ops + wp) = 2; }
+            }
+        }
+        if (!fits) { a.out[i].status = 2; a.out_list[atomicAdd(a.out_count, 1)] = i; continue; }
+        *at(o_ops + --wp) = 0;      // closing rule (:1220-1238): the alignment always starts with one more M column
+        const int nt = ntmax + 2 - wp;
+        // expansion from the front exactly like getAlignment (q walks the translated DNA from ref_begin, p the RNA), fused
+        // with the identity count and the stability sum of convertMyTriplex (float32, same operation order)
+        const bool with_tri = nt >= a.nt_min && nt <= a.nt_max;
+        const float pt = __int2float_rn(a.penalty_t), pc = __int2float_rn(a.penalty_c);
+        char* o_tfo = a.strpool ? a.strpool + J.out_off : nullptr;
+        char* o_tts = o_tfo ? o_tfo + nt + 1 : nullptr;
+        int q = ws + rb, p = qb, match = 0;
+        float tri = 0.0f, prev_val = 0.0f;
+        char prev_ch = 0;
+        for (int k = 0; k < nt; ++k) {
+            const int op = *at(o_ops + wp + k);
+            char rch = '-', sch = '-', tch = '-';
+            if (op != 2) rch = (char)a.rna_raw[p++];
+            if (op != 1) {
+                const int gi = gidx(q++);
+                const unsigned char raw = a.dna[J.seg_start + gi];
+                sch = td.comp_src ? comp_char(raw) : (char)raw;
+                const int dcode = td.img[gc[gi]];
+                tch = dcode < 4 ? "ACGT"[dcode] : 'N';
+            }
+            if (tch == rch) ++match;
+            if (with_tri) {
+                float val = stability_dev(sch, rch, td.para);
+                if (sch == prev_ch && sch == 'T') { tri = __fadd_rn(__fsub_rn(tri, prev_val), pt); val = pt; }
+                if (sch == prev_ch && sch == 'C') { tri = __fadd_rn(__fsub_rn(tri, prev_val), pc); val = pc; }
+                prev_val = val;
+                if (sch != '-') prev_ch = sch;
+                tri = __fadd_rn(tri, val);
+            }
+            if (o_tfo) { o_tfo[k] = rch; o_tts[k] = sch; }
+        }
+        if (o_tfo) { o_tfo[nt] = 0; o_tts[nt] = 0; }
+        if (with_tri) tri = __fdiv_rn(tri, __int2float_rn(nt));
+        TraceOut o1;
+        o1.status = 1; o1.nt = nt; o1.identity = __fdiv_rn(__int2float_rn(100 * match), __int2float_rn(nt)); o1.tri = tri;
         a.out[i] = o1;
     }
 }

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfasim_b200.so")
+LIB_PATH = os.environ.get("FASIM_B200_LIB") or os.path.join(HERE, "libfasim_b200.so")     # FASIM_B200_LIB: a tuning variant
 CLI_PATH = os.path.join(HERE, "fasim")
 
 PARAM_FIELDS = ["rule", "cut_length", "strand", "overlap", "nt_min", "nt_max", "min_identity", "min_stability", "penalty_t",
@@ -45,7 +45,7 @@ class TaskProbe(C.Structure):
 
 EXPORTS = ["ltg_create", "ltg_destroy", "ltg_last_error", "ltg_default_params", "ltg_set_params", "ltg_set_query",
            "ltg_scan_record", "ltg_scan_device", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
-           "ltg_write_tfosorted", "ltg_write_tfoclass", "ltg_main", "ltg_probe_segment", "ltg_probe_align", "ltg_stream",
+           "ltg_write_tfosorted", "ltg_write_tfoclass", "ltg_main", "ltg_probe_segment", "ltg_probe_align", "ltg_stream", "ltg_debug_stats",
            "ltg_device_count"]
 
 _lib = None
@@ -83,6 +83,7 @@ def lib():
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
         L.ltg_probe_align.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_uint32), C.c_int32]
+        L.ltg_debug_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
         _lib = L
     return _lib
 
@@ -153,6 +154,11 @@ class Engine:
         self.rna = rna
         b = rna.encode()
         _check(lib().ltg_set_query(self._h, name.encode(), b, len(b)))
+
+    def debug_stats(self, reset=False):
+        out = (C.c_int64 * 20)()
+        lib().ltg_debug_stats(self._h, out, 1 if reset else 0)
+        return {"windows": list(out[:10]), "cells": list(out[10:])}
 
     @property
     def stream(self):

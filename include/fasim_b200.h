@@ -146,6 +146,11 @@ int ltg_probe_segment(ltg_context* ctx, const char* seg, int32_t seg_len, ltg_ta
 int ltg_probe_align(ltg_context* ctx, const char* const* windows, const int32_t* window_len, int32_t n,
                     int32_t* out6, uint32_t* cigar, int32_t cigar_cap);
 
+/* window-stage work counters accumulated over the context's life: out20[2*round + retry] = windows planned in forward
+ * round 0..3 (retry 1 = second, wider sweep after an inconclusive pruned one), out20[8] = reverse sweeps,
+ * out20[10 + k] = the DP cells of the same entries.                                                          */
+void ltg_debug_stats(ltg_context* ctx, int64_t* out20, int reset);
+
 /* device-timing helpers for bench.py: opaque cudaStream_t of the context */
 void* ltg_stream(ltg_context* ctx);
 int ltg_device_count(void);

@@ -8,3 +8,6 @@ tail -5 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 2 --warmup 1 --region-mbp $REGION > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 cat gpurun_out/box.txt
+if [ -n "$2" ]; then
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/$2_launches.csv python bench.py --steps 1 --warmup 1 --region-mbp 5 --no-cpu-baseline > gpurun_out/ncu_$2.log 2>&1
+fi
