@@ -54,19 +54,6 @@ def splitmix_bases(seed, n, offset=0):
     return out
 
 
-def shard_range(n_bases, world, rank, cut=CUT, overlap=OVERLAP):
-    """Contiguous shard of the region's segments for `rank`: returns (first_base, n_bases_of_shard, n_segments).
-    Segments start every cut-overlap bases (cutSequence, fastsim.h:71-90); a shard carries whole segments, so its
-    byte range ends `overlap` bases after its last segment's stride."""
-    stride = cut - overlap
-    n_seg = (n_bases + stride - 1) // stride
-    lo_seg = (n_seg * rank) // world
-    hi_seg = (n_seg * (rank + 1)) // world
-    lo = lo_seg * stride
-    hi = min(n_bases, (hi_seg - 1) * stride + cut) if hi_seg > lo_seg else lo
-    return lo, hi - lo, hi_seg - lo_seg
-
-
 def region_cells(n_bases, m, cut=CUT, overlap=OVERLAP, tasks=TASKS_PER_SEG):
     stride = cut - overlap
     total = 0
@@ -210,7 +197,7 @@ def bench_gpu(args, rank, world, local_rank):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     region = int(args.region_mbp * 1e6)
-    lo, nb, nseg = shard_range(region, world, rank)
+    first_seg, nseg, lo, nb = fb.shard_segments(region, world, rank, CUT, OVERLAP)     # contiguous run of whole segments
     rna = splitmix_bases(RNA_SEED, RNA_NT).tobytes().decode()
     host = torch.from_numpy(splitmix_bases(DNA_SEED, nb, lo)).pin_memory()
     dev = host.to("cuda", non_blocking=False)
@@ -233,14 +220,14 @@ def bench_gpu(args, rank, world, local_rank):
         e0.record(stream)
         for _ in range(steps):
             res = C.POINTER(fb.Result)()
-            if device_resident:
-                rc = fb.lib().ltg_scan_device(eng._h, C.c_void_p(dev.data_ptr()), nb, b"chr1", lo + 1, C.byref(res))
-            else:
-                rc = fb.lib().ltg_scan_record(eng._h, C.cast(host.data_ptr(), C.c_char_p), nb, b"chr1", lo + 1, C.byref(res))
+            # the reference-facing C-ABI call; device_resident: DNA already in HBM, else HOST buffer (H2D inside the call)
+            rc = fb.lib().ltg_scan_shard(eng._h, C.c_void_p(dev.data_ptr() if device_resident else host.data_ptr()),
+                                         1 if device_resident else 0, nb, b"chr1", 1, region, first_seg, nseg, C.byref(res))
             if rc != 0:
                 raise RuntimeError(fb.lib().ltg_last_error().decode())
             r = res.contents
-            stats["cells"] += r.scan_cells; stats["bases"] += r.dna_bases; stats["rows"] += r.n_triplex
+            stats["cells"] += r.scan_cells; stats["bases"] += min(region, (first_seg + nseg) * (CUT - OVERLAP)) - first_seg * (CUT - OVERLAP)
+            stats["rows"] += r.n_triplex
             stats["launches"] += r.gpu_launches; stats["scan_ms"] += r.gpu_ms_scan_kernel; stats["scan_launches"] += r.n_scan_launches
             stats["win_ms"] += r.gpu_ms_window; stats["win_cells"] += r.window_cells; stats["peaks"] += r.n_peaks
             stats["lit_tasks"] += r.n_literal_tasks; stats["lit_windows"] += r.n_literal_windows

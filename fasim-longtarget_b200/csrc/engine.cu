@@ -131,7 +131,7 @@ struct ltg_context {
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
     HostBatch hb[2];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-    unsigned long long win_stats[20] = {0};     // windows / cells planned per (round, retry) + reverse (ltg_debug_stats)
+    unsigned long long win_stats[24] = {0};     // windows / cells planned per (round, retry) + reverse; [20..22] traceback tier hand-overs
 };
 
 namespace {
@@ -142,7 +142,7 @@ struct TaskInfo {
     TaskInfo(int* base, int n) : max(base), thr(base + n), npk(base + 2 * (size_t)n), flags(base + 3 * (size_t)n), jstar(base + 4 * (size_t)n) {}
 };
 
-enum { kCntScan = 0, kCntPeaks = 1, kCntOvf = 2 /* and 3 */, kCntCells = 16, kCntLit = 24, kCntLitTotal = 26, kCntTotal = 32 };
+enum { kCntScan = 0, kCntPeaks = 1, kCntOvf = 2 /* .. 5 */, kCntCells = 16, kCntLit = 24, kCntLitTotal = 26, kCntTotal = 32 };
 
 int upload_tables(ltg_context* c)
 {
@@ -342,9 +342,10 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     return LTG_OK;
 }
 
-// the three tiers of the traceback over a job list: shared-memory fast path for everything, then the generic kernel
-// with a 24 KB global scratch for what the fast path handed over, then an 8 MB scratch for the rare huge bands
-constexpr int kTraceTpb = 128, kTraceBytes = 896;
+// The tiers of the traceback over a job list: three shared-memory tiers (small region / many threads for the typical
+// alignment, larger regions / fewer threads for long alignments and wide bands), then the generic kernel with a 24 KB
+// global scratch, then with an 8 MB scratch for the rare huge bands.  Each tier hands what it cannot finish to the next through a device-side list.
+constexpr int kTrace1Tpb = 128, kTrace1Bytes = 452, kTrace2Tpb = 64, kTrace2Bytes = 1796, kTrace3Tpb = 32, kTrace3Bytes = 7172;
 int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* d_out, char* strpool)
 {
     const int tb_threads = c->num_sms * 64;
@@ -352,30 +353,40 @@ int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* 
     const int big_threads = 128;
     if (int e = c->d_scratch.ensure((size_t)tb_threads * scratch_small)) return e;
     if (int e = c->d_scratch_big.ensure((size_t)big_threads * scratch_big)) return e;
-    if (int e = c->d_ovf_list.ensure(sizeof(int) * 2 * (size_t)n_jobs)) return e;
+    if (int e = c->d_ovf_list.ensure(sizeof(int) * 4 * (size_t)n_jobs)) return e;
     int* cnt = c->d_counters.as<int>() + kCntOvf;
-    int* list1 = c->d_ovf_list.as<int>(), * list2 = list1 + n_jobs;
-    LTG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 2 * sizeof(int), c->stream));
+    int* list1 = c->d_ovf_list.as<int>(), * list2 = list1 + n_jobs, * list3 = list2 + n_jobs, * list4 = list3 + n_jobs;
+    LTG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), c->stream));
     TraceArgs ta;
     ta.jobs = d_jobs; ta.n_jobs = n_jobs; ta.codes = c->d_codes.as<uint8_t>(); ta.dna = c->d_dna.as<unsigned char>();
     ta.rna_ssw = c->d_rna_ssw.as<uint8_t>(); ta.rna_raw = c->d_rna_raw.as<unsigned char>();
     ta.nt_min = c->params.nt_min; ta.nt_max = c->params.nt_max; ta.penalty_t = c->params.penalty_t; ta.penalty_c = c->params.penalty_c;
     ta.out = d_out; ta.strpool = strpool;
+    ta.scratch = nullptr; ta.scratch_per_thread = 0;
     // tier 1
-    ta.scratch = nullptr; ta.scratch_per_thread = 0; ta.in_list = nullptr; ta.in_count = nullptr; ta.out_list = list1; ta.out_count = cnt;
-    const int smem = kTraceTpb * kTraceBytes;
-    LTG_CUDA_CHECK(cudaFuncSetAttribute(k_traceback_fast<kTraceTpb, kTraceBytes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int fast_blocks = std::max(1, std::min(c->num_sms * 2, (n_jobs + kTraceTpb - 1) / kTraceTpb));
-    k_traceback_fast<kTraceTpb, kTraceBytes><<<fast_blocks, kTraceTpb, smem, c->stream>>>(ta);
+    ta.in_list = nullptr; ta.in_count = nullptr; ta.out_list = list1; ta.out_count = cnt;
+    const int smem1 = kTrace1Tpb * kTrace1Bytes, smem2 = kTrace2Tpb * kTrace2Bytes, smem3 = kTrace3Tpb * kTrace3Bytes;
+    LTG_CUDA_CHECK(cudaFuncSetAttribute(k_traceback_fast<kTrace1Tpb, kTrace1Bytes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    LTG_CUDA_CHECK(cudaFuncSetAttribute(k_traceback_fast<kTrace2Tpb, kTrace2Bytes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    LTG_CUDA_CHECK(cudaFuncSetAttribute(k_traceback_fast<kTrace3Tpb, kTrace3Bytes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    const int blocks1 = std::max(1, std::min(c->num_sms * 4, (n_jobs + kTrace1Tpb - 1) / kTrace1Tpb));
+    k_traceback_fast<kTrace1Tpb, kTrace1Bytes><<<blocks1, kTrace1Tpb, smem1, c->stream>>>(ta);
     // tier 2
-    ta.scratch = c->d_scratch.as<unsigned char>(); ta.scratch_per_thread = scratch_small;
     ta.in_list = list1; ta.in_count = cnt; ta.out_list = list2; ta.out_count = cnt + 1;
-    k_traceback<<<tb_threads / 64, 64, 0, c->stream>>>(ta);
+    const int blocks2 = std::max(1, std::min(c->num_sms * 2, (n_jobs + kTrace2Tpb - 1) / kTrace2Tpb));
+    k_traceback_fast<kTrace2Tpb, kTrace2Bytes><<<blocks2, kTrace2Tpb, smem2, c->stream>>>(ta);
     // tier 3
+    ta.in_list = list2; ta.in_count = cnt + 1; ta.out_list = list3; ta.out_count = cnt + 2;
+    k_traceback_fast<kTrace3Tpb, kTrace3Bytes><<<c->num_sms, kTrace3Tpb, smem3, c->stream>>>(ta);
+    // tier 4
+    ta.scratch = c->d_scratch.as<unsigned char>(); ta.scratch_per_thread = scratch_small;
+    ta.in_list = list3; ta.in_count = cnt + 2; ta.out_list = list4; ta.out_count = cnt + 3;
+    k_traceback<<<tb_threads / 64, 64, 0, c->stream>>>(ta);
+    // tier 5
     ta.scratch = c->d_scratch_big.as<unsigned char>(); ta.scratch_per_thread = scratch_big;
-    ta.in_list = list2; ta.in_count = cnt + 1; ta.out_list = nullptr; ta.out_count = nullptr;
+    ta.in_list = list4; ta.in_count = cnt + 3; ta.out_list = nullptr; ta.out_count = nullptr;
     k_traceback<<<big_threads / 64, 64, 0, c->stream>>>(ta);
-    c->launches += 3;
+    c->launches += 5;
     LTG_CUDA_CHECK(cudaGetLastError());
     return LTG_OK;
 }
@@ -524,6 +535,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.p, counters + kCntCells, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 64, &c->d_win_sched.as<WinSched>()->st_windows[0], 20 * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 232, counters + kCntOvf, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         c->d2h_bytes += (int64_t)(sizeof(TraceJob) + sizeof(TraceOut)) * n_peaks + 64;
     } else {
         hb.n_peaks = want_alignments ? n_peaks : 0;
@@ -589,13 +601,17 @@ void host_phase(const ltg_context* c, HostBatch& hb, int threads)
     }
 }
 
-// cutSequence — fastsim.h:71-90
-int cut_segments(int64_t len, const ltg_params& P, std::vector<HostSeg>& segs)
+// cutSequence — fastsim.h:71-90.  A shard is the run of segments [first_seg, first_seg + n_seg) of a record of `record_len`
+// bases whose bytes start at the first segment's start; segment starts are relative to the shard's buffer, lengths follow
+// the RECORD's geometry (so the union of shards is exactly the record's segment list — no extra tail segments).
+int cut_segments(int64_t buf_len, int64_t record_len, int64_t first_seg, int64_t n_seg, const ltg_params& P, std::vector<HostSeg>& segs)
 {
     if (P.cut_length <= 0 || P.cut_length - P.overlap <= 0) { set_error("cut length must exceed the overlap"); return LTG_ERR_ARG; }
+    const int64_t stride = P.cut_length - P.overlap;
     segs.clear();
-    for (int64_t pos = 0; pos < len; pos += P.cut_length - P.overlap) {
-        HostSeg s; s.start = pos; s.len = (int32_t)std::min<int64_t>(P.cut_length, len - pos); s.flags = 0;
+    for (int64_t k = first_seg; (n_seg < 0 || k < first_seg + n_seg) && k * stride < record_len; ++k) {
+        HostSeg s; s.start = (k - first_seg) * stride; s.len = (int32_t)std::min<int64_t>(P.cut_length, record_len - k * stride); s.flags = 0;
+        if (s.start + s.len > buf_len) { set_error("shard buffer (%lld bytes) does not cover segment %lld", (long long)buf_len, (long long)k); return LTG_ERR_ARG; }
         segs.push_back(s);
     }
     return LTG_OK;
@@ -605,15 +621,16 @@ struct ResultBuilder {
     std::vector<ltg_triplex> tri;
     std::string text;
     int64_t chr_off = -1;
-    void add(const ltg_host::Triplex& t, const char* tfo, const char* tts, const char* chr, int64_t record_start, int record)
+    void add(const ltg_host::Triplex& t, const char* tfo, const char* tts, const char* chr, int64_t record_start, int64_t coord_offset, int record)
     {
         if (chr_off < 0) { chr_off = (int64_t)text.size(); text += (chr ? chr : ""); text += '\0'; }
         ltg_triplex o;
         memset(&o, 0, sizeof o);
-        o.stari = t.stari; o.endi = t.endi; o.starj = t.starj; o.endj = t.endj; o.reverse = t.reverse; o.strand = t.strand;
+        o.stari = t.stari; o.endi = t.endi; o.starj = (int32_t)(t.starj + coord_offset); o.endj = (int32_t)(t.endj + coord_offset);
+        o.reverse = t.reverse; o.strand = t.strand;
         o.rule = t.rule; o.nt = t.nt; o.score = t.score; o.identity = t.identity; o.tri_score = t.tri_score;
-        o.genomestart = t.starj + record_start - 1;         // Fasim-LongTarget.cpp:146-147
-        o.genomeend = t.endj + record_start - 1;
+        o.genomestart = o.starj + record_start - 1;         // Fasim-LongTarget.cpp:146-147
+        o.genomeend = o.endj + record_start - 1;
         o.tfo_off = (int64_t)text.size(); text.append(tfo, (size_t)t.nt); text += '\0';
         o.tts_off = (int64_t)text.size(); text.append(tts, (size_t)t.nt); text += '\0';
         o.chr_off = chr_off;
@@ -698,19 +715,23 @@ int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg
     st.window_cells += cells;
     st.n_literal_windows += sc[kCntLitTotal - kCntCells];
     for (int k = 0; k < 20; ++k) c->win_stats[k] += reinterpret_cast<const unsigned long long*>(hb.scalars.as<char>() + 64)[k];
+    for (int k = 0; k < 4; ++k) c->win_stats[20 + k] += (unsigned long long)reinterpret_cast<const int*>(hb.scalars.as<char>() + 232)[k];
     record_list.insert(record_list.end(), hb.rows.begin(), hb.rows.end());
     hb.rows.clear();
     return LTG_OK;
 }
 
 int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char* h_dna, int64_t len, const char* chr,
-                     int64_t record_start, ltg_result** out)
+                     int64_t record_start, ltg_result** out, int64_t record_len = -1, int64_t first_seg = 0, int64_t n_seg = -1)
 {
     if (!c || !out) { set_error("null argument"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
     const int64_t launches0 = c->launches, h2d0 = c->h2d_bytes, d2h0 = c->d2h_bytes;
     std::vector<HostSeg> segs;
-    if (int e = cut_segments(len, c->params, segs)) return e;
+    if (record_len < 0) record_len = len;
+    if (first_seg < 0 || len < 0) { set_error("bad shard geometry"); return LTG_ERR_ARG; }
+    if (int e = cut_segments(len, record_len, first_seg, n_seg, c->params, segs)) return e;
+    const int64_t coord_offset = first_seg * (int64_t)(c->params.cut_length - c->params.overlap);
     ResultBuilder rb;
     RecordStats st;
     if (len > 0) {
@@ -770,7 +791,7 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
         std::vector<int64_t> offs;
         if (int e = fetch_strings(c, keep, pool, offs)) return e;
         for (size_t i = 0; i < keep.size(); ++i)
-            rb.add(keep[i], pool.data() + offs[i], pool.data() + offs[i] + keep[i].nt + 1, chr, record_start, 0);
+            rb.add(keep[i], pool.data() + offs[i], pool.data() + offs[i] + keep[i].nt + 1, chr, record_start, coord_offset, 0);
     }
     ltg_result* r = finish_result(rb);
     r->n_segments = st.n_segments; r->n_tasks = st.n_tasks; r->scan_cells = st.scan_cells; r->dna_bases = len;
@@ -860,10 +881,10 @@ void ltg_destroy(ltg_context* c)
 
 void* ltg_stream(ltg_context* c) { return c ? (void*)c->stream : nullptr; }
 
-void ltg_debug_stats(ltg_context* c, int64_t* out20, int reset)
+void ltg_debug_stats(ltg_context* c, int64_t* out24, int reset)
 {
-    if (!c || !out20) return;
-    for (int k = 0; k < 20; ++k) { out20[k] = (int64_t)c->win_stats[k]; if (reset) c->win_stats[k] = 0; }
+    if (!c || !out24) return;
+    for (int k = 0; k < 24; ++k) { out24[k] = (int64_t)c->win_stats[k]; if (reset) c->win_stats[k] = 0; }
 }
 
 int ltg_set_params(ltg_context* c, const ltg_params* p)
@@ -912,6 +933,14 @@ int ltg_scan_device(ltg_context* c, const void* d_dna, int64_t len, const char* 
 {
     if (!d_dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
     return scan_device_impl(c, (const unsigned char*)d_dna, nullptr, len, chr, record_start, out);
+}
+
+int ltg_scan_shard(ltg_context* c, const void* dna, int dna_on_device, int64_t len, const char* chr, int64_t record_start,
+                   int64_t record_len, int64_t first_segment, int64_t n_segments, ltg_result** out)
+{
+    if (!dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
+    if (dna_on_device) return scan_device_impl(c, (const unsigned char*)dna, nullptr, len, chr, record_start, out, record_len, first_segment, n_segments);
+    return scan_device_impl(c, nullptr, (const char*)dna, len, chr, record_start, out, record_len, first_segment, n_segments);
 }
 
 int ltg_result_new(ltg_result** out)

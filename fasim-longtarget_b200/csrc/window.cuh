@@ -116,6 +116,9 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
                 if (pos - cut + 1 <= 0) cut = pos + 1;                 // fastsim.h:211
                 len = cut;
                 bound = sc;
+                // rounds >= 1 look at a shorter window with the same right end: its best score cannot exceed the previous
+                // round's (exact) one, which is therefore the better first guess (any guess is safe, exactness is verified)
+                if (round > 0) { const int prev = w.res[i].x; if (prev > 0 && prev < bound) bound = prev; }
             } else {
                 const int4 v = w.res[i];
                 if (w.w_done[i] || v.x >= w.w_bound[i]) active = false;      // exact already
@@ -667,24 +670,25 @@ __global__ void k_traceback(const TraceArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fast tier of the traceback: the same banded_sw + expansion, with the whole working set of an alignment in shared
-// memory (typical need: ~400 bytes).  The per-thread region is interleaved word-wise across the block
-// (word k of thread t at [k][t]), so every access of a warp is bank-conflict free whatever the threads index.
+// Fast tiers of the traceback: the same banded_sw + expansion, with the whole working set of an alignment in shared
+// memory (typical need: ~450 bytes).  Every thread owns BYTES contiguous bytes; BYTES/4 is odd, so threads that
+// touch the same offset of their regions (the common case) hit 32 different banks.
 // Differences to k_traceback are representational only: int16 score rows, the three direction planes of a band cell
-// packed into one byte (bit0: E opened, bit1: F opened, bits 2..4: H code), no staging of the expanded strings.
+// packed into one byte (bit0: E opened, bit1: F opened, bits 2..4: H code), the window's translated base codes cached
+// next to them, no staging of the expanded strings.
 // Anything that does not fit, and any traceback step that would leave the band of its row (where the reference reads
-// whatever lies next to it in memory), is handed to k_traceback through out_list.
+// whatever lies next to it in memory), is handed to the next tier through out_list.
 template <int TPB, int BYTES>
 __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
 {
+    static_assert(BYTES % 4 == 0 && (BYTES / 4) % 2 == 1, "per-thread region must be an odd number of words");
     extern __shared__ uint32_t tb_words[];
-    unsigned char* const sbase = reinterpret_cast<unsigned char*>(tb_words) + threadIdx.x * 4;
-    auto at = [&](int b) -> unsigned char* { return sbase + (size_t)(b >> 2) * (TPB * 4) + (b & 3); };
-    auto ld16 = [&](int off, int k) -> int { return *reinterpret_cast<const int16_t*>(at(off + 2 * k)); };
-    auto st16 = [&](int off, int k, int v) { *reinterpret_cast<int16_t*>(at(off + 2 * k)) = (int16_t)v; };
+    unsigned char* const reg = reinterpret_cast<unsigned char*>(tb_words) + (size_t)threadIdx.x * BYTES;
     const int tid = blockIdx.x * TPB + threadIdx.x, nthreads = gridDim.x * TPB;
-    for (int i = tid; i < a.n_jobs; i += nthreads) {
-        a.out[i].status = 0;
+    const int n_todo = a.in_list ? min(*a.in_count, a.n_jobs) : a.n_jobs;
+    for (int k0 = tid; k0 < n_todo; k0 += nthreads) {
+        const int i = a.in_list ? a.in_list[k0] : k0;
+        if (!a.in_list) a.out[i].status = 0;
         const TraceJob J = a.jobs[i];
         if (J.score <= 0) continue;
         const TaskDef td = c_tasks[J.tdef];
@@ -694,70 +698,88 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         auto gidx = [&](int q) -> int { return td.reversed ? (J.seg_len - 1 - q) : q; };     // seq2 index -> segment index
         const int ntmax = refLen + readLen;
 
-        int bw = abs(refLen - readLen) + 1, maxv = 0, width_d = 0, o_dir = 0, o_ops = 0;
+        // region: three int16 score rows | translated base codes of the window | direction nibbles, (2*bw+1) per row,
+        // rows padded to whole bytes | ops, 2 bits each
+        int bw = abs(refLen - readLen) + 1, maxv = 0, width_d = 0, lineb = 0;
+        unsigned char* dir = nullptr;
+        unsigned char* ops = nullptr;
         bool fits = true;
         for (;;) {
             const int width = bw * 2 + 3;
             width_d = bw * 2 + 1;
+            lineb = (width_d + 1) >> 1;
             const int rowb = ((width + 2) * 2 + 3) & ~3;
-            o_dir = 3 * rowb;
-            o_ops = o_dir + ((width_d * readLen + 3) & ~3);
-            if ((long long)o_ops + ntmax + 4 > BYTES || (long long)width_d * readLen > BYTES) { fits = false; break; }
-            const int HB = 0, EB = rowb, HC = 2 * rowb;
-            for (int j = 0; j < width + 2; ++j) { st16(HB, j, 0); st16(EB, j, 0); st16(HC, j, 0); }
+            const int o_ref = 3 * rowb;
+            const int o_dir = o_ref + ((refLen + 3) & ~3);
+            const long long o_ops = o_dir + (((long long)lineb * readLen + 3) & ~3LL);
+            if (o_ops + ((ntmax + 4 + 3) >> 2) > BYTES) { fits = false; break; }
+            int16_t* h_b = reinterpret_cast<int16_t*>(reg);
+            int16_t* e_b = reinterpret_cast<int16_t*>(reg + rowb);
+            int16_t* h_c = reinterpret_cast<int16_t*>(reg + 2 * rowb);
+            unsigned char* refc = reg + o_ref;
+            dir = reg + o_dir; ops = reg + o_ops;
+            for (int j = 0; j < width + 2; ++j) { h_b[j] = 0; e_b[j] = 0; h_c[j] = 0; }
+            for (int j = 0; j < refLen; ++j) refc[j] = (unsigned char)td.img[gc[gidx(ws + rb + j)]];
             for (int ii = 0; ii < readLen; ++ii) {
                 const int beg = max(0, ii - bw), end = min(refLen - 1, ii + bw);
                 const int edge = min(end + 1, width - 1);
                 int f = 0, u = 0;
-                st16(HB, 0, 0); st16(EB, 0, 0); st16(HB, edge, 0); st16(EB, edge, 0); st16(HC, 0, 0);
-                const int line = o_dir + width_d * ii;
+                h_b[0] = 0; e_b[0] = 0; h_b[edge] = 0; e_b[edge] = 0; h_c[0] = 0;
+                unsigned char* line = dir + lineb * ii;
                 const int rc = a.rna_ssw[qb + ii];
+                unsigned acc = 0;
                 for (int j = beg; j <= end; ++j) {
                     u = band_u(bw, ii, j);
-                    const int e = band_u(bw, ii - 1, j), b = band_u(bw, ii, j - 1), dd = band_u(bw, ii - 1, j - 1);
-                    int t1 = (ii == 0) ? -kGapOpen : ld16(HB, e) - kGapOpen;
-                    int t2 = (ii == 0) ? -kGapExt : ld16(EB, e) - kGapExt;
+                    const int e = band_u(bw, ii - 1, j), dd = band_u(bw, ii - 1, j - 1);
+                    int t1 = (ii == 0) ? -kGapOpen : h_b[e] - kGapOpen;
+                    int t2 = (ii == 0) ? -kGapExt : e_b[e] - kGapExt;
                     const int ev = t1 > t2 ? t1 : t2;
-                    const int de = t1 > t2 ? 3 : 2;
-                    st16(EB, u, ev);
-                    t1 = ld16(HC, b) - kGapOpen;
+                    const unsigned e_open = t1 > t2;                      // direction code 3 (else 2)
+                    e_b[u] = (int16_t)ev;
+                    t1 = h_c[u - 1] - kGapOpen;
                     t2 = f - kGapExt;
                     f = t1 > t2 ? t1 : t2;
-                    const int df = t1 > t2 ? 5 : 4;
+                    const unsigned f_open = t1 > t2;                      // direction code 5 (else 4)
                     const int e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;
                     t1 = e1 > f1 ? e1 : f1;
-                    const int rf = td.img[gc[gidx(ws + rb + j)]];
-                    t2 = ld16(HB, dd) + ((rf == rc && rf < 4) ? kMatch : kMismatch);
+                    const int rf = refc[j];
+                    t2 = h_b[dd] + ((rf == rc && rf < 4) ? kMatch : kMismatch);
                     const int hv = t1 > t2 ? t1 : t2;
-                    st16(HC, u, hv);
+                    h_c[u] = (int16_t)hv;
                     if (hv > maxv) maxv = hv;
-                    const int dh = (t1 <= t2) ? 1 : (e1 > f1 ? de : df);
-                    *at(line + (j - beg)) = (unsigned char)((de & 1) | ((df & 1) << 1) | (dh << 2));
+                    const unsigned hsel = (t1 <= t2) ? 0u : (e1 > f1 ? 1u : 2u);      // H came from: diagonal / E / F
+                    const unsigned nib = e_open | (f_open << 1) | (hsel << 2);
+                    const int c = j - beg;
+                    if (c & 1) line[c >> 1] = (unsigned char)(acc | (nib << 4)); else acc = nib;
                 }
-                for (int j = 1; j <= u; ++j) st16(HB, j, ld16(HC, j));
+                if (end >= beg && !((end - beg) & 1)) line[(end - beg) >> 1] = (unsigned char)acc;
+                for (int j = 1; j <= u; ++j) h_b[j] = h_c[j];
             }
             if (maxv >= score) break;
             bw *= 2;
         }
         // traceback (sswNew.cpp:1159-1238): ops come out end -> start; written backwards into `ops`
         int wp = ntmax + 2;
+        auto put_op = [&](int k, unsigned op) { const unsigned sh = (k & 3) * 2; ops[k >> 2] = (unsigned char)((ops[k >> 2] & ~(3u << sh)) | (op << sh)); };
         if (fits) {
             int ii = readLen - 1, j = refLen - 1, plane = 2;
             while (ii > 0) {
                 const int c = j - max(0, ii - bw);
                 if (j < 0 || c < 0 || c >= width_d || wp <= 2) { fits = false; break; }     // off the band: the generic tier decides
-                const int byte = *at(o_dir + width_d * ii + c);
-                const int dv = plane == 0 ? 2 + (byte & 1) : (plane == 1 ? 4 + ((byte >> 1) & 1) : (byte >> 2));
+                const unsigned nib = (dir[lineb * ii + (c >> 1)] >> ((c & 1) * 4)) & 15u;
+                const unsigned hsel = nib >> 2;
+                const int dv = plane == 0 ? 2 + (int)(nib & 1) : (plane == 1 ? 4 + (int)((nib >> 1) & 1)
+                               : (hsel == 0 ? 1 : (hsel == 1 ? 2 + (int)(nib & 1) : 4 + (int)((nib >> 1) & 1))));
                 --wp;
-                if (dv == 1) { --ii; --j; plane = 2; *at(o_ops + wp) = 0; }
-                else if (dv == 2) { --ii; plane = 0; *at(o_ops + wp) = 1; }
-                else if (dv == 3) { --ii; plane = 2; *at(o_ops + wp) = 1; }
-                else if (dv == 4) { --j; plane = 1; *at(o_ops + wp) = 2; }
-                else { --j; plane = 2; *at(o_ops + wp) = 2; }
+                if (dv == 1) { --ii; --j; plane = 2; put_op(wp, 0); }
+                else if (dv == 2) { --ii; plane = 0; put_op(wp, 1); }
+                else if (dv == 3) { --ii; plane = 2; put_op(wp, 1); }
+                else if (dv == 4) { --j; plane = 1; put_op(wp, 2); }
+                else { --j; plane = 2; put_op(wp, 2); }
             }
         }
         if (!fits) { a.out[i].status = 2; a.out_list[atomicAdd(a.out_count, 1)] = i; continue; }
-        *at(o_ops + --wp) = 0;      // closing rule (:1220-1238): the alignment always starts with one more M column
+        put_op(--wp, 0);            // closing rule (:1220-1238): the alignment always starts with one more M column
         const int nt = ntmax + 2 - wp;
         // expansion from the front exactly like getAlignment (q walks the translated DNA from ref_begin, p the RNA), fused
         // with the identity count and the stability sum of convertMyTriplex (float32, same operation order)
@@ -769,7 +791,7 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         float tri = 0.0f, prev_val = 0.0f;
         char prev_ch = 0;
         for (int k = 0; k < nt; ++k) {
-            const int op = *at(o_ops + wp + k);
+            const int op = (ops[(wp + k) >> 2] >> (((wp + k) & 3) * 2)) & 3;
             char rch = '-', sch = '-', tch = '-';
             if (op != 2) rch = (char)a.rna_raw[p++];
             if (op != 1) {

@@ -44,7 +44,7 @@ class TaskProbe(C.Structure):
 
 
 EXPORTS = ["ltg_create", "ltg_destroy", "ltg_last_error", "ltg_default_params", "ltg_set_params", "ltg_set_query",
-           "ltg_scan_record", "ltg_scan_device", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
+           "ltg_scan_record", "ltg_scan_device", "ltg_scan_shard", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
            "ltg_write_tfosorted", "ltg_write_tfoclass", "ltg_main", "ltg_probe_segment", "ltg_probe_align", "ltg_stream", "ltg_debug_stats",
            "ltg_device_count"]
 
@@ -73,6 +73,8 @@ def lib():
         L.ltg_set_query.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int64]
         L.ltg_scan_record.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.POINTER(Result))]
         L.ltg_scan_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.POINTER(Result))]
+        L.ltg_scan_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                     C.POINTER(C.POINTER(Result))]
         L.ltg_result_free.argtypes = [C.POINTER(Result)]
         L.ltg_result_new.argtypes = [C.POINTER(C.POINTER(Result))]
         L.ltg_result_append.argtypes = [C.POINTER(Result), C.POINTER(Result)]
@@ -156,9 +158,9 @@ class Engine:
         _check(lib().ltg_set_query(self._h, name.encode(), b, len(b)))
 
     def debug_stats(self, reset=False):
-        out = (C.c_int64 * 20)()
+        out = (C.c_int64 * 24)()
         lib().ltg_debug_stats(self._h, out, 1 if reset else 0)
-        return {"windows": list(out[:10]), "cells": list(out[10:])}
+        return {"windows": list(out[:10]), "cells": list(out[10:20]), "traceback_handed_over": list(out[20:24])}
 
     @property
     def stream(self):
@@ -219,6 +221,19 @@ class Engine:
         _check(lib().ltg_scan_device(self._h, C.c_void_p(dev_ptr), length, chr_tag.encode(), record_start, C.byref(res)))
         return res
 
+    def scan_shard(self, dna, record_len, first_segment, n_segments, chr_tag="", record_start=0, device_ptr=None):
+        """Segments [first_segment, first_segment + n_segments) of a record of record_len bases; `dna` holds the bytes from
+        the first segment's start (or pass device_ptr + length as `dna`)."""
+        res = C.POINTER(Result)()
+        if device_ptr is not None:
+            _check(lib().ltg_scan_shard(self._h, C.c_void_p(device_ptr), 1, int(dna), chr_tag.encode(), record_start, record_len,
+                                        first_segment, n_segments, C.byref(res)))
+        else:
+            b = dna.encode() if isinstance(dna, str) else dna
+            _check(lib().ltg_scan_shard(self._h, C.cast(C.c_char_p(b), C.c_void_p), 0, len(b), chr_tag.encode(), record_start, record_len,
+                                        first_segment, n_segments, C.byref(res)))
+        return res
+
     def LongTarget(self, dna, chr_tag="", record_start=0):
         res = self.scan_record(dna, chr_tag, record_start)
         rows = result_rows(res)
@@ -234,6 +249,27 @@ class Engine:
     @staticmethod
     def free(res):
         lib().ltg_result_free(res)
+
+
+def shard_segments(n_bases, world, rank, cut=5000, overlap=100):
+    """Contiguous shard of a record's segments for `rank` of `world` (cutSequence geometry, fastsim.h:71-90):
+    -> (first_segment, n_segments, first_byte, n_bytes).  The byte range covers the shard's segments completely."""
+    stride = cut - overlap
+    n_seg = (n_bases + stride - 1) // stride if n_bases > 0 else 0
+    lo, hi = (n_seg * rank) // world, (n_seg * (rank + 1)) // world
+    if hi <= lo:
+        return lo, 0, min(lo * stride, n_bases), 0
+    first_byte = lo * stride
+    last_byte = min(n_bases, (hi - 1) * stride + cut)
+    return lo, hi - lo, first_byte, last_byte - first_byte
+
+
+def merge_shard_rows(parts):
+    """Concatenate per-rank row lists in rank (= segment) order: the order ltg_scan_record produces for the whole record."""
+    out = []
+    for rows in parts:
+        out.extend(rows)
+    return out
 
 
 def run_cli(args, cwd=None):

@@ -107,6 +107,14 @@ int ltg_scan_record(ltg_context* ctx, const char* dna, int64_t len, const char* 
 int ltg_scan_device(ltg_context* ctx, const void* d_dna, int64_t len, const char* chr, int64_t record_start,
                     ltg_result** out);
 
+/* One shard of a record for the one-process-per-GPU deployment: scans the segments
+ * [first_segment, first_segment + n_segments) of cutSequence's enumeration (fastsim.h:71-90) of a record of `record_len`
+ * bases.  `dna` points at the first byte of segment `first_segment` (host memory, or device memory when dna_on_device),
+ * `len` bytes are readable.  Coordinates in the result are those of the whole record, so appending the shards' results in
+ * shard order (ltg_result_append) reproduces ltg_scan_record of the whole record exactly.                              */
+int ltg_scan_shard(ltg_context* ctx, const void* dna, int dna_on_device, int64_t len, const char* chr, int64_t record_start,
+                   int64_t record_len, int64_t first_segment, int64_t n_segments, ltg_result** out);
+
 /* concatenates src into dst (dst may be empty); triplex order is preserved (main() :150-163)          */
 int ltg_result_append(ltg_result* dst, const ltg_result* src);
 int ltg_result_new(ltg_result** out);
@@ -146,10 +154,11 @@ int ltg_probe_segment(ltg_context* ctx, const char* seg, int32_t seg_len, ltg_ta
 int ltg_probe_align(ltg_context* ctx, const char* const* windows, const int32_t* window_len, int32_t n,
                     int32_t* out6, uint32_t* cigar, int32_t cigar_cap);
 
-/* window-stage work counters accumulated over the context's life: out20[2*round + retry] = windows planned in forward
- * round 0..3 (retry 1 = second, wider sweep after an inconclusive pruned one), out20[8] = reverse sweeps,
- * out20[10 + k] = the DP cells of the same entries.                                                          */
-void ltg_debug_stats(ltg_context* ctx, int64_t* out20, int reset);
+/* window-stage work counters accumulated over the context's life: out[2*round + retry] = windows planned in forward
+ * round 0..3 (retry 1 = second, wider sweep after an inconclusive pruned one), out[8] = reverse sweeps,
+ * out[10 + k] = the DP cells of the same entries, out[20..23] = alignments handed on by traceback tiers 1..4.
+ * `out` holds 24 entries.                                                                                       */
+void ltg_debug_stats(ltg_context* ctx, int64_t* out24, int reset);
 
 /* device-timing helpers for bench.py: opaque cudaStream_t of the context */
 void* ltg_stream(ltg_context* ctx);

@@ -271,6 +271,24 @@ def test_full_size_properties_1mbp(engine):
         assert rows_as_oracle_text(engine.LongTarget(seg)) == oracle_text_rows(O.longtarget(rna, seg))
 
 
+def test_shards_reproduce_the_whole_record(engine):
+    """Multi-GPU path on one GPU: scanning a record as 3 shards through ltg_scan_shard (what each rank of bench.py --gpus N
+    does) and concatenating the results in shard order gives exactly the rows of the unsharded scan."""
+    n = 160_000
+    dna = splitmix_bases(1001, n)
+    rna = splitmix_bases(2001, 1200)
+    engine.set_params(c_length=25)
+    engine.set_query("synRNA", rna)
+    whole = engine.LongTarget(dna, "chr1", 7)
+    world, parts = 3, []
+    for r in range(world):
+        first, count, first_byte, n_bytes = fb.shard_segments(n, world, r)
+        res = engine.scan_shard(dna[first_byte:first_byte + n_bytes], n, first, count, "chr1", 7)
+        parts.append(fb.result_rows(res))
+        engine.free(res)
+    assert fb.merge_shard_rows(parts) == whole and len(whole) > 0
+
+
 def test_row_pruning_is_exact(data_dir):
     """The window stage skips RNA rows that provably cannot hold a window's best cell (window.cuh).  With LTG_NO_PRUNE=1
     every window sweeps the whole lncRNA like the reference does: both modes must give identical rows, on random DNA
