@@ -183,8 +183,8 @@ def int_simd_peak():
     p = os.path.join(ROOT, "profiles", "int_simd_peak.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return j["peak_gcups"], j.get("source", "profiles/int_simd_peak.json")
-    return 8170.0, "fallback: 77.46 thread-instr/clk/SM measured in round 1 -> 8.17 TCUPS at 1.958 GHz"
+        return j["peak_gcups"], j.get("source", "profiles/int_simd_peak.json"), j.get("scan_dram_bytes_per_segment")
+    return 8170.0, "fallback: 77.46 thread-instr/clk/SM measured in round 1 -> 8.17 TCUPS at 1.958 GHz", None
 
 
 def bench_gpu(args, rank, world, local_rank):
@@ -212,7 +212,7 @@ def bench_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def run(device_resident, steps):
-        stats = dict(cells=0, bases=0, rows=0, launches=0, scan_ms=0.0, scan_launches=0, win_ms=0.0, win_cells=0, peaks=0, d2h=0, h2d=0,
+        stats = dict(cells=0, bases=0, rows=0, segs=0, launches=0, scan_ms=0.0, scan_launches=0, win_ms=0.0, win_cells=0, peaks=0, d2h=0, h2d=0,
                      lit_tasks=0, lit_windows=0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -227,7 +227,7 @@ def bench_gpu(args, rank, world, local_rank):
                 raise RuntimeError(fb.lib().ltg_last_error().decode())
             r = res.contents
             stats["cells"] += r.scan_cells; stats["bases"] += min(region, (first_seg + nseg) * (CUT - OVERLAP)) - first_seg * (CUT - OVERLAP)
-            stats["rows"] += r.n_triplex
+            stats["rows"] += r.n_triplex; stats["segs"] += r.n_segments
             stats["launches"] += r.gpu_launches; stats["scan_ms"] += r.gpu_ms_scan_kernel; stats["scan_launches"] += r.n_scan_launches
             stats["win_ms"] += r.gpu_ms_window; stats["win_cells"] += r.window_cells; stats["peaks"] += r.n_peaks
             stats["lit_tasks"] += r.n_literal_tasks; stats["lit_windows"] += r.n_literal_windows
@@ -264,7 +264,7 @@ def bench_gpu(args, rank, world, local_rank):
     if rank == 0:
         gcups = st["cells"] / (ms * 1e-3) / 1e9
         gcups_e = st_e["cells"] / (ms_e * 1e-3) / 1e9
-        peak, peak_src = int_simd_peak()
+        peak, peak_src, dram_per_seg = int_simd_peak()
         # roofline of the dominant kernel: algorithmic cells of one k_scan launch / its CUDA-event duration.  With N ranks
         # each rank runs its own launches concurrently: per-GPU achieved = cells / N / (max-over-ranks scan time).
         scan_gcups = st["cells"] / world / (st["scan_ms"] * 1e-3) / 1e9 if st["scan_ms"] > 0 else 0.0
@@ -289,7 +289,11 @@ def bench_gpu(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(st_e["d2h"] / args.steps), "ms_per_step": ms_e / args.steps,
                     "mbp_per_s": st_e["bases"] / (ms_e * 1e-3) / 1e6},
             "roofline": {"bound": "int_simd", "kernel": "k_scan<16,4>", "achieved": scan_gcups, "peak": peak, "unit": "GCUPS",
-                         "frac": scan_gcups / peak if peak else None, "peak_source": peak_src, "traffic": None,
+                         "frac": scan_gcups / peak if peak else None, "peak_source": peak_src,
+                         "cells_per_launch": st["cells"] / max(st["scan_launches"], 1),
+                         "ms_per_launch": st["scan_ms"] / max(st["scan_launches"] / world, 1),
+                         "traffic": (dram_per_seg * st["segs"] / max(st["scan_launches"], 1)) if dram_per_seg else None,
+                         "traffic_unit": "DRAM bytes per k_scan launch (ncu dram__bytes_read+write of one launch, scaled by segments per launch)",
                          "note": "integer-ALU bound (SURVEY.md 8d): HBM traffic is ~1 B per %d cells; hbm_gbs_algorithmic=%.3f"
                                  % (RNA_NT * TASKS_PER_SEG, dna_bytes / max(st["scan_ms"], 1e-9) / 1e6)},
             "clocks": clocks,

@@ -9,6 +9,7 @@
 //                 de-duplication / ranking / filters of fastSIM's tail (fastsim.h:273-288)
 // -> record filter -> traceback pass 2 (strings of the surviving rows only) -> result.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -727,6 +728,10 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
     if (!c || !out) { set_error("null argument"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
     const int64_t launches0 = c->launches, h2d0 = c->h2d_bytes, d2h0 = c->d2h_bytes;
+    const bool trace_time = getenv("LTG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_prep = 0, t_loop = 0, t_retire = 0, t_filter = 0, t_strings = 0;
     std::vector<HostSeg> segs;
     if (record_len < 0) record_len = len;
     if (first_seg < 0 || len < 0) { set_error("bad shard geometry"); return LTG_ERR_ARG; }
@@ -764,6 +769,7 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
         std::vector<ltg_host::Triplex> record_list;
         int rc = LTG_OK;
         size_t nb = 0;
+        t_prep = now();
         for (size_t b0 = 0; b0 < active.size() && rc == LTG_OK; b0 += bs, ++nb) {
             HostBatch& hb = c->hb[nb & 1];
             if ((rc = retire_batch(c, hb, st, record_list)) != LTG_OK) break;       // batch nb-2: slot free again
@@ -777,6 +783,7 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
                 host_phase(ctx, *slot, ctx->host_threads);
             });
         }
+        t_loop = now();
         // retire in batch order: the older slot first
         for (size_t k = 0; k < 2; ++k) {
             HostBatch& hb = c->hb[(nb + k) & 1];
@@ -784,12 +791,15 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
             if (rc == LTG_OK) rc = e;
         }
         if (rc != LTG_OK) { cudaStreamSynchronize(c->stream); return rc; }
+        t_retire = now();
         std::vector<ltg_host::Triplex> keep;
         for (const ltg_host::Triplex& t : record_list)
             if (ltg_host::passes_record_filter(t, c->params)) keep.push_back(t);
         std::vector<char> pool;
         std::vector<int64_t> offs;
+        t_filter = now();
         if (int e = fetch_strings(c, keep, pool, offs)) return e;
+        t_strings = now();
         for (size_t i = 0; i < keep.size(); ++i)
             rb.add(keep[i], pool.data() + offs[i], pool.data() + offs[i] + keep[i].nt + 1, chr, record_start, coord_offset, 0);
     }
@@ -800,6 +810,9 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
     r->gpu_launches = c->launches - launches0;
     r->gpu_ms_scan_kernel = st.ms_scan_kernel; r->n_scan_launches = st.n_scan_launches;
     r->h2d_bytes = c->h2d_bytes - h2d0; r->d2h_bytes = c->d2h_bytes - d2h0;
+    if (trace_time && len > 0)
+        fprintf(stderr, "[ltg timing] prep %.1f ms, batches %.1f, last retire %.1f, record filter %.1f, strings %.1f, result %.1f (total %.1f)\n",
+                t_prep - t_begin, t_loop - t_prep, t_retire - t_loop, t_filter - t_retire, t_strings - t_filter, now() - t_strings, now() - t_begin);
     *out = r;
     return LTG_OK;
 }
