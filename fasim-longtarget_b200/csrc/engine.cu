@@ -93,7 +93,11 @@ struct HostSeg { int64_t start; int32_t len; int32_t flags; };
 struct HostBatch {
     std::vector<HostSeg> segs;
     int n_tasks = 0, n_peaks = 0;
-    PinBuf task_off, jobs, tout, task_info, scalars;
+    PinBuf task_off, jobs, tout, task_info, scalars, c_task, c_poff;
+    bool keep_only_literal = false;                 // kLitOnly batches: the host phase keeps the literal tasks' rows only
+    DevBuf d_cjobs, d_ctout, d_ctask, d_cpoff;      // compacted records of this batch (kept until the slot is retired)
+    int n_ctasks = 0, n_cpeaks = 0;
+    int64_t d2h_late = 0;                           // bytes the worker copied
     cudaEvent_t ready = nullptr, ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timed = false, timed_windows = false, has_stats_pass = false;
     int n_literal_tasks = 0;
@@ -111,7 +115,7 @@ struct ltg_context {
     int num_sms = 0;
     int host_threads = 1;
     bool prune = true;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     ltg_params params;
     // task tables (depend on params.rule / params.strand)
     std::vector<TaskDef> tasks;
@@ -125,7 +129,7 @@ struct ltg_context {
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_colmax, d_bnd, d_counters;
-    DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow;
+    DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
     DevBuf d_w[18], d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
     DevBuf d_jobs, d_tout, d_strpool, d_scratch, d_scratch_big;
@@ -143,7 +147,7 @@ struct TaskInfo {
     TaskInfo(int* base, int n) : max(base), thr(base + n), npk(base + 2 * (size_t)n), flags(base + 3 * (size_t)n), jstar(base + 4 * (size_t)n) {}
 };
 
-enum { kCntScan = 0, kCntPeaks = 1, kCntOvf = 2 /* .. 5 */, kCntCells = 16, kCntLit = 24, kCntLitTotal = 26, kCntTotal = 32 };
+enum { kCntScan = 0, kCntPeaks = 1, kCntOvf = 2 /* .. 5 */, kCntCand = 6 /* peaks, tasks, unfinished */, kCntCells = 16, kCntLit = 24, kCntLitTotal = 26, kCntTotal = 32 };
 
 int upload_tables(ltg_context* c)
 {
@@ -394,7 +398,16 @@ int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* 
 
 // Device phase of one batch of segments: scan -> peaks -> windows -> traceback pass 1 -> async D2H into `hb`.
 // The host only synchronises where it needs a count (literal tasks, number of peaks).
-int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch& hb, bool want_alignments, ProbeOut* probe)
+// How a batch treats the tasks that need the literal (Q4) re-run, which is slow per task (one half-warp sweeps the whole
+// matrix) but embarrassingly parallel across tasks:
+//   kLitInline  re-run them inside the batch (function-level probes)
+//   kLitDefer   leave them out (no peaks) and report them in `deferred`; the record collects them ...
+//   kLitOnly    ... and runs them together in batches of this kind: only the pairs that carry a task of `only_tasks`
+//               are scanned, and the host phase keeps the rows of exactly those tasks
+enum LitMode { kLitInline, kLitDefer, kLitOnly };
+
+int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch& hb, bool want_alignments, ProbeOut* probe,
+                     LitMode lit_mode = kLitInline, std::vector<int>* deferred = nullptr, const std::vector<int>* only_tasks = nullptr)
 {
     const int T = (int)c->tasks.size(), P = (int)c->pairs.size();
     const int S = (int)segs.size();
@@ -402,9 +415,21 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     bool any_stats = !c->rna_plain;
     for (const HostSeg& s : segs) { max_len = std::max(max_len, s.len); if (s.flags & kSegNonACGT) any_stats = true; }
     max_len = (max_len + 3) & ~3;
-    const int n_items = S * P, n_tasks = S * T;
+    // scan items: every pair of every segment, or (kLitOnly) just the pairs that carry a requested task
+    std::vector<ScanItem> items;
+    if (lit_mode == kLitOnly) {
+        std::vector<char> want((size_t)S * P, 0);
+        for (int t : *only_tasks) want[(size_t)(t / T) * P + c->tasks[t % T].pair] = 1;
+        for (int s = 0; s < S; ++s) for (int p = 0; p < P; ++p) if (want[(size_t)s * P + p]) { ScanItem it; it.seg = s; it.pair = p; items.push_back(it); }
+    } else {
+        items.resize((size_t)S * P);
+        for (int s = 0; s < S; ++s) for (int p = 0; p < P; ++p) { items[(size_t)s * P + p].seg = s; items[(size_t)s * P + p].pair = p; }
+    }
+    const int n_items = (int)items.size(), n_tasks = S * T;
     hb.segs = segs; hb.n_tasks = n_tasks; hb.n_peaks = 0; hb.rows.clear(); hb.error.clear();
+    hb.keep_only_literal = (lit_mode == kLitOnly);
     hb.timed = true; hb.timed_windows = false; hb.has_stats_pass = any_stats; hb.n_literal_tasks = 0;
+    hb.n_ctasks = 0; hb.n_cpeaks = 0; hb.d2h_late = 0;
 
     if (int e = c->d_segs.ensure(sizeof(SegDesc) * S)) return e;
     if (int e = c->d_items.ensure(sizeof(ScanItem) * n_items)) return e;
@@ -417,16 +442,14 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     if (int e = c->d_task_litrow.ensure(sizeof(int) * (size_t)n_tasks)) return e;
     if (int e = hb.task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
     if (int e = hb.task_off.ensure(sizeof(int) * ((size_t)n_tasks + 1))) return e;
-    if (int e = hb.scalars.ensure(256)) return e;
+    if (int e = hb.scalars.ensure(320)) return e;
     TaskInfo ti(c->d_task_info.as<int>(), n_tasks), hti(hb.task_info.as<int>(), n_tasks);
     int* counters = c->d_counters.as<int>();
 
     std::vector<SegDesc> hs(S);
-    std::vector<ScanItem> items(n_items);
-    for (int s = 0; s < S; ++s) {
-        hs[s].start = segs[s].start; hs[s].len = segs[s].len; hs[s].flags = segs[s].flags;
-        for (int p = 0; p < P; ++p) { items[(size_t)s * P + p].seg = s; items[(size_t)s * P + p].pair = p; }
-    }
+    for (int s = 0; s < S; ++s) { hs[s].start = segs[s].start; hs[s].len = segs[s].len; hs[s].flags = segs[s].flags; }
+    // tasks without an item in this batch (kLitOnly) must read as "no peaks, no flags"
+    if (lit_mode == kLitOnly) LTG_CUDA_CHECK(cudaMemsetAsync(c->d_task_info.p, 0, sizeof(int) * 5 * (size_t)n_tasks, c->stream));
     // (pageable sources: these copies return once the data is staged, so the vectors may die at scope exit)
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_segs.p, hs.data(), sizeof(SegDesc) * S, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_items.p, items.data(), sizeof(ScanItem) * n_items, cudaMemcpyHostToDevice, c->stream));
@@ -466,6 +489,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     for (int t = 0; t < n_tasks; ++t) {
         if (hti.flags[t] & kTaskRange) { set_error("alignment score exceeds the 16-bit range (segment too long for this build)"); return LTG_ERR_LIMIT; }
         if (hti.flags[t] & kTaskLiteral) {
+            if (lit_mode == kLitDefer) { deferred->push_back(t); continue; }
             LiteralJob j; memset(&j, 0, sizeof j);
             j.kind = 0; j.task = t; j.seg = t / T; j.tdef = t % T; j.ref_start = 0; j.ref_len = segs[t / T].len;
             j.read_start = 0; j.read_len = c->m; j.read_dir = 1; j.ref_dir = 0; j.terminate = 255; j.peak = -1;
@@ -525,58 +549,83 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     }
     if (want_alignments && n_peaks > 0) {
         LTG_CUDA_CHECK(cudaEventRecord(hb.ev[2], c->stream));
-        if (int e = run_windows(c, n_peaks, T, nullptr, c->d_colmax.as<uint32_t>(), max_len, &hb)) return e;
+        if (int e = run_windows(c, n_peaks, T, nullptr, lit_mode == kLitOnly ? nullptr : c->d_colmax.as<uint32_t>(), max_len, &hb)) return e;
         if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), n_peaks, c->d_tout.as<TraceOut>(), nullptr)) return e;
         LTG_CUDA_CHECK(cudaEventRecord(hb.ev[3], c->stream));
         hb.timed_windows = true;
+        // ship only the tasks that own a candidate row (k_task_flag): flags -> two exclusive scans -> compaction into this
+        // slot's device buffers; the worker thread copies the (few) records on the copy stream once the counts are known
         if (int e = hb.jobs.ensure(sizeof(TraceJob) * (size_t)n_peaks)) return e;
         if (int e = hb.tout.ensure(sizeof(TraceOut) * (size_t)n_peaks)) return e;
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.jobs.p, c->d_jobs.p, sizeof(TraceJob) * (size_t)n_peaks, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.tout.p, c->d_tout.p, sizeof(TraceOut) * (size_t)n_peaks, cudaMemcpyDeviceToHost, c->stream));
+        if (int e = hb.c_task.ensure(sizeof(int) * (size_t)n_tasks)) return e;
+        if (int e = hb.c_poff.ensure(sizeof(int) * (size_t)n_tasks)) return e;
+        if (int e = hb.d_cjobs.ensure(sizeof(TraceJob) * (size_t)n_peaks)) return e;
+        if (int e = hb.d_ctout.ensure(sizeof(TraceOut) * (size_t)n_peaks)) return e;
+        if (int e = hb.d_ctask.ensure(sizeof(int) * (size_t)n_tasks)) return e;
+        if (int e = hb.d_cpoff.ensure(sizeof(int) * (size_t)n_tasks)) return e;
+        if (int e = c->d_cand.ensure(sizeof(int) * 4 * (size_t)n_tasks)) return e;
+        CompactArgs ca;
+        ca.jobs = c->d_jobs.as<TraceJob>(); ca.tout = c->d_tout.as<TraceOut>(); ca.task_off = c->d_task_off.as<int>();
+        ca.n_tasks = n_tasks; ca.n_peaks = n_peaks;
+        ca.need_nt = std::max(c->params.nt_min, c->params.c_length);
+        ca.min_id = (float)c->params.min_identity; ca.min_st = (float)c->params.min_stability;
+        int* cand = c->d_cand.as<int>();
+        ca.cand_cnt = cand; ca.cand_flag = cand + n_tasks; ca.cand_poff = cand + 2 * (size_t)n_tasks; ca.cand_toff = cand + 3 * (size_t)n_tasks;
+        ca.c_jobs = hb.d_cjobs.as<TraceJob>(); ca.c_tout = hb.d_ctout.as<TraceOut>(); ca.c_task = hb.d_ctask.as<int>(); ca.c_poff = hb.d_cpoff.as<int>();
+        ca.n_unfinished = counters + kCntCand + 2;
+        LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCand, 0, 3 * sizeof(int), c->stream));
+        const int task_blocks = (n_tasks * 32 + 255) / 256;
+        k_task_flag<<<task_blocks, 256, 0, c->stream>>>(ca);
+        k_exclusive_scan<<<1, 1024, 0, c->stream>>>(ca.cand_cnt, cand + 2 * (size_t)n_tasks, n_tasks, counters + kCntCand);
+        k_exclusive_scan<<<1, 1024, 0, c->stream>>>(ca.cand_flag, cand + 3 * (size_t)n_tasks, n_tasks, counters + kCntCand + 1);
+        k_task_compact<<<task_blocks, 256, 0, c->stream>>>(ca);
+        c->launches += 4;
+        LTG_CUDA_CHECK(cudaGetLastError());
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.c_task.p, hb.d_ctask.p, sizeof(int) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.c_poff.p, hb.d_cpoff.p, sizeof(int) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.p, counters + kCntCells, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 64, &c->d_win_sched.as<WinSched>()->st_windows[0], 20 * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 232, counters + kCntOvf, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        c->d2h_bytes += (int64_t)(sizeof(TraceJob) + sizeof(TraceOut)) * n_peaks + 64;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 248, counters + kCntCand, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        c->d2h_bytes += (int64_t)sizeof(int) * 2 * n_tasks + 272;
     } else {
         hb.n_peaks = want_alignments ? n_peaks : 0;
-        memset(hb.scalars.p, 0, 256);
+        memset(hb.scalars.p, 0, 320);
     }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ready, c->stream));
     return LTG_OK;
 }
 
-// Host phase of one batch (fastSIM's tail, fastsim.h:253-288, per task in the reference's task order): runs on
-// `threads` worker threads over contiguous task ranges; the per-thread outputs are concatenated in order.
+// Host phase of one batch (fastSIM's tail, fastsim.h:253-288, per task in the reference's task order) over the tasks the
+// device shipped (those owning at least one candidate row): runs on `threads` worker threads over contiguous ranges of
+// shipped tasks; the per-thread outputs are concatenated in order.
 void host_phase(const ltg_context* c, HostBatch& hb, int threads)
 {
     const int T = (int)c->tasks.size();
-    const int n_tasks = hb.n_tasks, n_peaks = hb.n_peaks;
+    const int n_ct = hb.n_ctasks, n_cp = hb.n_cpeaks;
     hb.rows.clear();
-    if (n_peaks == 0) return;
-    const int* off = hb.task_off.as<int>();
+    if (n_ct == 0) return;
+    const int* ctask = hb.c_task.as<int>();
+    const int* cpoff = hb.c_poff.as<int>();
     const TraceJob* jobs = hb.jobs.as<TraceJob>();
     const TraceOut* tout = hb.tout.as<TraceOut>();
-    threads = std::max(1, std::min(threads, n_tasks / 256 + 1));
+    const int* task_flags = TaskInfo(hb.task_info.as<int>(), hb.n_tasks).flags;
+    threads = std::max(1, std::min(threads, n_ct / 64 + 1));
     std::vector<std::vector<ltg_host::Triplex>> part(threads);
-    std::vector<std::string> errs(threads);
     auto work = [&](int k) {
-        // balance by peak count: thread k takes the tasks whose first peak falls into its slice of the peak pool
-        const long long p0 = (long long)n_peaks * k / threads, p1 = (long long)n_peaks * (k + 1) / threads;
-        int t0 = (int)(std::lower_bound(off, off + n_tasks, (int)p0) - off);
-        int t1 = (k + 1 == threads) ? n_tasks : (int)(std::lower_bound(off, off + n_tasks, (int)p1) - off);
-        if (k == 0) t0 = 0;
+        const int i0 = (int)((long long)n_ct * k / threads), i1 = (int)((long long)n_ct * (k + 1) / threads);
         std::vector<ltg_host::Triplex> mine;
-        for (int task = t0; task < t1; ++task) {
-            const int b = off[task], e = (task + 1 < n_tasks) ? off[task + 1] : n_peaks;
-            if (b == e) continue;
+        for (int idx = i0; idx < i1; ++idx) {
+            const int task = ctask[idx];
+            if (hb.keep_only_literal && !(task_flags[task] & kTaskLiteral)) continue;
+            const int b = cpoff[idx], e = (idx + 1 < n_ct) ? cpoff[idx + 1] : n_cp;
             mine.clear();
             const HostSeg& sg = hb.segs[task / T];
             const TaskDef& td = c->tasks[task % T];
             for (int i = b; i < e; ++i) {                       // peaks of a task come in ascending column order
                 const TraceJob& J = jobs[i];
                 if (J.score <= 0) continue;                     // fastsim.h:253 (sw_score == 0 -> skipped)
-                if (tout[i].status == 2) { errs[k] = "traceback band exceeds the device scratch"; continue; }
                 if (tout[i].status != 1) continue;              // banded_sw failed -> sw_score 0 (ssw_cpp.cpp:627-633)
                 ltg_host::DeviceAlignment al;
                 al.sw_score = J.score; al.ws = J.ws; al.rb = J.rb; al.re = J.re; al.query_begin = J.qb; al.query_end = J.qe;
@@ -596,10 +645,27 @@ void host_phase(const ltg_context* c, HostBatch& hb, int threads)
     size_t total = 0;
     for (auto& v : part) total += v.size();
     hb.rows.reserve(total);
-    for (int k = 0; k < threads; ++k) {
-        hb.rows.insert(hb.rows.end(), part[k].begin(), part[k].end());
-        if (!errs[k].empty()) hb.error = errs[k];
+    for (int k = 0; k < threads; ++k) hb.rows.insert(hb.rows.end(), part[k].begin(), part[k].end());
+}
+
+// Worker of a batch slot: waits for the device phase, fetches the shipped records on the copy stream (concurrent with
+// the next batch's kernels), runs the host phase.
+void batch_worker(ltg_context* c, HostBatch* hb)
+{
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(hb->ready) != cudaSuccess) { hb->error = "device phase failed"; return; }
+    if (hb->n_peaks == 0) return;
+    const int* cand = reinterpret_cast<const int*>(hb->scalars.as<char>() + 248);
+    hb->n_cpeaks = cand[0]; hb->n_ctasks = cand[1];
+    if (cand[2] > 0) { hb->error = "traceback band exceeds the device scratch"; return; }
+    if (hb->n_cpeaks > 0) {
+        cudaError_t e1 = cudaMemcpyAsync(hb->jobs.p, hb->d_cjobs.p, sizeof(TraceJob) * (size_t)hb->n_cpeaks, cudaMemcpyDeviceToHost, c->copy_stream);
+        cudaError_t e2 = cudaMemcpyAsync(hb->tout.p, hb->d_ctout.p, sizeof(TraceOut) * (size_t)hb->n_cpeaks, cudaMemcpyDeviceToHost, c->copy_stream);
+        cudaError_t e3 = cudaStreamSynchronize(c->copy_stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { hb->error = "copy of the batch records failed"; return; }
+        hb->d2h_late = (int64_t)(sizeof(TraceJob) + sizeof(TraceOut)) * hb->n_cpeaks;
     }
+    host_phase(c, *hb, c->host_threads);
 }
 
 // cutSequence — fastsim.h:71-90.  A shard is the run of segments [first_seg, first_seg + n_seg) of a record of `record_len`
@@ -701,15 +767,24 @@ int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg
     if (!hb.error.empty()) { set_error("%s", hb.error.c_str()); return LTG_ERR_LIMIT; }
     float ms = 0;
     LTG_CUDA_CHECK(cudaEventSynchronize(hb.ready));
-    LTG_CUDA_CHECK(cudaEventElapsedTime(&ms, hb.ev[0], hb.ev[1])); st.ms_scan += ms;
-    LTG_CUDA_CHECK(cudaEventElapsedTime(&ms, hb.ev[4], hb.ev[5])); st.ms_scan_kernel += ms;
-    if (hb.timed_windows) { LTG_CUDA_CHECK(cudaEventElapsedTime(&ms, hb.ev[2], hb.ev[3])); st.ms_window += ms; }
+    float ms01 = 0, ms45 = 0, ms23 = 0, ms12 = 0;
+    LTG_CUDA_CHECK(cudaEventElapsedTime(&ms01, hb.ev[0], hb.ev[1])); st.ms_scan += ms01;
+    LTG_CUDA_CHECK(cudaEventElapsedTime(&ms45, hb.ev[4], hb.ev[5])); st.ms_scan_kernel += ms45;
+    if (hb.timed_windows) {
+        LTG_CUDA_CHECK(cudaEventElapsedTime(&ms23, hb.ev[2], hb.ev[3])); st.ms_window += ms23;
+        LTG_CUDA_CHECK(cudaEventElapsedTime(&ms12, hb.ev[1], hb.ev[2]));
+    }
+    if (getenv("LTG_TIMING"))
+        fprintf(stderr, "[ltg batch] %zu segs, %d peaks: scan+peaks %.1f ms (k_scan %.1f), gap %.1f, windows+traceback %.1f, shipped %d tasks / %d records\n",
+                hb.segs.size(), hb.n_peaks, ms01, ms45, ms12, ms23, hb.n_ctasks, hb.n_cpeaks);
+    (void)ms;
     st.n_scan_launches += 1;
     const int T = (int)c->tasks.size();
     st.n_segments += (int64_t)hb.segs.size();
     st.n_tasks += (int64_t)hb.segs.size() * T;
     for (const HostSeg& sg : hb.segs) st.scan_cells += (int64_t)sg.len * c->m * T;
     st.n_peaks += hb.n_peaks;
+    c->d2h_bytes += hb.d2h_late;
     st.n_literal_tasks += hb.n_literal_tasks;
     const int* sc = hb.scalars.as<int>();
     long long cells = 0; memcpy(&cells, sc, 8);
@@ -769,19 +844,19 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
         std::vector<ltg_host::Triplex> record_list;
         int rc = LTG_OK;
         size_t nb = 0;
+        const int T = (int)c->tasks.size();
         t_prep = now();
+        struct Deferred { HostSeg seg; int tdef; };
+        std::vector<Deferred> deferred;                 // literal (Q4-guard) tasks of the record, in task order
+        std::vector<int> batch_deferred;
         for (size_t b0 = 0; b0 < active.size() && rc == LTG_OK; b0 += bs, ++nb) {
             HostBatch& hb = c->hb[nb & 1];
             if ((rc = retire_batch(c, hb, st, record_list)) != LTG_OK) break;       // batch nb-2: slot free again
             std::vector<HostSeg> batch(active.begin() + b0, active.begin() + std::min(active.size(), b0 + bs));
-            if ((rc = run_batch_device(c, batch, hb, true, nullptr)) != LTG_OK) { hb.timed = false; break; }
-            ltg_context* ctx = c;
-            HostBatch* slot = &hb;
-            hb.worker = std::thread([ctx, slot]() {
-                cudaSetDevice(ctx->device);
-                if (cudaEventSynchronize(slot->ready) != cudaSuccess) { slot->error = "device phase failed"; return; }
-                host_phase(ctx, *slot, ctx->host_threads);
-            });
+            batch_deferred.clear();
+            if ((rc = run_batch_device(c, batch, hb, true, nullptr, kLitDefer, &batch_deferred)) != LTG_OK) { hb.timed = false; break; }
+            for (int t : batch_deferred) { Deferred d; d.seg = batch[t / T]; d.tdef = t % T; deferred.push_back(d); }
+            hb.worker = std::thread(batch_worker, c, &hb);
         }
         t_loop = now();
         // retire in batch order: the older slot first
@@ -789,6 +864,40 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
             HostBatch& hb = c->hb[(nb + k) & 1];
             const int e = retire_batch(c, hb, st, record_list);
             if (rc == LTG_OK) rc = e;
+        }
+        // the deferred literal tasks, all together (they run concurrently on the device); their rows are merged back into
+        // the record's (segment, task) order
+        if (rc == LTG_OK && !deferred.empty()) {
+            std::vector<ltg_host::Triplex> lit_rows;
+            RecordStats lit_st;
+            for (size_t d0 = 0; d0 < deferred.size() && rc == LTG_OK;) {
+                std::vector<HostSeg> lsegs;
+                std::vector<int> ltasks;
+                size_t d1 = d0;
+                for (; d1 < deferred.size(); ++d1) {
+                    if (lsegs.empty() || lsegs.back().start != deferred[d1].seg.start) {
+                        if (lsegs.size() >= bs) break;
+                        lsegs.push_back(deferred[d1].seg);
+                    }
+                    ltasks.push_back((int)(lsegs.size() - 1) * T + deferred[d1].tdef);
+                }
+                HostBatch& hb = c->hb[0];
+                if ((rc = run_batch_device(c, lsegs, hb, true, nullptr, kLitOnly, nullptr, &ltasks)) != LTG_OK) { hb.timed = false; break; }
+                hb.worker = std::thread(batch_worker, c, &hb);
+                rc = retire_batch(c, hb, lit_st, lit_rows);
+                d0 = d1;
+            }
+            st.n_literal_tasks += (int64_t)deferred.size();
+            st.n_peaks += lit_st.n_peaks; st.window_cells += lit_st.window_cells; st.n_literal_windows += lit_st.n_literal_windows;
+            st.ms_scan += lit_st.ms_scan; st.ms_window += lit_st.ms_window;
+            if (rc == LTG_OK && !lit_rows.empty()) {
+                auto key_less = [](const ltg_host::Triplex& x, const ltg_host::Triplex& y) {
+                    return x.seg_start != y.seg_start ? x.seg_start < y.seg_start : x.tdef < y.tdef;
+                };
+                std::vector<ltg_host::Triplex> merged(record_list.size() + lit_rows.size());
+                std::merge(record_list.begin(), record_list.end(), lit_rows.begin(), lit_rows.end(), merged.begin(), key_less);
+                record_list.swap(merged);
+            }
         }
         if (rc != LTG_OK) { cudaStreamSynchronize(c->stream); return rc; }
         t_retire = now();
@@ -854,6 +963,7 @@ int ltg_create(int device, ltg_context** out)
     c->num_sms = prop.multiProcessorCount;
     ltg_default_params(&c->params);
     LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (HostBatch& hb : c->hb) {
         LTG_CUDA_CHECK(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
         for (int i = 0; i < 6; ++i) LTG_CUDA_CHECK(cudaEventCreate(&hb.ev[i]));
@@ -877,18 +987,20 @@ void ltg_destroy(ltg_context* c)
     cudaStreamSynchronize(c->stream);
     for (HostBatch& hb : c->hb) {
         if (hb.worker.joinable()) hb.worker.join();
-        for (PinBuf* b : {&hb.task_off, &hb.jobs, &hb.tout, &hb.task_info, &hb.scalars}) b->release();
+        for (PinBuf* b : {&hb.task_off, &hb.jobs, &hb.tout, &hb.task_info, &hb.scalars, &hb.c_task, &hb.c_poff}) b->release();
+        for (DevBuf* b : {&hb.d_cjobs, &hb.d_ctout, &hb.d_ctask, &hb.d_cpoff}) b->release();
         if (hb.ready) cudaEventDestroy(hb.ready);
         for (int i = 0; i < 6; ++i) if (hb.ev[i]) cudaEventDestroy(hb.ev[i]);
     }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
                       &c->d_segs, &c->d_items, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
-                      &c->d_stats_max, &c->d_task_litrow, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
+                      &c->d_stats_max, &c->d_task_litrow, &c->d_cand, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs})
         b->release();
     for (int k = 0; k < 18; ++k) c->d_w[k].release();
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 

@@ -364,6 +364,7 @@ __global__ void k_epilogue(const EpiArgs a)
             if (a.mode == 1 && !is_lit) continue;
             thr = a.task_thr[task];
             jstar = a.task_jstar[task];
+            if (is_lit && a.lit_colmax == nullptr) continue;      // deferred to a literal-only batch: no peaks here
             if (is_lit) lit = a.lit_colmax + (size_t)a.task_litrow[task] * a.max_len;
         }
         const bool write = (a.mode == 2);

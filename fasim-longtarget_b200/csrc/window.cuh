@@ -33,7 +33,10 @@
 
 namespace ltg {
 
-constexpr int kWinR = 8;            // window columns per lane
+#ifndef LTG_WIN_R
+#define LTG_WIN_R 10
+#endif
+constexpr int kWinR = LTG_WIN_R;    // window columns per lane (10: the dominant 67..80-column windows fill 28..32 lanes; 8..12 measured within 1 %)
 constexpr int kMaxWindow = 32 * kWinR;
 constexpr int kWinRowBuckets = 64;  // stream-length buckets of 64 rows (the last one takes everything longer)
 constexpr int kWinKeys = 32 * kWinRowBuckets;
@@ -352,10 +355,10 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                 Hd[r] = hh;
                 hlast = hh;
             }
-            uint32_t ms = __vimax3_s16x2(t[0], t[1], t[2]);
-            ms = __vimax3_s16x2(ms, t[3], t[4]);
-            ms = __vimax3_s16x2(ms, t[5], t[6]);
-            ms = __vmaxs2(ms, t[7]);
+            uint32_t ms = t[0];
+#pragma unroll
+            for (int r = 1; r + 1 < R; r += 2) ms = __vimax3_s16x2(ms, t[r], t[r + 1]);
+            if ((R & 1) == 0) ms = __vmaxs2(ms, t[R - 1]);
             if (!REV) runmax = __vmaxs2(runmax, ms);
             if (__vmaxs2(trigm1, ms) != trigm1) {
                 const int row = s - lig;
@@ -698,13 +701,29 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         auto gidx = [&](int q) -> int { return td.reversed ? (J.seg_len - 1 - q) : q; };     // seq2 index -> segment index
         const int ntmax = refLen + readLen;
 
+        // Gapless shortcut (most alignments on the bench workload).  If the box is square and its main diagonal scores exactly
+        // `score` with every prefix sum positive, banded_sw reproduces that diagonal: no cell of the box can exceed `score`
+        // (the forward pass found it as the window maximum), so no path reaches a diagonal cell with more than its prefix
+        // sum, every diagonal cell holds exactly its prefix sum, and the direction rule prefers the diagonal on ties
+        // (sswNew.cpp:1148).  The band |dlen|+1 = 1 contains the diagonal, so the first pass already reaches `score`.
+        bool gapless = false;
+        if (refLen == readLen && score < kQ4Guard) {      // (literal-scored alignments may sit below the exact maximum: no proof)
+            int sum = 0;
+            bool pos = true;
+            for (int k = 0; k < refLen; ++k) {
+                const int rf = td.img[gc[gidx(ws + rb + k)]], rc = a.rna_ssw[qb + k];
+                sum += (rf == rc && rf < 4) ? kMatch : kMismatch;
+                pos &= sum > 0;
+            }
+            gapless = pos && sum == score;
+        }
         // region: three int16 score rows | translated base codes of the window | direction nibbles, (2*bw+1) per row,
         // rows padded to whole bytes | ops, 2 bits each
         int bw = abs(refLen - readLen) + 1, maxv = 0, width_d = 0, lineb = 0;
         unsigned char* dir = nullptr;
         unsigned char* ops = nullptr;
         bool fits = true;
-        for (;;) {
+        for (; !gapless;) {
             const int width = bw * 2 + 3;
             width_d = bw * 2 + 1;
             lineb = (width_d + 1) >> 1;
@@ -761,7 +780,8 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         // traceback (sswNew.cpp:1159-1238): ops come out end -> start; written backwards into `ops`
         int wp = ntmax + 2;
         auto put_op = [&](int k, unsigned op) { const unsigned sh = (k & 3) * 2; ops[k >> 2] = (unsigned char)((ops[k >> 2] & ~(3u << sh)) | (op << sh)); };
-        if (fits) {
+        if (gapless) wp = ntmax + 2 - (readLen - 1);       // readLen - 1 diagonal steps, all 'M' (ops are not materialised)
+        else if (fits) {
             int ii = readLen - 1, j = refLen - 1, plane = 2;
             while (ii > 0) {
                 const int c = j - max(0, ii - bw);
@@ -779,7 +799,7 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
             }
         }
         if (!fits) { a.out[i].status = 2; a.out_list[atomicAdd(a.out_count, 1)] = i; continue; }
-        put_op(--wp, 0);            // closing rule (:1220-1238): the alignment always starts with one more M column
+        if (gapless) --wp; else put_op(--wp, 0);            // closing rule (:1220-1238): the alignment always starts with one more M column
         const int nt = ntmax + 2 - wp;
         // expansion from the front exactly like getAlignment (q walks the translated DNA from ref_begin, p the RNA), fused
         // with the identity count and the stability sum of convertMyTriplex (float32, same operation order)
@@ -791,7 +811,7 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         float tri = 0.0f, prev_val = 0.0f;
         char prev_ch = 0;
         for (int k = 0; k < nt; ++k) {
-            const int op = (ops[(wp + k) >> 2] >> (((wp + k) & 3) * 2)) & 3;
+            const int op = gapless ? 0 : (ops[(wp + k) >> 2] >> (((wp + k) & 3) * 2)) & 3;
             char rch = '-', sch = '-', tch = '-';
             if (op != 2) rch = (char)a.rna_raw[p++];
             if (op != 1) {
@@ -818,6 +838,53 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         o1.status = 1; o1.nt = nt; o1.identity = __fdiv_rn(__int2float_rn(100 * match), __int2float_rn(nt)); o1.tri = tri;
         a.out[i] = o1;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate compaction.  A row reaches the output only if it passes the per-task filter (fastsim.h:284-288) and the
+// record filter (Fasim-LongTarget.cpp:589-597) itself; the sort / unique rounds in between only remove rows.  So only
+// the tasks that own at least one such alignment need their records on the host (all of them: the others still take
+// part in that task's de-duplication).  One warp per task.
+struct CompactArgs {
+    const TraceJob* jobs; const TraceOut* tout;
+    const int* task_off; int n_tasks; int n_peaks;
+    int need_nt; float min_id, min_st;
+    int* cand_cnt;      // [task] number of records to ship (0: none)
+    int* cand_flag;     // [task] 0 / 1
+    const int* cand_poff; const int* cand_toff;        // exclusive scans of the two
+    TraceJob* c_jobs; TraceOut* c_tout;                // compacted records
+    int* c_task; int* c_poff;                          // per shipped task: task index, first compacted record
+    int* n_unfinished;  // alignments no traceback tier could finish (status 2) — reported as an error by the host
+};
+
+__global__ void k_task_flag(const CompactArgs a)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= a.n_tasks) return;
+    const int b = a.task_off[t], e = (t + 1 < a.n_tasks) ? a.task_off[t + 1] : a.n_peaks;
+    bool any = false, bad = false;
+    for (int i = b + lane; i < e; i += 32) {
+        const TraceOut o = a.tout[i];
+        const bool live = a.jobs[i].score > 0;
+        bad |= live && o.status == 2;
+        any |= live && o.status == 1 && o.nt >= a.need_nt && o.identity >= a.min_id && o.tri >= a.min_st;
+    }
+    any = __any_sync(0xffffffffu, any);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        a.cand_cnt[t] = any ? e - b : 0;
+        a.cand_flag[t] = any ? 1 : 0;
+        if (bad) atomicAdd(a.n_unfinished, 1);
+    }
+}
+
+__global__ void k_task_compact(const CompactArgs a)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= a.n_tasks || !a.cand_flag[t]) return;
+    const int b = a.task_off[t], n = a.cand_cnt[t], dst = a.cand_poff[t];
+    if (lane == 0) { const int pos = a.cand_toff[t]; a.c_task[pos] = t; a.c_poff[pos] = dst; }
+    for (int i = lane; i < n; i += 32) { a.c_jobs[dst + i] = a.jobs[b + i]; a.c_tout[dst + i] = a.tout[b + i]; }
 }
 
 }  // namespace ltg
