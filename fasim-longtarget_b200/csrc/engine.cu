@@ -10,6 +10,7 @@
 // -> record filter -> traceback pass 2 (strings of the surviving rows only) -> result.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -114,7 +115,7 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
-    bool prune = true;
+    bool prune = true, dead_rule = true;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     ltg_params params;
     // task tables (depend on params.rule / params.strand)
@@ -136,7 +137,7 @@ struct ltg_context {
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
     HostBatch hb[2];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-    unsigned long long win_stats[24] = {0};     // windows / cells planned per (round, retry) + reverse; [20..22] traceback tier hand-overs
+    unsigned long long win_stats[30] = {0};     // windows / cells planned per (round, retry) + reverse; [20..22] traceback tier hand-overs
 };
 
 namespace {
@@ -282,7 +283,7 @@ int literal_windows(ltg_context* c, const WinState& w, bool reverse)
 }
 
 // ---------------- window stage: peaks (device-resident pool) -> chosen alignments -> traceback pass 1 ----------------
-int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* gran_colmax, int max_len, HostBatch* hb)
+int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* gran_colmax, int max_len, HostBatch* hb, bool dead_rule)
 {
     for (int k = 0; k < 18; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
     if (int e = c->d_win_list.ensure(sizeof(int) * (size_t)n_peaks)) return e;
@@ -341,7 +342,11 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     // traceback pass 1: nt / identity / stability of every chosen alignment
     if (int e = c->d_jobs.ensure(sizeof(TraceJob) * (size_t)n_peaks)) return e;
     if (int e = c->d_tout.ensure(sizeof(TraceOut) * (size_t)n_peaks)) return e;
-    k_make_trace_jobs<<<pb, 256, 0, c->stream>>>(w, c->d_jobs.as<TraceJob>());
+    DeadRule dr;
+    dr.need_nt = std::max(c->params.nt_min, c->params.c_length); dr.nt_min = c->params.nt_min; dr.nt_max = c->params.nt_max;
+    dr.penalty_t = c->params.penalty_t; dr.penalty_c = c->params.penalty_c; dr.min_st = (float)c->params.min_stability;
+    dr.dna = (dead_rule && c->dead_rule) ? c->d_dna.as<unsigned char>() : nullptr;     // nullptr: trace everything
+    k_make_trace_jobs<<<pb, 256, 0, c->stream>>>(w, c->d_jobs.as<TraceJob>(), c->d_tout.as<TraceOut>(), dr);
     c->launches += 1;
     (void)hb;
     return LTG_OK;
@@ -351,7 +356,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
 // alignment, larger regions / fewer threads for long alignments and wide bands), then the generic kernel with a 24 KB
 // global scratch, then with an 8 MB scratch for the rare huge bands.  Each tier hands what it cannot finish to the next through a device-side list.
 constexpr int kTrace1Tpb = 128, kTrace1Bytes = 452, kTrace2Tpb = 64, kTrace2Bytes = 1796, kTrace3Tpb = 32, kTrace3Bytes = 7172;
-int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* d_out, char* strpool)
+int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* d_out, char* strpool, bool skip_dead = false)
 {
     const int tb_threads = c->num_sms * 64;
     const long long scratch_small = 24 * 1024, scratch_big = 8LL << 20;
@@ -366,7 +371,7 @@ int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* 
     ta.jobs = d_jobs; ta.n_jobs = n_jobs; ta.codes = c->d_codes.as<uint8_t>(); ta.dna = c->d_dna.as<unsigned char>();
     ta.rna_ssw = c->d_rna_ssw.as<uint8_t>(); ta.rna_raw = c->d_rna_raw.as<unsigned char>();
     ta.nt_min = c->params.nt_min; ta.nt_max = c->params.nt_max; ta.penalty_t = c->params.penalty_t; ta.penalty_c = c->params.penalty_c;
-    ta.out = d_out; ta.strpool = strpool;
+    ta.out = d_out; ta.strpool = strpool; ta.skip_dead = skip_dead ? 1 : 0;
     ta.scratch = nullptr; ta.scratch_per_thread = 0;
     // tier 1
     ta.in_list = nullptr; ta.in_count = nullptr; ta.out_list = list1; ta.out_count = cnt;
@@ -549,8 +554,8 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     }
     if (want_alignments && n_peaks > 0) {
         LTG_CUDA_CHECK(cudaEventRecord(hb.ev[2], c->stream));
-        if (int e = run_windows(c, n_peaks, T, nullptr, lit_mode == kLitOnly ? nullptr : c->d_colmax.as<uint32_t>(), max_len, &hb)) return e;
-        if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), n_peaks, c->d_tout.as<TraceOut>(), nullptr)) return e;
+        if (int e = run_windows(c, n_peaks, T, nullptr, lit_mode == kLitOnly ? nullptr : c->d_colmax.as<uint32_t>(), max_len, &hb, true)) return e;
+        if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), n_peaks, c->d_tout.as<TraceOut>(), nullptr, true)) return e;
         LTG_CUDA_CHECK(cudaEventRecord(hb.ev[3], c->stream));
         hb.timed_windows = true;
         // ship only the tasks that own a candidate row (k_task_flag): flags -> two exclusive scans -> compaction into this
@@ -573,6 +578,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
         ca.cand_cnt = cand; ca.cand_flag = cand + n_tasks; ca.cand_poff = cand + 2 * (size_t)n_tasks; ca.cand_toff = cand + 3 * (size_t)n_tasks;
         ca.c_jobs = hb.d_cjobs.as<TraceJob>(); ca.c_tout = hb.d_ctout.as<TraceOut>(); ca.c_task = hb.d_ctask.as<int>(); ca.c_poff = hb.d_cpoff.as<int>();
         ca.n_unfinished = counters + kCntCand + 2;
+        ca.filt = getenv("LTG_FILTER_STATS") ? &c->d_win_sched.as<WinSched>()->st_filter[0] : nullptr;
         LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCand, 0, 3 * sizeof(int), c->stream));
         const int task_blocks = (n_tasks * 32 + 255) / 256;
         k_task_flag<<<task_blocks, 256, 0, c->stream>>>(ca);
@@ -588,6 +594,8 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
                                        cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 232, counters + kCntOvf, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 248, counters + kCntCand, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 264, &c->d_win_sched.as<WinSched>()->st_filter[0], 6 * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, c->stream));
         c->d2h_bytes += (int64_t)sizeof(int) * 2 * n_tasks + 272;
     } else {
         hb.n_peaks = want_alignments ? n_peaks : 0;
@@ -626,10 +634,12 @@ void host_phase(const ltg_context* c, HostBatch& hb, int threads)
             for (int i = b; i < e; ++i) {                       // peaks of a task come in ascending column order
                 const TraceJob& J = jobs[i];
                 if (J.score <= 0) continue;                     // fastsim.h:253 (sw_score == 0 -> skipped)
-                if (tout[i].status != 1) continue;              // banded_sw failed -> sw_score 0 (ssw_cpp.cpp:627-633)
+                if (tout[i].status != 1 && tout[i].status != 4) continue;       // banded_sw failed -> sw_score 0 (ssw_cpp.cpp:627-633)
                 ltg_host::DeviceAlignment al;
                 al.sw_score = J.score; al.ws = J.ws; al.rb = J.rb; al.re = J.re; al.query_begin = J.qb; al.query_end = J.qe;
                 al.nt = tout[i].nt; al.identity = tout[i].identity; al.tri_score = tout[i].tri;
+                // dead alignment (window.cuh DeadRule): de-duplicates like any other, fails every output filter
+                if (tout[i].status == 4) { al.identity = -INFINITY; al.tri_score = -INFINITY; }
                 ltg_host::make_triplex(al, task % T, sg.len, (long)sg.start, td.para, td.strand, td.rule, c->params, mine);
             }
             if (!mine.empty()) ltg_host::finish_task(mine, c->params, part[k]);
@@ -792,6 +802,7 @@ int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg
     st.n_literal_windows += sc[kCntLitTotal - kCntCells];
     for (int k = 0; k < 20; ++k) c->win_stats[k] += reinterpret_cast<const unsigned long long*>(hb.scalars.as<char>() + 64)[k];
     for (int k = 0; k < 4; ++k) c->win_stats[20 + k] += (unsigned long long)reinterpret_cast<const int*>(hb.scalars.as<char>() + 232)[k];
+    for (int k = 0; k < 6; ++k) c->win_stats[24 + k] += reinterpret_cast<const unsigned long long*>(hb.scalars.as<char>() + 264)[k];
     record_list.insert(record_list.end(), hb.rows.begin(), hb.rows.end());
     hb.rows.clear();
     return LTG_OK;
@@ -976,6 +987,8 @@ int ltg_create(int device, ltg_context** out)
     c->host_threads = threads;
     // LTG_NO_PRUNE=1 makes every window sweep the whole lncRNA (the reference's amount of work); results are identical
     if (const char* e = getenv("LTG_NO_PRUNE")) c->prune = atoi(e) == 0;
+    // LTG_NO_DEAD=1 traces every alignment, also those that provably cannot be reported (window.cuh DeadRule)
+    if (const char* e = getenv("LTG_NO_DEAD")) c->dead_rule = atoi(e) == 0;
     *out = c;
     return LTG_OK;
 }
@@ -1006,10 +1019,10 @@ void ltg_destroy(ltg_context* c)
 
 void* ltg_stream(ltg_context* c) { return c ? (void*)c->stream : nullptr; }
 
-void ltg_debug_stats(ltg_context* c, int64_t* out24, int reset)
+void ltg_debug_stats(ltg_context* c, int64_t* out30, int reset)
 {
-    if (!c || !out24) return;
-    for (int k = 0; k < 24; ++k) { out24[k] = (int64_t)c->win_stats[k]; if (reset) c->win_stats[k] = 0; }
+    if (!c || !out30) return;
+    for (int k = 0; k < 30; ++k) { out30[k] = (int64_t)c->win_stats[k]; if (reset) c->win_stats[k] = 0; }
 }
 
 int ltg_set_params(ltg_context* c, const ltg_params* p)
@@ -1209,7 +1222,7 @@ int ltg_probe_align(ltg_context* c, const char* const* windows, const int32_t* w
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_pk_pos.p, pk_pos.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_pk_score.p, pk_score.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_stats_max.p, fcut.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    if (int e = run_windows(c, n, 1, c->d_stats_max.as<int>(), nullptr, 0, nullptr)) return e;
+    if (int e = run_windows(c, n, 1, c->d_stats_max.as<int>(), nullptr, 0, nullptr, false)) return e;
     if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), n, c->d_tout.as<TraceOut>(), nullptr)) return e;
     std::vector<TraceJob> jobs(n);
     std::vector<TraceOut> tout(n);

@@ -57,6 +57,7 @@ struct WinSched {
     // statistics (LTG_STATS): windows / cells planned per (round, retry); [8] = reverse pass
     unsigned long long st_windows[10];
     unsigned long long st_cells[10];
+    unsigned long long st_filter[6];        // LTG_FILTER_STATS: see CompactArgs::filt
 };
 
 struct WinState {
@@ -475,8 +476,9 @@ struct TraceJob {
 };
 
 struct TraceOut {
-    int status;                // 0 none, 1 ok, 2 needs a larger scratch, 3 traceback left the band (sw_score -> 0)
-    int nt;                    // alignment columns
+    int status;                // 0 none, 1 ok, 2 needs a larger scratch, 3 traceback left the band (sw_score -> 0),
+                               // 4 dead: not traced, can never be reported, takes part in the de-duplication (k_make_trace_jobs)
+    int nt;                    // alignment columns (status 4: a lower bound that passes the ntMin gate)
     float identity, tri;       // MeanIdentity(%) / MeanStability, float32 evaluated exactly as fastsim.h:323-383
 };
 
@@ -487,6 +489,7 @@ struct TraceArgs {
     const uint8_t* rna_ssw;        // lncRNA, SSW codes
     const unsigned char* rna_raw;  // raw lncRNA bytes (for the TFO string)
     unsigned char* scratch; long long scratch_per_thread;
+    int skip_dead;                             // pass 1: jobs preset to status 4 by k_make_trace_jobs are left alone
     const int* in_list; const int* in_count;   // work list (nullptr: all jobs)
     int* out_list; int* out_count;             // jobs this launch could not finish (status 2) — input of the next tier
     int nt_min, nt_max, penalty_t, penalty_c;
@@ -494,21 +497,53 @@ struct TraceArgs {
     char* strpool;                 // pass 2 only (nullptr in pass 1): tfo at out_off, tts at out_off + nt + 1, both NUL-terminated
 };
 
-__global__ void k_make_trace_jobs(const WinState w, TraceJob* jobs)
+// Alignments that provably cannot be reported skip the traceback ("dead", status 4).  A row is reported only if it passes
+// nt >= max(ntMin, cLength), identity >= minIdentity and stability >= minStability (fastsim.h:284-288,
+// Fasim-LongTarget.cpp:589-597).  Two necessary conditions need no alignment:
+//  (i)  nt = refLen + readLen - #M and #M >= ceil(score / 5), so nt <= refLen + readLen - ceil(score / 5);
+//  (ii) every base of ref[rb..re] occupies a column, so two adjacent T's of the source strand always meet as consecutive
+//       non-gap source characters and fire the penaltyT rule (fastsim.h:363-367): with penaltyT < 0 the stability sum is
+//       at most max(4.5, pc) * (nt - 1) + max(pc, 0) * nt + 2 * penaltyT, i.e. the mean is below
+//       max(4.5, pc) + max(pc, 0) + 2 * penaltyT / (refLen + readLen).
+// A dead alignment still takes part in its task's de-duplication (which looks at coordinates and score only), provided it
+// is certain to pass convertMyTriplex's nt >= ntMin gate (nt >= max(refLen, readLen)); otherwise it is traced normally.
+struct DeadRule { int need_nt, nt_min, nt_max, penalty_t, penalty_c; float min_st; const unsigned char* dna; };
+
+__global__ void k_make_trace_jobs(const WinState w, TraceJob* jobs, TraceOut* tout, const DeadRule dr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.n_peaks) return;
     TraceJob J;
     const int task = w.pk_task[i];
     const SegDesc sd = w.segs[task / w.tasks_per_seg];
+    const TaskDef td = c_tasks[task % w.tasks_per_seg];
     J.seg_start = sd.start; J.seg_len = sd.len; J.tdef = task % w.tasks_per_seg;
     J.score = w.fin_sw[i];
     J.ws = 0; J.rb = J.re = J.qb = J.qe = 0; J.out_off = 0;
+    TraceOut o; o.status = 0; o.nt = 0; o.identity = 0.0f; o.tri = 0.0f;
     if (J.score > 0) {
         J.ws = w.pk_pos[i] - w.fin_cut[i] + 1;
         J.rb = w.fin_rb[i]; J.re = w.fin_re[i]; J.qb = w.fin_qb[i]; J.qe = w.fin_qe[i];
+        const int refLen = J.re - J.rb + 1, readLen = J.qe - J.qb + 1;
+        if (dr.dna != nullptr && max(refLen, readLen) >= dr.nt_min) {
+            bool dead = refLen + readLen - (J.score + 4) / 5 < dr.need_nt;
+            if (!dead && dr.penalty_t < 0 && refLen + readLen <= dr.nt_max) {     // (nt > ntMax would zero the stability instead)
+                const float pcf = (float)dr.penalty_c;
+                const float ub = fmaxf(4.5f, pcf) + fmaxf(pcf, 0.0f) + 2.0f * (float)dr.penalty_t / (float)(refLen + readLen);
+                if (ub < dr.min_st - 0.05f) {
+                    // adjacent T's of the source strand = adjacent T's (A's for the complemented strands) of the record
+                    const int q0 = J.ws + J.rb, q1 = J.ws + J.re;
+                    const int g0 = td.reversed ? sd.len - 1 - q1 : q0;
+                    const unsigned char want = td.comp_src ? 'A' : 'T';
+                    const unsigned char* p = dr.dna + sd.start + g0;
+                    for (int k = 0; k + 1 < refLen; ++k) if (p[k] == want && p[k + 1] == want) { dead = true; break; }
+                }
+            }
+            if (dead) { o.status = 4; o.nt = max(refLen, readLen); }
+        }
     }
     jobs[i] = J;
+    tout[i] = o;
 }
 
 __device__ inline int band_u(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x + 1; }
@@ -543,7 +578,10 @@ __global__ void k_traceback(const TraceArgs a)
     const int n_todo = a.in_list ? min(*a.in_count, a.n_jobs) : a.n_jobs;
     for (int k0 = tid; k0 < n_todo; k0 += nthreads) {
         const int i = a.in_list ? a.in_list[k0] : k0;
-        if (!a.in_list) a.out[i].status = 0;
+        if (!a.in_list) {
+            if (a.skip_dead && a.out[i].status == 4) continue;
+            a.out[i].status = 0;
+        }
         const TraceJob J = a.jobs[i];
         if (J.score <= 0) continue;
 
@@ -691,7 +729,10 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
     const int n_todo = a.in_list ? min(*a.in_count, a.n_jobs) : a.n_jobs;
     for (int k0 = tid; k0 < n_todo; k0 += nthreads) {
         const int i = a.in_list ? a.in_list[k0] : k0;
-        if (!a.in_list) a.out[i].status = 0;
+        if (!a.in_list) {
+            if (a.skip_dead && a.out[i].status == 4) continue;
+            a.out[i].status = 0;
+        }
         const TraceJob J = a.jobs[i];
         if (J.score <= 0) continue;
         const TaskDef td = c_tasks[J.tdef];
@@ -855,6 +896,7 @@ struct CompactArgs {
     TraceJob* c_jobs; TraceOut* c_tout;                // compacted records
     int* c_task; int* c_poff;                          // per shipped task: task index, first compacted record
     int* n_unfinished;  // alignments no traceback tier could finish (status 2) — reported as an error by the host
+    unsigned long long* filt;   // statistics: [0] live alignments, [1] nt upper bound < need_nt, [2] nt ok, [3] identity ok, [4] stability ok, [5] all
 };
 
 __global__ void k_task_flag(const CompactArgs a)
@@ -867,7 +909,21 @@ __global__ void k_task_flag(const CompactArgs a)
         const TraceOut o = a.tout[i];
         const bool live = a.jobs[i].score > 0;
         bad |= live && o.status == 2;
-        any |= live && o.status == 1 && o.nt >= a.need_nt && o.identity >= a.min_id && o.tri >= a.min_st;
+        const bool ok = live && o.status == 1;
+        any |= ok && o.nt >= a.need_nt && o.identity >= a.min_id && o.tri >= a.min_st;
+        if (a.filt) {
+            const TraceJob J = a.jobs[i];
+            const int ub = (J.re - J.rb + 1) + (J.qe - J.qb + 1) - (J.score + 4) / 5;
+            const unsigned m0 = __ballot_sync(__activemask(), live), m1 = __ballot_sync(__activemask(), live && ub < a.need_nt);
+            const unsigned m2 = __ballot_sync(__activemask(), ok && o.nt >= a.need_nt), m3 = __ballot_sync(__activemask(), ok && o.identity >= a.min_id);
+            const unsigned m4 = __ballot_sync(__activemask(), ok && o.tri >= a.min_st);
+            const unsigned m5 = __ballot_sync(__activemask(), ok && o.nt >= a.need_nt && o.identity >= a.min_id && o.tri >= a.min_st);
+            if ((__activemask() & ((1u << lane) - 1)) == 0) {
+                atomicAdd(&a.filt[0], (unsigned long long)__popc(m0)); atomicAdd(&a.filt[1], (unsigned long long)__popc(m1));
+                atomicAdd(&a.filt[2], (unsigned long long)__popc(m2)); atomicAdd(&a.filt[3], (unsigned long long)__popc(m3));
+                atomicAdd(&a.filt[4], (unsigned long long)__popc(m4)); atomicAdd(&a.filt[5], (unsigned long long)__popc(m5));
+            }
+        }
     }
     any = __any_sync(0xffffffffu, any);
     bad = __any_sync(0xffffffffu, bad);

@@ -158,9 +158,10 @@ class Engine:
         _check(lib().ltg_set_query(self._h, name.encode(), b, len(b)))
 
     def debug_stats(self, reset=False):
-        out = (C.c_int64 * 24)()
+        out = (C.c_int64 * 30)()
         lib().ltg_debug_stats(self._h, out, 1 if reset else 0)
-        return {"windows": list(out[:10]), "cells": list(out[10:20]), "traceback_handed_over": list(out[20:24])}
+        return {"windows": list(out[:10]), "cells": list(out[10:20]), "traceback_handed_over": list(out[20:24]),
+                "filters(live,nt_bound_fail,nt_ok,identity_ok,stability_ok,all_ok)": list(out[24:30])}
 
     @property
     def stream(self):

@@ -157,8 +157,9 @@ int ltg_probe_align(ltg_context* ctx, const char* const* windows, const int32_t*
 /* window-stage work counters accumulated over the context's life: out[2*round + retry] = windows planned in forward
  * round 0..3 (retry 1 = second, wider sweep after an inconclusive pruned one), out[8] = reverse sweeps,
  * out[10 + k] = the DP cells of the same entries, out[20..23] = alignments handed on by traceback tiers 1..4.
- * `out` holds 24 entries.                                                                                       */
-void ltg_debug_stats(ltg_context* ctx, int64_t* out24, int reset);
+ * out[24..29] (only with LTG_FILTER_STATS=1) = alignments: live, nt bound below the cut, nt ok, identity ok, stability ok,
+ * all three ok.  `out` holds 30 entries.                                                                        */
+void ltg_debug_stats(ltg_context* ctx, int64_t* out30, int reset);
 
 /* device-timing helpers for bench.py: opaque cudaStream_t of the context */
 void* ltg_stream(ltg_context* ctx);

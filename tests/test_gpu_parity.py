@@ -297,25 +297,34 @@ def test_row_pruning_is_exact(data_dir):
     rna = splitmix_bases(2001, 3000)
     drna, _, ddna = demo(data_dir)
     os.environ["LTG_NO_PRUNE"] = "1"
+    os.environ["LTG_NO_DEAD"] = "1"          # and trace every alignment, not only those that can still be reported
     try:
         full = fb.Engine(0)
     finally:
         del os.environ["LTG_NO_PRUNE"]
+        del os.environ["LTG_NO_DEAD"]
     pruned = fb.Engine(0)
     try:
-        for eng in (full, pruned):
-            eng.set_params(c_length=20)
         outs = []
         for eng in (full, pruned):
+            eng.set_params(c_length=20)
             eng.set_query("synRNA3k", rna)
             res = eng.scan_record(dna, "chr1", 1)
             rows, cells = fb.result_rows(res), res.contents.window_cells
             eng.free(res)
             eng.set_query("H19", drna)
             rows2 = eng.LongTarget(ddna, "chr11", 1)
-            outs.append((rows, rows2, cells))
+            # the dead-alignment rule under other filter settings: positive penaltyC, mild penaltyT, default cLength
+            eng.set_params(penalty_c=1, penalty_t=-3, min_stability=2, min_identity=50)
+            eng.set_query("synRNA3k", rna)
+            rows3 = eng.LongTarget(dna[:150_000], "chr1", 1)
+            eng.set_params(penalty_t=-500, penalty_c=1, nt_min=25, min_identity=70, c_length=60, c_distance=10)
+            eng.set_query("H19", drna)
+            rows4 = eng.LongTarget(ddna, "chr11", 1)
+            outs.append((rows, rows2, cells, rows3, rows4))
         assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 0
         assert outs[0][1] == outs[1][1] and len(outs[0][1]) > 0
+        assert outs[0][3] == outs[1][3] and outs[0][4] == outs[1][4] and len(outs[0][4]) > 0
         assert outs[1][2] * 2 < outs[0][2]          # and it actually prunes: fewer than half of the window cells
     finally:
         full.close()
