@@ -88,7 +88,14 @@ constexpr int kScanCtasPerSm = LTG_SCAN_CTAS;
 constexpr int kBatchSegments = 1024;
 constexpr size_t kStripBytesPerBatch = 16ull << 30;     // cap of the granule-maxima buffer of one batch
 
-struct HostSeg { int64_t start; int32_t len; int32_t flags; };
+struct HostSeg {
+    int64_t start;      // offset in the device DNA buffer of this call (records are laid out back to back)
+    int32_t len;
+    int32_t flags;
+    int64_t coord;      // offset of the segment in its own record (what StartInSeq / EndInSeq count from)
+    int32_t record;     // index of the record within the call
+    int32_t pad_;
+};
 
 // what one batch leaves on the host: pinned copies filled by asynchronous D2H, consumed by the host phase
 struct HostBatch {
@@ -640,7 +647,7 @@ void host_phase(const ltg_context* c, HostBatch& hb, int threads)
                 al.nt = tout[i].nt; al.identity = tout[i].identity; al.tri_score = tout[i].tri;
                 // dead alignment (window.cuh DeadRule): de-duplicates like any other, fails every output filter
                 if (tout[i].status == 4) { al.identity = -INFINITY; al.tri_score = -INFINITY; }
-                ltg_host::make_triplex(al, task % T, sg.len, (long)sg.start, td.para, td.strand, td.rule, c->params, mine);
+                ltg_host::make_triplex(al, task % T, sg.len, (long)sg.start, (long)sg.coord, sg.record, td.para, td.strand, td.rule, c->params, mine);
             }
             if (!mine.empty()) ltg_host::finish_task(mine, c->params, part[k]);
         }
@@ -681,14 +688,15 @@ void batch_worker(ltg_context* c, HostBatch* hb)
 // cutSequence — fastsim.h:71-90.  A shard is the run of segments [first_seg, first_seg + n_seg) of a record of `record_len`
 // bases whose bytes start at the first segment's start; segment starts are relative to the shard's buffer, lengths follow
 // the RECORD's geometry (so the union of shards is exactly the record's segment list — no extra tail segments).
-int cut_segments(int64_t buf_len, int64_t record_len, int64_t first_seg, int64_t n_seg, const ltg_params& P, std::vector<HostSeg>& segs)
+int cut_segments(int64_t buf_len, int64_t record_len, int64_t first_seg, int64_t n_seg, const ltg_params& P, int64_t base, int record,
+                 std::vector<HostSeg>& segs)
 {
     if (P.cut_length <= 0 || P.cut_length - P.overlap <= 0) { set_error("cut length must exceed the overlap"); return LTG_ERR_ARG; }
     const int64_t stride = P.cut_length - P.overlap;
-    segs.clear();
     for (int64_t k = first_seg; (n_seg < 0 || k < first_seg + n_seg) && k * stride < record_len; ++k) {
-        HostSeg s; s.start = (k - first_seg) * stride; s.len = (int32_t)std::min<int64_t>(P.cut_length, record_len - k * stride); s.flags = 0;
-        if (s.start + s.len > buf_len) { set_error("shard buffer (%lld bytes) does not cover segment %lld", (long long)buf_len, (long long)k); return LTG_ERR_ARG; }
+        HostSeg s; s.start = base + (k - first_seg) * stride; s.len = (int32_t)std::min<int64_t>(P.cut_length, record_len - k * stride); s.flags = 0;
+        s.coord = k * stride; s.record = record; s.pad_ = 0;
+        if (s.start - base + s.len > buf_len) { set_error("shard buffer (%lld bytes) does not cover segment %lld", (long long)buf_len, (long long)k); return LTG_ERR_ARG; }
         segs.push_back(s);
     }
     return LTG_OK;
@@ -697,20 +705,21 @@ int cut_segments(int64_t buf_len, int64_t record_len, int64_t first_seg, int64_t
 struct ResultBuilder {
     std::vector<ltg_triplex> tri;
     std::string text;
-    int64_t chr_off = -1;
-    void add(const ltg_host::Triplex& t, const char* tfo, const char* tts, const char* chr, int64_t record_start, int64_t coord_offset, int record)
+    std::vector<int64_t> chr_off;       // per record: offset of its chromosome tag in `text` (-1: not stored yet)
+    void add(const ltg_host::Triplex& t, const char* tfo, const char* tts, const char* chr, int64_t record_start, int record)
     {
-        if (chr_off < 0) { chr_off = (int64_t)text.size(); text += (chr ? chr : ""); text += '\0'; }
+        if ((size_t)record >= chr_off.size()) chr_off.resize((size_t)record + 1, -1);
+        if (chr_off[record] < 0) { chr_off[record] = (int64_t)text.size(); text += (chr ? chr : ""); text += '\0'; }
         ltg_triplex o;
         memset(&o, 0, sizeof o);
-        o.stari = t.stari; o.endi = t.endi; o.starj = (int32_t)(t.starj + coord_offset); o.endj = (int32_t)(t.endj + coord_offset);
+        o.stari = t.stari; o.endi = t.endi; o.starj = t.starj; o.endj = t.endj;
         o.reverse = t.reverse; o.strand = t.strand;
         o.rule = t.rule; o.nt = t.nt; o.score = t.score; o.identity = t.identity; o.tri_score = t.tri_score;
         o.genomestart = o.starj + record_start - 1;         // Fasim-LongTarget.cpp:146-147
         o.genomeend = o.endj + record_start - 1;
         o.tfo_off = (int64_t)text.size(); text.append(tfo, (size_t)t.nt); text += '\0';
         o.tts_off = (int64_t)text.size(); text.append(tts, (size_t)t.nt); text += '\0';
-        o.chr_off = chr_off;
+        o.chr_off = chr_off[record];
         o.record = record;
         tri.push_back(o);
     }
@@ -808,44 +817,64 @@ int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg
     return LTG_OK;
 }
 
-int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char* h_dna, int64_t len, const char* chr,
-                     int64_t record_start, ltg_result** out, int64_t record_len = -1, int64_t first_seg = 0, int64_t n_seg = -1)
+// one DNA record (or shard of a record) of a scan call
+struct RecordIn {
+    const char* h_dna = nullptr;               // host bytes, or ...
+    const unsigned char* d_dna = nullptr;      // ... device bytes
+    int64_t len = 0;                           // readable bytes
+    const char* chr = nullptr;
+    int64_t record_start = 0;
+    int64_t record_len = -1, first_seg = 0, n_seg = -1;     // shard geometry (ltg_scan_shard); defaults: the whole record
+};
+
+int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result** out)
 {
-    if (!c || !out) { set_error("null argument"); return LTG_ERR_ARG; }
+    if (!c || !out || (n_recs > 0 && !recs)) { set_error("null argument"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
     const int64_t launches0 = c->launches, h2d0 = c->h2d_bytes, d2h0 = c->d2h_bytes;
     const bool trace_time = getenv("LTG_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     double t_prep = 0, t_loop = 0, t_retire = 0, t_filter = 0, t_strings = 0;
+    // records back to back in one device buffer; every record is cut on its own (cutSequence never spans records)
     std::vector<HostSeg> segs;
-    if (record_len < 0) record_len = len;
-    if (first_seg < 0 || len < 0) { set_error("bad shard geometry"); return LTG_ERR_ARG; }
-    if (int e = cut_segments(len, record_len, first_seg, n_seg, c->params, segs)) return e;
-    const int64_t coord_offset = first_seg * (int64_t)(c->params.cut_length - c->params.overlap);
+    std::vector<int64_t> base((size_t)n_recs + 1, 0);
+    for (int64_t r = 0; r < n_recs; ++r) {
+        const RecordIn& R = recs[r];
+        if (R.first_seg < 0 || R.len < 0 || (R.len > 0 && !R.h_dna && !R.d_dna)) { set_error("bad record %lld", (long long)r); return LTG_ERR_ARG; }
+        if (int e = cut_segments(R.len, R.record_len < 0 ? R.len : R.record_len, R.first_seg, R.n_seg, c->params, base[r], (int)r, segs)) return e;
+        base[r + 1] = base[r] + R.len;
+    }
+    const int64_t len = base[n_recs];
     ResultBuilder rb;
     RecordStats st;
     if (len > 0) {
-        // the record lives in d_dna (either copied from the host or device-to-device from the user's buffer)
         if (int e = c->d_dna.ensure((size_t)len)) return e;
         if (int e = c->d_codes.ensure((size_t)len)) return e;
-        if (h_dna) { LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_dna.p, h_dna, (size_t)len, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += len; }
-        else LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_dna.p, d_dna_user, (size_t)len, cudaMemcpyDeviceToDevice, c->stream));
+        for (int64_t r = 0; r < n_recs; ++r) {
+            const RecordIn& R = recs[r];
+            if (R.len == 0) continue;
+            unsigned char* dst = c->d_dna.as<unsigned char>() + base[r];
+            if (R.h_dna) { LTG_CUDA_CHECK(cudaMemcpyAsync(dst, R.h_dna, (size_t)R.len, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += R.len; }
+            else LTG_CUDA_CHECK(cudaMemcpyAsync(dst, R.d_dna, (size_t)R.len, cudaMemcpyDeviceToDevice, c->stream));
+        }
         k_encode<<<(int)std::min<int64_t>((len + 255) / 256, 148 * 16), 256, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_codes.as<uint8_t>(), len);
         c->launches += 1;
-        // segment flags (same_seq + non-ACGT) for the whole record
+        // segment flags (same_seq + non-ACGT) for every segment of the call
         const int NS = (int)segs.size();
-        if (int e = c->d_segs.ensure(sizeof(SegDesc) * NS)) return e;
+        if (int e = c->d_segs.ensure(sizeof(SegDesc) * std::max(NS, 1))) return e;
         std::vector<SegDesc> hs(NS);
         for (int s = 0; s < NS; ++s) { hs[s].start = segs[s].start; hs[s].len = segs[s].len; hs[s].flags = 0; }
-        LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_segs.p, hs.data(), sizeof(SegDesc) * NS, cudaMemcpyHostToDevice, c->stream));
-        k_seg_flags<<<(NS * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_segs.as<SegDesc>(), NS);
-        c->launches += 1;
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hs.data(), c->d_segs.p, sizeof(SegDesc) * NS, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        c->h2d_bytes += (int64_t)sizeof(SegDesc) * NS; c->d2h_bytes += (int64_t)sizeof(SegDesc) * NS;
         std::vector<HostSeg> active;
-        for (int s = 0; s < NS; ++s) { segs[s].flags = hs[s].flags; if (!(hs[s].flags & kSegSkip)) active.push_back(segs[s]); }
+        if (NS > 0) {
+            LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_segs.p, hs.data(), sizeof(SegDesc) * NS, cudaMemcpyHostToDevice, c->stream));
+            k_seg_flags<<<(NS * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_segs.as<SegDesc>(), NS);
+            c->launches += 1;
+            LTG_CUDA_CHECK(cudaMemcpyAsync(hs.data(), c->d_segs.p, sizeof(SegDesc) * NS, cudaMemcpyDeviceToHost, c->stream));
+            LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            c->h2d_bytes += (int64_t)sizeof(SegDesc) * NS; c->d2h_bytes += (int64_t)sizeof(SegDesc) * NS;
+            for (int s = 0; s < NS; ++s) { segs[s].flags = hs[s].flags; if (!(hs[s].flags & kSegSkip)) active.push_back(segs[s]); }
+        }
 
         // batch size: bounded by the strip-maxima buffer; at least two batches when there is enough work so that the
         // host phase of one overlaps the device phase of the next
@@ -921,7 +950,7 @@ int scan_device_impl(ltg_context* c, const unsigned char* d_dna_user, const char
         if (int e = fetch_strings(c, keep, pool, offs)) return e;
         t_strings = now();
         for (size_t i = 0; i < keep.size(); ++i)
-            rb.add(keep[i], pool.data() + offs[i], pool.data() + offs[i] + keep[i].nt + 1, chr, record_start, coord_offset, 0);
+            rb.add(keep[i], pool.data() + offs[i], pool.data() + offs[i] + keep[i].nt + 1, recs[keep[i].record].chr, recs[keep[i].record].record_start, keep[i].record);
     }
     ltg_result* r = finish_result(rb);
     r->n_segments = st.n_segments; r->n_tasks = st.n_tasks; r->scan_cells = st.scan_cells; r->dna_bases = len;
@@ -1064,21 +1093,37 @@ int ltg_set_query(ltg_context* c, const char* name, const char* rna, int64_t len
 int ltg_scan_record(ltg_context* c, const char* dna, int64_t len, const char* chr, int64_t record_start, ltg_result** out)
 {
     if (!dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
-    return scan_device_impl(c, nullptr, dna, len, chr, record_start, out);
+    RecordIn R; R.h_dna = dna; R.len = len; R.chr = chr; R.record_start = record_start;
+    return scan_impl(c, &R, 1, out);
+}
+
+int ltg_scan_records(ltg_context* c, int64_t n_records, const char* const* dna, const int64_t* len, const char* const* chr,
+                     const int64_t* record_start, ltg_result** out)
+{
+    if (n_records < 0 || (n_records > 0 && (!dna || !len))) { set_error("null argument"); return LTG_ERR_ARG; }
+    std::vector<RecordIn> recs((size_t)n_records);
+    for (int64_t r = 0; r < n_records; ++r) {
+        if (!dna[r] && len[r] > 0) { set_error("null DNA in record %lld", (long long)r); return LTG_ERR_ARG; }
+        recs[r].h_dna = dna[r]; recs[r].len = len[r]; recs[r].chr = chr ? chr[r] : nullptr; recs[r].record_start = record_start ? record_start[r] : 0;
+    }
+    return scan_impl(c, recs.data(), n_records, out);
 }
 
 int ltg_scan_device(ltg_context* c, const void* d_dna, int64_t len, const char* chr, int64_t record_start, ltg_result** out)
 {
     if (!d_dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
-    return scan_device_impl(c, (const unsigned char*)d_dna, nullptr, len, chr, record_start, out);
+    RecordIn R; R.d_dna = (const unsigned char*)d_dna; R.len = len; R.chr = chr; R.record_start = record_start;
+    return scan_impl(c, &R, 1, out);
 }
 
 int ltg_scan_shard(ltg_context* c, const void* dna, int dna_on_device, int64_t len, const char* chr, int64_t record_start,
                    int64_t record_len, int64_t first_segment, int64_t n_segments, ltg_result** out)
 {
     if (!dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
-    if (dna_on_device) return scan_device_impl(c, (const unsigned char*)dna, nullptr, len, chr, record_start, out, record_len, first_segment, n_segments);
-    return scan_device_impl(c, nullptr, (const char*)dna, len, chr, record_start, out, record_len, first_segment, n_segments);
+    RecordIn R;
+    if (dna_on_device) R.d_dna = (const unsigned char*)dna; else R.h_dna = (const char*)dna;
+    R.len = len; R.chr = chr; R.record_start = record_start; R.record_len = record_len; R.first_seg = first_segment; R.n_seg = n_segments;
+    return scan_impl(c, &R, 1, out);
 }
 
 int ltg_result_new(ltg_result** out)
@@ -1141,7 +1186,7 @@ int ltg_probe_segment(ltg_context* c, const char* seg, int32_t seg_len, ltg_task
     k_encode<<<(seg_len + 255) / 256, 256, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_codes.as<uint8_t>(), seg_len);
     c->launches += 1;
     std::vector<HostSeg> segs(1);
-    segs[0].start = 0; segs[0].len = seg_len; segs[0].flags = 0;
+    segs[0].start = 0; segs[0].len = seg_len; segs[0].flags = 0; segs[0].coord = 0; segs[0].record = 0; segs[0].pad_ = 0;
     for (int i = 0; i < seg_len; ++i) { const char ch = seg[i]; if (!(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T')) segs[0].flags |= kSegNonACGT; }
     ProbeOut po;
     HostBatch& hb = c->hb[0];

@@ -44,7 +44,7 @@ class TaskProbe(C.Structure):
 
 
 EXPORTS = ["ltg_create", "ltg_destroy", "ltg_last_error", "ltg_default_params", "ltg_set_params", "ltg_set_query",
-           "ltg_scan_record", "ltg_scan_device", "ltg_scan_shard", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
+           "ltg_scan_record", "ltg_scan_records", "ltg_scan_device", "ltg_scan_shard", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
            "ltg_write_tfosorted", "ltg_write_tfoclass", "ltg_main", "ltg_probe_segment", "ltg_probe_align", "ltg_stream", "ltg_debug_stats",
            "ltg_device_count"]
 
@@ -73,6 +73,8 @@ def lib():
         L.ltg_set_query.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int64]
         L.ltg_scan_record.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.POINTER(Result))]
         L.ltg_scan_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.POINTER(Result))]
+        L.ltg_scan_records.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_char_p),
+                                       C.POINTER(C.c_int64), C.POINTER(C.POINTER(Result))]
         L.ltg_scan_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                      C.POINTER(C.POINTER(Result))]
         L.ltg_result_free.argtypes = [C.POINTER(Result)]
@@ -220,6 +222,16 @@ class Engine:
     def scan_device(self, dev_ptr, length, chr_tag="", record_start=0):
         res = C.POINTER(Result)()
         _check(lib().ltg_scan_device(self._h, C.c_void_p(dev_ptr), length, chr_tag.encode(), record_start, C.byref(res)))
+        return res
+
+    def scan_records(self, records):
+        """records: list of (dna, chr_tag, record_start) — all records of a multi-record FASTA in one call."""
+        n = len(records)
+        enc = [(d.encode() if isinstance(d, str) else d) for d, _, _ in records]
+        tags = [t.encode() for _, t, _ in records]
+        res = C.POINTER(Result)()
+        _check(lib().ltg_scan_records(self._h, n, (C.c_char_p * n)(*enc), (C.c_int64 * n)(*[len(b) for b in enc]), (C.c_char_p * n)(*tags),
+                                      (C.c_int64 * n)(*[int(s) for _, _, s in records]), C.byref(res)))
         return res
 
     def scan_shard(self, dna, record_len, first_segment, n_segments, chr_tag="", record_start=0, device_ptr=None):

@@ -215,10 +215,24 @@ int ltg_main(int argc, char* const* argv)
     if (rc == LTG_OK) rc = ltg_set_query(ctx, lnc_name.c_str(), lnc.c_str(), (int64_t)lnc.size());
     ltg_result* all = nullptr;
     if (rc == LTG_OK) rc = ltg_result_new(&all);
-    for (size_t i = 0; rc == LTG_OK && i < recs.size(); ++i) {
-        ltg_result* one = nullptr;
-        rc = ltg_scan_record(ctx, recs[i].seq.data(), (int64_t)recs[i].seq.size(), recs[i].chr.c_str(), recs[i].start, &one);
-        if (rc == LTG_OK) { rc = ltg_result_append(all, one); ltg_result_free(one); }
+    // all records of the file through the batched entry point, in chunks of at most ~256 MB of sequence
+    for (size_t i = 0; rc == LTG_OK && i < recs.size();) {
+        std::vector<const char*> dna, chr;
+        std::vector<int64_t> len, start;
+        size_t j = i, bytes = 0;
+        for (; j < recs.size() && (j == i || bytes + recs[j].seq.size() <= (256u << 20)); ++j) {
+            dna.push_back(recs[j].seq.data()); len.push_back((int64_t)recs[j].seq.size());
+            chr.push_back(recs[j].chr.c_str()); start.push_back(recs[j].start);
+            bytes += recs[j].seq.size();
+        }
+        ltg_result* part = nullptr;
+        rc = ltg_scan_records(ctx, (int64_t)(j - i), dna.data(), len.data(), chr.data(), start.data(), &part);
+        if (rc == LTG_OK) {
+            for (int64_t k = 0; k < part->n_triplex; ++k) part->triplex[k].record += (int32_t)i;
+            rc = ltg_result_append(all, part);
+            ltg_result_free(part);
+        }
+        i = j;
     }
     if (rc != LTG_OK) { fprintf(stderr, "fasim: %s\n", ltg_last_error()); ltg_result_free(all); ltg_destroy(ctx); return 3; }
     ltg_cluster(all, &P);

@@ -23,7 +23,8 @@ struct Triplex {
     float score = 0, identity = 0, tri_score = 0;
     // where the alignment lives: input of the string pass (window.cuh TraceJob)
     int tdef = 0, seg_len = 0, ws = 0, rb = 0, re = 0, qb = 0, qe = 0;
-    long seg_start = 0;
+    long seg_start = 0;     // offset of the segment in the device DNA buffer of the call
+    int record = 0;         // record index within the call
 };
 
 struct DeviceAlignment {        // one chosen alignment as it comes back from the GPU (pass 1 of the traceback)
@@ -33,8 +34,8 @@ struct DeviceAlignment {        // one chosen alignment as it comes back from th
 };
 
 // tail of convertMyTriplex — fastsim.h:385-405: orientation-dependent coordinates (:389-396), nt >= ntMin gate (:397)
-inline void make_triplex(const DeviceAlignment& al, int tdef, int seg_len, long seg_start, int para, int strand, int rule,
-                         const ltg_params& P, std::vector<Triplex>& out)
+inline void make_triplex(const DeviceAlignment& al, int tdef, int seg_len, long seg_start, long seg_coord, int record, int para, int strand,
+                         int rule, const ltg_params& P, std::vector<Triplex>& out)
 {
     if (al.nt < P.nt_min) return;
     const int ref_begin = al.ws + al.rb, ref_end = al.ws + al.re;
@@ -43,10 +44,10 @@ inline void make_triplex(const DeviceAlignment& al, int tdef, int seg_len, long 
     else { a = ref_begin + 1; b = ref_end + 1; }
     Triplex t;
     t.stari = al.query_begin + 1; t.endi = al.query_end + 1;
-    t.starj = (int)(a + seg_start); t.endj = (int)(b + seg_start);
+    t.starj = (int)(a + seg_coord); t.endj = (int)(b + seg_coord);        // dnaStartPos of fastSIM = the segment's offset in its record
     t.strand = strand; t.reverse = para; t.rule = rule; t.nt = al.nt;
     t.score = (float)al.sw_score; t.identity = al.identity; t.tri_score = al.tri_score;
-    t.tdef = tdef; t.seg_len = seg_len; t.seg_start = seg_start;
+    t.tdef = tdef; t.seg_len = seg_len; t.seg_start = seg_start; t.record = record;
     t.ws = al.ws; t.rb = al.rb; t.re = al.re; t.qb = al.query_begin; t.qe = al.query_end;
     out.push_back(t);
 }

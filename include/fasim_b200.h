@@ -102,6 +102,12 @@ int ltg_set_query(ltg_context* ctx, const char* name, const char* rna, int64_t l
 int ltg_scan_record(ltg_context* ctx, const char* dna, int64_t len, const char* chr, int64_t record_start,
                     ltg_result** out);
 
+/* Several records in one call (the multi-record -f1 file of main(), Fasim-LongTarget.cpp:133-163): the segments of all
+ * records share the device batches, which keeps the GPU busy when the records are short.  The result equals the
+ * concatenation of ltg_scan_record over the records; ltg_triplex.record is the index into the arrays.                  */
+int ltg_scan_records(ltg_context* ctx, int64_t n_records, const char* const* dna, const int64_t* len, const char* const* chr,
+                     const int64_t* record_start, ltg_result** out);
+
 /* Same computation with the DNA already resident in HBM (device pointer to `len` ASCII bytes). Used by
  * bench.py for the device-resident throughput figure.                                                  */
 int ltg_scan_device(ltg_context* ctx, const void* d_dna, int64_t len, const char* chr, int64_t record_start,

@@ -3,6 +3,7 @@ unmodified reference and against the CPU oracle on the same seeded inputs.  Inte
 bit-exact; the float32 columns (score, identity, stability) are compared by bit pattern as well (the stated
 tolerance of 1e-6 relative is therefore met with margin 0)."""
 import ctypes as C
+import gzip
 import os
 import random
 import struct
@@ -191,6 +192,38 @@ def test_cli_meg3_multi_record(tmp_path, data_dir, golden):
                           open(os.path.join(data_dir, "MEG3-ENST00000451743.fa")).read(), ["-lg", "60"])
     got = [v for k, v in files.items() if k.endswith("TFOsorted")][0]
     assert got == open(os.path.join(GOLDEN, "meg3_first12_mr__TFOsorted")).read()
+
+
+def test_cli_meg3_all_532_regions_default_flags(tmp_path, data_dir):
+    """BASELINE.json configs[1]: the MEG3 lncRNA against its 532 example regions, default flags (-c 5000 -i 60).  Golden =
+    the reference run on the whole file (tests/golden/make_golden_meg3_full.py)."""
+    dna = gzip.open(os.path.join(data_dir, "MEG3-DNAseq.fa.gz")).read().decode()
+    files = run_cli_files(tmp_path, "MEG3-DNAseq.fa", dna, "MEG3.fa", open(os.path.join(data_dir, "MEG3-ENST00000451743.fa")).read(), [])
+    got = [v for k, v in files.items() if k.endswith("TFOsorted")][0]
+    exp = gzip.open(os.path.join(GOLDEN, "meg3_full_mr_defaults__TFOsorted.gz")).read().decode()
+    assert len(exp.splitlines()) > 3000
+    assert got == exp
+
+
+def test_scan_records_equals_record_by_record(engine, data_dir):
+    """ltg_scan_records (all records share the device batches) == ltg_scan_record per record, rows and order."""
+    rna = read_fasta(os.path.join(data_dir, "MEG3-ENST00000451743.fa"))[0][1]
+    recs = read_fasta(os.path.join(data_dir, "MEG3-DNAseq-first12.fa"))
+    engine.set_params(c_length=30)
+    engine.set_query("MEG3", rna)
+    one_by_one, batch_in = [], []
+    for k, (hdr, dna) in enumerate(recs):
+        sp, ch, rng = hdr.split("|")
+        start = int(rng.split("-")[0])
+        rows = engine.LongTarget(dna, ch, start)
+        for r in rows:
+            r["record"] = k
+        one_by_one += rows
+        batch_in.append((dna, ch, start))
+    res = engine.scan_records(batch_in + [("", "chrE", 5)])        # an empty record in the mix
+    got = fb.result_rows(res)
+    engine.free(res)
+    assert got == one_by_one and len(got) > 50
 
 
 def test_meg3_single_records(engine, data_dir, golden):
