@@ -122,7 +122,7 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
-    bool prune = true, dead_rule = true;
+    bool prune = true, dead_rule = true, skip_rounds = true;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     ltg_params params;
     // task tables (depend on params.rule / params.strand)
@@ -139,7 +139,7 @@ struct ltg_context {
     DevBuf d_dna, d_codes, d_segs, d_items, d_colmax, d_bnd, d_counters;
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
-    DevBuf d_w[18], d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
+    DevBuf d_w[20], d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
     DevBuf d_jobs, d_tout, d_strpool, d_scratch, d_scratch_big;
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
     HostBatch hb[2];
@@ -262,28 +262,42 @@ int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, 
 // the list is empty, so no host round trip is needed to decide whether to launch.
 int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const int* n_jobs_dev, int max_read_len, const WinState* w, int max_len)
 {
-    const int L = (max_read_len + 15) / 16;
-    const long long per_slot = (long long)L * 16 * 4 + 64;
-    const int blocks = n_jobs >= 0 ? std::max(1, std::min((n_jobs + 7) / 8, c->num_sms * 8)) : c->num_sms * 2;   // 128 threads = 8 half-warp slots per block
-    const int nslots = blocks * 8;
-    if (int e = c->d_lit_work.ensure((size_t)nslots * per_slot)) return e;
+    // workspace per half-warp slot: kLitArrays uint16 arrays of 16 lanes x pitch; in shared memory when at least one slot fits
+    const int pitch = literal_pitch(max_read_len);
+    const long long per_slot = 2LL * 16 * kLitArrays * pitch;
+    const long long smem_budget = 200 * 1024;
+    int spb = (int)std::min<long long>(8, smem_budget / per_slot);          // slots per block
+    const bool use_smem = spb >= 1;
+    if (!use_smem) spb = 8;
+    const int threads = std::max(32, ((spb * 16 + 31) / 32) * 32);
+    const int want_blocks = n_jobs >= 0 ? std::max(1, (n_jobs + spb - 1) / spb) : c->num_sms * 2;
+    const int blocks = std::min(want_blocks, c->num_sms * 8);
     LiteralArgs la;
     la.jobs = d_jobs; la.n_jobs = n_jobs; la.n_jobs_dev = n_jobs_dev; la.codes = c->d_codes.as<uint8_t>(); la.segs = c->d_segs.as<SegDesc>();
-    la.rna_ssw = c->d_rna_ssw.as<uint8_t>(); la.work = c->d_lit_work.as<unsigned char>(); la.work_per_slot = per_slot;
+    la.rna_ssw = c->d_rna_ssw.as<uint8_t>(); la.use_smem = use_smem ? 1 : 0; la.slots_per_block = spb; la.pitch = pitch;
+    la.work = nullptr; la.work_per_slot = per_slot;
+    size_t smem = 0;
+    if (use_smem) {
+        smem = (size_t)spb * per_slot;
+        LTG_CUDA_CHECK(cudaFuncSetAttribute(k_literal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+        if (int e = c->d_lit_work.ensure((size_t)blocks * spb * per_slot)) return e;
+        la.work = c->d_lit_work.as<unsigned char>();
+    }
     la.lit_colmax = c->d_lit_colmax.as<uint16_t>(); la.max_len = max_len; la.task_litrow = c->d_task_litrow.as<int>();
     if (w) la.w = *w; else memset(&la.w, 0, sizeof la.w);
-    k_literal<<<blocks, 128, 0, c->stream>>>(la);
+    k_literal<<<blocks, threads, smem, c->stream>>>(la);
     c->launches += 1;
     LTG_CUDA_CHECK(cudaGetLastError());
     return LTG_OK;
 }
 
-int literal_windows(ltg_context* c, const WinState& w, bool reverse)
+int literal_windows(ltg_context* c, const WinState& w, bool reverse, int round)
 {
     if (int e = c->d_lit_jobs.ensure(sizeof(LiteralJob) * (size_t)w.n_peaks)) return e;
     int* cnt = c->d_counters.as<int>() + kCntLit + (reverse ? 1 : 0);
     LTG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
-    k_lit_collect<<<(w.n_peaks + 255) / 256, 256, 0, c->stream>>>(w, reverse ? 1 : 0, c->d_lit_jobs.as<LiteralJob>(), cnt,
+    k_lit_collect<<<(w.n_peaks + 255) / 256, 256, 0, c->stream>>>(w, reverse ? 1 : 0, round, c->d_lit_jobs.as<LiteralJob>(), cnt,
                                                                  c->d_counters.as<int>() + kCntLitTotal);
     c->launches += 1;
     return launch_literal(c, c->d_lit_jobs.as<LiteralJob>(), -1, cnt, c->m, &w, 0);
@@ -292,7 +306,7 @@ int literal_windows(ltg_context* c, const WinState& w, bool reverse)
 // ---------------- window stage: peaks (device-resident pool) -> chosen alignments -> traceback pass 1 ----------------
 int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* gran_colmax, int max_len, HostBatch* hb, bool dead_rule)
 {
-    for (int k = 0; k < 18; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
+    for (int k = 0; k < 20; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
     if (int e = c->d_win_list.ensure(sizeof(int) * (size_t)n_peaks)) return e;
     if (int e = c->d_win_sched.ensure(sizeof(WinSched))) return e;
     if (int e = c->d_res.ensure(sizeof(int4) * (size_t)n_peaks)) return e;
@@ -304,7 +318,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.best_sw = c->d_w[2].as<int>(); w.best_cut = c->d_w[3].as<int>(); w.best_re = c->d_w[4].as<int>(); w.best_qe = c->d_w[5].as<int>();
     w.fin_sw = c->d_w[6].as<int>(); w.fin_cut = c->d_w[7].as<int>(); w.fin_re = c->d_w[8].as<int>(); w.fin_qe = c->d_w[9].as<int>();
     w.fin_rb = c->d_w[10].as<int>(); w.fin_qb = c->d_w[11].as<int>();
-    w.w_lo = c->d_w[12].as<int>(); w.w_rows = c->d_w[13].as<int>(); w.w_bound = c->d_w[14].as<int>(); w.w_key = c->d_w[15].as<int>(); w.w_floor = c->d_w[16].as<int>();
+    w.w_lo = c->d_w[12].as<int>(); w.w_rows = c->d_w[13].as<int>(); w.w_bound = c->d_w[14].as<int>(); w.w_key = c->d_w[15].as<int>(); w.w_floor = c->d_w[16].as<int>(); w.w_next = c->d_w[17].as<int>(); w.w_probe = c->d_w[18].as<int>();
     w.sched = c->d_win_sched.as<WinSched>(); w.list = c->d_win_list.as<int>();
     w.res = c->d_res.as<int4>();
     w.codes = c->d_codes.as<uint8_t>(); w.segs = c->d_segs.as<SegDesc>(); w.tasks_per_seg = T;
@@ -333,9 +347,16 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
             c->launches += 1;
         }
         // Q4 guard for windows: exact forward scores >= 148 are recomputed by the literal emulation
-        if (int e = literal_windows(c, w, /*reverse=*/false)) return e;
+        if (int e = literal_windows(c, w, /*reverse=*/false, round)) return e;
         k_win_decide<<<pb, 256, 0, c->stream>>>(w, round);
         c->launches += 1;
+        if (round < 3 && c->skip_rounds) {
+            // reverse probe of the rounds that failed without a candidate: may skip later rounds or finish the peak
+            schedule(-2, 0);
+            k_win_dp<true><<<dp_blocks, 128, 0, c->stream>>>(w);
+            k_win_probe<<<pb, 256, 0, c->stream>>>(w, round);
+            c->launches += 2;
+        }
         LTG_CUDA_CHECK(cudaGetLastError());
     }
     // reverse pass over the chosen alignments
@@ -343,7 +364,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     k_win_dp<true><<<dp_blocks, 128, 0, c->stream>>>(w);
     k_win_finish<<<pb, 256, 0, c->stream>>>(w);
     c->launches += 2;
-    if (int e = literal_windows(c, w, /*reverse=*/true)) return e;
+    if (int e = literal_windows(c, w, /*reverse=*/true, -1)) return e;
     LTG_CUDA_CHECK(cudaGetLastError());
 
     // traceback pass 1: nt / identity / stability of every chosen alignment
@@ -1018,6 +1039,8 @@ int ltg_create(int device, ltg_context** out)
     if (const char* e = getenv("LTG_NO_PRUNE")) c->prune = atoi(e) == 0;
     // LTG_NO_DEAD=1 traces every alignment, also those that provably cannot be reported (window.cuh DeadRule)
     if (const char* e = getenv("LTG_NO_DEAD")) c->dead_rule = atoi(e) == 0;
+    // LTG_NO_SKIP=1 runs every window round of fastSIM's loop even when it provably repeats the previous result
+    if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     *out = c;
     return LTG_OK;
 }
@@ -1040,7 +1063,7 @@ void ltg_destroy(ltg_context* c)
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs})
         b->release();
-    for (int k = 0; k < 18; ++k) c->d_w[k].release();
+    for (int k = 0; k < 20; ++k) c->d_w[k].release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;

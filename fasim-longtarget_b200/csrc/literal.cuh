@@ -31,7 +31,8 @@ struct LiteralArgs {
     const LiteralJob* jobs; int n_jobs;
     const int* n_jobs_dev;                              // used when n_jobs < 0: the count was produced on the device
     const uint8_t* codes; const SegDesc* segs; const uint8_t* rna_ssw;
-    unsigned char* work; long long work_per_slot;       // 4 * L * 16 bytes per half-warp slot
+    unsigned char* work; long long work_per_slot;       // global workspace per half-warp slot (used when use_smem == 0)
+    int use_smem, slots_per_block, pitch;               // shared-memory workspace: slots per block, elements per (array, lane)
     uint16_t* lit_colmax; int max_len;                  // scan jobs: row `job index` receives the literal column maxima
     int* task_litrow;                                   // scan jobs: [task] -> that row
     WinState w;
@@ -39,24 +40,55 @@ struct LiteralArgs {
 
 __device__ inline int sat8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
+// elements per (array, lane): the stripe length rounded up to 4 * odd, so that a lane's arrays are 8-byte aligned and the
+// 16 lanes of a half-warp, which walk their stripes in lock step with 64-bit accesses, cover all 32 banks exactly once
+__host__ __device__ inline int literal_pitch(int read_len) { int q = (((read_len + 15) / 16) + 3) / 4; if ((q & 1) == 0) ++q; return 4 * q; }
+constexpr int kLitArrays = 9;       // H stored, H previous column, E, H at the best column, 5 profile rows
+
+// One half-warp (16 threads = 16 SSE lanes) per job.  Workspace per job: uint16 arrays [lane][t] — H of the column
+// being stored, H of the previous column, E, H at the best column, and the profile (score + bias) of the lane's stripe
+// for each of the 5 base codes — in shared memory (global memory only for lncRNAs beyond ~10 knt).  All values are the
+// reference's unsigned bytes, held in 16-bit lanes so that the native packed 16x2 instructions apply.
+//
+// The stripe loop of a column is sequential in the reference (vF runs down the stripe).  Here only
+//     F' = max(F - 4, max(hbase - 16, 0)),     hbase = max(subs(adds(Hdiag, profile), bias), E)
+// runs step by step (one VIADDMNMX each; it equals the reference's F' = max(subs(F,4), subs(max(hbase,F),16)) because
+// F - 16 < F - 4); hbase before it and H = max(hbase, F), E' = max(subs(E,4), subs(H,16)) after it are computed four
+// steps at a time.  The lazy-F loop with its signed-byte exit test (Q4) is literal.
 __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
 {
+    extern __shared__ uint32_t lit_smem[];
     const int lane = threadIdx.x & 31, s = lane & 15, halfw = lane >> 4;
     const unsigned hmask = halfw ? 0xffff0000u : 0x0000ffffu;
-    const int slot = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2 + halfw;
-    const int nslots = ((gridDim.x * blockDim.x) >> 5) * 2;
+    const int slot_in_block = threadIdx.x >> 4, spb = a.use_smem ? a.slots_per_block : (int)(blockDim.x >> 4);
+    if (slot_in_block >= spb) return;
+    const int slot = blockIdx.x * spb + slot_in_block;
+    const int nslots = gridDim.x * spb;
     const int bias = 4;
+    const uint32_t kFF = 0x00FF00FFu, kM4 = 0xFFFCFFFCu, kM16 = 0xFFF0FFF0u;
     const int n_jobs = a.n_jobs >= 0 ? a.n_jobs : *a.n_jobs_dev;
     for (int jb = slot; jb < n_jobs; jb += nslots) {
         const LiteralJob J = a.jobs[jb];
         const SegDesc sd = a.segs[J.seg];
         const TaskDef td = c_tasks[J.tdef];
         const int L = (J.read_len + 15) / 16;
-        unsigned char* Hs = a.work + (size_t)slot * a.work_per_slot;
-        unsigned char* Hl = Hs + (size_t)L * 16;
-        unsigned char* Ev = Hl + (size_t)L * 16;
-        unsigned char* Hm = Ev + (size_t)L * 16;
-        for (int t = 0; t < L; ++t) { Hs[t * 16 + s] = 0; Hl[t * 16 + s] = 0; Ev[t * 16 + s] = 0; Hm[t * 16 + s] = 0; }
+        const int P = a.pitch;                                   // >= literal_pitch(J.read_len)
+        uint16_t* base = a.use_smem ? reinterpret_cast<uint16_t*>(lit_smem) + (size_t)slot_in_block * (16 * kLitArrays * (size_t)P)
+                                    : reinterpret_cast<uint16_t*>(a.work + (size_t)slot * a.work_per_slot);
+        uint16_t* hs = base + (size_t)s * P;                     // this lane's stripes
+        uint16_t* hl = hs + 16 * (size_t)P;
+        uint16_t* ev = hl + 16 * (size_t)P;
+        uint16_t* hm = ev + 16 * (size_t)P;
+        uint16_t* prof = hm + 16 * (size_t)P;                    // prof + x * 16 * P: profile row of base code x
+        for (int t = 0; t < P; ++t) {
+            hs[t] = 0; hl[t] = 0; ev[t] = 0; hm[t] = 0;
+            const int row = s * L + t;
+            const bool real = t < L && row < J.read_len;
+            const int r = real ? a.rna_ssw[J.read_start + J.read_dir * row] : -1;
+#pragma unroll
+            for (int x = 0; x < 5; ++x)     // qP_byte (sswNew.cpp:176-200): score + bias, pad rows = bias
+                prof[(size_t)x * 16 * P + t] = (uint16_t)(real ? (((r == x && x < 4) ? kMatch : kMismatch) + bias) : bias);
+        }
         uint16_t* cmrow = nullptr;
         if (J.kind == 0) {
             cmrow = a.lit_colmax + (size_t)jb * a.max_len;
@@ -67,37 +99,62 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
         int vMaxScore = 0, vMaxMark = 0, maxv = 0, end_ref = -1;
         bool overflow = false;
         const int begin = J.ref_dir ? J.ref_len - 1 : 0, end = J.ref_dir ? -1 : J.ref_len, step = J.ref_dir ? -1 : 1;
+        const int L4 = L & ~3;
         for (int i = begin; i != end; i += step) {
             const int q = J.ref_start + i;
             const int c = td.img[a.codes[sd.start + (td.reversed ? (sd.len - 1 - q) : q)]];
-            int vF = 0, vMaxCol = 0;
-            int vH = __shfl_up_sync(hmask, (int)Hs[(L - 1) * 16 + s], 1, 16);
+            const uint16_t* pc = prof + (size_t)c * 16 * P;
+            int vF = 0;
+            uint32_t vH = (uint32_t)__shfl_up_sync(hmask, (int)hs[L - 1], 1, 16);
             if (s == 0) vH = 0;
-            { unsigned char* tmp = Hl; Hl = Hs; Hs = tmp; }
-            for (int t = 0; t < L; ++t) {
-                const int row = s * L + t;
-                int p = bias;
-                if (row < J.read_len) { const int r = a.rna_ssw[J.read_start + J.read_dir * row]; p = ((r == c && c < 4) ? kMatch : kMismatch) + bias; }
-                int h = sat8(sat8(vH + p) - bias);
-                int e = Ev[t * 16 + s];
+            { uint16_t* tmp = hl; hl = hs; hs = tmp; }
+            uint32_t vmax2 = 0;
+            int t0 = 0;
+            for (; t0 < L4; t0 += 4) {
+                const uint2 hlw = *reinterpret_cast<const uint2*>(hl + t0);
+                const uint2 ew = *reinterpret_cast<const uint2*>(ev + t0);
+                const uint2 pw = *reinterpret_cast<const uint2*>(pc + t0);
+                // H diagonal of steps t0..t0+3 = H of the previous column at steps t0-1..t0+2
+                const uint32_t vHa = __byte_perm(vH, hlw.x, 0x5410), vHb = __byte_perm(hlw.x, hlw.y, 0x5432);
+                vH = hlw.y >> 16;
+                const uint32_t hba = __vmaxs2(__viaddmax_s16x2(__vmins2(__vadd2(vHa, pw.x), kFF), kM4, 0u), ew.x);
+                const uint32_t hbb = __vmaxs2(__viaddmax_s16x2(__vmins2(__vadd2(vHb, pw.y), kFF), kM4, 0u), ew.y);
+                const uint32_t ga = __viaddmax_s16x2(hba, kM16, 0u), gb = __viaddmax_s16x2(hbb, kM16, 0u);
+                // the sequential part: F entering each of the four steps
+                const int f0 = vF;
+                const int f1 = __viaddmax_s32(f0, -kGapExt, (int)(ga & 0xffffu));
+                const int f2 = __viaddmax_s32(f1, -kGapExt, (int)(ga >> 16));
+                const int f3 = __viaddmax_s32(f2, -kGapExt, (int)(gb & 0xffffu));
+                vF = __viaddmax_s32(f3, -kGapExt, (int)(gb >> 16));
+                const uint32_t ha = __vmaxs2(hba, __byte_perm((uint32_t)f0, (uint32_t)f1, 0x5410));
+                const uint32_t hb = __vmaxs2(hbb, __byte_perm((uint32_t)f2, (uint32_t)f3, 0x5410));
+                vmax2 = __vimax3_s16x2(vmax2, ha, hb);
+                *reinterpret_cast<uint2*>(hs + t0) = make_uint2(ha, hb);
+                // E' = max(subs(E, 4), subs(H, 16));  subs(H,16) >= 0 makes the floor of the first term redundant
+                *reinterpret_cast<uint2*>(ev + t0) = make_uint2(__viaddmax_s16x2(ew.x, kM4, __viaddmax_s16x2(ha, kM16, 0u)),
+                                                                 __viaddmax_s16x2(ew.y, kM4, __viaddmax_s16x2(hb, kM16, 0u)));
+            }
+            int vMaxCol = max((int)(vmax2 & 0xffffu), (int)(vmax2 >> 16));
+            for (int t = t0; t < L; ++t) {                       // the last (L mod 4) steps, step by step
+                int h = sat8(sat8((int)vH + (int)pc[t]) - bias);
+                int e = ev[t];
                 h = max(h, e); h = max(h, vF);
                 vMaxCol = max(vMaxCol, h);
-                Hs[t * 16 + s] = (unsigned char)h;
+                hs[t] = (uint16_t)h;
                 const int open = sat8(h - kGapOpen);
-                e = max(sat8(e - kGapExt), open);
-                Ev[t * 16 + s] = (unsigned char)e;
+                ev[t] = (uint16_t)max(sat8(e - kGapExt), open);
                 vF = max(sat8(vF - kGapExt), open);
-                vH = Hl[t * 16 + s];
+                vH = hl[t];
             }
             bool done = false;
             for (int k = 0; k < 16 && !done; ++k) {
                 vF = __shfl_up_sync(hmask, vF, 1, 16);
                 if (s == 0) vF = 0;
                 for (int t = 0; t < L; ++t) {
-                    int h = Hs[t * 16 + s];
+                    int h = hs[t];
                     h = max(h, vF);
                     vMaxCol = max(vMaxCol, h);
-                    Hs[t * 16 + s] = (unsigned char)h;
+                    hs[t] = (uint16_t)h;
                     const int open = sat8(h - kGapOpen);
                     vF = sat8(vF - kGapExt);
                     const bool gt = (int)(int8_t)vF > (int)(int8_t)open;        // signed byte compare (Q4)
@@ -115,7 +172,7 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
                     maxv = temp;
                     if (maxv + bias >= 255) { overflow = true; break; }
                     end_ref = i;
-                    for (int t = 0; t < L; ++t) Hm[t * 16 + s] = Hs[t * 16 + s];
+                    for (int t = 0; t < P; t += 4) *reinterpret_cast<uint2*>(hm + t) = *reinterpret_cast<const uint2*>(hs + t);
                 }
             }
             int cm = vMaxCol;
@@ -124,9 +181,10 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
             if (cmrow && s == 0) cmrow[i] = (uint16_t)cm;
             if (cm == J.terminate) break;
         }
+        __syncwarp(hmask);
         if (J.kind == 0) continue;
         int end_read = J.read_len - 1;
-        for (int t = 0; t < L; ++t) if (Hm[t * 16 + s] == maxv) end_read = min(end_read, t + s * L);
+        for (int t = 0; t < L; ++t) if (hm[t] == maxv) end_read = min(end_read, t + s * L);
 #pragma unroll
         for (int o = 8; o; o >>= 1) end_read = min(end_read, __shfl_xor_sync(hmask, end_read, o, 16));
         if (s != 0) continue;
@@ -145,7 +203,7 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
 }
 
 // collect the windows whose exact score reaches the Q4 guard
-__global__ void k_lit_collect(const WinState w, int reverse, LiteralJob* jobs, int* count, int* count_total)
+__global__ void k_lit_collect(const WinState w, int reverse, int round, LiteralJob* jobs, int* count, int* count_total)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.n_peaks) return;
@@ -153,7 +211,7 @@ __global__ void k_lit_collect(const WinState w, int reverse, LiteralJob* jobs, i
     const int task = w.pk_task[i];
     J.task = task; J.seg = task / w.tasks_per_seg; J.tdef = task % w.tasks_per_seg; J.peak = i;
     if (!reverse) {
-        if (w.w_done[i]) return;
+        if (w.w_done[i] || w.w_next[i] != round) return;       // only the windows swept in this round
         const int4 v = w.res[i];
         if (v.x < kQ4Guard || v.x >= kOverflowU8) return;
         const int cut = w.w_len[i];

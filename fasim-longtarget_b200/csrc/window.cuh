@@ -75,6 +75,8 @@ struct WinState {
                        // lower bound), so the per-lane result tracker starts there
     int* w_key;        // sort key of the window in flight, -1: not in flight
     int* w_done;       // 1: final alignment chosen
+    int* w_next;       // next forward round this peak takes part in (rounds in between are provably no-ops, see k_win_probe)
+    int* w_probe;      // 1: the round's result waits for its reverse probe; 2: fin_rb / fin_qb are final already
     int* best_sw; int* best_cut; int* best_re; int* best_qe;
     int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb;
     WinSched* sched;
@@ -93,6 +95,9 @@ struct WinState {
 
 // rows spanned by a positive-score local alignment over `cols` columns: < 2.25 * cols + 1
 __host__ __device__ inline int win_margin(int cols) { return (9 * cols) / 4 + 2; }
+// ... and by one that scores at least `s`: d diagonal steps and `ins` inserted rows give s <= 5d - 4*ins - 12, so
+// rows = d + ins <= 2.25 * cols - (s + 12) / 4 (or just d <= cols without insertions)
+__host__ __device__ inline int win_margin_for(int cols, int s) { return max(cols, (9 * cols - s - 12) / 4 + 1) + 1; }
 __device__ inline int win_key(int len, int rows)
 {
     const int g = (len + kWinR - 1) / kWinR;
@@ -114,8 +119,8 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
         if (round >= 0) {
             const int sc = w.pk_score[i], pos = w.pk_pos[i];
             if (!retry) {
-                if (round == 0) { if (sub == 0) { w.w_done[i] = 0; w.best_sw[i] = 0; w.fin_sw[i] = 0; } }
-                else if (w.w_done[i]) active = false;
+                if (round == 0) { if (sub == 0) { w.w_done[i] = 0; w.best_sw[i] = 0; w.fin_sw[i] = 0; w.w_next[i] = 0; w.w_probe[i] = 0; } }
+                else if (w.w_done[i] || w.w_next[i] != round) active = false;
                 int cut = w.forced_cut ? w.forced_cut[i] : w.cut_table[min(sc, 255) * 4 + round];
                 if (pos - cut + 1 <= 0) cut = pos + 1;                 // fastsim.h:211
                 len = cut;
@@ -125,13 +130,15 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
                 if (round > 0) { const int prev = w.res[i].x; if (prev > 0 && prev < bound) bound = prev; }
             } else {
                 const int4 v = w.res[i];
-                if (w.w_done[i] || v.x >= w.w_bound[i]) active = false;      // exact already
+                if (w.w_done[i] || w.w_next[i] != round || v.x >= w.w_bound[i]) active = false;      // not in flight / exact already
                 len = w.w_len[i];
                 bound = max(v.x, 0);
                 proven = bound;              // a cell with this value exists: anything below it is irrelevant now
             }
         } else {
+            // reverse plans: round -1 = every chosen alignment whose begin is not known yet, round -2 = reverse probes
             if (w.fin_sw[i] <= 0) active = false;
+            if (round == -1 ? (w.w_probe[i] == 2) : (w.w_probe[i] != 1 || w.w_done[i])) active = false;
             len = w.fin_re[i] + 1;
         }
     }
@@ -169,7 +176,8 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
         int lo = 0, floor_v = max(proven - 1, 0);
         rows = w.m; bound = 0;
         if (khi >= 0) {
-            lo = max(0, klo * w.gran_rows - win_margin(len));
+            // only cells above `outside` matter (a result r > outside is exact), and their alignments span at most this many rows
+            lo = max(0, klo * w.gran_rows - win_margin_for(len, outside + 1));
             const int hi = min(w.m - 1, (khi + 1) * w.gran_rows - 1);
             if (hi - lo + 1 < w.m) { rows = hi - lo + 1; bound = outside + 1; floor_v = max(floor_v, outside); } else lo = 0;
         }
@@ -179,8 +187,8 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
         atomicAdd(&w.sched->st_cells[round * 2 + retry], (unsigned long long)len * (unsigned long long)rows);
     } else {
         rows = min(w.fin_qe[i] + 1, win_margin(len));
-        atomicAdd(&w.sched->st_windows[8], 1ull);
-        atomicAdd(&w.sched->st_cells[8], (unsigned long long)len * (unsigned long long)rows);
+        atomicAdd(&w.sched->st_windows[round == -1 ? 8 : 9], 1ull);
+        atomicAdd(&w.sched->st_cells[round == -1 ? 8 : 9], (unsigned long long)len * (unsigned long long)rows);
     }
     w.w_len[i] = len;
     const int key = win_key(len, rows);
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 __global__ void k_win_decide(const WinState w, int round)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.n_peaks || w.w_done[i]) return;
+    if (i >= w.n_peaks || w.w_done[i] || w.w_next[i] != round) return;
     const int cut = w.w_len[i];
     const int4 v = w.res[i];
     int sw = 0, re = 0, qe = 0;
@@ -430,18 +438,54 @@ __global__ void k_win_decide(const WinState w, int round)
             return;
         }
     }
-    if (round == 3) {
+    // an exact score of 0 stays 0 in every nested window: nothing will be accepted or become a candidate any more
+    const bool dead_end = (sw == 0 && v.w == 0);
+    if (round == 3 || dead_end) {
         if (w.best_sw[i] > 0) { w.fin_sw[i] = w.best_sw[i]; w.fin_cut[i] = w.best_cut[i]; w.fin_re[i] = w.best_re[i]; w.fin_qe[i] = w.best_qe[i]; }
         else { w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; }
         w.w_done[i] = 1;
+        return;
     }
+    w.w_next[i] = round + 1;
+    // exact result, no candidate so far: park it in fin_* for the reverse probe (k_win_probe) that may skip rounds
+    if (v.w == 0 && w.best_sw[i] == 0) {
+        w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe;
+        w.w_probe[i] = 1;
+    }
+}
+
+// Round skipping (exact).  Round k found its best cell e (score s < S, not in the last column) and the reverse probe the
+// latest start column rb of an alignment that reaches s at e.  A later round looks at the last cut' columns of the same
+// window.  While that window still contains column rb, the alignment fits, so the window's maximum is still s, its
+// maximal cells are a subset of round k's and contain e, hence the tie rules pick e again: the round reports the same
+// alignment, which still misses S and the last column and so changes nothing (fastsim.h:218-235).  The peak jumps to
+// the first round whose window starts after rb; if there is none, the last round's alignment is this one (fastsim.h:253).
+__global__ void k_win_probe(const WinState w, int round)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n_peaks || w.w_done[i] || w.w_probe[i] != 1) return;
+    w.w_probe[i] = 0;
+    const int S = w.fin_sw[i];
+    const int4 v = w.res[i];
+    if (v.x != S) return;                        // (cannot happen for an exact forward score) take every round
+    const int rb = w.fin_re[i] - v.y, qb = w.fin_qe[i] - v.z;
+    const int pos = w.pk_pos[i], sc = w.pk_score[i];
+    const int start_col = pos - w.fin_cut[i] + 1 + rb;       // in translated-segment coordinates
+    int k = round + 1;
+    for (; k <= 3; ++k) {
+        int cut = w.forced_cut ? w.forced_cut[i] : w.cut_table[min(sc, 255) * 4 + k];
+        if (pos - cut + 1 <= 0) cut = pos + 1;
+        if (pos - cut + 1 > start_col) break;                 // this window no longer holds the alignment
+    }
+    if (k > 3) { w.fin_rb[i] = rb; w.fin_qb[i] = qb; w.w_probe[i] = 2; w.w_done[i] = 1; }
+    else w.w_next[i] = k;
 }
 
 // reverse result: beginning of the alignment (sswNew.cpp:1518-1520)
 __global__ void k_win_finish(const WinState w)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.n_peaks || w.fin_sw[i] <= 0) return;
+    if (i >= w.n_peaks || w.fin_sw[i] <= 0 || w.w_probe[i] == 2) return;
     const int S = w.fin_sw[i];
     const int4 v = w.res[i];
     int col = -1, row = 0;

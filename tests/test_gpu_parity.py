@@ -331,11 +331,13 @@ def test_row_pruning_is_exact(data_dir):
     drna, _, ddna = demo(data_dir)
     os.environ["LTG_NO_PRUNE"] = "1"
     os.environ["LTG_NO_DEAD"] = "1"          # and trace every alignment, not only those that can still be reported
+    os.environ["LTG_NO_SKIP"] = "1"          # and run every window round
     try:
         full = fb.Engine(0)
     finally:
         del os.environ["LTG_NO_PRUNE"]
         del os.environ["LTG_NO_DEAD"]
+        del os.environ["LTG_NO_SKIP"]
     pruned = fb.Engine(0)
     try:
         outs = []
