@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
             uint32_t hout = 0, fout = 0, cmout = 0, hdiag = 0;
             const int steps = n + 31;
+#ifdef LTG_SCAN_V1
             // software pipeline: the packed scores of step s+1 are loaded while step s computes, and the base code
             // two steps ahead is fetched, so no step starts by waiting on a shared-memory round trip
             const uint8_t* cp = s_codes + (32 - lane);
@@ -262,6 +263,89 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 if (gran_tail && s >= lane && s - lane < n) cm_lane[s] = cm;
                 if (lane == 31 && !last && s >= 31) bnd[s - 31] = make_uint2(hout, fout);
             }
+#else
+            // Steps run in blocks of 32 (the ring of strip-boundary packets is refilled per block).  Shared memory is
+            // addressed with explicit 32-bit shared addresses (one add per profile fetch instead of a generic-pointer
+            // conversion); the packed scores of step s+1 are loaded while step s computes and the base code two steps
+            // ahead is fetched.  Blocks in which every lane is inside its column range ("interior": all but the first
+            // and the last two) need no per-step store predicates: they are loop invariants of the lane.
+            const uint32_t sa_prof = (uint32_t)__cvta_generic_to_shared(s_prof) + lane * 16;
+            const uint32_t sa_code = (uint32_t)__cvta_generic_to_shared(s_codes) + (32 - lane);
+            const uint32_t sa_ring = (uint32_t)__cvta_generic_to_shared(s_ring);
+            uint4 sc[R / 4];
+            uint32_t xn;
+            {
+                uint32_t x0;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(x0) : "r"(sa_code));
+                const uint32_t ad = sa_prof + x0 * (PLANE * 16);
+#pragma unroll
+                for (int k = 0; k < R / 4; ++k)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sc[k].x), "=r"(sc[k].y), "=r"(sc[k].z), "=r"(sc[k].w) : "r"(ad + k * 512));
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(xn) : "r"(sa_code + 1));
+            }
+            uint32_t* cm_ptr = cm_lane;                           // cm_ptr[0] is this lane's slot for step s
+            uint2* bnd_ptr = bnd - 31;                            // bnd_ptr[0] is lane 31's slot for step s
+            const bool st_bnd = (lane == 31) && !last;
+
+#define LTG_SCAN_STEP(GUARD, S, K)                                                                              \
+            {                                                                                                   \
+                uint4 scn[R / 4];                                                                               \
+                {                                                                                               \
+                    const uint32_t ad = sa_prof + xn * (PLANE * 16);                                            \
+                    _Pragma("unroll") for (int k = 0; k < R / 4; ++k)                                           \
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"                                 \
+                                     : "=r"(scn[k].x), "=r"(scn[k].y), "=r"(scn[k].z), "=r"(scn[k].w) : "r"(ad + k * 512)); \
+                    const uint32_t ca = sa_code + (GUARD ? (uint32_t)min((S) + 2, steps) : (uint32_t)((S) + 2)); \
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(xn) : "r"(ca));                                \
+                }                                                                                               \
+                uint32_t hin = __shfl_up_sync(0xffffffffu, hout, 1);                                            \
+                uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);                                            \
+                uint32_t cmin = __shfl_up_sync(0xffffffffu, cmout, 1);                                          \
+                if (gran_head) cmin = 0;                                                                        \
+                if (lane == 0) {                                                                                \
+                    if (first) { hin = 0; fin = 0; }                                                            \
+                    else asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hin), "=r"(fin) : "r"(sa_ring + (K) * 8)); \
+                }                                                                                               \
+                uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;                                              \
+                uint32_t tv[2];                                                                                 \
+                _Pragma("unroll") for (int k = 0; k < R / 4; ++k) {                                             \
+                    LTG_CELL(sc[k].x, 4 * k + 0)                                                                \
+                    LTG_CELL(sc[k].y, 4 * k + 1)                                                                \
+                    LTG_CELL(sc[k].z, 4 * k + 2)                                                                \
+                    LTG_CELL(sc[k].w, 4 * k + 3)                                                                \
+                }                                                                                               \
+                _Pragma("unroll") for (int k = 0; k < R / 4; ++k) sc[k] = scn[k];                               \
+                hdiag = hin;                                                                                    \
+                hout = hlast; fout = f; cmout = cm;                                                             \
+                if (GUARD) {                                                                                    \
+                    if (gran_tail && (S) >= lane && (S) - lane < n) cm_ptr[(K)] = cm;                           \
+                    if (st_bnd && (S) >= 31 && (S) - 31 < n) bnd_ptr[(K)] = make_uint2(hout, fout);             \
+                } else {                                                                                        \
+                    if (gran_tail) cm_ptr[(K)] = cm;                                                            \
+                    if (st_bnd) bnd_ptr[(K)] = make_uint2(hout, fout);                                          \
+                }                                                                                               \
+            }
+
+            for (int s0 = 0; s0 < steps; s0 += 32) {
+                if (!first) {
+                    __syncwarp();
+                    const int j = s0 + lane;
+                    uint2 pk = make_uint2(0, 0);
+                    if (j < n) pk = bnd[j];
+                    s_ring[lane] = pk;
+                    __syncwarp();
+                }
+                if (s0 >= 32 && s0 + 33 < n) {
+#pragma unroll 4
+                    for (int k = 0; k < 32; ++k) LTG_SCAN_STEP(false, s0 + k, k)
+                } else {
+                    const int cnt = min(32, steps - s0);
+                    for (int k = 0; k < cnt; ++k) LTG_SCAN_STEP(true, s0 + k, k)
+                }
+                cm_ptr += 32; bnd_ptr += 32;
+            }
+#undef LTG_SCAN_STEP
+#endif
         }
     }
 }
