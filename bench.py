@@ -288,7 +288,7 @@ def bench_gpu(args, rank, world, local_rank):
             "e2e": {"value": gcups_e, "unit": "GCUPS", "h2d_bytes_per_step": int(st_e["h2d"] / args.steps),
                     "d2h_bytes_per_step": int(st_e["d2h"] / args.steps), "ms_per_step": ms_e / args.steps,
                     "mbp_per_s": st_e["bases"] / (ms_e * 1e-3) / 1e6},
-            "roofline": {"bound": "int_simd", "kernel": "k_scan<16,4>", "achieved": scan_gcups, "peak": peak, "unit": "GCUPS",
+            "roofline": {"bound": "int_simd", "kernel": "k_scan<32,4> (rows per lane chosen per lncRNA length: 32 here)", "achieved": scan_gcups, "peak": peak, "unit": "GCUPS",
                          "frac": scan_gcups / peak if peak else None, "peak_source": peak_src,
                          "cells_per_launch": st["cells"] / max(st["scan_launches"], 1),
                          "ms_per_launch": st["scan_ms"] / max(st["scan_launches"] / world, 1),

@@ -73,18 +73,24 @@ struct PinBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-#ifndef LTG_SCAN_R
-#define LTG_SCAN_R 16
-#endif
+// Scan tiling: R RNA rows per lane (strip = 32 * R rows).  R = 32 has the lowest per-cell overhead; R = 16 halves the
+// strip and is chosen for lncRNAs that would mostly pad a 1024-row strip.  LTG_SCAN_R forces one of them (tuning builds).
 #ifndef LTG_SCAN_WARPS
 #define LTG_SCAN_WARPS 4
 #endif
-#ifndef LTG_SCAN_CTAS
-#define LTG_SCAN_CTAS 3
-#endif
-constexpr int kScanR = LTG_SCAN_R;          // RNA rows per lane in the scan kernel (strip = 32 * kScanR rows)
 constexpr int kScanWarps = LTG_SCAN_WARPS;  // warps per CTA
-constexpr int kScanCtasPerSm = LTG_SCAN_CTAS;
+inline int scan_ctas_per_sm(int R) { return R >= 32 ? 2 : 3; }
+inline int choose_scan_r(int m)
+{
+#ifdef LTG_SCAN_R
+    (void)m;
+    return LTG_SCAN_R;
+#else
+    const long long m16 = 16LL * ((m + 15) / 16);
+    const long long pad32 = ((m16 + 1023) / 1024) * 1024, pad16 = ((m16 + 511) / 512) * 512;
+    return pad32 * 100 <= pad16 * 104 ? 32 : 16;      // R = 32 is ~4.5 % faster per row
+#endif
+}
 constexpr int kBatchSegments = 1024;
 constexpr size_t kStripBytesPerBatch = 16ull << 30;     // cap of the granule-maxima buffer of one batch
 
@@ -132,7 +138,7 @@ struct ltg_context {
     // query
     std::string rna_name, rna;
     bool rna_plain = true;          // only ACGT (any case): the SSW-side and Farrar-side scorings coincide
-    int m = 0, n_strips = 0;
+    int m = 0, n_strips = 0, scan_r = 32;
     bool profiles_dirty = true;
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
@@ -202,17 +208,21 @@ int upload_tables(ltg_context* c)
 int build_profiles(ltg_context* c)
 {
     if (c->m <= 0) { set_error("no lncRNA loaded (call ltg_set_query first)"); return LTG_ERR_STATE; }
-    const int strip_rows = 32 * kScanR;
+    c->scan_r = choose_scan_r(c->m);
+    const int strip_rows = 32 * c->scan_r;
     const int m16 = 16 * ((c->m + 15) / 16);
     c->n_strips = (m16 + strip_rows - 1) / strip_rows;
-    const size_t words = (size_t)c->pairs.size() * c->n_strips * 5 * 32 * kScanR;
+    const size_t words = (size_t)c->pairs.size() * c->n_strips * 5 * 32 * c->scan_r;
     if (int e = c->d_prof_ssw.ensure(words * 4)) return e;
     if (int e = c->d_prof_stats.ensure(words * 4)) return e;
     const int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 8);
-    k_build_profiles<kScanR><<<blocks, 256, 0, c->stream>>>(c->d_rna_ssw.as<uint8_t>(), c->d_rna_stats.as<uint8_t>(), c->m,
-                                                             (int)c->pairs.size(), c->n_strips, 0, c->d_prof_ssw.as<uint32_t>());
-    k_build_profiles<kScanR><<<blocks, 256, 0, c->stream>>>(c->d_rna_ssw.as<uint8_t>(), c->d_rna_stats.as<uint8_t>(), c->m,
-                                                             (int)c->pairs.size(), c->n_strips, 1, c->d_prof_stats.as<uint32_t>());
+    for (int kind = 0; kind < 2; ++kind) {
+        uint32_t* dst = kind ? c->d_prof_stats.as<uint32_t>() : c->d_prof_ssw.as<uint32_t>();
+        if (c->scan_r == 32)
+            k_build_profiles<32><<<blocks, 256, 0, c->stream>>>(c->d_rna_ssw.as<uint8_t>(), c->d_rna_stats.as<uint8_t>(), c->m, (int)c->pairs.size(), c->n_strips, kind, dst);
+        else
+            k_build_profiles<16><<<blocks, 256, 0, c->stream>>>(c->d_rna_ssw.as<uint8_t>(), c->d_rna_stats.as<uint8_t>(), c->m, (int)c->pairs.size(), c->n_strips, kind, dst);
+    }
     c->launches += 2;
     LTG_CUDA_CHECK(cudaGetLastError());
     c->profiles_dirty = false;
@@ -240,10 +250,10 @@ struct ProbeOut {
 
 int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax)
 {
-    const int blocks = c->num_sms * kScanCtasPerSm;
-    const size_t smem = (size_t)kScanWarps * scan_warp_smem_bytes<kScanR>(max_len);
+    const int R = c->scan_r;
+    const int blocks = c->num_sms * scan_ctas_per_sm(R);
+    const size_t smem = (size_t)kScanWarps * (R == 32 ? scan_warp_smem_bytes<32>(max_len) : scan_warp_smem_bytes<16>(max_len));
     if (smem > 227 * 1024) { set_error("segment length %d needs %zu bytes of shared memory per CTA", max_len, smem); return LTG_ERR_LIMIT; }
-    LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<kScanR, kScanWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (int e = c->d_bnd.ensure((size_t)blocks * kScanWarps * max_len * sizeof(uint2))) return e;
     int* counters = c->d_counters.as<int>();
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntScan, 0, sizeof(int), c->stream));
@@ -251,7 +261,13 @@ int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, 
     a.codes = c->d_codes.as<uint8_t>(); a.segs = c->d_segs.as<SegDesc>(); a.items = c->d_items.as<ScanItem>();
     a.n_items = n_items; a.profiles = prof; a.n_strips = c->n_strips; a.max_len = max_len;
     a.colmax = colmax; a.bnd = c->d_bnd.as<uint2>(); a.counter = counters + kCntScan;
-    k_scan<kScanR, kScanWarps><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+    if (R == 32) {
+        LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_scan<32, kScanWarps><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+    } else {
+        LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<16, kScanWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_scan<16, kScanWarps><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+    }
     c->launches += 1;
     LTG_CUDA_CHECK(cudaGetLastError());
     return LTG_OK;
@@ -325,7 +341,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.rna_ssw = c->d_rna_ssw.as<uint8_t>(); w.m = c->m; w.cut_table = c->d_cut.as<int>();
     w.cell_counter = reinterpret_cast<long long*>(counters + kCntCells);
     w.forced_cut = forced_cut;
-    w.gran_colmax = c->prune ? gran_colmax : nullptr; w.n_gran = c->n_strips * kGranPerStrip; w.gran_rows = kGranLanes * kScanR; w.max_len = max_len;
+    w.gran_colmax = c->prune ? gran_colmax : nullptr; w.n_gran = c->n_strips * (32 * c->scan_r / kGranRows); w.gran_rows = kGranRows; w.max_len = max_len;
     w.n_pairs = (int)c->pairs.size();
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCells, 0, 8, c->stream));
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntLitTotal, 0, sizeof(int), c->stream));
@@ -466,7 +482,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
 
     if (int e = c->d_segs.ensure(sizeof(SegDesc) * S)) return e;
     if (int e = c->d_items.ensure(sizeof(ScanItem) * n_items)) return e;
-    const int n_gran = c->n_strips * kGranPerStrip;
+    const int n_gran = c->n_strips * (32 * c->scan_r / kGranRows);
     if (int e = c->d_colmax.ensure((size_t)n_items * n_gran * max_len * 4)) return e;
     if (int e = c->d_colmax_all.ensure((size_t)n_items * max_len * 4)) return e;
     if (int e = c->d_task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
@@ -899,7 +915,7 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
 
         // batch size: bounded by the strip-maxima buffer; at least two batches when there is enough work so that the
         // host phase of one overlaps the device phase of the next
-        const size_t per_seg = (size_t)c->pairs.size() * c->n_strips * kGranPerStrip * (size_t)((c->params.cut_length + 3) & ~3) * 4;
+        const size_t per_seg = (size_t)c->pairs.size() * c->n_strips * (32 * c->scan_r / kGranRows) * (size_t)((c->params.cut_length + 3) & ~3) * 4;
         size_t bs = std::max<size_t>(16, std::min<size_t>(kBatchSegments, kStripBytesPerBatch / std::max<size_t>(1, per_seg)));
         if (active.size() > 256 && active.size() < 2 * bs) bs = (active.size() + 1) / 2;
         std::vector<ltg_host::Triplex> record_list;

@@ -128,7 +128,7 @@ struct ScanArgs {
     int n_strips;
     int max_len;                // row pitch of colmax / bnd (>= longest segment)
     uint32_t* colmax;           // [item][granule][max_len] packed column maxima of the two tasks, one row per granule of
-                                // kGranLanes*R RNA rows (n_strips * 32/kGranLanes granules per item)
+                                // kGranRows RNA rows (n_strips * 32 * R / kGranRows granules per item)
     uint2* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F)
     int* counter;               // work queue head
 };
@@ -161,12 +161,11 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
         hlast = h_;                                               \
     }
 
-// The column maxima are kept PER GRANULE of kGranLanes lanes (kGranLanes*R RNA rows; the running maximum that
+// The column maxima are kept PER GRANULE of kGranRows / R lanes (kGranRows RNA rows; the running maximum that
 // travels along the lanes restarts at every granule head and the granule's last lane stores it): the epilogue
 // combines them into the reference's per-column maximum, and the window stage uses them as upper bounds to
 // skip RNA rows that cannot hold a window's best cell (window.cuh, "row pruning").
-constexpr int kGranLanes = 8;                    // lanes per granule
-constexpr int kGranPerStrip = 32 / kGranLanes;   // granules per strip
+constexpr int kGranRows = 128;                   // RNA rows per granule (kGranRows / R lanes; 32 * R / kGranRows granules per strip)
 
 template <int R, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
@@ -198,6 +197,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             const int j = i - 32;
             s_codes[i] = (j < 0 || j >= n) ? (uint8_t)kBaseOther : gcodes[rev ? (n - 1 - j) : j];
         }
+        constexpr int kGranLanes = kGranRows / R, kGranPerStrip = 32 / kGranLanes;
+        static_assert(kGranLanes >= 1 && kGranLanes * R == kGranRows, "R must divide the granule");
         uint32_t* cm_item = a.colmax + (size_t)item * a.n_strips * kGranPerStrip * a.max_len;
         const bool gran_head = (lane & (kGranLanes - 1)) == 0, gran_tail = (lane & (kGranLanes - 1)) == kGranLanes - 1;
 

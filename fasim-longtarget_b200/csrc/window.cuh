@@ -18,7 +18,7 @@
 //      (every inserted row costs >= 4, every column yields <= 5), so the value of a cell only depends on
 //      the win_margin(c) rows above it;
 //  (2) a window cell can never exceed the same cell of the whole-segment matrix, and the scan stage kept,
-//      per granule of kGranLanes*R_scan RNA rows, the column maxima of that matrix (scan.cuh).
+//      per granule of kGranRows RNA rows, the column maxima of that matrix (scan.cuh).
 // For a guess L of the window's best score, the stream covers the granules whose maximum over the window's
 // columns reaches L, the granules between them, and the margin above the first.  Let B be the largest such
 // maximum among the granules left out.  Values computed on a sub-range of rows are lower bounds of the true
