@@ -138,6 +138,7 @@ struct ltg_context {
     // query
     std::string rna_name, rna;
     bool rna_plain = true;          // only ACGT (any case): the SSW-side and Farrar-side scorings coincide
+    bool rna_acgt = true;           // every SSW code of the lncRNA is 0..3 (A/C/G/T, U counts as A): table lookup scoring applies
     int m = 0, n_strips = 0, scan_r = 32;
     bool profiles_dirty = true;
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_prof_ssw, d_prof_stats, d_cut;
@@ -359,7 +360,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     for (int round = 0; round < 4; ++round) {
         for (int retry = 0; retry < (w.gran_colmax ? 2 : 1); ++retry) {
             schedule(round, retry);
-            k_win_dp<false><<<dp_blocks, 128, 0, c->stream>>>(w);
+            if (c->rna_acgt) k_win_dp<false, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<false, false><<<dp_blocks, 128, 0, c->stream>>>(w);
             c->launches += 1;
         }
         // Q4 guard for windows: exact forward scores >= 148 are recomputed by the literal emulation
@@ -369,7 +370,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
         if (round < 3 && c->skip_rounds) {
             // reverse probe of the rounds that failed without a candidate: may skip later rounds or finish the peak
             schedule(-2, 0);
-            k_win_dp<true><<<dp_blocks, 128, 0, c->stream>>>(w);
+            if (c->rna_acgt) k_win_dp<true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false><<<dp_blocks, 128, 0, c->stream>>>(w);
             k_win_probe<<<pb, 256, 0, c->stream>>>(w, round);
             c->launches += 2;
         }
@@ -377,7 +378,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     }
     // reverse pass over the chosen alignments
     schedule(-1, 0);
-    k_win_dp<true><<<dp_blocks, 128, 0, c->stream>>>(w);
+    if (c->rna_acgt) k_win_dp<true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false><<<dp_blocks, 128, 0, c->stream>>>(w);
     k_win_finish<<<pb, 256, 0, c->stream>>>(w);
     c->launches += 2;
     if (int e = literal_windows(c, w, /*reverse=*/true, -1)) return e;
@@ -1114,11 +1115,12 @@ int ltg_set_query(ltg_context* c, const char* name, const char* rna, int64_t len
     c->rna.assign(rna, (size_t)len);
     c->m = (int)len;
     std::vector<uint8_t> q1(len), q2(len);
-    c->rna_plain = true;
+    c->rna_plain = true; c->rna_acgt = true;
     for (int64_t i = 0; i < len; ++i) {
         const unsigned char ch = (unsigned char)rna[i];
         q1[i] = (uint8_t)ssw_code(ch); q2[i] = (uint8_t)stats_code(ch);
         if (q1[i] == 4 || q2[i] >= 4) c->rna_plain = false;      // U or any non-ACGT letter: scorings differ (Q3)
+        if (q1[i] == 4) c->rna_acgt = false;
     }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats}) if (int e = b->ensure((size_t)len)) return e;
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_raw.p, rna, (size_t)len, cudaMemcpyHostToDevice, c->stream));

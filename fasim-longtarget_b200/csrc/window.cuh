@@ -246,7 +246,8 @@ __global__ void k_win_place(const WinState w)
     w.list[w.sched->off[key] + atomicAdd(&w.sched->fill[key], 1)] = i;
 }
 
-template <bool REV>
+// TAB: score lookup with one PRMT per cell pair (needs an lncRNA made of A/C/G/T/U only); otherwise XNOR + VIADDMNMX.
+template <bool REV, bool TAB>
 __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 {
     constexpr int R = kWinR;
@@ -274,9 +275,11 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 
         // per-half window description for this lane's group
         int wi[2], len[2], slen[2], sbase[2], sdir[2];
-        uint32_t dq[R];
+        // per owned column: the scaled base codes of the two windows (XNOR path), or (TAB) two 4-entry score tables — byte x of
+        // ta[r] / tb[r] is the score of RNA code x against the column of the low / high half's window
+        uint32_t dq[TAB ? 1 : R], ta[TAB ? R : 1], tb[TAB ? R : 1];
 #pragma unroll
-        for (int r = 0; r < R; ++r) dq[r] = 0;
+        for (int r = 0; r < (TAB ? 1 : R); ++r) dq[r] = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int slot = (b * 2 + h) * gpw + grp;
@@ -309,7 +312,13 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                 }
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) dq[r] |= (uint32_t)colcode[r] << (16 * h);
+            for (int r = 0; r < R; ++r) {
+                if (TAB) {
+                    // 0xFC = -4 everywhere, 0x05 at the byte of the column's own code (pad / N columns: no match at all)
+                    const uint32_t tab = colcode[r] < 64 ? (0xFCFCFCFCu ^ (0xF9u << (colcode[r] >> 1))) : 0xFCFCFCFCu;
+                    if (h == 0) ta[r] = tab; else tb[r] = tab;
+                } else dq[r] |= (uint32_t)colcode[r] << (16 * h);
+            }
         }
         int nsteps = max(slen[0], slen[1]);
 #pragma unroll
@@ -331,15 +340,20 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
         uint32_t Hd[R], E[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
-        uint32_t hout = 0, fout = 0, xout = pack16(64, 64), hdiag = 0;
+        // The stream symbol travels with the wavefront.  XNOR path: the scaled codes of the two halves' RNA rows (64 = none).
+        // TAB path: a ready PRMT selector — for code x of the low half the nibbles (x, x|8) pick the score byte and its sign
+        // extension out of ta[r], for the high half (4+x, 4+x|8) out of tb[r]; "none" (past the end of a stream) selects two
+        // sign bytes, i.e. a score of -1 or 0, which like -4 can never raise a maximum.
+        const uint32_t kNoneLo = TAB ? 0x88u : 64u, kNoneHi = TAB ? 0xCCu : 64u;
+        uint32_t hout = 0, fout = 0, xout = kNoneLo | (kNoneHi << (TAB ? 8 : 16)), hdiag = 0;
         // leader prefetch of the stream symbol
         auto fetch = [&](int s) -> uint32_t {
-            int c0 = 64, c1 = 64;
+            uint32_t c0 = kNoneLo, c1 = kNoneHi;
             if (leader) {
-                if (s < slen[0]) { const int q = w.rna_ssw[sbase[0] + sdir[0] * s]; c0 = q < 4 ? q * 16 : 64; }
-                if (s < slen[1]) { const int q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = q < 4 ? q * 16 : 64; }
+                if (s < slen[0]) { const uint32_t q = w.rna_ssw[sbase[0] + sdir[0] * s]; c0 = TAB ? (q | ((q | 8u) << 4)) : (q < 4 ? q * 16 : 64u); }
+                if (s < slen[1]) { const uint32_t q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = TAB ? ((4u + q) | ((12u + q) << 4)) : (q < 4 ? q * 16 : 64u); }
             }
-            return pack16(c0, c1);
+            return c0 | (c1 << (TAB ? 8 : 16));
         };
         uint32_t xnext = fetch(0);
         for (int s = 0; s < nsteps; ++s) {
@@ -353,8 +367,9 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
             uint32_t t[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t y = ~(xin ^ dq[r]);
-                const uint32_t sc2 = __viaddmax_s16x2(y, kSix, kMis);         // +5 on equal codes, -4 otherwise
+                uint32_t sc2;
+                if (TAB) asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc2) : "r"(ta[r]), "r"(tb[r]), "r"(xin));     // +5 / -4 looked up and sign-extended (selector bit 3)
+                else sc2 = __viaddmax_s16x2(~(xin ^ dq[r]), kSix, kMis);      // +5 on equal codes, -4 otherwise
                 t[r] = __viaddmax_s16x2_relu(d, sc2, E[r]);
                 const uint32_t u = __vadd2(t[r], kNegOpen);
                 E[r] = __viaddmax_s16x2(E[r], kNegExt, u);
