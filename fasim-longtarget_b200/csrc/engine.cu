@@ -141,7 +141,7 @@ struct ltg_context {
     bool rna_acgt = true;           // every SSW code of the lncRNA is 0..3 (A/C/G/T, U counts as A): table lookup scoring applies
     int m = 0, n_strips = 0, scan_r = 32;
     bool profiles_dirty = true;
-    DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_prof_ssw, d_prof_stats, d_cut;
+    DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_colmax, d_bnd, d_counters;
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
@@ -339,7 +339,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.sched = c->d_win_sched.as<WinSched>(); w.list = c->d_win_list.as<int>();
     w.res = c->d_res.as<int4>();
     w.codes = c->d_codes.as<uint8_t>(); w.segs = c->d_segs.as<SegDesc>(); w.tasks_per_seg = T;
-    w.rna_ssw = c->d_rna_ssw.as<uint8_t>(); w.m = c->m; w.cut_table = c->d_cut.as<int>();
+    w.rna_ssw = c->d_rna_ssw.as<uint8_t>(); w.rna_sel = c->d_rna_sel.as<uint16_t>(); w.m = c->m; w.cut_table = c->d_cut.as<int>();
     w.cell_counter = reinterpret_cast<long long*>(counters + kCntCells);
     w.forced_cut = forced_cut;
     w.gran_colmax = c->prune ? gran_colmax : nullptr; w.n_gran = c->n_strips * (32 * c->scan_r / kGranRows); w.gran_rows = kGranRows; w.max_len = max_len;
@@ -1074,7 +1074,7 @@ void ltg_destroy(ltg_context* c)
         if (hb.ready) cudaEventDestroy(hb.ready);
         for (int i = 0; i < 6; ++i) if (hb.ev[i]) cudaEventDestroy(hb.ev[i]);
     }
-    for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
+    for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_rna_sel, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
                       &c->d_segs, &c->d_items, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
                       &c->d_stats_max, &c->d_task_litrow, &c->d_cand, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
@@ -1123,6 +1123,14 @@ int ltg_set_query(ltg_context* c, const char* name, const char* rna, int64_t len
         if (q1[i] == 4) c->rna_acgt = false;
     }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats}) if (int e = b->ensure((size_t)len)) return e;
+    // PRMT selectors of every row for the window DP's table-lookup scoring (window.cuh, k_win_dp TAB)
+    std::vector<uint16_t> sel(len);
+    for (int64_t i = 0; i < len; ++i) {
+        const unsigned q = q1[i] & 3u;
+        sel[i] = (uint16_t)((q | ((q | 8u) << 4)) | (((4u + q) | ((12u + q) << 4)) << 8));
+    }
+    if (int e = c->d_rna_sel.ensure(sizeof(uint16_t) * (size_t)len)) return e;
+    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_sel.p, sel.data(), sizeof(uint16_t) * (size_t)len, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_raw.p, rna, (size_t)len, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_ssw.p, q1.data(), (size_t)len, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_stats.p, q2.data(), (size_t)len, cudaMemcpyHostToDevice, c->stream));

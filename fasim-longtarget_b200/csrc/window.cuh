@@ -86,6 +86,7 @@ struct WinState {
     // geometry
     const uint8_t* codes; const SegDesc* segs; int tasks_per_seg;
     const uint8_t* rna_ssw; int m;
+    const uint16_t* rna_sel;  // per lncRNA row: PRMT selector bytes of its code for the low (bits 0..7) and high (8..15) half (k_win_dp TAB)
     const int* cut_table;   // [256][4]  cut length per (peak score, round) — fastsim.h:210 evaluated in float32 on the host
     long long* cell_counter;
     const int* forced_cut;  // probe path: explicit window length per peak (nullptr in the product path)
@@ -348,14 +349,25 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
         uint32_t hout = 0, fout = 0, xout = kNoneLo | (kNoneHi << (TAB ? 8 : 16)), hdiag = 0;
         // leader prefetch of the stream symbol
         auto fetch = [&](int s) -> uint32_t {
+            if (TAB) {
+                // both selector bytes of a row are precomputed (rna_sel); the low half takes byte 0 of its row's entry, the high
+                // half byte 1 of its own row's entry; past the end of a stream the "none" selector stays
+                uint32_t v0 = 0xCC88u, v1 = 0xCC88u;
+                if (leader) {
+                    if (s < slen[0]) v0 = w.rna_sel[sbase[0] + sdir[0] * s];
+                    if (s < slen[1]) v1 = w.rna_sel[sbase[1] + sdir[1] * s];
+                }
+                return (v0 & 0xFFu) | (v1 & 0xFF00u);
+            }
             uint32_t c0 = kNoneLo, c1 = kNoneHi;
             if (leader) {
-                if (s < slen[0]) { const uint32_t q = w.rna_ssw[sbase[0] + sdir[0] * s]; c0 = TAB ? (q | ((q | 8u) << 4)) : (q < 4 ? q * 16 : 64u); }
-                if (s < slen[1]) { const uint32_t q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = TAB ? ((4u + q) | ((12u + q) << 4)) : (q < 4 ? q * 16 : 64u); }
+                if (s < slen[0]) { const uint32_t q = w.rna_ssw[sbase[0] + sdir[0] * s]; c0 = q < 4 ? q * 16 : 64u; }
+                if (s < slen[1]) { const uint32_t q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = q < 4 ? q * 16 : 64u; }
             }
-            return c0 | (c1 << (TAB ? 8 : 16));
+            return c0 | (c1 << 16);
         };
         uint32_t xnext = fetch(0);
+#pragma unroll 2
         for (int s = 0; s < nsteps; ++s) {
             const uint32_t myx = xnext;
             xnext = fetch(s + 1);
