@@ -192,6 +192,9 @@ def bench_gpu(args, rank, world, local_rank):
     import fasim_b200 as fb
     dist = None
     if world > 1:
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG asks for it; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
