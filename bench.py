@@ -153,7 +153,7 @@ def bench_reference(args, rank, world):
     cores = os.cpu_count() or 1
     rna = splitmix_bases(RNA_SEED, RNA_NT).tobytes().decode()
     if reference_binary() is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fasim was not built (reference sources absent)"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fasim was not built (reference sources absent)"}), file=OUT, flush=True)
         return
     chunk_bp = args.ref_chunk_bp
     for w in range(args.warmup):
@@ -173,7 +173,7 @@ def bench_reference(args, rank, world):
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": "reference",
                              "sample": "%d x %d bp chunks per step x %d steps (linear extrapolation to 100 Mbp)" % (cores, chunk_bp, args.steps)},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -309,7 +309,7 @@ def bench_gpu(args, rank, world, local_rank):
                                               % (cores, args.ref_chunk_bp, secs)}
         elif world == 1:
             line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "reference", "sample": "reference binary not built"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=OUT, flush=True)
         if args.debug_stats:
             print(json.dumps({"window_stage_stats": eng.debug_stats()}), file=sys.stderr)
     eng.close()
@@ -318,7 +318,15 @@ def bench_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+OUT = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE JSON line: whatever libraries print on fd 1 (e.g. NCCL's version banner) goes to stderr
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
