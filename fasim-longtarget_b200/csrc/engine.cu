@@ -143,7 +143,7 @@ struct ltg_context {
     bool profiles_dirty = true;
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
-    DevBuf d_dna, d_codes, d_segs, d_items, d_colmax, d_bnd, d_counters;
+    DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_colmax, d_bnd, d_counters;
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
     DevBuf d_w[20], d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
@@ -249,7 +249,7 @@ struct ProbeOut {
     int max_len = 0;
 };
 
-int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax)
+int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax)
 {
     const int R = c->scan_r;
     const int blocks = c->num_sms * scan_ctas_per_sm(R);
@@ -259,7 +259,7 @@ int launch_scan(ltg_context* c, int n_items, int max_len, const uint32_t* prof, 
     int* counters = c->d_counters.as<int>();
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntScan, 0, sizeof(int), c->stream));
     ScanArgs a;
-    a.codes = c->d_codes.as<uint8_t>(); a.segs = c->d_segs.as<SegDesc>(); a.items = c->d_items.as<ScanItem>();
+    a.codes = c->d_codes.as<uint8_t>(); a.segs = c->d_segs.as<SegDesc>(); a.items = d_items;
     a.n_items = n_items; a.profiles = prof; a.n_strips = c->n_strips; a.max_len = max_len;
     a.colmax = colmax; a.bnd = c->d_bnd.as<uint2>(); a.counter = counters + kCntScan;
     if (R == 32) {
@@ -505,24 +505,32 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_items.p, items.data(), sizeof(ScanItem) * n_items, cudaMemcpyHostToDevice, c->stream));
 
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[0], c->stream));
-    // optional N/U-aware threshold pass (Q3): exact maxima under the Farrar-side scoring
+    // optional N/U-aware threshold pass (Q3): exact maxima under the Farrar-side scoring.  With a plain (ACGT) lncRNA only
+    // the segments that contain a byte outside ACGT need it; with U / N in the lncRNA every segment does.
     const int* stats_max = nullptr;
     if (any_stats) {
-        if (int e = launch_scan(c, n_items, max_len, c->d_prof_stats.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
-        k_rowmax<<<(n_items * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_colmax.as<uint32_t>(), c->d_items.as<ScanItem>(), c->d_segs.as<SegDesc>(),
-                                                                   n_items, n_gran, max_len, T, c->d_stats_max.as<int>());
+        std::vector<ScanItem> sitems;
+        if (c->rna_plain) { for (const ScanItem& it : items) if (segs[it.seg].flags & kSegNonACGT) sitems.push_back(it); }
+        else sitems = items;
+        const int ns = (int)sitems.size();
+        if (int e = c->d_items_stats.ensure(sizeof(ScanItem) * (size_t)std::max(ns, 1))) return e;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_items_stats.p, sitems.data(), sizeof(ScanItem) * (size_t)ns, cudaMemcpyHostToDevice, c->stream));
+        if (int e = launch_scan(c, c->d_items_stats.as<ScanItem>(), ns, max_len, c->d_prof_stats.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
+        k_rowmax<<<(ns * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_colmax.as<uint32_t>(), c->d_items_stats.as<ScanItem>(), c->d_segs.as<SegDesc>(),
+                                                              ns, n_gran, max_len, T, c->d_stats_max.as<int>());
         c->launches += 1;
         stats_max = c->d_stats_max.as<int>();
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));          // `sitems` is host memory of this scope
     }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[4], c->stream));
-    if (int e = launch_scan(c, n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
+    if (int e = launch_scan(c, c->d_items.as<ScanItem>(), n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[5], c->stream));
 
     // peaks: statistics + count, literal re-runs, count of those, exclusive scan, write
     EpiArgs ea;
     ea.colmax = c->d_colmax.as<uint32_t>(); ea.n_gran = n_gran; ea.colmax_all = c->d_colmax_all.as<uint32_t>(); ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
     ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
-    ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.mode = 0;
+    ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.stats_all = c->rna_plain ? 0 : 1; ea.mode = 0;
     ea.task_max = ti.max; ea.task_thr = ti.thr; ea.task_npeaks = ti.npk; ea.task_flags = ti.flags; ea.task_jstar = ti.jstar;
     ea.task_off = c->d_task_off.as<int>(); ea.pk_task = nullptr; ea.pk_pos = nullptr; ea.pk_score = nullptr;
     const int epi_blocks = (n_items * 32 + 127) / 128;
@@ -1075,7 +1083,7 @@ void ltg_destroy(ltg_context* c)
         for (int i = 0; i < 6; ++i) if (hb.ev[i]) cudaEventDestroy(hb.ev[i]);
     }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_rna_sel, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
-                      &c->d_segs, &c->d_items, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
+                      &c->d_segs, &c->d_items, &c->d_items_stats, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
                       &c->d_stats_max, &c->d_task_litrow, &c->d_cand, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs})

@@ -375,6 +375,7 @@ struct EpiArgs {
     int max_len;
     int tasks_per_seg;
     const int* stats_max;    // [seg*T + task] exact calc_score_once maxima from the N-aware pass, or nullptr
+    int stats_all;           // 1: valid for every task; 0: only for the tasks of segments flagged kSegNonACGT
     int mode;
     int* task_max;           // [seg*T + task]
     int* task_thr;
@@ -436,7 +437,7 @@ __global__ void k_epilogue(const EpiArgs a)
                 mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 jstar = min(jstar, __shfl_xor_sync(0xffffffffu, jstar, o));
             }
-            const int score = a.stats_max ? a.stats_max[task] : mx;
+            const int score = (a.stats_max && (a.stats_all || (sd.flags & kSegNonACGT))) ? a.stats_max[task] : mx;
             thr = (int)((double)score * 0.8);
             const int flags = (jstar < n ? kTaskOverflow : 0) | (mx >= kQ4Guard ? kTaskLiteral : 0) | (mx >= 32000 ? kTaskRange : 0);
             if (lane == 0) {

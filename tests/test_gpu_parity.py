@@ -123,6 +123,23 @@ def test_n_and_u_scoring(engine, golden):
         assert (r["colmax"] == O.colmax(g2["rna"], s2)).all()
 
 
+def test_n_in_some_segments_only(engine):
+    """The N-aware threshold pass (Q3) runs only for the segments that contain a byte outside ACGT; the other segments of
+    the same batch keep the single-pass threshold.  Three segments, N's in the middle one."""
+    rna = splitmix_bases(2001, 600)
+    dna = list(splitmix_bases(1001, 12000))
+    hit = rna[200:260].translate(str.maketrans("TG", "AT"))
+    for at in (1500, 6500, 11000):                       # the same planted target in every segment
+        dna[at:at + 60] = hit
+    for at in (6100, 6520, 6533, 7000):                  # N's: inside and next to the target of the second segment
+        dna[at] = "N"
+    dna = "".join(dna)
+    engine.set_params(c_length=20)
+    engine.set_query("r", rna)
+    rows = engine.LongTarget(dna, "chrN", 1)
+    assert rows_as_oracle_text(rows) == oracle_text_rows(O.longtarget(rna, dna, cLength=20)) and len(rows) > 0
+
+
 @pytest.mark.parametrize("key", ["tail", "homopolymer"])
 def test_segment_edge_cases(engine, golden, key):
     g = golden[key]
