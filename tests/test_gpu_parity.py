@@ -123,6 +123,28 @@ def test_n_and_u_scoring(engine, golden):
         assert (r["colmax"] == O.colmax(g2["rna"], s2)).all()
 
 
+@pytest.mark.parametrize("cut,overlap,n", [(6500, 0, 14000), (6500, 500, 9000), (300, 100, 3100), (150, 100, 1234), (400, 390, 700)])
+def test_unusual_segmentations_vs_oracle(engine, cut, overlap, n):
+    """-c / -o at the edges of the supported envelope: the largest cut length (16-bit cells), tiny cuts, stride 1."""
+    rna = splitmix_bases(2001, 500)
+    dna = list(splitmix_bases(1001, n))
+    hit = rna[100:170].translate(str.maketrans("TG", "AT"))
+    for at in range(200, n - 100, 1700):
+        dna[at:at + 70] = hit
+    dna = "".join(dna)
+    engine.set_params(cut_length=cut, overlap=overlap, c_length=20)
+    engine.set_query("r", rna)
+    rows = engine.LongTarget(dna, "chrS", 1)
+    assert rows_as_oracle_text(rows) == oracle_text_rows(O.longtarget(rna, dna, cutLength=cut, overlap=overlap, cLength=20))
+    assert len(rows) > 0
+
+
+def test_cut_length_beyond_the_envelope_is_refused(engine):
+    with pytest.raises(fb.FasimError):
+        engine.set_params(cut_length=7000)
+    engine.set_params()
+
+
 def test_n_in_some_segments_only(engine):
     """The N-aware threshold pass (Q3) runs only for the segments that contain a byte outside ACGT; the other segments of
     the same batch keep the single-pass threshold.  Three segments, N's in the middle one."""
