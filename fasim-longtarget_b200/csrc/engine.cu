@@ -129,7 +129,8 @@ struct ltg_context {
     int num_sms = 0;
     int host_threads = 1;
     bool prune = true, dead_rule = true, skip_rounds = true;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, lit_stream = nullptr;
+    cudaEvent_t lit_event = nullptr;
     ltg_params params;
     // task tables (depend on params.rule / params.strand)
     std::vector<TaskDef> tasks;
@@ -149,6 +150,8 @@ struct ltg_context {
     DevBuf d_w[20], d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
     DevBuf d_jobs, d_tout, d_strpool, d_scratch, d_scratch_big;
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
+    DevBuf d_side_jobs, d_side_colmax;       // literal scan jobs running on the side stream while the main batches compute
+    int side_rows = 0, side_pitch = 0;
     HostBatch hb[2];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     unsigned long long win_stats[30] = {0};     // windows / cells planned per (round, retry) + reverse; [20..22] traceback tier hand-overs
@@ -277,7 +280,8 @@ int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_le
 // ---- literal (Q4) slow path launchers ---------------------------------------------------------
 // n_jobs < 0: the job count lives on the device (n_jobs_dev); the grid is sized for the worst case and idles when
 // the list is empty, so no host round trip is needed to decide whether to launch.
-int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const int* n_jobs_dev, int max_read_len, const WinState* w, int max_len)
+int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const int* n_jobs_dev, int max_read_len, const WinState* w, int max_len,
+                   bool side = false, int row_base = 0)
 {
     // workspace per half-warp slot: kLitArrays uint16 arrays of 16 lanes x pitch; in shared memory when at least one slot fits
     const int pitch = literal_pitch(max_read_len);
@@ -301,9 +305,10 @@ int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const i
         if (int e = c->d_lit_work.ensure((size_t)blocks * spb * per_slot)) return e;
         la.work = c->d_lit_work.as<unsigned char>();
     }
-    la.lit_colmax = c->d_lit_colmax.as<uint16_t>(); la.max_len = max_len; la.task_litrow = c->d_task_litrow.as<int>();
+    la.lit_colmax = c->d_lit_colmax.as<uint16_t>(); la.max_len = max_len; la.task_litrow = c->d_task_litrow.as<int>(); la.row_base = row_base;
+    if (side) { la.segs = nullptr; la.lit_colmax = c->d_side_colmax.as<uint16_t>(); la.task_litrow = nullptr; }      // jobs carry their geometry
     if (w) la.w = *w; else memset(&la.w, 0, sizeof la.w);
-    k_literal<<<blocks, threads, smem, c->stream>>>(la);
+    k_literal<<<blocks, threads, smem, side ? c->lit_stream : c->stream>>>(la);
     c->launches += 1;
     LTG_CUDA_CHECK(cudaGetLastError());
     return LTG_OK;
@@ -456,8 +461,11 @@ int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* 
 //               are scanned, and the host phase keeps the rows of exactly those tasks
 enum LitMode { kLitInline, kLitDefer, kLitOnly };
 
+constexpr int kSideCap = 4096;      // literal scan jobs a call may park on the side stream
+
 int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch& hb, bool want_alignments, ProbeOut* probe,
-                     LitMode lit_mode = kLitInline, std::vector<int>* deferred = nullptr, const std::vector<int>* only_tasks = nullptr)
+                     LitMode lit_mode = kLitInline, std::vector<std::pair<int, int>>* deferred = nullptr,
+                     const std::vector<int>* only_tasks = nullptr, const std::vector<int>* only_rows = nullptr)
 {
     const int T = (int)c->tasks.size(), P = (int)c->pairs.size();
     const int S = (int)segs.size();
@@ -543,19 +551,54 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     LTG_CUDA_CHECK(cudaMemcpyAsync(hti.flags, ti.flags, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
     LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
-    std::vector<LiteralJob> jobs;
+    // kLitOnly: were all requested tasks already swept by the side stream (their literal column maxima wait in d_side_colmax)?
+    bool from_side = (lit_mode == kLitOnly && only_rows && !only_rows->empty());
+    if (from_side) for (int r : *only_rows) if (r < 0) from_side = false;
+    std::vector<LiteralJob> jobs, side_jobs;
     for (int t = 0; t < n_tasks; ++t) {
         if (hti.flags[t] & kTaskRange) { set_error("alignment score exceeds the 16-bit range (segment too long for this build)"); return LTG_ERR_LIMIT; }
         if (hti.flags[t] & kTaskLiteral) {
-            if (lit_mode == kLitDefer) { deferred->push_back(t); continue; }
             LiteralJob j; memset(&j, 0, sizeof j);
             j.kind = 0; j.task = t; j.seg = t / T; j.tdef = t % T; j.ref_start = 0; j.ref_len = segs[t / T].len;
             j.read_start = 0; j.read_len = c->m; j.read_dir = 1; j.ref_dir = 0; j.terminate = 255; j.peak = -1;
+            j.seg_start = segs[t / T].start; j.seg_len = segs[t / T].len;
+            if (lit_mode == kLitDefer) {
+                // start the (slow, single half-warp) literal sweep of this task right away on the side stream; the call
+                // collects its column maxima at the end
+                int row = -1;
+                if (c->side_pitch > 0 && c->side_rows + (int)side_jobs.size() < kSideCap) { row = c->side_rows + (int)side_jobs.size(); side_jobs.push_back(j); }
+                deferred->push_back(std::make_pair(t, row));
+                continue;
+            }
             jobs.push_back(j);
         }
     }
+    if (!side_jobs.empty()) {
+        if (int e = c->d_side_jobs.ensure(sizeof(LiteralJob) * kSideCap)) return e;
+        if (int e = c->d_side_colmax.ensure(sizeof(uint16_t) * (size_t)kSideCap * c->side_pitch)) return e;
+        LiteralJob* dj = c->d_side_jobs.as<LiteralJob>() + c->side_rows;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(dj, side_jobs.data(), sizeof(LiteralJob) * side_jobs.size(), cudaMemcpyHostToDevice, c->lit_stream));
+        if (int e = launch_literal(c, dj, (int)side_jobs.size(), nullptr, c->m, nullptr, c->side_pitch, /*side=*/true, c->side_rows)) return e;
+        LTG_CUDA_CHECK(cudaEventRecord(c->lit_event, c->lit_stream));
+        c->side_rows += (int)side_jobs.size();
+        c->h2d_bytes += (int64_t)(sizeof(LiteralJob) * side_jobs.size());
+    }
     hb.n_literal_tasks = (int)jobs.size();
-    if (!jobs.empty()) {
+    ea.lit_pitch = max_len;
+    if (from_side) {
+        // the literal sweeps ran on the side stream: point the tasks at their rows and wait for that stream
+        std::vector<int> litrow(n_tasks, -1);
+        for (size_t k = 0; k < only_tasks->size(); ++k) litrow[(*only_tasks)[k]] = (*only_rows)[k];
+        for (const LiteralJob& j : jobs) if (litrow[j.task] < 0) { set_error("literal task without a side-stream row"); return LTG_ERR_STATE; }
+        LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_task_litrow.p, litrow.data(), sizeof(int) * (size_t)n_tasks, cudaMemcpyHostToDevice, c->stream));
+        LTG_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->lit_event, 0));
+        ea.lit_colmax = c->d_side_colmax.as<uint16_t>(); ea.lit_pitch = c->side_pitch;
+        ea.mode = 1;
+        k_epilogue<<<epi_blocks, 128, 0, c->stream>>>(ea);
+        c->launches += 1;
+        LTG_CUDA_CHECK(cudaGetLastError());
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // `litrow` is host memory of this scope
+    } else if (!jobs.empty()) {
         if (int e = c->d_lit_jobs.ensure(sizeof(LiteralJob) * jobs.size())) return e;
         if (int e = c->d_lit_colmax.ensure(sizeof(uint16_t) * jobs.size() * (size_t)max_len)) return e;
         LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_lit_jobs.p, jobs.data(), sizeof(LiteralJob) * jobs.size(), cudaMemcpyHostToDevice, c->stream));
@@ -877,6 +920,7 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
 {
     if (!c || !out || (n_recs > 0 && !recs)) { set_error("null argument"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
+    LTG_CUDA_CHECK(cudaStreamSynchronize(c->lit_stream));
     const int64_t launches0 = c->launches, h2d0 = c->h2d_bytes, d2h0 = c->d2h_bytes;
     const bool trace_time = getenv("LTG_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -932,16 +976,19 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
         size_t nb = 0;
         const int T = (int)c->tasks.size();
         t_prep = now();
-        struct Deferred { HostSeg seg; int tdef; };
+        struct Deferred { HostSeg seg; int tdef; int side_row; };
         std::vector<Deferred> deferred;                 // literal (Q4-guard) tasks of the record, in task order
-        std::vector<int> batch_deferred;
+        std::vector<std::pair<int, int>> batch_deferred;
+        // side-stream literal sweeps need their workspace in shared memory (the global fallback workspace is shared with the main stream)
+        c->side_rows = 0;
+        c->side_pitch = (2LL * 16 * kLitArrays * literal_pitch(c->m) <= 200 * 1024) ? ((c->params.cut_length + 3) & ~3) : 0;
         for (size_t b0 = 0; b0 < active.size() && rc == LTG_OK; b0 += bs, ++nb) {
             HostBatch& hb = c->hb[nb & 1];
             if ((rc = retire_batch(c, hb, st, record_list)) != LTG_OK) break;       // batch nb-2: slot free again
             std::vector<HostSeg> batch(active.begin() + b0, active.begin() + std::min(active.size(), b0 + bs));
             batch_deferred.clear();
             if ((rc = run_batch_device(c, batch, hb, true, nullptr, kLitDefer, &batch_deferred)) != LTG_OK) { hb.timed = false; break; }
-            for (int t : batch_deferred) { Deferred d; d.seg = batch[t / T]; d.tdef = t % T; deferred.push_back(d); }
+            for (const std::pair<int, int>& tr : batch_deferred) { Deferred d; d.seg = batch[tr.first / T]; d.tdef = tr.first % T; d.side_row = tr.second; deferred.push_back(d); }
             hb.worker = std::thread(batch_worker, c, &hb);
         }
         t_loop = now();
@@ -958,7 +1005,7 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
             RecordStats lit_st;
             for (size_t d0 = 0; d0 < deferred.size() && rc == LTG_OK;) {
                 std::vector<HostSeg> lsegs;
-                std::vector<int> ltasks;
+                std::vector<int> ltasks, lrows;
                 size_t d1 = d0;
                 for (; d1 < deferred.size(); ++d1) {
                     if (lsegs.empty() || lsegs.back().start != deferred[d1].seg.start) {
@@ -966,9 +1013,10 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
                         lsegs.push_back(deferred[d1].seg);
                     }
                     ltasks.push_back((int)(lsegs.size() - 1) * T + deferred[d1].tdef);
+                    lrows.push_back(deferred[d1].side_row);
                 }
                 HostBatch& hb = c->hb[0];
-                if ((rc = run_batch_device(c, lsegs, hb, true, nullptr, kLitOnly, nullptr, &ltasks)) != LTG_OK) { hb.timed = false; break; }
+                if ((rc = run_batch_device(c, lsegs, hb, true, nullptr, kLitOnly, nullptr, &ltasks, &lrows)) != LTG_OK) { hb.timed = false; break; }
                 hb.worker = std::thread(batch_worker, c, &hb);
                 rc = retire_batch(c, hb, lit_st, lit_rows);
                 d0 = d1;
@@ -985,7 +1033,8 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
                 record_list.swap(merged);
             }
         }
-        if (rc != LTG_OK) { cudaStreamSynchronize(c->stream); return rc; }
+        if (rc != LTG_OK) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->lit_stream); return rc; }
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->lit_stream));      // (normally long finished: the literal-only batch waited for it)
         t_retire = now();
         std::vector<ltg_host::Triplex> keep;
         for (const ltg_host::Triplex& t : record_list)
@@ -1050,6 +1099,8 @@ int ltg_create(int device, ltg_context** out)
     ltg_default_params(&c->params);
     LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->lit_stream, cudaStreamNonBlocking));
+    LTG_CUDA_CHECK(cudaEventCreateWithFlags(&c->lit_event, cudaEventDisableTiming));
     for (HostBatch& hb : c->hb) {
         LTG_CUDA_CHECK(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
         for (int i = 0; i < 6; ++i) LTG_CUDA_CHECK(cudaEventCreate(&hb.ev[i]));
@@ -1086,11 +1137,13 @@ void ltg_destroy(ltg_context* c)
                       &c->d_segs, &c->d_items, &c->d_items_stats, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
                       &c->d_stats_max, &c->d_task_litrow, &c->d_cand, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
-                      &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs})
+                      &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs, &c->d_side_jobs, &c->d_side_colmax})
         b->release();
     for (int k = 0; k < 20; ++k) c->d_w[k].release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->lit_stream) { cudaStreamSynchronize(c->lit_stream); cudaStreamDestroy(c->lit_stream); }
+    if (c->lit_event) cudaEventDestroy(c->lit_event);
     delete c;
 }
 

@@ -25,6 +25,7 @@ struct LiteralJob {
     int read_start, read_len, read_dir;     // rows: rna[read_start + read_dir * k], k in [0, read_len)
     int terminate;
     int peak;          // window jobs: peak index
+    long long seg_start; int seg_len;       // explicit segment geometry (side-stream scan jobs: LiteralArgs::segs == nullptr)
 };
 
 struct LiteralArgs {
@@ -33,8 +34,9 @@ struct LiteralArgs {
     const uint8_t* codes; const SegDesc* segs; const uint8_t* rna_ssw;
     unsigned char* work; long long work_per_slot;       // global workspace per half-warp slot (used when use_smem == 0)
     int use_smem, slots_per_block, pitch;               // shared-memory workspace: slots per block, elements per (array, lane)
-    uint16_t* lit_colmax; int max_len;                  // scan jobs: row `job index` receives the literal column maxima
-    int* task_litrow;                                   // scan jobs: [task] -> that row
+    uint16_t* lit_colmax; int max_len;                  // scan jobs: row `row_base + job index` receives the literal column maxima
+    int row_base;
+    int* task_litrow;                                   // scan jobs: [task] -> that row (nullptr: the host keeps the mapping)
     WinState w;
 };
 
@@ -69,7 +71,8 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
     const int n_jobs = a.n_jobs >= 0 ? a.n_jobs : *a.n_jobs_dev;
     for (int jb = slot; jb < n_jobs; jb += nslots) {
         const LiteralJob J = a.jobs[jb];
-        const SegDesc sd = a.segs[J.seg];
+        SegDesc sd;
+        if (a.segs) sd = a.segs[J.seg]; else { sd.start = J.seg_start; sd.len = J.seg_len; sd.flags = 0; }
         const TaskDef td = c_tasks[J.tdef];
         const int L = (J.read_len + 15) / 16;
         const int P = a.pitch;                                   // >= literal_pitch(J.read_len)
@@ -91,9 +94,9 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
         }
         uint16_t* cmrow = nullptr;
         if (J.kind == 0) {
-            cmrow = a.lit_colmax + (size_t)jb * a.max_len;
+            cmrow = a.lit_colmax + (size_t)(a.row_base + jb) * a.max_len;
             for (int j = s; j < J.ref_len; j += 16) cmrow[j] = 0;
-            if (s == 0) a.task_litrow[J.task] = jb;
+            if (s == 0 && a.task_litrow) a.task_litrow[J.task] = a.row_base + jb;
         }
         __syncwarp(hmask);
         int vMaxScore = 0, vMaxMark = 0, maxv = 0, end_ref = -1;

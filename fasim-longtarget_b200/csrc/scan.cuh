@@ -367,7 +367,8 @@ struct EpiArgs {
     const uint32_t* colmax;      // [item][granule][max_len]
     int n_gran;                  // granule rows per item
     uint32_t* colmax_all;        // [item][max_len] maximum over the granules (written by mode 0, read by modes 1 and 2)
-    const uint16_t* lit_colmax;  // [literal row][max_len] column maxima of the literal re-runs
+    const uint16_t* lit_colmax;  // [literal row][lit_pitch] column maxima of the literal re-runs
+    int lit_pitch;
     const int* task_litrow;      // [task] row in lit_colmax (valid when the task carries kTaskLiteral)
     const ScanItem* items;
     const SegDesc* segs;
@@ -451,7 +452,7 @@ __global__ void k_epilogue(const EpiArgs a)
             thr = a.task_thr[task];
             jstar = a.task_jstar[task];
             if (is_lit && a.lit_colmax == nullptr) continue;      // deferred to a literal-only batch: no peaks here
-            if (is_lit) lit = a.lit_colmax + (size_t)a.task_litrow[task] * a.max_len;
+            if (is_lit) lit = a.lit_colmax + (size_t)a.task_litrow[task] * a.lit_pitch;
         }
         const bool write = (a.mode == 2);
         const int base = write ? a.task_off[task] : 0;
