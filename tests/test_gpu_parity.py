@@ -145,6 +145,23 @@ def test_cut_length_beyond_the_envelope_is_refused(engine):
     engine.set_params()
 
 
+def test_multi_query_switching(engine):
+    """Config 5 style use: several lncRNAs against the same DNA through one context, switching back and forth (different
+    lengths select different scan tilings and strip counts; every buffer of the context is reused)."""
+    dna = list(splitmix_bases(1001, 11000))
+    rnas = [splitmix_bases(4001 + k, m) for k, m in enumerate([300, 1500, 777, 2100])]
+    for k, r in enumerate(rnas):
+        at = 900 + 2400 * k
+        dna[at:at + 64] = r[20:84].translate(str.maketrans("TG", "AT"))
+    dna = "".join(dna)
+    engine.set_params(c_length=20)
+    expect = [oracle_text_rows(O.longtarget(r, dna, cLength=20)) for r in rnas]
+    for k in [0, 1, 2, 3, 1, 0, 3, 2]:
+        engine.set_query("q%d" % k, rnas[k])
+        assert rows_as_oracle_text(engine.LongTarget(dna, "chrQ", 1)) == expect[k], k
+    assert all(len(e) > 0 for e in expect)
+
+
 def test_n_in_some_segments_only(engine):
     """The N-aware threshold pass (Q3) runs only for the segments that contain a byte outside ACGT; the other segments of
     the same batch keep the single-pass threshold.  Three segments, N's in the middle one."""

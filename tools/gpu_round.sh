@@ -3,7 +3,7 @@
 REGION=${1:-10}
 mkdir -p gpurun_out
 { nproc; free -g | head -2; nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv; } > gpurun_out/box.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; python -c "import __graft_entry__ as g; g.smoke()" >> gpurun_out/pytest_gpu.log 2>&1; echo "smoke rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 2 --warmup 1 --region-mbp $REGION > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.log; tail -5 gpurun_out/bench.err
