@@ -147,7 +147,7 @@ struct ltg_context {
     DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_colmax, d_bnd, d_counters;
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
-    DevBuf d_w[20], d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
+    DevBuf d_w[20], d_pc[4], d_res64, d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
     DevBuf d_jobs, d_tout, d_strpool, d_scratch, d_scratch_big;
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
     DevBuf d_side_jobs, d_side_colmax;       // literal scan jobs running on the side stream while the main batches compute
@@ -329,7 +329,10 @@ int literal_windows(ltg_context* c, const WinState& w, bool reverse, int round)
 int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* gran_colmax, int max_len, HostBatch* hb, bool dead_rule)
 {
     for (int k = 0; k < 20; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
-    if (int e = c->d_win_list.ensure(sizeof(int) * (size_t)n_peaks)) return e;
+    const int pc_cap = 4 * n_peaks;          // kMaxRuns pieces per peak at most
+    if (int e = c->d_win_list.ensure(sizeof(int) * (size_t)pc_cap)) return e;
+    for (int k = 0; k < 4; ++k) if (int e = c->d_pc[k].ensure(sizeof(int) * (size_t)pc_cap)) return e;
+    if (int e = c->d_res64.ensure(sizeof(unsigned long long) * (size_t)n_peaks)) return e;
     if (int e = c->d_win_sched.ensure(sizeof(WinSched))) return e;
     if (int e = c->d_res.ensure(sizeof(int4) * (size_t)n_peaks)) return e;
     int* counters = c->d_counters.as<int>();
@@ -340,7 +343,9 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.best_sw = c->d_w[2].as<int>(); w.best_cut = c->d_w[3].as<int>(); w.best_re = c->d_w[4].as<int>(); w.best_qe = c->d_w[5].as<int>();
     w.fin_sw = c->d_w[6].as<int>(); w.fin_cut = c->d_w[7].as<int>(); w.fin_re = c->d_w[8].as<int>(); w.fin_qe = c->d_w[9].as<int>();
     w.fin_rb = c->d_w[10].as<int>(); w.fin_qb = c->d_w[11].as<int>();
-    w.w_lo = c->d_w[12].as<int>(); w.w_rows = c->d_w[13].as<int>(); w.w_bound = c->d_w[14].as<int>(); w.w_key = c->d_w[15].as<int>(); w.w_floor = c->d_w[16].as<int>(); w.w_next = c->d_w[17].as<int>(); w.w_probe = c->d_w[18].as<int>();
+    w.w_bound = c->d_w[14].as<int>(); w.w_flight = c->d_w[15].as<int>(); w.w_floor = c->d_w[16].as<int>();
+    w.pc_peak = c->d_pc[0].as<int>(); w.pc_lo = c->d_pc[1].as<int>(); w.pc_rows = c->d_pc[2].as<int>(); w.pc_key = c->d_pc[3].as<int>(); w.pc_cap = pc_cap;
+    w.res64 = c->d_res64.as<unsigned long long>(); w.w_next = c->d_w[17].as<int>(); w.w_probe = c->d_w[18].as<int>();
     w.sched = c->d_win_sched.as<WinSched>(); w.list = c->d_win_list.as<int>();
     w.res = c->d_res.as<int4>();
     w.codes = c->d_codes.as<uint8_t>(); w.segs = c->d_segs.as<SegDesc>(); w.tasks_per_seg = T;
@@ -352,21 +357,29 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCells, 0, 8, c->stream));
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntLitTotal, 0, sizeof(int), c->stream));
     LTG_CUDA_CHECK(cudaMemsetAsync(w.sched, 0, sizeof(WinSched), c->stream));
-    LTG_CUDA_CHECK(cudaMemsetAsync(w.w_key, 0xff, sizeof(int) * (size_t)n_peaks, c->stream));
+    LTG_CUDA_CHECK(cudaMemsetAsync(w.w_flight, 0, sizeof(int) * (size_t)n_peaks, c->stream));
     const int pb = (n_peaks + 255) / 256, plan_blocks = (n_peaks * 8 + 255) / 256;
     const int dp_blocks = c->num_sms * 4;
     // plan -> key offsets -> placement: the sorted work list of the next k_win_dp launch
+    const int place_blocks = (pc_cap + 255) / 256;
     auto schedule = [&](int round, int retry) {
+        cudaMemsetAsync(&w.sched->n_pieces, 0, sizeof(int), c->stream);
         k_win_plan<<<plan_blocks, 256, 0, c->stream>>>(w, round, retry);
         k_win_offsets<<<1, 1024, 0, c->stream>>>(w.sched);
-        k_win_place<<<pb, 256, 0, c->stream>>>(w);
+        k_win_place<<<place_blocks, 256, 0, c->stream>>>(w);
         c->launches += 3;
+    };
+    // the sweep itself, then the per-peak combination of its pieces
+    auto sweep = [&](bool rev) {
+        if (rev) { if (c->rna_acgt) k_win_dp<true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false><<<dp_blocks, 128, 0, c->stream>>>(w); }
+        else { if (c->rna_acgt) k_win_dp<false, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<false, false><<<dp_blocks, 128, 0, c->stream>>>(w); }
+        k_win_combine<<<pb, 256, 0, c->stream>>>(w);
+        c->launches += 2;
     };
     for (int round = 0; round < 4; ++round) {
         for (int retry = 0; retry < (w.gran_colmax ? 2 : 1); ++retry) {
             schedule(round, retry);
-            if (c->rna_acgt) k_win_dp<false, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<false, false><<<dp_blocks, 128, 0, c->stream>>>(w);
-            c->launches += 1;
+            sweep(false);
         }
         // Q4 guard for windows: exact forward scores >= 148 are recomputed by the literal emulation
         if (int e = literal_windows(c, w, /*reverse=*/false, round)) return e;
@@ -375,17 +388,17 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
         if (round < 3 && c->skip_rounds) {
             // reverse probe of the rounds that failed without a candidate: may skip later rounds or finish the peak
             schedule(-2, 0);
-            if (c->rna_acgt) k_win_dp<true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false><<<dp_blocks, 128, 0, c->stream>>>(w);
+            sweep(true);
             k_win_probe<<<pb, 256, 0, c->stream>>>(w, round);
-            c->launches += 2;
+            c->launches += 1;
         }
         LTG_CUDA_CHECK(cudaGetLastError());
     }
     // reverse pass over the chosen alignments
     schedule(-1, 0);
-    if (c->rna_acgt) k_win_dp<true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false><<<dp_blocks, 128, 0, c->stream>>>(w);
+    sweep(true);
     k_win_finish<<<pb, 256, 0, c->stream>>>(w);
-    c->launches += 2;
+    c->launches += 1;
     if (int e = literal_windows(c, w, /*reverse=*/true, -1)) return e;
     LTG_CUDA_CHECK(cudaGetLastError());
 
@@ -1140,6 +1153,8 @@ void ltg_destroy(ltg_context* c)
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs, &c->d_side_jobs, &c->d_side_colmax})
         b->release();
     for (int k = 0; k < 20; ++k) c->d_w[k].release();
+    for (int k = 0; k < 4; ++k) c->d_pc[k].release();
+    c->d_res64.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->lit_stream) { cudaStreamSynchronize(c->lit_stream); cudaStreamDestroy(c->lit_stream); }

@@ -54,6 +54,7 @@ struct WinSched {
     int bin_start[32];         // first bin (warp work unit) of the class
     int total_bins;
     int bin_counter;
+    int n_pieces;              // work items of the launch being planned
     // statistics (LTG_STATS): windows / cells planned per (round, retry); [8] = reverse pass
     unsigned long long st_windows[10];
     unsigned long long st_cells[10];
@@ -68,20 +69,24 @@ struct WinState {
     const int* pk_score;
     // per peak
     int* w_len;        // columns of the window in flight (cut, or re+1 in the reverse pass)
-    int* w_lo;         // first RNA row of the forward stream in flight
-    int* w_rows;       // number of RNA rows streamed
     int* w_bound;      // a result >= w_bound is exact (row pruning, see the header comment); 0: all rows were streamed
     int* w_floor;      // cells <= w_floor cannot matter for this sweep (they neither prove exactness nor beat a proven
                        // lower bound), so the per-lane result tracker starts there
-    int* w_key;        // sort key of the window in flight, -1: not in flight
+    int* w_flight;     // 1: the peak has work items in the launch being planned / run
     int* w_done;       // 1: final alignment chosen
     int* w_next;       // next forward round this peak takes part in (rounds in between are provably no-ops, see k_win_probe)
     int* w_probe;      // 1: the round's result waits for its reverse probe; 2: fin_rb / fin_qb are final already
     int* best_sw; int* best_cut; int* best_re; int* best_qe;
     int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb;
     WinSched* sched;
-    int* list;         // [n_peaks] window indices in key order
-    // dp result per peak: (best value, column, row, 1 if written by the literal emulation)
+    // Work items ("pieces") of a launch: a peak's window swept over one range of RNA rows.  First sweeps and reverse
+    // sweeps have one piece per peak; a re-planned forward sweep has one piece per run of qualifying granules.
+    int* pc_peak; int* pc_lo; int* pc_rows; int* pc_key; int pc_cap;
+    int* list;         // [pc_cap] piece indices in key order
+    // best cell per peak over its pieces, packed so that atomicMax implements the tie rules:
+    // value << 36 | (0xFFF - column) << 24 | (0xFFFFFF - row); low 36 bits 0 = "no cell above the floor, value = plain maximum"
+    unsigned long long* res64;
+    // decoded result per peak: (best value, column, row, 1 if written by the literal emulation)
     int4* res;
     // geometry
     const uint8_t* codes; const SegDesc* segs; int tasks_per_seg;
@@ -143,9 +148,12 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
             len = w.fin_re[i] + 1;
         }
     }
-    // granule bound scan (forward plans only): granules klo..khi can hold a cell >= bound inside the window's columns;
+    // granule bound scan (forward plans only): which granules can hold a cell >= bound inside the window's columns
+    // (span klo..khi, and — for re-planned sweeps over at most 64 granules — the exact set as a bit mask);
     // `outside` = the largest bound of any granule left out (a result above it is exact)
     int klo = -1, khi = -1, outside = 0;
+    unsigned long long qmask = 0ull;
+    const bool multi = retry && w.n_gran <= 64;         // a re-planned sweep may be split into runs of qualifying granules
     if (round >= 0 && w.gran_colmax != nullptr) {
         const bool scan = active && bound > 0;
         int task = 0, pos = 0;
@@ -167,34 +175,84 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
             if (scan && b >= bound) {
                 if (klo < 0) { klo = k; outside = pending; }      // everything before the first qualifying granule is left out
                 khi = k;
-                pending = 0;                                       // granules between two qualifying ones are streamed too
+                if (multi) qmask |= 1ull << k; else pending = 0;   // single span: the granules in between are swept too
             } else pending = max(pending, b);
+            // (multi: `pending` keeps every non-qualifying granule — those inside a joined gap are swept although counted as
+            //  left out, which only makes `outside` conservative; it still stays below `bound`, so the sweep is conclusive)
         }
         outside = max(outside, pending);
     }
-    if (!active || sub != 0) return;
-    if (round >= 0) {
-        int lo = 0, floor_v = max(proven - 1, 0);
-        rows = w.m; bound = 0;
-        if (khi >= 0) {
-            // only cells above `outside` matter (a result r > outside is exact), and their alignments span at most this many rows
-            lo = max(0, klo * w.gran_rows - win_margin_for(len, outside + 1));
-            const int hi = min(w.m - 1, (khi + 1) * w.gran_rows - 1);
-            if (hi - lo + 1 < w.m) { rows = hi - lo + 1; bound = outside + 1; floor_v = max(floor_v, outside); } else lo = 0;
+    // From here on one thread per peak works (sub == 0 of an active peak); the others only take part in the warp-wide
+    // reservation of piece slots (one atomic per warp instead of one per peak).
+    const bool mine = active && sub == 0;
+    int floor_v = max(proven - 1, 0);
+    // only cells above `outside` matter (a result r > outside is exact), and their alignments span at most `margin` rows
+    const int margin = win_margin_for(len, outside + 1);
+    const int join = (win_margin(len) + w.gran_rows - 1) / w.gran_rows;     // a gap this short would be covered by the next margin
+    // walks the runs of qualifying granules (gaps <= join joined, at most 4 runs); f(lo, rows) per run; returns their number
+    auto for_runs = [&](auto&& f) -> int {
+        int nr = 0, cur_lo = klo, cur_hi = multi ? klo : khi;
+        unsigned long long rest = multi ? (qmask & ~(1ull << klo)) : 0ull;
+        for (;;) {
+            int nxt = -1;
+            if (rest) { nxt = __ffsll((long long)rest) - 1; rest &= rest - 1; }
+            if (nxt >= 0 && (nxt - cur_hi - 1 <= join || nr == 3)) { cur_hi = nxt; continue; }
+            const int lo = max(0, cur_lo * w.gran_rows - margin);
+            f(lo, min(w.m - 1, (cur_hi + 1) * w.gran_rows - 1) - lo + 1);
+            ++nr;
+            if (nxt < 0) break;
+            cur_lo = cur_hi = nxt;
         }
-        w.w_lo[i] = lo; w.w_rows[i] = rows; w.w_bound[i] = bound; w.w_floor[i] = floor_v;
-        if (w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, (unsigned long long)len * (unsigned long long)rows);
-        atomicAdd(&w.sched->st_windows[round * 2 + retry], 1ull);
-        atomicAdd(&w.sched->st_cells[round * 2 + retry], (unsigned long long)len * (unsigned long long)rows);
-    } else {
-        rows = min(w.fin_qe[i] + 1, win_margin(len));
-        atomicAdd(&w.sched->st_windows[round == -1 ? 8 : 9], 1ull);
-        atomicAdd(&w.sched->st_cells[round == -1 ? 8 : 9], (unsigned long long)len * (unsigned long long)rows);
+        return nr;
+    };
+    int np = 0;
+    bool pruned = false;
+    if (mine) {
+        np = 1;
+        if (round >= 0 && khi >= 0) {
+            long long total = 0;
+            const int nr = for_runs([&](int, int rows) { total += rows; });
+            if (total < w.m) { pruned = true; np = nr; }
+        }
     }
-    w.w_len[i] = len;
-    const int key = win_key(len, rows);
-    w.w_key[i] = key;
-    atomicAdd(&w.sched->hist[key], 1);
+    // reserve np slots per thread: warp-inclusive scan, one atomicAdd by the last lane
+    const int lane = threadIdx.x & 31;
+    int incl = np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    int base = 0;
+    if (lane == 31 && incl > 0) base = atomicAdd(&w.sched->n_pieces, incl);      // (pc_cap = 4 * n_peaks: cannot overflow)
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned long long cells = 0;
+    if (mine) {
+        int p = base + incl - np;
+        w.w_len[i] = len;
+        w.w_flight[i] = 1;
+        w.res64[i] = 0ull;
+        auto emit = [&](int lo, int rows) {
+            const int key = win_key(len, rows);
+            w.pc_peak[p] = i; w.pc_lo[p] = lo; w.pc_rows[p] = rows; w.pc_key[p] = key;
+            ++p;
+            atomicAdd(&w.sched->hist[key], 1);
+            cells += (unsigned long long)len * (unsigned long long)rows;
+        };
+        if (round < 0) emit(0, min(w.fin_qe[i] + 1, win_margin(len)));
+        else {
+            if (pruned) { for_runs(emit); bound = outside + 1; floor_v = max(floor_v, outside); }
+            else { bound = 0; emit(0, w.m); }
+            w.w_bound[i] = bound; w.w_floor[i] = floor_v;
+        }
+    }
+    // statistics: one atomic per warp
+    unsigned long long cnt = mine ? 1ull : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { cells += __shfl_xor_sync(0xffffffffu, cells, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if (lane == 0 && cnt) {
+        const int slot = round >= 0 ? round * 2 + retry : (round == -1 ? 8 : 9);
+        atomicAdd(&w.sched->st_windows[slot], cnt);
+        atomicAdd(&w.sched->st_cells[slot], cells);
+        if (round >= 0 && w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, cells);
+    }
 }
 
 // exclusive prefix of the key histogram, per-class counts / list offsets / bin ranges (one block of 1024 threads)
@@ -239,12 +297,22 @@ __global__ void __launch_bounds__(1024) k_win_offsets(WinSched* sc)
 
 __global__ void k_win_place(const WinState w)
 {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= w.sched->n_pieces) return;
+    const int key = w.pc_key[p];
+    w.list[w.sched->off[key] + atomicAdd(&w.sched->fill[key], 1)] = p;
+}
+
+// best cell of every peak that had pieces in the launch: unpack res64 into res
+__global__ void k_win_combine(const WinState w)
+{
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.n_peaks) return;
-    const int key = w.w_key[i];
-    if (key < 0) return;
-    w.w_key[i] = -1;
-    w.list[w.sched->off[key] + atomicAdd(&w.sched->fill[key], 1)] = i;
+    if (i >= w.n_peaks || w.w_flight[i] != 1) return;
+    w.w_flight[i] = 0;
+    const unsigned long long v = w.res64[i];
+    const int val = (int)(v >> 36);
+    if ((v & 0xFFFFFFFFFull) == 0) w.res[i] = make_int4(val, 0x7fffffff, 0, 0);       // nothing above the floor: value only
+    else w.res[i] = make_int4(val, 0xFFF - (int)((v >> 24) & 0xFFF), 0xFFFFFF - (int)(v & 0xFFFFFF), 0);
 }
 
 // TAB: score lookup with one PRMT per cell pair (needs an lncRNA made of A/C/G/T/U only); otherwise XNOR + VIADDMNMX.
@@ -284,7 +352,8 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int slot = (b * 2 + h) * gpw + grp;
-            wi[h] = (!idle && slot < cls_count) ? w.list[cls_off + slot] : -1;
+            const int piece = (!idle && slot < cls_count) ? w.list[cls_off + slot] : -1;
+            wi[h] = piece >= 0 ? w.pc_peak[piece] : -1;
             len[h] = 0; slen[h] = 0; sbase[h] = 0; sdir[h] = 1;
             int colcode[R];
 #pragma unroll
@@ -299,7 +368,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                 const int cutw = REV ? w.fin_cut[i] : L;
                 const int ws = w.pk_pos[i] - cutw + 1;                    // window start in seq2 coordinates
                 if (REV) { slen[h] = min(w.fin_qe[i] + 1, win_margin(L)); sbase[h] = w.fin_qe[i]; sdir[h] = -1; }
-                else { slen[h] = w.w_rows[i]; sbase[h] = w.w_lo[i]; sdir[h] = 1; }
+                else { slen[h] = w.pc_rows[piece]; sbase[h] = w.pc_lo[piece]; sdir[h] = 1; }
                 const int off = g * R - L;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -430,11 +499,15 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                 }
             }
             // forward: absolute RNA row; reverse: index into the reversed stream (k_win_finish subtracts it from qe).
-            // A forward sweep in which no cell rose above the floor reports its plain maximum (position unknown, never used:
-            // such a result is below w_bound, so the window is re-planned from it).
+            // A sweep in which no cell rose above the floor reports its plain maximum (position unknown, never used: such
+            // a result is below w_bound, so the window is re-planned from it).  atomicMax over the peak's pieces = highest
+            // value, then smallest column, then smallest row.
             if (leader && wi[h] >= 0) {
-                if (!REV && bcol[h] == 0x7fffffff) w.res[wi[h]] = make_int4(rmx, 0, 0, 0);
-                else w.res[wi[h]] = make_int4(best[h], bcol[h], REV ? brow[h] : sbase[h] + brow[h], 0);
+                unsigned long long key;
+                if (bcol[h] == 0x7fffffff) key = (unsigned long long)max(REV ? best[h] : rmx, 0) << 36;
+                else key = ((unsigned long long)best[h] << 36) | ((unsigned long long)(0xFFF - bcol[h]) << 24) |
+                           (unsigned long long)(0xFFFFFF - (REV ? brow[h] : sbase[h] + brow[h]));
+                atomicMax(&w.res64[wi[h]], key);
             }
         }
     }
