@@ -145,6 +145,42 @@ def test_cut_length_beyond_the_envelope_is_refused(engine):
     engine.set_params()
 
 
+def test_microsatellite_stress_vs_oracle(engine):
+    """Repeat-rich input: noisy (GA)n / (TC)n / (GGA)n stretches against an lncRNA with (CT)n / (GA)n / (GT)n tracts.  Hundreds
+    of overlapping hits per task, run merging, >= 251 overflow (stop-recording), literal-scored tasks and windows, wide
+    traceback bands, top-50 truncation — under strict, relaxed and positive-penalty filter settings."""
+    rnd = random.Random(3)
+
+    def noisy(unit, n, rate):
+        s = list((unit * (n // len(unit) + 1))[:n])
+        for i in range(n):
+            if rnd.random() < rate:
+                s[i] = rnd.choice("ACGT")
+        return "".join(s)
+
+    rna = (splitmix_bases(2001, 150) + noisy("CT", 130, 0.06) + splitmix_bases(2002, 100) + noisy("GA", 90, 0.04) + splitmix_bases(2003, 80)
+           + noisy("GT", 70, 0.05) + splitmix_bases(2004, 60))
+    dna = (splitmix_bases(1001, 1500) + noisy("GA", 1800, 0.08) + splitmix_bases(1002, 900) + noisy("TC", 700, 0.05) + splitmix_bases(1003, 1200)
+           + noisy("GGA", 600, 0.1) + splitmix_bases(1004, 800))
+    engine.set_query("stress", rna)
+    total = 0
+    for kw, ekw in ((dict(c_length=20), dict(cLength=20)),
+                    (dict(c_length=15, nt_min=10, penalty_t=0, penalty_c=0, min_stability=0, min_identity=40),
+                     dict(cLength=15, ntMin=10, penaltyT=0, penaltyC=0, minStability=0, minIdentity=40)),
+                    (dict(c_length=30, penalty_t=-3, penalty_c=2, min_stability=1, min_identity=50, cut_length=3000, overlap=500),
+                     dict(cLength=30, penaltyT=-3, penaltyC=2, minStability=1, minIdentity=50, cutLength=3000, overlap=500))):
+        engine.set_params(**kw)
+        res = engine.scan_record(dna, "chrM", 1)
+        rows = fb.result_rows(res)
+        lit = (res.contents.n_literal_tasks, res.contents.n_literal_windows)
+        engine.free(res)
+        assert rows_as_oracle_text(rows) == oracle_text_rows(O.longtarget(rna, dna, **ekw)), kw
+        assert lit[0] > 0 and lit[1] > 0          # the literal (Q4) paths were exercised
+        total += len(rows)
+    assert total > 1000
+    engine.set_params()
+
+
 def test_multi_query_switching(engine):
     """Config 5 style use: several lncRNAs against the same DNA through one context, switching back and forth (different
     lengths select different scan tilings and strip counts; every buffer of the context is reused)."""
