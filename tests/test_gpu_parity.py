@@ -342,6 +342,17 @@ def test_cli_long_lncrnas_complex_flags(tmp_path, data_dir, name):
     assert got == open(os.path.join(GOLDEN, "%s_testDNA_complex__TFOsorted" % name)).read()
 
 
+@pytest.mark.parametrize("name", ["NEAT1", "MALAT1"])
+def test_cli_long_lncrnas_vs_meg3_regions(tmp_path, data_dir, name):
+    """BASELINE configs[2] on the second substitute DNA set: NEAT1 (22.8 knt) / MALAT1 (8.7 knt) against the first 12 MEG3
+    regions (multi-record file), complex flags; golden from the reference (tests/golden/make_golden_config3.py)."""
+    files = run_cli_files(tmp_path, "MEG3-12.fa", open(os.path.join(data_dir, "MEG3-DNAseq-first12.fa")).read(), name + ".fa",
+                          open(os.path.join(data_dir, name + ".fa")).read(),
+                          ["-i", "70", "-S", "1.0", "-ni", "25", "-pt", "-500", "-ds", "10", "-lg", "60"])
+    got = [v for k, v in files.items() if k.endswith("TFOsorted")][0]
+    assert got == open(os.path.join(GOLDEN, "%s_meg3first12_complex__TFOsorted" % name)).read()
+
+
 def test_cli_synthetic_and_planted(tmp_path, golden):
     sdna, srna = splitmix_bases(1001, 30000), splitmix_bases(2001, 1000)
     files = run_cli_files(tmp_path, "syn.fa", ">syn|chr1|1-30000\n%s\n" % sdna, "synRNA.fa", ">synRNA1k\n%s\n" % srna, ["-lg", "20"])
