@@ -187,6 +187,17 @@ def int_simd_peak():
     return 8170.0, "fallback: 77.46 thread-instr/clk/SM measured in round 1 -> 8.17 TCUPS at 1.958 GHz", None
 
 
+def hbm_peak():
+    """Measured HBM copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md"
+
+
 def bench_gpu(args, rank, world, local_rank):
     import torch
     import fasim_b200 as fb
@@ -272,6 +283,13 @@ def bench_gpu(args, rank, world, local_rank):
         # each rank runs its own launches concurrently: per-GPU achieved = cells / N / (max-over-ranks scan time).
         scan_gcups = st["cells"] / world / (st["scan_ms"] * 1e-3) / 1e9 if st["scan_ms"] > 0 else 0.0
         dna_bytes = st["bases"]            # 1 B/base read once per item pair-group, hits out are negligible
+        # secondary counter: DRAM bandwidth of the dominant kernel against the measured copy peak
+        hbm_pk, hbm_src = hbm_peak()
+        ms_launch = st["scan_ms"] / max(st["scan_launches"] / world, 1)
+        hbm_secondary = None
+        if dram_per_seg and ms_launch > 0:
+            gbs = dram_per_seg * st["segs"] / max(st["scan_launches"], 1) / (ms_launch * 1e-3) / 1e9
+            hbm_secondary = {"achieved": gbs, "peak": hbm_pk, "unit": "GB/s", "frac": gbs / hbm_pk, "peak_source": hbm_src}
         line = {
             "metric": "GCUPS (scan cells m*n per task, counted once) of the triplex scan, 100 Mbp x 3 kb lncRNA",
             "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -297,6 +315,7 @@ def bench_gpu(args, rank, world, local_rank):
                          "ms_per_launch": st["scan_ms"] / max(st["scan_launches"] / world, 1),
                          "traffic": (dram_per_seg * st["segs"] / max(st["scan_launches"], 1)) if dram_per_seg else None,
                          "traffic_unit": "DRAM bytes per k_scan launch (ncu dram__bytes_read+write of one launch, scaled by segments per launch)",
+                         "hbm_secondary": hbm_secondary,
                          "note": "integer-ALU bound (SURVEY.md 8d): HBM traffic is ~1 B per %d cells; hbm_gbs_algorithmic=%.3f"
                                  % (RNA_NT * TASKS_PER_SEG, dna_bytes / max(st["scan_ms"], 1e-9) / 1e6)},
             "clocks": clocks,
