@@ -103,6 +103,17 @@ struct HostSeg {
     int32_t pad_;
 };
 
+// counters of a batch's device phase as they land in pinned memory (each member is the target of one D2H copy)
+struct BatchScalars {
+    long long window_cells;                 // counters[kCntCells..]
+    int cells_pad[6];
+    int lit[2]; int lit_total; int lit_pad[5];          // counters[kCntLit], [kCntLit+1], [kCntLitTotal]
+    unsigned long long win_stats[20];       // WinSched::st_windows, st_cells
+    int trace_handed[4];                    // counters[kCntOvf..]
+    int cand[4];                            // shipped records, shipped tasks, unfinished alignments
+    unsigned long long filter_stats[6];     // WinSched::st_filter
+};
+
 // what one batch leaves on the host: pinned copies filled by asynchronous D2H, consumed by the host phase
 struct HostBatch {
     std::vector<HostSeg> segs;
@@ -513,7 +524,8 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     if (int e = c->d_task_litrow.ensure(sizeof(int) * (size_t)n_tasks)) return e;
     if (int e = hb.task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
     if (int e = hb.task_off.ensure(sizeof(int) * ((size_t)n_tasks + 1))) return e;
-    if (int e = hb.scalars.ensure(320)) return e;
+    if (int e = hb.scalars.ensure(sizeof(BatchScalars))) return e;
+    BatchScalars* bs = hb.scalars.as<BatchScalars>();
     TaskInfo ti(c->d_task_info.as<int>(), n_tasks), hti(hb.task_info.as<int>(), n_tasks);
     int* counters = c->d_counters.as<int>();
 
@@ -698,17 +710,18 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
         LTG_CUDA_CHECK(cudaGetLastError());
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.c_task.p, hb.d_ctask.p, sizeof(int) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
         LTG_CUDA_CHECK(cudaMemcpyAsync(hb.c_poff.p, hb.d_cpoff.p, sizeof(int) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.p, counters + kCntCells, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 64, &c->d_win_sched.as<WinSched>()->st_windows[0], 20 * sizeof(unsigned long long),
+        static_assert(kCntLit - kCntCells == 8 && kCntLitTotal - kCntLit == 2, "BatchScalars mirrors counters[kCntCells .. kCntCells + 16)");
+        LTG_CUDA_CHECK(cudaMemcpyAsync(&bs->window_cells, counters + kCntCells, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(bs->win_stats, &c->d_win_sched.as<WinSched>()->st_windows[0], 20 * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 232, counters + kCntOvf, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 248, counters + kCntCand, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        LTG_CUDA_CHECK(cudaMemcpyAsync(hb.scalars.as<char>() + 264, &c->d_win_sched.as<WinSched>()->st_filter[0], 6 * sizeof(unsigned long long),
+        LTG_CUDA_CHECK(cudaMemcpyAsync(bs->trace_handed, counters + kCntOvf, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(bs->cand, counters + kCntCand, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(bs->filter_stats, &c->d_win_sched.as<WinSched>()->st_filter[0], 6 * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, c->stream));
         c->d2h_bytes += (int64_t)sizeof(int) * 2 * n_tasks + 272;
     } else {
         hb.n_peaks = want_alignments ? n_peaks : 0;
-        memset(hb.scalars.p, 0, 320);
+        memset(bs, 0, sizeof(BatchScalars));
     }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ready, c->stream));
     return LTG_OK;
@@ -774,7 +787,7 @@ void batch_worker(ltg_context* c, HostBatch* hb)
     cudaSetDevice(c->device);
     if (cudaEventSynchronize(hb->ready) != cudaSuccess) { hb->error = "device phase failed"; return; }
     if (hb->n_peaks == 0) return;
-    const int* cand = reinterpret_cast<const int*>(hb->scalars.as<char>() + 248);
+    const int* cand = hb->scalars.as<BatchScalars>()->cand;
     hb->n_cpeaks = cand[0]; hb->n_ctasks = cand[1];
     if (cand[2] > 0) { hb->error = "traceback band exceeds the device scratch"; return; }
     if (hb->n_cpeaks > 0) {
@@ -907,13 +920,12 @@ int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg
     st.n_peaks += hb.n_peaks;
     c->d2h_bytes += hb.d2h_late;
     st.n_literal_tasks += hb.n_literal_tasks;
-    const int* sc = hb.scalars.as<int>();
-    long long cells = 0; memcpy(&cells, sc, 8);
-    st.window_cells += cells;
-    st.n_literal_windows += sc[kCntLitTotal - kCntCells];
-    for (int k = 0; k < 20; ++k) c->win_stats[k] += reinterpret_cast<const unsigned long long*>(hb.scalars.as<char>() + 64)[k];
-    for (int k = 0; k < 4; ++k) c->win_stats[20 + k] += (unsigned long long)reinterpret_cast<const int*>(hb.scalars.as<char>() + 232)[k];
-    for (int k = 0; k < 6; ++k) c->win_stats[24 + k] += reinterpret_cast<const unsigned long long*>(hb.scalars.as<char>() + 264)[k];
+    const BatchScalars* bs = hb.scalars.as<BatchScalars>();
+    st.window_cells += bs->window_cells;
+    st.n_literal_windows += bs->lit_total;
+    for (int k = 0; k < 20; ++k) c->win_stats[k] += bs->win_stats[k];
+    for (int k = 0; k < 4; ++k) c->win_stats[20 + k] += (unsigned long long)bs->trace_handed[k];
+    for (int k = 0; k < 6; ++k) c->win_stats[24 + k] += bs->filter_stats[k];
     record_list.insert(record_list.end(), hb.rows.begin(), hb.rows.end());
     hb.rows.clear();
     return LTG_OK;
