@@ -1,6 +1,7 @@
 // Drop-in process surface of the reference `fasim` (Fasim-LongTarget.cpp:78-172 main, :269-377 initEnv,
 // :174-267 FASTA readers, :797-845 printResult, :694-795 print_cluster) on top of the C ABI above.
 // Included at the end of engine.cu (same translation unit: it uses the anonymous-namespace helpers).
+#include <atomic>
 #include <fstream>
 #include <getopt.h>
 #include <time.h>
@@ -73,7 +74,9 @@ void usage()
            "  -ni N min triplex nt (20)     -na N max triplex nt (100000)\n"
            "  -pc N penalty C (0)           -pt N penalty T (-1000)\n"
            "  -ds N cluster distance (15)   -lg N min length for clustering (50)\n"
-           "  --device N  CUDA device (default 0)\n");
+           "  --device N  CUDA device (default 0)\n"
+           "  --devices a,b,..|all   several GPUs in one process: one context and one host thread per GPU pull chunks of the\n"
+           "                         file from a shared queue (results are identical to a single-GPU run)\n");
 }
 
 }  // namespace
@@ -162,7 +165,7 @@ int ltg_main(int argc, char* const* argv)
 {
     ltg_params P;
     ltg_default_params(&P);
-    std::string f1 = "./", f2 = "./", outdir = "./";
+    std::string f1 = "./", f2 = "./", outdir = "./", devices_arg;
     int device = 0;
     // same option table as initEnv (Fasim-LongTarget.cpp:271-283); -m, -d, -cn, -F are accepted and ignored
     // (-F selects the SIM path, which this build does not provide: it is reported as an error)
@@ -171,7 +174,7 @@ int ltg_main(int argc, char* const* argv)
         {"f1", required_argument, nullptr, 'f'}, {"f2", required_argument, nullptr, 's'}, {"ni", required_argument, nullptr, 'y'},
         {"na", required_argument, nullptr, 'z'}, {"pc", required_argument, nullptr, 'Y'}, {"pt", required_argument, nullptr, 'Z'},
         {"cn", required_argument, nullptr, 'C'}, {"ds", required_argument, nullptr, 'D'}, {"lg", required_argument, nullptr, 'E'},
-        {"device", required_argument, nullptr, 1000}, {nullptr, 0, nullptr, 0}};
+        {"device", required_argument, nullptr, 1000}, {"devices", required_argument, nullptr, 1001}, {nullptr, 0, nullptr, 0}};
     if (argc <= 1) { usage(); return 1; }
     optind = 1;
     int opt;
@@ -196,6 +199,7 @@ int ltg_main(int argc, char* const* argv)
         case 'F': want_sim = true; break;
         case 'h': usage(); return 1;
         case 1000: device = atoi(optarg); break;
+        case 1001: devices_arg = optarg; break;
         default: break;
         }
     }
@@ -209,32 +213,100 @@ int ltg_main(int argc, char* const* argv)
     if (!read_rna_fasta(f2, lnc_name, lnc) || lnc.empty()) { fprintf(stderr, "fasim: cannot read RNA file %s\n", f2.c_str()); return 2; }
     printf("%s\n", lnc_name.c_str());
 
-    ltg_context* ctx = nullptr;
-    if (ltg_create(device, &ctx) != LTG_OK) { fprintf(stderr, "fasim: %s\n", ltg_last_error()); return 3; }
-    int rc = ltg_set_params(ctx, &P);
-    if (rc == LTG_OK) rc = ltg_set_query(ctx, lnc_name.c_str(), lnc.c_str(), (int64_t)lnc.size());
-    ltg_result* all = nullptr;
-    if (rc == LTG_OK) rc = ltg_result_new(&all);
-    // all records of the file through the batched entry point, in chunks of at most ~256 MB of sequence
-    for (size_t i = 0; rc == LTG_OK && i < recs.size();) {
-        std::vector<const char*> dna, chr;
-        std::vector<int64_t> len, start;
-        size_t j = i, bytes = 0;
-        for (; j < recs.size() && (j == i || bytes + recs[j].seq.size() <= (256u << 20)); ++j) {
-            dna.push_back(recs[j].seq.data()); len.push_back((int64_t)recs[j].seq.size());
-            chr.push_back(recs[j].chr.c_str()); start.push_back(recs[j].start);
-            bytes += recs[j].seq.size();
+    // devices: --device N, or --devices a,b,.. / all (one context + one host thread per entry; an entry may repeat)
+    std::vector<int> devs;
+    if (devices_arg == "all") { for (int d = 0; d < ltg_device_count(); ++d) devs.push_back(d); }
+    else if (!devices_arg.empty()) {
+        size_t at = 0;
+        while (at <= devices_arg.size()) {
+            const size_t comma = devices_arg.find(',', at);
+            const std::string tok = devices_arg.substr(at, comma == std::string::npos ? std::string::npos : comma - at);
+            if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
+            if (comma == std::string::npos) break;
+            at = comma + 1;
         }
-        ltg_result* part = nullptr;
-        rc = ltg_scan_records(ctx, (int64_t)(j - i), dna.data(), len.data(), chr.data(), start.data(), &part);
-        if (rc == LTG_OK) {
-            for (int64_t k = 0; k < part->n_triplex; ++k) part->triplex[k].record += (int32_t)i;
-            rc = ltg_result_append(all, part);
-            ltg_result_free(part);
-        }
-        i = j;
     }
-    if (rc != LTG_OK) { fprintf(stderr, "fasim: %s\n", ltg_last_error()); ltg_result_free(all); ltg_destroy(ctx); return 3; }
+    if (devs.empty()) devs.push_back(device);
+
+    // Work units in file order: runs of whole records (short records share device batches), or shards of
+    // kUnitSegments segments of a long record.  GPUs pull units from one atomic queue; the results are appended in unit order,
+    // which is the order a single ltg_scan_records call over the file would produce.
+    struct Unit { size_t r0, r1; int64_t first_seg, n_seg; ltg_result* res; };
+    std::vector<Unit> units;
+    {
+        const int64_t stride = P.cut_length - P.overlap;
+        const int64_t kUnitSegments = 2048, unit_bases = kUnitSegments * (stride > 0 ? stride : 1);
+        if (stride <= 0) { fprintf(stderr, "fasim: cut length (%d) must exceed the overlap (%d)\n", P.cut_length, P.overlap); return 2; }
+        size_t i = 0;
+        while (i < recs.size()) {
+            const int64_t n = (int64_t)recs[i].seq.size();
+            if (n > unit_bases + stride && devs.size() > 1) {                 // a long record: shards of whole segments
+                const int64_t n_seg = (n + stride - 1) / stride;
+                for (int64_t s0 = 0; s0 < n_seg; s0 += kUnitSegments) units.push_back(Unit{i, i + 1, s0, std::min(kUnitSegments, n_seg - s0), nullptr});
+                ++i;
+                continue;
+            }
+            size_t j = i;
+            int64_t bytes = 0;
+            const int64_t cap = devs.size() > 1 ? unit_bases : (256ll << 20);
+            for (; j < recs.size() && (j == i || bytes + (int64_t)recs[j].seq.size() <= cap); ++j) {
+                if (j > i && (int64_t)recs[j].seq.size() > unit_bases + stride && devs.size() > 1) break;
+                bytes += (int64_t)recs[j].seq.size();
+            }
+            units.push_back(Unit{i, j, 0, -1, nullptr});
+            i = j;
+        }
+    }
+    std::atomic<size_t> next_unit(0);
+    std::atomic<int> failed(0);
+    std::vector<std::string> errors(devs.size());
+    auto gpu_worker = [&](size_t w) {
+        ltg_context* ctx = nullptr;
+        int rc = ltg_create(devs[w], &ctx);
+        if (rc == LTG_OK) rc = ltg_set_params(ctx, &P);
+        if (rc == LTG_OK) rc = ltg_set_query(ctx, lnc_name.c_str(), lnc.c_str(), (int64_t)lnc.size());
+        while (rc == LTG_OK && !failed.load()) {
+            const size_t u = next_unit.fetch_add(1);
+            if (u >= units.size()) break;
+            Unit& U = units[u];
+            if (U.n_seg >= 0) {                                  // shard of one long record
+                const FastaRecord& R = recs[U.r0];
+                const int64_t stride = P.cut_length - P.overlap, lo = U.first_seg * stride;
+                const int64_t hi = std::min<int64_t>((int64_t)R.seq.size(), (U.first_seg + U.n_seg - 1) * stride + P.cut_length);
+                rc = ltg_scan_shard(ctx, R.seq.data() + lo, 0, hi - lo, R.chr.c_str(), R.start, (int64_t)R.seq.size(), U.first_seg, U.n_seg, &U.res);
+            } else {
+                std::vector<const char*> dna, chr;
+                std::vector<int64_t> len, start;
+                for (size_t r = U.r0; r < U.r1; ++r) {
+                    dna.push_back(recs[r].seq.data()); len.push_back((int64_t)recs[r].seq.size());
+                    chr.push_back(recs[r].chr.c_str()); start.push_back(recs[r].start);
+                }
+                rc = ltg_scan_records(ctx, (int64_t)(U.r1 - U.r0), dna.data(), len.data(), chr.data(), start.data(), &U.res);
+            }
+        }
+        if (rc != LTG_OK) { errors[w] = ltg_last_error(); failed.store(1); }
+        if (ctx) ltg_destroy(ctx);
+    };
+    {
+        std::vector<std::thread> pool;
+        for (size_t w = 1; w < devs.size(); ++w) pool.emplace_back(gpu_worker, w);
+        gpu_worker(0);
+        for (std::thread& t : pool) t.join();
+    }
+    ltg_result* all = nullptr;
+    int rc = failed.load() ? LTG_ERR_CUDA : ltg_result_new(&all);
+    for (size_t u = 0; rc == LTG_OK && u < units.size(); ++u) {
+        ltg_result* part = units[u].res;
+        if (!part) { rc = LTG_ERR_STATE; break; }
+        for (int64_t k = 0; k < part->n_triplex; ++k) part->triplex[k].record += (int32_t)units[u].r0;
+        rc = ltg_result_append(all, part);
+    }
+    for (Unit& U : units) if (U.res) ltg_result_free(U.res);
+    if (rc != LTG_OK) {
+        for (const std::string& e : errors) if (!e.empty()) fprintf(stderr, "fasim: %s\n", e.c_str());
+        if (all) ltg_result_free(all);
+        return 3;
+    }
     ltg_cluster(all, &P);
     // output name: <O>/<species>-<lncName>-<f1 minus last 3 chars>-TFOsorted (Fasim-LongTarget.cpp:123, 800-802); the
     // directory part of -f1 is dropped (the reference embeds it and then silently fails to open the file, Q14)
@@ -254,7 +326,6 @@ int ltg_main(int argc, char* const* argv)
                (long)all->n_segments, (long)all->n_tasks, (long)all->n_peaks, (double)all->scan_cells, all->gpu_ms_scan, all->gpu_ms_window,
                (long)all->n_literal_tasks, (long)all->n_literal_windows);
     ltg_result_free(all);
-    ltg_destroy(ctx);
     return rc == LTG_OK ? 0 : 3;
 }
 

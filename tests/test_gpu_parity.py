@@ -353,6 +353,25 @@ def test_cli_long_lncrnas_vs_meg3_regions(tmp_path, data_dir, name):
     assert got == open(os.path.join(GOLDEN, "%s_meg3first12_complex__TFOsorted" % name)).read()
 
 
+def test_cli_multi_device_work_queue(tmp_path):
+    """--devices: one context + host thread per entry pulling shards / record groups from a shared queue.  Two contexts on
+    GPU 0 ("0,0") exercise the path on a single-GPU box; the files must equal the single-context run byte for byte."""
+    rna = splitmix_bases(2001, 1200)
+    recs = [(11_000_000, 1001), (400_000, 1002), (2_600_000, 1003), (37, 1004), (5_000_000, 1005), (900_000, 1006)]
+    fasta = "".join(">syn|chr%d|%d-%d\n%s\n" % (k + 1, 1000 * k + 1, 1000 * k + n, splitmix_bases(seed, n)) for k, (n, seed) in enumerate(recs))
+    d = str(tmp_path)
+    open(os.path.join(d, "multi.fa"), "w").write(fasta)
+    open(os.path.join(d, "rna.fa"), "w").write(">synRNA\n%s\n" % rna)
+    outs = []
+    for tag, extra in (("one", ["--device", "0"]), ("two", ["--devices", "0,0"])):
+        os.makedirs(os.path.join(d, tag), exist_ok=True)
+        r = fb.run_cli(["-f1", "multi.fa", "-f2", "rna.fa", "-O", tag + "/", "-lg", "30"] + extra, cwd=d)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append({f: open(os.path.join(d, tag, f)).read() for f in sorted(os.listdir(os.path.join(d, tag)))})
+    assert outs[0] == outs[1] and len(outs[0]) == 3
+    assert len([v for k, v in outs[0].items() if k.endswith("TFOsorted")][0].splitlines()) > 1000
+
+
 def test_cli_synthetic_and_planted(tmp_path, golden):
     sdna, srna = splitmix_bases(1001, 30000), splitmix_bases(2001, 1000)
     files = run_cli_files(tmp_path, "syn.fa", ">syn|chr1|1-30000\n%s\n" % sdna, "synRNA.fa", ">synRNA1k\n%s\n" % srna, ["-lg", "20"])
