@@ -206,12 +206,19 @@ int ltg_main(int argc, char* const* argv)
     if (want_sim) { fprintf(stderr, "fasim: -F (SIM mode) is not available in the B200 build\n"); return 2; }
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
+    const bool timing = getenv("LTG_TIMING") != nullptr;
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[fasim timing] %-10s at %.3f s\n", what, (t.tv_sec - t0.tv_sec) + 1e-9 * (t.tv_nsec - t0.tv_nsec));
+    };
     printf("Searching triplexes using Fasim\n");
     std::vector<FastaRecord> recs;
     if (!read_dna_fasta(f1, recs) || recs.empty()) { fprintf(stderr, "fasim: cannot read DNA file %s\n", f1.c_str()); return 2; }
     std::string lnc_name, lnc;
     if (!read_rna_fasta(f2, lnc_name, lnc) || lnc.empty()) { fprintf(stderr, "fasim: cannot read RNA file %s\n", f2.c_str()); return 2; }
     printf("%s\n", lnc_name.c_str());
+    lap("read");
 
     // devices: --device N, or --devices a,b,.. / all (one context + one host thread per entry; an entry may repeat)
     std::vector<int> devs;
@@ -293,6 +300,7 @@ int ltg_main(int argc, char* const* argv)
         gpu_worker(0);
         for (std::thread& t : pool) t.join();
     }
+    lap("scan");
     ltg_result* all = nullptr;
     int rc = failed.load() ? LTG_ERR_CUDA : ltg_result_new(&all);
     for (size_t u = 0; rc == LTG_OK && u < units.size(); ++u) {
@@ -307,7 +315,9 @@ int ltg_main(int argc, char* const* argv)
         if (all) ltg_result_free(all);
         return 3;
     }
+    lap("merge");
     ltg_cluster(all, &P);
+    lap("cluster");
     // output name: <O>/<species>-<lncName>-<f1 minus last 3 chars>-TFOsorted (Fasim-LongTarget.cpp:123, 800-802); the
     // directory part of -f1 is dropped (the reference embeds it and then silently fails to open the file, Q14)
     std::string base = f1;
@@ -318,6 +328,7 @@ int ltg_main(int argc, char* const* argv)
     rc = ltg_write_tfosorted(all, out_path.c_str());
     if (rc == LTG_OK) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, (int64_t)recs[0].seq.size(), lnc_name.c_str());
     if (rc != LTG_OK) fprintf(stderr, "fasim: %s\n", ltg_last_error());
+    lap("write");
     clock_gettime(CLOCK_MONOTONIC, &t1);
     const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     printf("finished normally\nRunning time is %g\n", secs);

@@ -110,17 +110,27 @@ inline void cluster(std::vector<ltg_triplex>& v, int dd, int length, std::map<si
             if (wk > top) { top = wk; center = mid + k; found = true; }
         }
     }
+    // The reference walks the whole list for every position of every class window (quadratic in the number of rows).
+    // Same assignment order from an index: rows grouped by MidPoint, each group in list order.  (Rows that were not
+    // counted above keep MidPoint 0 and can be claimed by a window that covers position 0, Q9.)
+    std::map<long, std::vector<size_t>> by_mid;
+    for (size_t i = 0; i < v.size(); ++i) by_mid[v[i].middle].push_back(i);
     int cls = 1;
     while (found) {
         for (long p = center - dd; p <= center + dd; ++p) {
-            for (ltg_triplex& t : v) {
-                if (t.middle != p || t.motif != 0) continue;
-                t.motif = cls;
-                t.center = (int)center;
-                if (class_cov && cls <= 5) {
-                    if (t.endj > t.starj) for (int j = t.starj; j < t.endj; ++j) class_cov[cls][(size_t)j]++;
-                    else for (int j = t.endj; j < t.starj; ++j) class_cov[cls][(size_t)j]++;
+            auto it = by_mid.find(p);
+            if (it != by_mid.end()) {
+                for (size_t i : it->second) {
+                    ltg_triplex& t = v[i];
+                    if (t.motif != 0) continue;
+                    t.motif = cls;
+                    t.center = (int)center;
+                    if (class_cov && cls <= 5) {
+                        if (t.endj > t.starj) for (int j = t.starj; j < t.endj; ++j) class_cov[cls][(size_t)j]++;
+                        else for (int j = t.endj; j < t.starj; ++j) class_cov[cls][(size_t)j]++;
+                    }
                 }
+                by_mid.erase(it);           // every row of the group is assigned now
             }
             weight.erase(p);
         }
