@@ -215,56 +215,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
             uint32_t hout = 0, fout = 0, cmout = 0, hdiag = 0;
             const int steps = n + 31;
-#ifdef LTG_SCAN_V1
-            // software pipeline: the packed scores of step s+1 are loaded while step s computes, and the base code
-            // two steps ahead is fetched, so no step starts by waiting on a shared-memory round trip
-            const uint8_t* cp = s_codes + (32 - lane);
-            uint4 sc[R / 4];
-            {
-                const uint4* pp0 = s_prof + (int)cp[0] * PLANE + lane;
-#pragma unroll
-                for (int k = 0; k < R / 4; ++k) sc[k] = pp0[k * 32];
-            }
-            int xn = cp[1];
-            for (int s = 0; s < steps; ++s) {
-                if (!first && (s & 31) == 0) {
-                    __syncwarp();
-                    const int j = s + lane;
-                    uint2 pk = make_uint2(0, 0);
-                    if (j < n) pk = bnd[j];
-                    s_ring[lane] = pk;
-                    __syncwarp();
-                }
-                const uint4* ppn = s_prof + xn * PLANE + lane;
-                uint4 scn[R / 4];
-#pragma unroll
-                for (int k = 0; k < R / 4; ++k) scn[k] = ppn[k * 32];
-                xn = cp[min(s + 2, steps)];
-                uint32_t hin = __shfl_up_sync(0xffffffffu, hout, 1);
-                uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);
-                uint32_t cmin = __shfl_up_sync(0xffffffffu, cmout, 1);
-                if (gran_head) cmin = 0;
-                if (lane == 0) {
-                    if (first) { hin = 0; fin = 0; }
-                    else { const uint2 pk = s_ring[s & 31]; hin = pk.x; fin = pk.y; }
-                }
-                uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;
-                uint32_t tv[2];
-#pragma unroll
-                for (int k = 0; k < R / 4; ++k) {
-                    LTG_CELL(sc[k].x, 4 * k + 0)
-                    LTG_CELL(sc[k].y, 4 * k + 1)
-                    LTG_CELL(sc[k].z, 4 * k + 2)
-                    LTG_CELL(sc[k].w, 4 * k + 3)
-                }
-#pragma unroll
-                for (int k = 0; k < R / 4; ++k) sc[k] = scn[k];
-                hdiag = hin;
-                hout = hlast; fout = f; cmout = cm;
-                if (gran_tail && s >= lane && s - lane < n) cm_lane[s] = cm;
-                if (lane == 31 && !last && s >= 31) bnd[s - 31] = make_uint2(hout, fout);
-            }
-#else
             // Steps run in blocks of 32 (the ring of strip-boundary packets is refilled per block).  Shared memory is
             // addressed with explicit 32-bit shared addresses (one add per profile fetch instead of a generic-pointer
             // conversion); the packed scores of step s+1 are loaded while step s computes and the base code two steps
@@ -346,7 +296,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 cm_ptr += 32; bnd_ptr += 32;
             }
 #undef LTG_SCAN_STEP
-#endif
         }
     }
 }
