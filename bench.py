@@ -54,6 +54,15 @@ def splitmix_bases(seed, n, offset=0):
     return out
 
 
+def splitmix_first(seed):
+    """First SplitMix64 output of a stream (lncRNA length = 1000 + z % 9001)."""
+    M = (1 << 64) - 1
+    z = (seed + 0x9E3779B97F4A7C15) & M
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+    return z ^ (z >> 31)
+
+
 def region_cells(n_bases, m, cut=CUT, overlap=OVERLAP, tasks=TASKS_PER_SEG):
     stride = cut - overlap
     total = 0
@@ -213,10 +222,17 @@ def bench_gpu(args, rank, world, local_rank):
     region = int(args.region_mbp * 1e6)
     first_seg, nseg, lo, nb = fb.shard_segments(region, world, rank, CUT, OVERLAP)     # contiguous run of whole segments
     rna = splitmix_bases(RNA_SEED, RNA_NT).tobytes().decode()
-    host = torch.from_numpy(splitmix_bases(DNA_SEED, nb, lo)).pin_memory()
+    if args.queries > 0:
+        # BASELINE.json configs[4]: lncRNAs of 1000 + z % 9001 nt, seeds 4001.., DNA seed 1002; every
+        # step scans all of them against the rank's shard, switching the context's query inside the timed region
+        queries = [("synRNA%d" % k, splitmix_bases(4001 + k, 1000 + splitmix_first(4001 + k) % 9001).tobytes().decode()) for k in range(args.queries)]
+        dna_seed = 1002
+    else:
+        queries, dna_seed = [("synRNA3k", rna)], DNA_SEED
+    host = torch.from_numpy(splitmix_bases(dna_seed, nb, lo)).pin_memory()
     dev = host.to("cuda", non_blocking=False)
     eng = fb.Engine(local_rank)
-    eng.set_query("synRNA3k", rna)
+    eng.set_query(*queries[0])
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -232,7 +248,9 @@ def bench_gpu(args, rank, world, local_rank):
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(steps):
+        for qname, qseq in [q for _ in range(steps) for q in queries]:
+            if len(queries) > 1:
+                eng.set_query(qname, qseq)
             res = C.POINTER(fb.Result)()
             # the reference-facing C-ABI call; device_resident: DNA already in HBM, else HOST buffer (H2D inside the call)
             rc = fb.lib().ltg_scan_shard(eng._h, C.c_void_p(dev.data_ptr() if device_resident else host.data_ptr()),
@@ -291,12 +309,16 @@ def bench_gpu(args, rank, world, local_rank):
             gbs = dram_per_seg * st["segs"] / max(st["scan_launches"], 1) / (ms_launch * 1e-3) / 1e9
             hbm_secondary = {"achieved": gbs, "peak": hbm_pk, "unit": "GB/s", "frac": gbs / hbm_pk, "peak_source": hbm_src}
         line = {
-            "metric": "GCUPS (scan cells m*n per task, counted once) of the triplex scan, 100 Mbp x 3 kb lncRNA",
+            "metric": "GCUPS (scan cells m*n per task, counted once) of the triplex scan, " + ("100 Mbp x 3 kb lncRNA" if args.queries <= 0 else "multi-query batch"),
             "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int16x2 (packed SIMD-in-register)", "data": "synthetic",
-            "config": {"workload": "synthetic %g Mbp region x 3 kb lncRNA, 48 tasks per 5000-bp segment, sharded over %d GPU(s) "
-                                   "(BASELINE.json configs[3])" % (args.region_mbp, world),
+            "config": {"workload": ("synthetic %g Mbp region x 3 kb lncRNA, 48 tasks per 5000-bp segment, sharded over %d GPU(s) "
+                                    "(BASELINE.json configs[3])" % (args.region_mbp, world)) if args.queries <= 0 else
+                                   ("%d synthetic lncRNAs (%d..%d nt, %d nt in all) x synthetic %g Mbp DNA, sharded over %d GPU(s) "
+                                    "(BASELINE.json configs[4] at reduced size; not the headline workload)"
+                                    % (len(queries), min(len(q[1]) for q in queries), max(len(q[1]) for q in queries),
+                                       sum(len(q[1]) for q in queries), args.region_mbp, world)),
                        "l2": "inputs (%.0f MB of DNA + per-batch column-max buffers > 126 MB) exceed L2" % (st["bases"] / args.steps / 1e6)},
             "mbp_per_s": st["bases"] / (ms * 1e-3) / 1e6,
             "wall_ms_per_step": 1e3 * wall / args.steps,
@@ -320,7 +342,9 @@ def bench_gpu(args, rank, world, local_rank):
                                  % (RNA_NT * TASKS_PER_SEG, dna_bytes / max(st["scan_ms"], 1e-9) / 1e6)},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline and reference_binary():
+        if args.queries > 0:
+            line["mbp_per_s_note"] = "DNA bases x lncRNAs scanned per second (each lncRNA is a full pass over the DNA)"
+        elif world == 1 and not args.no_cpu_baseline and reference_binary():
             cores = os.cpu_count() or 1
             g, mb, secs = cpu_baseline(rna, args.ref_chunk_bp, cores)
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": "reference", "mbp_per_s": mb,
@@ -355,6 +379,7 @@ def main():
     ap.add_argument("--ref-chunk-bp", type=int, default=49100)        # 10 full segments + tail per core and step
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--debug-stats", action="store_true")
+    ap.add_argument("--queries", type=int, default=0, help="multi-query workload (configs[4]): this many lncRNAs of 1-10 kb per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -62,6 +62,24 @@ bool read_rna_fasta(const std::string& path, std::string& name, std::string& seq
     return true;
 }
 
+// --queries: a multi-record -f2 file, one lncRNA per '>' record (new surface, SURVEY 8d config 5: the reference reads one
+// lncRNA per run and would splice a second header line into the sequence).  Names are cleaned like readRna does.
+bool read_rna_fasta_multi(const std::string& path, std::vector<std::pair<std::string, std::string> >& out)
+{
+    std::ifstream in(path.c_str());
+    if (!in) return false;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line[0] == '>') {
+            out.emplace_back();
+            for (char ch : line) if (ch != '>' && ch != '\r' && ch != '\n') out.back().first += ch;
+        } else if (!out.empty()) {
+            for (char ch : line) if (ch != '\r' && ch != '\n') out.back().second += ch;
+        }
+    }
+    return true;
+}
+
 void usage()
 {
     printf("fasim (B200 build) — genome-wide lncRNA:DNA triplex scan\n"
@@ -76,7 +94,9 @@ void usage()
            "  -ds N cluster distance (15)   -lg N min length for clustering (50)\n"
            "  --device N  CUDA device (default 0)\n"
            "  --devices a,b,..|all   several GPUs in one process: one context and one host thread per GPU pull chunks of the\n"
-           "                         file from a shared queue (results are identical to a single-GPU run)\n");
+           "                         file from a shared queue (results are identical to a single-GPU run)\n"
+           "  --queries   -f2 holds several lncRNAs (one per '>' record): every lncRNA is scanned against -f1 and gets its own\n"
+           "              output files; the (lncRNA, chunk) pairs go through the same queue\n");
 }
 
 }  // namespace
@@ -174,11 +194,12 @@ int ltg_main(int argc, char* const* argv)
         {"f1", required_argument, nullptr, 'f'}, {"f2", required_argument, nullptr, 's'}, {"ni", required_argument, nullptr, 'y'},
         {"na", required_argument, nullptr, 'z'}, {"pc", required_argument, nullptr, 'Y'}, {"pt", required_argument, nullptr, 'Z'},
         {"cn", required_argument, nullptr, 'C'}, {"ds", required_argument, nullptr, 'D'}, {"lg", required_argument, nullptr, 'E'},
-        {"device", required_argument, nullptr, 1000}, {"devices", required_argument, nullptr, 1001}, {nullptr, 0, nullptr, 0}};
+        {"device", required_argument, nullptr, 1000}, {"devices", required_argument, nullptr, 1001}, {"queries", no_argument, nullptr, 1002},
+        {nullptr, 0, nullptr, 0}};
     if (argc <= 1) { usage(); return 1; }
     optind = 1;
     int opt;
-    bool want_sim = false;
+    bool want_sim = false, multi_query = false;
     while ((opt = getopt_long_only(argc, argv, optstring, long_options, nullptr)) != -1) {
         switch (opt) {
         case 'f': f1 = optarg; break;
@@ -200,6 +221,7 @@ int ltg_main(int argc, char* const* argv)
         case 'h': usage(); return 1;
         case 1000: device = atoi(optarg); break;
         case 1001: devices_arg = optarg; break;
+        case 1002: multi_query = true; break;
         default: break;
         }
     }
@@ -215,9 +237,16 @@ int ltg_main(int argc, char* const* argv)
     printf("Searching triplexes using Fasim\n");
     std::vector<FastaRecord> recs;
     if (!read_dna_fasta(f1, recs) || recs.empty()) { fprintf(stderr, "fasim: cannot read DNA file %s\n", f1.c_str()); return 2; }
-    std::string lnc_name, lnc;
-    if (!read_rna_fasta(f2, lnc_name, lnc) || lnc.empty()) { fprintf(stderr, "fasim: cannot read RNA file %s\n", f2.c_str()); return 2; }
-    printf("%s\n", lnc_name.c_str());
+    std::vector<std::pair<std::string, std::string> > queries;            // (name, sequence); one entry unless --queries
+    if (multi_query) {
+        if (!read_rna_fasta_multi(f2, queries)) queries.clear();
+        for (size_t q = 0; q < queries.size();) { if (queries[q].second.empty()) queries.erase(queries.begin() + q); else ++q; }
+    } else {
+        std::string lnc_name, lnc;
+        if (read_rna_fasta(f2, lnc_name, lnc) && !lnc.empty()) queries.emplace_back(lnc_name, lnc);
+    }
+    if (queries.empty()) { fprintf(stderr, "fasim: cannot read RNA file %s\n", f2.c_str()); return 2; }
+    for (const auto& q : queries) printf("%s\n", q.first.c_str());
     lap("read");
 
     // devices: --device N, or --devices a,b,.. / all (one context + one host thread per entry; an entry may repeat)
@@ -238,7 +267,7 @@ int ltg_main(int argc, char* const* argv)
     // Work units in file order: runs of whole records (short records share device batches), or shards of
     // kUnitSegments segments of a long record.  GPUs pull units from one atomic queue; the results are appended in unit order,
     // which is the order a single ltg_scan_records call over the file would produce.
-    struct Unit { size_t r0, r1; int64_t first_seg, n_seg; ltg_result* res; };
+    struct Unit { size_t r0, r1; int64_t first_seg, n_seg; };
     std::vector<Unit> units;
     {
         const int64_t stride = P.cut_length - P.overlap;
@@ -249,7 +278,7 @@ int ltg_main(int argc, char* const* argv)
             const int64_t n = (int64_t)recs[i].seq.size();
             if (n > unit_bases + stride && devs.size() > 1) {                 // a long record: shards of whole segments
                 const int64_t n_seg = (n + stride - 1) / stride;
-                for (int64_t s0 = 0; s0 < n_seg; s0 += kUnitSegments) units.push_back(Unit{i, i + 1, s0, std::min(kUnitSegments, n_seg - s0), nullptr});
+                for (int64_t s0 = 0; s0 < n_seg; s0 += kUnitSegments) units.push_back(Unit{i, i + 1, s0, std::min(kUnitSegments, n_seg - s0)});
                 ++i;
                 continue;
             }
@@ -260,27 +289,71 @@ int ltg_main(int argc, char* const* argv)
                 if (j > i && (int64_t)recs[j].seq.size() > unit_bases + stride && devs.size() > 1) break;
                 bytes += (int64_t)recs[j].seq.size();
             }
-            units.push_back(Unit{i, j, 0, -1, nullptr});
+            units.push_back(Unit{i, j, 0, -1});
             i = j;
         }
     }
-    std::atomic<size_t> next_unit(0);
+    // Jobs = (lncRNA, unit) pairs, lncRNA-major, so the GPUs work on the same lncRNA most of the time and a context changes
+    // its query only when it pulls a job of the next one.  The worker that completes the last unit of a lncRNA merges,
+    // clusters and writes that lncRNA's files, so results do not pile up over a many-query run.
+    const size_t n_units = units.size(), n_jobs = n_units * queries.size();
+    std::vector<ltg_result*> results(n_jobs, nullptr);
+    std::vector<std::atomic<size_t> > remaining(queries.size());
+    for (auto& r : remaining) r.store(n_units);
+    std::atomic<size_t> next_job(0);
     std::atomic<int> failed(0);
     std::vector<std::string> errors(devs.size());
+    std::string base = f1;                                      // output name, see finish_query
+    {
+        const size_t slash = base.find_last_of('/');
+        if (slash != std::string::npos) base = base.substr(slash + 1);
+        base = base.substr(0, base.size() >= 3 ? base.size() - 3 : 0);
+    }
+    // <O>/<species>-<lncName>-<f1 minus last 3 chars>-TFOsorted (Fasim-LongTarget.cpp:123, 800-802); the directory part of
+    // -f1 is dropped (the reference embeds it and then silently fails to open the file, Q14)
+    auto finish_query = [&](size_t q) -> int {
+        ltg_result* all = nullptr;
+        int rc = ltg_result_new(&all);
+        for (size_t u = 0; rc == LTG_OK && u < n_units; ++u) {
+            ltg_result* part = results[q * n_units + u];
+            if (!part) { rc = LTG_ERR_STATE; break; }
+            for (int64_t k = 0; k < part->n_triplex; ++k) part->triplex[k].record += (int32_t)units[u].r0;
+            rc = ltg_result_append(all, part);
+        }
+        for (size_t u = 0; u < n_units; ++u) if (results[q * n_units + u]) { ltg_result_free(results[q * n_units + u]); results[q * n_units + u] = nullptr; }
+        if (rc == LTG_OK) rc = ltg_cluster(all, &P);
+        const std::string& lnc_name = queries[q].first;
+        const std::string out_path = outdir + "/" + recs[0].species + "-" + lnc_name + "-" + base + "-TFOsorted";
+        if (rc == LTG_OK) rc = ltg_write_tfosorted(all, out_path.c_str());
+        if (rc == LTG_OK) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, (int64_t)recs[0].seq.size(), lnc_name.c_str());
+        if (rc == LTG_OK && all->scan_cells > 0)
+            printf("[b200] %s: segments=%ld tasks=%ld peaks=%ld scan_cells=%.3e gpu_scan_ms=%.2f gpu_window_ms=%.2f literal_tasks=%ld literal_windows=%ld\n",
+                   lnc_name.c_str(), (long)all->n_segments, (long)all->n_tasks, (long)all->n_peaks, (double)all->scan_cells, all->gpu_ms_scan,
+                   all->gpu_ms_window, (long)all->n_literal_tasks, (long)all->n_literal_windows);
+        if (all) ltg_result_free(all);
+        return rc;
+    };
     auto gpu_worker = [&](size_t w) {
         ltg_context* ctx = nullptr;
         int rc = ltg_create(devs[w], &ctx);
         if (rc == LTG_OK) rc = ltg_set_params(ctx, &P);
-        if (rc == LTG_OK) rc = ltg_set_query(ctx, lnc_name.c_str(), lnc.c_str(), (int64_t)lnc.size());
+        size_t cur_q = (size_t)-1;
         while (rc == LTG_OK && !failed.load()) {
-            const size_t u = next_unit.fetch_add(1);
-            if (u >= units.size()) break;
-            Unit& U = units[u];
+            const size_t job = next_job.fetch_add(1);
+            if (job >= n_jobs) break;
+            const size_t q = job / n_units, u = job % n_units;
+            if (q != cur_q) {
+                rc = ltg_set_query(ctx, queries[q].first.c_str(), queries[q].second.c_str(), (int64_t)queries[q].second.size());
+                if (rc != LTG_OK) break;
+                cur_q = q;
+            }
+            const Unit& U = units[u];
+            ltg_result** out = &results[job];
             if (U.n_seg >= 0) {                                  // shard of one long record
                 const FastaRecord& R = recs[U.r0];
                 const int64_t stride = P.cut_length - P.overlap, lo = U.first_seg * stride;
                 const int64_t hi = std::min<int64_t>((int64_t)R.seq.size(), (U.first_seg + U.n_seg - 1) * stride + P.cut_length);
-                rc = ltg_scan_shard(ctx, R.seq.data() + lo, 0, hi - lo, R.chr.c_str(), R.start, (int64_t)R.seq.size(), U.first_seg, U.n_seg, &U.res);
+                rc = ltg_scan_shard(ctx, R.seq.data() + lo, 0, hi - lo, R.chr.c_str(), R.start, (int64_t)R.seq.size(), U.first_seg, U.n_seg, out);
             } else {
                 std::vector<const char*> dna, chr;
                 std::vector<int64_t> len, start;
@@ -288,8 +361,9 @@ int ltg_main(int argc, char* const* argv)
                     dna.push_back(recs[r].seq.data()); len.push_back((int64_t)recs[r].seq.size());
                     chr.push_back(recs[r].chr.c_str()); start.push_back(recs[r].start);
                 }
-                rc = ltg_scan_records(ctx, (int64_t)(U.r1 - U.r0), dna.data(), len.data(), chr.data(), start.data(), &U.res);
+                rc = ltg_scan_records(ctx, (int64_t)(U.r1 - U.r0), dna.data(), len.data(), chr.data(), start.data(), out);
             }
+            if (rc == LTG_OK && remaining[q].fetch_sub(1) == 1) rc = finish_query(q);
         }
         if (rc != LTG_OK) { errors[w] = ltg_last_error(); failed.store(1); }
         if (ctx) ltg_destroy(ctx);
@@ -300,44 +374,16 @@ int ltg_main(int argc, char* const* argv)
         gpu_worker(0);
         for (std::thread& t : pool) t.join();
     }
-    lap("scan");
-    ltg_result* all = nullptr;
-    int rc = failed.load() ? LTG_ERR_CUDA : ltg_result_new(&all);
-    for (size_t u = 0; rc == LTG_OK && u < units.size(); ++u) {
-        ltg_result* part = units[u].res;
-        if (!part) { rc = LTG_ERR_STATE; break; }
-        for (int64_t k = 0; k < part->n_triplex; ++k) part->triplex[k].record += (int32_t)units[u].r0;
-        rc = ltg_result_append(all, part);
-    }
-    for (Unit& U : units) if (U.res) ltg_result_free(U.res);
-    if (rc != LTG_OK) {
+    lap("scan+write");
+    for (ltg_result* r : results) if (r) ltg_result_free(r);
+    if (failed.load()) {
         for (const std::string& e : errors) if (!e.empty()) fprintf(stderr, "fasim: %s\n", e.c_str());
-        if (all) ltg_result_free(all);
         return 3;
     }
-    lap("merge");
-    ltg_cluster(all, &P);
-    lap("cluster");
-    // output name: <O>/<species>-<lncName>-<f1 minus last 3 chars>-TFOsorted (Fasim-LongTarget.cpp:123, 800-802); the
-    // directory part of -f1 is dropped (the reference embeds it and then silently fails to open the file, Q14)
-    std::string base = f1;
-    const size_t slash = base.find_last_of('/');
-    if (slash != std::string::npos) base = base.substr(slash + 1);
-    base = base.substr(0, base.size() >= 3 ? base.size() - 3 : 0);
-    const std::string out_path = outdir + "/" + recs[0].species + "-" + lnc_name + "-" + base + "-TFOsorted";
-    rc = ltg_write_tfosorted(all, out_path.c_str());
-    if (rc == LTG_OK) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, (int64_t)recs[0].seq.size(), lnc_name.c_str());
-    if (rc != LTG_OK) fprintf(stderr, "fasim: %s\n", ltg_last_error());
-    lap("write");
     clock_gettime(CLOCK_MONOTONIC, &t1);
     const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     printf("finished normally\nRunning time is %g\n", secs);
-    if (all->scan_cells > 0 && secs > 0)
-        printf("[b200] segments=%ld tasks=%ld peaks=%ld scan_cells=%.3e gpu_scan_ms=%.2f gpu_window_ms=%.2f literal_tasks=%ld literal_windows=%ld\n",
-               (long)all->n_segments, (long)all->n_tasks, (long)all->n_peaks, (double)all->scan_cells, all->gpu_ms_scan, all->gpu_ms_window,
-               (long)all->n_literal_tasks, (long)all->n_literal_windows);
-    ltg_result_free(all);
-    return rc == LTG_OK ? 0 : 3;
+    return 0;
 }
 
 }  // extern "C"

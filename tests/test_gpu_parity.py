@@ -372,6 +372,36 @@ def test_cli_multi_device_work_queue(tmp_path):
     assert len([v for k, v in outs[0].items() if k.endswith("TFOsorted")][0].splitlines()) > 1000
 
 
+def test_cli_multi_query_work_queue(tmp_path):
+    """--queries (the multi-query work-queue path): a multi-record -f2 file; the (lncRNA, chunk) jobs go
+    through the shared queue of two contexts.  Every lncRNA's files must equal those of a single-query run of the plain CLI."""
+    lens = [1000 + 977 * k for k in range(4)] + [312]
+    rnas = [("synRNA%d" % k, splitmix_bases(4001 + k, m)) for k, m in enumerate(lens)]
+    recs = [(11_000_000, 1002), (600_000, 1003), (41, 1004)]
+    planted = list(splitmix_bases(1002, recs[0][0]))
+    for k, (_, r) in enumerate(rnas):                     # one planted target per lncRNA so that every output has rows
+        at = 300_000 + 1_700_000 * k
+        planted[at:at + 80] = r[100:180].translate(str.maketrans("TG", "AT"))
+    seqs = ["".join(planted)] + [splitmix_bases(seed, n) for n, seed in recs[1:]]
+    d = str(tmp_path)
+    open(os.path.join(d, "dna.fa"), "w").write("".join(">syn|chr%d|%d-%d\n%s\n" % (k + 1, 1, len(sq), sq) for k, sq in enumerate(seqs)))
+    open(os.path.join(d, "all.fa"), "w").write("".join(">%s\n%s\n" % (n, "\n".join(r[i:i + 70] for i in range(0, len(r), 70))) for n, r in rnas))
+    os.makedirs(os.path.join(d, "multi"))
+    r = fb.run_cli(["-f1", "dna.fa", "-f2", "all.fa", "-O", "multi/", "-lg", "30", "--queries", "--devices", "0,0"], cwd=d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    multi = {f: open(os.path.join(d, "multi", f)).read() for f in sorted(os.listdir(os.path.join(d, "multi")))}
+    assert len(multi) == 3 * len(rnas)
+    for name, rna in rnas:
+        open(os.path.join(d, name + ".fa"), "w").write(">%s\n%s\n" % (name, rna))
+        os.makedirs(os.path.join(d, name))
+        r = fb.run_cli(["-f1", "dna.fa", "-f2", name + ".fa", "-O", name + "/", "-lg", "30"], cwd=d)
+        assert r.returncode == 0, r.stdout + r.stderr
+        for f in os.listdir(os.path.join(d, name)):
+            assert multi[f] == open(os.path.join(d, name, f)).read(), f
+            if f.endswith("TFOsorted"):
+                assert len(multi[f].splitlines()) > 1, f
+
+
 def test_cli_synthetic_and_planted(tmp_path, golden):
     sdna, srna = splitmix_bases(1001, 30000), splitmix_bases(2001, 1000)
     files = run_cli_files(tmp_path, "syn.fa", ">syn|chr1|1-30000\n%s\n" % sdna, "synRNA.fa", ">synRNA1k\n%s\n" % srna, ["-lg", "20"])
