@@ -149,11 +149,15 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
         }
     }
     // granule bound scan (forward plans only): which granules can hold a cell >= bound inside the window's columns
-    // (span klo..khi, and — for re-planned sweeps over at most 64 granules — the exact set as a bit mask);
-    // `outside` = the largest bound of any granule left out (a result above it is exact)
+    // (first/last klo/khi and the set as a bit mask); `outside` = the largest bound of any granule left out (a result
+    // above it is exact)
     int klo = -1, khi = -1, outside = 0;
     unsigned long long qmask = 0ull;
-    const bool multi = retry && w.n_gran <= 64;         // a re-planned sweep may be split into runs of qualifying granules
+    // Sweeps are split into runs of qualifying granules (far-apart granules are not bridged); gaps of at most `join` mask
+    // bits are swept with their neighbours, so their granules do not count as left out.
+    const int gq = (w.n_gran + 63) >> 6;                // granules per mask bit (1 up to 8192 rows; long lncRNAs share bits)
+    const int bit_rows = gq * w.gran_rows;
+    const int join = (win_margin(len) + bit_rows - 1) / bit_rows;           // a gap this short would be covered by the next margin anyway
     if (round >= 0 && w.gran_colmax != nullptr) {
         const bool scan = active && bound > 0;
         int task = 0, pos = 0;
@@ -173,12 +177,13 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
             b = max(b, __shfl_xor_sync(0xffffffffu, b, 2));
             b = max(b, __shfl_xor_sync(0xffffffffu, b, 4));
             if (scan && b >= bound) {
-                if (klo < 0) { klo = k; outside = pending; }      // everything before the first qualifying granule is left out
+                // the granules since the previous qualifying one are left out unless the gap is short enough to be joined
+                if (klo < 0) { klo = k; outside = pending; }
+                else if (k / gq - khi / gq - 1 > join) outside = max(outside, pending);
+                pending = 0;
                 khi = k;
-                if (multi) qmask |= 1ull << k; else pending = 0;   // single span: the granules in between are swept too
+                qmask |= 1ull << (k / gq);
             } else pending = max(pending, b);
-            // (multi: `pending` keeps every non-qualifying granule — those inside a joined gap are swept although counted as
-            //  left out, which only makes `outside` conservative; it still stays below `bound`, so the sweep is conclusive)
         }
         outside = max(outside, pending);
     }
@@ -188,17 +193,17 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
     int floor_v = max(proven - 1, 0);
     // only cells above `outside` matter (a result r > outside is exact), and their alignments span at most `margin` rows
     const int margin = win_margin_for(len, outside + 1);
-    const int join = (win_margin(len) + w.gran_rows - 1) / w.gran_rows;     // a gap this short would be covered by the next margin
     // walks the runs of qualifying granules (gaps <= join joined, at most 4 runs); f(lo, rows) per run; returns their number
     auto for_runs = [&](auto&& f) -> int {
-        int nr = 0, cur_lo = klo, cur_hi = multi ? klo : khi;
-        unsigned long long rest = multi ? (qmask & ~(1ull << klo)) : 0ull;
+        const int first = klo / gq;
+        int nr = 0, cur_lo = first, cur_hi = first;
+        unsigned long long rest = qmask & ~(1ull << first);
         for (;;) {
             int nxt = -1;
             if (rest) { nxt = __ffsll((long long)rest) - 1; rest &= rest - 1; }
             if (nxt >= 0 && (nxt - cur_hi - 1 <= join || nr == 3)) { cur_hi = nxt; continue; }
-            const int lo = max(0, cur_lo * w.gran_rows - margin);
-            f(lo, min(w.m - 1, (cur_hi + 1) * w.gran_rows - 1) - lo + 1);
+            const int lo = max(0, cur_lo * bit_rows - margin);
+            f(lo, min(w.m - 1, (cur_hi + 1) * bit_rows - 1) - lo + 1);
             ++nr;
             if (nxt < 0) break;
             cur_lo = cur_hi = nxt;
