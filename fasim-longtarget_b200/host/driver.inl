@@ -6,45 +6,12 @@
 #include <getopt.h>
 #include <time.h>
 
+#include "dna_input.hpp"
+
 namespace {
 
-struct FastaRecord { std::string species, chr; long start = 0; std::string header, seq; };
-
-// readDna — Fasim-LongTarget.cpp:202-267.  Header ">species|chr|start-end".  Unlike the canonical variant
-// (which never resets its accumulator) every record is parsed on its own, like
-// fasim-LongTarget.cpp:215-263 does.
-bool read_dna_fasta(const std::string& path, std::vector<FastaRecord>& out)
-{
-    std::ifstream in(path.c_str());
-    if (!in) return false;
-    std::string line;
-    FastaRecord cur;
-    bool have = false;
-    auto flush = [&]() { if (have) out.push_back(cur); };
-    while (std::getline(in, line)) {
-        while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
-        if (!line.empty() && line[0] == '>') {
-            flush();
-            cur = FastaRecord();
-            have = true;
-            cur.header = line.substr(1);
-            std::string field, startstr;
-            int bars = 0;
-            for (size_t i = 1; i < line.size(); ++i) {
-                const char ch = line[i];
-                if (ch == '|' && bars == 0) { cur.species = field; field.clear(); ++bars; continue; }
-                if (ch == '|' && bars == 1) { cur.chr = field; field.clear(); ++bars; continue; }
-                if (ch == '-' && bars == 2) { startstr = field; field.clear(); continue; }
-                field += ch;
-            }
-            cur.start = atoi(startstr.c_str());
-        } else if (have) {
-            cur.seq += line;
-        }
-    }
-    flush();
-    return true;
-}
+using ltg_host::FastaRecord;
+using ltg_host::read_dna_fasta;
 
 // readRna — Fasim-LongTarget.cpp:174-200: first line is the name (every '>' removed), all other lines are
 // concatenated.
@@ -95,6 +62,10 @@ void usage()
            "  --device N  CUDA device (default 0)\n"
            "  --devices a,b,..|all   several GPUs in one process: one context and one host thread per GPU pull chunks of the\n"
            "                         file from a shared queue (results are identical to a single-GPU run)\n"
+           "  -f1 also takes a gzip/bgzip-compressed FASTA and a UCSC .2bit file; for .2bit:\n"
+           "  --seq name[:start-end][,...]   sequences / 1-based inclusive regions to scan (default: every sequence, whole)\n"
+           "  --species S                    species field of the output file name (default: the .2bit file's base name)\n"
+           "  --list-records   print the DNA records -f1 yields (species, chr, start, length, CRC-32) and exit (no GPU needed)\n"
            "  --queries   -f2 holds several lncRNAs (one per '>' record): every lncRNA is scanned against -f1 and gets its own\n"
            "              output files; the (lncRNA, chunk) pairs go through the same queue\n");
 }
@@ -195,11 +166,13 @@ int ltg_main(int argc, char* const* argv)
         {"na", required_argument, nullptr, 'z'}, {"pc", required_argument, nullptr, 'Y'}, {"pt", required_argument, nullptr, 'Z'},
         {"cn", required_argument, nullptr, 'C'}, {"ds", required_argument, nullptr, 'D'}, {"lg", required_argument, nullptr, 'E'},
         {"device", required_argument, nullptr, 1000}, {"devices", required_argument, nullptr, 1001}, {"queries", no_argument, nullptr, 1002},
+        {"seq", required_argument, nullptr, 1003}, {"species", required_argument, nullptr, 1004}, {"list-records", no_argument, nullptr, 1005},
         {nullptr, 0, nullptr, 0}};
     if (argc <= 1) { usage(); return 1; }
     optind = 1;
     int opt;
-    bool want_sim = false, multi_query = false;
+    bool want_sim = false, multi_query = false, list_records = false;
+    std::string seq_arg, species_arg;
     while ((opt = getopt_long_only(argc, argv, optstring, long_options, nullptr)) != -1) {
         switch (opt) {
         case 'f': f1 = optarg; break;
@@ -222,6 +195,9 @@ int ltg_main(int argc, char* const* argv)
         case 1000: device = atoi(optarg); break;
         case 1001: devices_arg = optarg; break;
         case 1002: multi_query = true; break;
+        case 1003: seq_arg = seq_arg.empty() ? std::string(optarg) : seq_arg + "," + optarg; break;
+        case 1004: species_arg = optarg; break;
+        case 1005: list_records = true; break;
         default: break;
         }
     }
@@ -235,8 +211,33 @@ int ltg_main(int argc, char* const* argv)
         fprintf(stderr, "[fasim timing] %-10s at %.3f s\n", what, (t.tv_sec - t0.tv_sec) + 1e-9 * (t.tv_nsec - t0.tv_nsec));
     };
     printf("Searching triplexes using Fasim\n");
+    // base name of -f1: the reference drops the last 3 characters (".fa", Fasim-LongTarget.cpp:800); the new input kinds
+    // drop their own extension (".2bit"; ".gz" and then 3 more)
+    std::string base = f1;
+    {
+        const size_t slash = base.find_last_of('/');
+        if (slash != std::string::npos) base = base.substr(slash + 1);
+    }
+    auto ends_with = [](const std::string& s, const char* suf) { const size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; };
     std::vector<FastaRecord> recs;
-    if (!read_dna_fasta(f1, recs) || recs.empty()) { fprintf(stderr, "fasim: cannot read DNA file %s\n", f1.c_str()); return 2; }
+    if (ltg_host::TwoBitFile::is_twobit(f1)) {
+        if (ends_with(base, ".2bit")) base = base.substr(0, base.size() - 5);
+        std::string err;
+        if (!ltg_host::read_dna_twobit(f1, seq_arg, species_arg.empty() ? base : species_arg, recs, err)) { fprintf(stderr, "fasim: %s\n", err.c_str()); return 2; }
+    } else {
+        if (!seq_arg.empty()) { fprintf(stderr, "fasim: --seq needs a .2bit file as -f1\n"); return 2; }
+        if (!read_dna_fasta(f1, recs)) recs.clear();
+        if (ends_with(base, ".gz")) base = base.substr(0, base.size() - 3);
+        base = base.substr(0, base.size() >= 3 ? base.size() - 3 : 0);
+        if (!species_arg.empty()) for (FastaRecord& r : recs) r.species = species_arg;
+    }
+    if (recs.empty()) { fprintf(stderr, "fasim: cannot read DNA file %s\n", f1.c_str()); return 2; }
+    if (list_records) {
+        for (const FastaRecord& r : recs)
+            printf("record\t%s\t%s\t%ld\t%zu\t%08lx\n", r.species.c_str(), r.chr.c_str(), r.start, r.seq.size(),
+                   (unsigned long)crc32(0L, (const Bytef*)r.seq.data(), (uInt)r.seq.size()));
+        return 0;
+    }
     std::vector<std::pair<std::string, std::string> > queries;            // (name, sequence); one entry unless --queries
     if (multi_query) {
         if (!read_rna_fasta_multi(f2, queries)) queries.clear();
@@ -303,12 +304,6 @@ int ltg_main(int argc, char* const* argv)
     std::atomic<size_t> next_job(0);
     std::atomic<int> failed(0);
     std::vector<std::string> errors(devs.size());
-    std::string base = f1;                                      // output name, see finish_query
-    {
-        const size_t slash = base.find_last_of('/');
-        if (slash != std::string::npos) base = base.substr(slash + 1);
-        base = base.substr(0, base.size() >= 3 ? base.size() - 3 : 0);
-    }
     // <O>/<species>-<lncName>-<f1 minus last 3 chars>-TFOsorted (Fasim-LongTarget.cpp:123, 800-802); the directory part of
     // -f1 is dropped (the reference embeds it and then silently fails to open the file, Q14)
     auto finish_query = [&](size_t q) -> int {

@@ -402,6 +402,37 @@ def test_cli_multi_query_work_queue(tmp_path):
                 assert len(multi[f].splitlines()) > 1, f
 
 
+def test_cli_gzip_and_twobit_inputs(tmp_path):
+    """-f1 as gzip FASTA and as UCSC .2bit (+ --seq regions): the output files equal those of the plain FASTA of the same bases."""
+    import gzip
+    from test_inputs_cpu import write_twobit
+    rna = splitmix_bases(2001, 900)
+    chrom = list(splitmix_bases(1001, 30000))
+    for at in (4000, 12000, 21000):
+        chrom[at:at + 70] = rna[100:170].translate(str.maketrans("TG", "AT"))
+    chrom[15000:15040] = "N" * 40
+    chrom = "".join(chrom)
+    d = str(tmp_path)
+    open(os.path.join(d, "rna.fa"), "w").write(">q\n%s\n" % rna)
+    lo, hi = 2001, 26000                                        # 1-based inclusive region
+    fasta = ">sp|chrT|%d-%d\n%s\n" % (lo, hi, chrom[lo - 1:hi])
+    open(os.path.join(d, "reg.fa"), "w").write(fasta)
+    with gzip.open(os.path.join(d, "reg.fa.gz"), "wt") as f:
+        f.write(fasta)
+    write_twobit(os.path.join(d, "reg.2bit"), [("chrOther", "ACGT" * 10), ("chrT", chrom)])
+    outs = {}
+    for tag, args in (("plain", ["-f1", "reg.fa"]), ("gz", ["-f1", "reg.fa.gz"]),
+                      ("twobit", ["-f1", "reg.2bit", "--seq", "chrT:%d-%d" % (lo, hi), "--species", "sp"])):
+        os.makedirs(os.path.join(d, tag))
+        r = fb.run_cli(args + ["-f2", "rna.fa", "-O", tag + "/", "-lg", "30"], cwd=d)
+        assert r.returncode == 0, r.stdout + r.stderr
+        names = sorted(os.listdir(os.path.join(d, tag)))
+        assert names == ["sp-q-reg-TFOclass1-15-30", "sp-q-reg-TFOclass2-15-30", "sp-q-reg-TFOsorted"], names
+        outs[tag] = [open(os.path.join(d, tag, f)).read() for f in names]
+    assert outs["gz"] == outs["plain"] and outs["twobit"] == outs["plain"]
+    assert len(outs["plain"][2].splitlines()) > 3
+
+
 def test_cli_synthetic_and_planted(tmp_path, golden):
     sdna, srna = splitmix_bases(1001, 30000), splitmix_bases(2001, 1000)
     files = run_cli_files(tmp_path, "syn.fa", ">syn|chr1|1-30000\n%s\n" % sdna, "synRNA.fa", ">synRNA1k\n%s\n" % srna, ["-lg", "20"])

@@ -1,0 +1,98 @@
+"""CPU: the DNA input kinds of the `fasim` command line (plain FASTA as the reference's readDna parses it, gzip FASTA, UCSC
+.2bit with regions) through `fasim --list-records`, which needs no GPU."""
+import gzip
+import os
+import struct
+import zlib
+
+import pytest
+
+import fasim_b200 as fb
+from _harness import splitmix_bases
+
+
+def write_twobit(path, seqs, byteswap=False):
+    """seqs: list of (name, sequence with ACGTN, upper or lower case).  UCSC .2bit version 0."""
+    e = ">" if byteswap else "<"
+    code = {"T": 0, "C": 1, "A": 2, "G": 3, "N": 0}
+    recs = []
+    for name, s in seqs:
+        up = s.upper()
+        nblocks, mblocks = [], []
+        for blocks, pred in ((nblocks, lambda c: c in "Nn"), (mblocks, lambda c: c.islower())):
+            i = 0
+            while i < len(s):
+                if pred(s[i]):
+                    j = i
+                    while j < len(s) and pred(s[j]):
+                        j += 1
+                    blocks.append((i, j - i))
+                    i = j
+                else:
+                    i += 1
+        packed = bytearray((len(up) + 3) // 4)
+        for i, c in enumerate(up):
+            packed[i // 4] |= code[c] << (6 - 2 * (i % 4))
+        body = struct.pack(e + "II", len(up), len(nblocks))
+        body += b"".join(struct.pack(e + "I", a) for a, _ in nblocks) + b"".join(struct.pack(e + "I", n) for _, n in nblocks)
+        body += struct.pack(e + "I", len(mblocks))
+        body += b"".join(struct.pack(e + "I", a) for a, _ in mblocks) + b"".join(struct.pack(e + "I", n) for _, n in mblocks)
+        body += struct.pack(e + "I", 0) + bytes(packed)
+        recs.append(body)
+    header = struct.pack(e + "IIII", 0x1A412743, 0, len(seqs), 0)
+    index_size = sum(1 + len(n) + 4 for n, _ in seqs)
+    off = len(header) + index_size
+    index = b""
+    for (name, _), body in zip(seqs, recs):
+        index += struct.pack("B", len(name)) + name.encode() + struct.pack(e + "I", off)
+        off += len(body)
+    open(path, "wb").write(header + index + b"".join(recs))
+
+
+def list_records(args, cwd):
+    r = fb.run_cli(list(args) + ["--list-records"], cwd=cwd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [l.split("\t")[1:] for l in r.stdout.splitlines() if l.startswith("record\t")]
+    return [(sp, ch, int(st), int(n), crc) for sp, ch, st, n, crc in rows]
+
+
+def crc(s):
+    return "%08x" % (zlib.crc32(s.encode()) & 0xFFFFFFFF)
+
+
+@pytest.fixture(scope="module")
+def seqs():
+    a = list(splitmix_bases(7001, 10007))
+    for lo, hi in ((0, 13), (4999, 5003), (9000, 9400)):
+        a[lo:hi] = "N" * (hi - lo)
+    a = "".join(a)
+    a = a[:2000] + a[2000:2600].lower() + a[2600:]            # a soft-masked stretch (lower case in the .2bit's FASTA view)
+    return [("chr1", a), ("chrUn_x", splitmix_bases(7002, 37)), ("chr2", splitmix_bases(7003, 6001))]
+
+
+def test_fasta_plain_and_gzip_give_the_same_records(tmp_path, seqs):
+    fb.build()
+    d = str(tmp_path)
+    text = "".join(">hg|%s|%d-%d\n%s\n" % (n, 101 + k, 100 + k + len(s), "\n".join(s.upper()[i:i + 60] for i in range(0, len(s), 60)))
+                   for k, (n, s) in enumerate(seqs))
+    open(os.path.join(d, "x.fa"), "w").write(text)
+    with gzip.open(os.path.join(d, "x.fa.gz"), "wt") as f:
+        f.write(text.replace("\n", "\r\n"))                     # CR/LF line ends are stripped like the reference does
+    expect = [("hg", n, 101 + k, len(s), crc(s.upper())) for k, (n, s) in enumerate(seqs)]
+    assert list_records(["-f1", "x.fa"], d) == expect
+    assert list_records(["-f1", "x.fa.gz"], d) == expect
+
+
+@pytest.mark.parametrize("byteswap", [False, True])
+def test_twobit_whole_sequences_and_regions(tmp_path, seqs, byteswap):
+    fb.build()
+    d = str(tmp_path)
+    write_twobit(os.path.join(d, "mini.2bit"), seqs, byteswap)
+    whole = list_records(["-f1", "mini.2bit"], d)
+    assert whole == [("mini", n, 1, len(s), crc(s.upper())) for n, s in seqs]
+    a = seqs[0][1].upper()
+    got = list_records(["-f1", "mini.2bit", "--seq", "chr1:5-5010,chr2", "--seq", "chr1:9399-20000", "--species", "hg38"], d)
+    assert got == [("hg38", "chr1", 5, 5006, crc(a[4:5010])), ("hg38", "chr2", 1, 6001, crc(seqs[2][1])),
+                   ("hg38", "chr1", 9399, len(a) - 9398, crc(a[9398:]))]
+    r = fb.run_cli(["-f1", "mini.2bit", "--seq", "chrZ", "--list-records"], cwd=d)
+    assert r.returncode != 0 and "chrZ" in r.stderr
