@@ -442,6 +442,61 @@ def test_cli_synthetic_and_planted(tmp_path, golden):
     assert files["syn-plRNA-pl-TFOsorted"] == open(os.path.join(GOLDEN, "planted20k_lg30__TFOsorted")).read()
 
 
+def test_reference_binary_repeat_rich_chunks(tmp_path):
+    """At-scale file parity against the UNMODIFIED reference binary run on the box's host cores (oracle/_ref travels with the
+    repo): 16 chunks of 60 kb of repeat-rich DNA - microsatellites with substitutions, purine tracts, one Alu-like element
+    copied with mutations into every chunk, N runs - against an lncRNA with (CT)/(GA)/(GT)-rich tracts (overflows >= 251,
+    long hit runs, top-50 truncation, literal-emulated tasks).  All three output files of every chunk must be byte-equal."""
+    import random
+    import subprocess
+    from _harness import ref_binary
+    if not os.path.exists(ref_binary()):
+        pytest.skip("oracle/_ref/fasim not built")
+    rng = random.Random(20240607)
+    def mutate(s, rate):
+        return "".join(rng.choice("ACGT") if rng.random() < rate else c for c in s)
+    rna = list(splitmix_bases(2001, 1500))
+    for at, unit in ((200, "CT"), (700, "GA"), (1200, "GT")):
+        rna[at:at + 160] = mutate(unit * 80, 0.08)
+    rna = "".join(rna)
+    alu = splitmix_bases(555, 150) + mutate("GA" * 40, 0.05) + splitmix_bases(556, 70)
+    d = str(tmp_path)
+    open(os.path.join(d, "rna.fa"), "w").write(">lnc\n%s\n" % rna)
+    n_chunks, n = 16, 60000
+    for k in range(n_chunks):
+        dna = list(splitmix_bases(9000 + k, n))
+        for _ in range(15):
+            at = rng.randrange(0, n - 400)
+            unit = rng.choice(["GA", "CT", "GAA", "CCT", "A", "GGA", "TC", "AG"])
+            L = rng.randrange(30, 260)
+            dna[at:at + L] = mutate((unit * L)[:L], rng.choice([0.0, 0.05, 0.12]))
+        for _ in range(5):
+            at = rng.randrange(0, n - 400)
+            dna[at:at + len(alu)] = mutate(alu, 0.06)
+        at = rng.randrange(0, n - 100)
+        L = rng.randrange(1, 40)
+        dna[at:at + L] = "N" * L
+        dna = "".join(dna)[:n]
+        open(os.path.join(d, "c%02d.fa" % k), "w").write(">syn|chr%d|%d-%d\n%s\n" % (k + 1, 1000 * k + 1, 1000 * k + len(dna), dna))
+    os.makedirs(os.path.join(d, "ref"))
+    os.makedirs(os.path.join(d, "gpu"))
+    procs = [subprocess.Popen([ref_binary(), "-f1", "c%02d.fa" % k, "-f2", "rna.fa", "-O", "ref/", "-lg", "30"], cwd=d,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for k in range(n_chunks)]
+    for k in range(n_chunks):
+        r = fb.run_cli(["-f1", "c%02d.fa" % k, "-f2", "rna.fa", "-O", "gpu/", "-lg", "30"], cwd=d)
+        assert r.returncode == 0, r.stdout + r.stderr
+    for pr in procs:
+        assert pr.wait(timeout=900) == 0
+    names = sorted(os.listdir(os.path.join(d, "ref")))
+    assert len(names) == 3 * n_chunks and names == sorted(os.listdir(os.path.join(d, "gpu")))
+    rows = 0
+    for f in names:
+        want, got = open(os.path.join(d, "ref", f)).read(), open(os.path.join(d, "gpu", f)).read()
+        assert got == want, f
+        rows += len(want.splitlines()) - 1 if f.endswith("TFOsorted") else 0
+    assert rows > 1500
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_1mbp(engine):
     """Size-independent properties at bench scale (1 Mbp x 3 kb): determinism, shard-invariance (scanning the region as
