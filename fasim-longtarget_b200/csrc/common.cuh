@@ -77,6 +77,7 @@ constexpr int kGapExt = 4;       // each further one 4
 constexpr int kMatch = 5, kMismatch = -4;
 constexpr int kGhost = -16384;   // score of rows beyond the padded query (never reaches a column maximum)
 constexpr int kOverflowU8 = 251; // 8-bit scan stops recording once the running maximum reaches 251 (sswNew.cpp:384-396)
+constexpr int kQ4CarryF = 132;   // smallest carried F whose decayed value (>= 128) the reference's signed lazy-F test misreads
 constexpr int kQ4Guard = 148;    // smallest H that can carry F >= 132 across a stripe boundary
 
 #define LTG_CUDA_CHECK(expr)                                                                       \

@@ -139,7 +139,8 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
-    bool prune = true, dead_rule = true, skip_rounds = true;
+    bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true;
+    int64_t n_probe_items = 0;          // pairs swept a second time by the Q4 probe (diagnostics)
     cudaStream_t stream = nullptr, copy_stream = nullptr, lit_stream = nullptr;
     cudaEvent_t lit_event = nullptr;
     ltg_params params;
@@ -156,6 +157,7 @@ struct ltg_context {
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_colmax, d_bnd, d_counters;
+    DevBuf d_probe_items, d_probe_orig, d_probe_out;
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
     DevBuf d_w[20], d_pc[4], d_res64, d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
@@ -263,7 +265,9 @@ struct ProbeOut {
     int max_len = 0;
 };
 
-int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax)
+// probe_out != nullptr: the Q4 probe variant (no column maxima; per item the largest F carried into a stripe start)
+int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax,
+                uint32_t* probe_out = nullptr, const int* task_jstar = nullptr)
 {
     const int R = c->scan_r;
     const int blocks = c->num_sms * scan_ctas_per_sm(R);
@@ -276,7 +280,16 @@ int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_le
     a.codes = c->d_codes.as<uint8_t>(); a.segs = c->d_segs.as<SegDesc>(); a.items = d_items;
     a.n_items = n_items; a.profiles = prof; a.n_strips = c->n_strips; a.max_len = max_len;
     a.colmax = colmax; a.bnd = c->d_bnd.as<uint2>(); a.counter = counters + kCntScan;
-    if (R == 32) {
+    a.probe_out = probe_out; a.task_jstar = task_jstar; a.tasks_per_seg = (int)c->tasks.size(); a.stripe_len = (c->m + 15) / 16;
+    if (probe_out) {
+        if (R == 32) {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_scan<32, kScanWarps, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+        } else {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<16, kScanWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_scan<16, kScanWarps, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+        }
+    } else if (R == 32) {
         LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_scan<32, kScanWarps><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
     } else {
@@ -294,8 +307,30 @@ int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_le
 int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const int* n_jobs_dev, int max_read_len, const WinState* w, int max_len,
                    bool side = false, int row_base = 0)
 {
-    // workspace per half-warp slot: kLitArrays uint16 arrays of 16 lanes x pitch; in shared memory when at least one slot fits
     const int pitch = literal_pitch(max_read_len);
+    // column-parallel kernel (one CTA per job, byte workspace in shared memory) for all but short reads
+    const long long col_smem = (long long)kLitColArrays * 16 * pitch;
+    if (c->lit_col && max_read_len >= 256 && col_smem <= 220 * 1024) {
+        const int L = (max_read_len + 15) / 16;
+        int CH = 8;
+        while (CH < kLitColMaxChunks && L > 24 * CH) CH *= 2;
+        const int threads = 16 * CH;
+        const int per_sm = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, 2048 / threads), (220 * 1024) / col_smem));
+        const int blocks = n_jobs >= 0 ? std::max(1, std::min(n_jobs, c->num_sms * per_sm)) : c->num_sms * per_sm;
+        LiteralArgs la;
+        la.jobs = d_jobs; la.n_jobs = n_jobs; la.n_jobs_dev = n_jobs_dev; la.codes = c->d_codes.as<uint8_t>(); la.segs = c->d_segs.as<SegDesc>();
+        la.rna_ssw = c->d_rna_ssw.as<uint8_t>(); la.use_smem = 1; la.slots_per_block = 1; la.pitch = pitch;
+        la.work = nullptr; la.work_per_slot = 0;
+        la.lit_colmax = c->d_lit_colmax.as<uint16_t>(); la.max_len = max_len; la.task_litrow = c->d_task_litrow.as<int>(); la.row_base = row_base;
+        if (side) { la.segs = nullptr; la.lit_colmax = c->d_side_colmax.as<uint16_t>(); la.task_litrow = nullptr; }
+        if (w) la.w = *w; else memset(&la.w, 0, sizeof la.w);
+        LTG_CUDA_CHECK(cudaFuncSetAttribute(k_literal_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
+        k_literal_col<<<blocks, threads, (size_t)col_smem, side ? c->lit_stream : c->stream>>>(la);
+        c->launches += 1;
+        LTG_CUDA_CHECK(cudaGetLastError());
+        return LTG_OK;
+    }
+    // workspace per half-warp slot: kLitArrays uint16 arrays of 16 lanes x pitch; in shared memory when at least one slot fits
     const long long per_slot = 2LL * 16 * kLitArrays * pitch;
     const long long smem_budget = 200 * 1024;
     int spb = (int)std::min<long long>(8, smem_budget / per_slot);          // slots per block
@@ -563,6 +598,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     EpiArgs ea;
     ea.colmax = c->d_colmax.as<uint32_t>(); ea.n_gran = n_gran; ea.colmax_all = c->d_colmax_all.as<uint32_t>(); ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
     ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
+    ea.item_orig = nullptr; ea.probe = nullptr;
     ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.stats_all = c->rna_plain ? 0 : 1; ea.mode = 0;
     ea.task_max = ti.max; ea.task_thr = ti.thr; ea.task_npeaks = ti.npk; ea.task_flags = ti.flags; ea.task_jstar = ti.jstar;
     ea.task_off = c->d_task_off.as<int>(); ea.pk_task = nullptr; ea.pk_pos = nullptr; ea.pk_score = nullptr;
@@ -576,6 +612,38 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     LTG_CUDA_CHECK(cudaMemcpyAsync(hti.flags, ti.flags, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
     LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
+    // Q4 probe: a second sweep of the pairs that carry a flagged task finds the largest F carried into a stripe start of the
+    // reference's layout; below 132 the signed compare cannot misfire and the task returns to the exact path (mode 3)
+    if (c->q4_probe) {
+        std::vector<ScanItem> pitems;
+        std::vector<int> porig;
+        for (int i = 0; i < n_items; ++i) {
+            const PairDef& pd = c->pairs[items[i].pair];
+            const int base = items[i].seg * T;
+            if ((hti.flags[base + pd.task[0]] | hti.flags[base + pd.task[1]]) & kTaskLiteral) { pitems.push_back(items[i]); porig.push_back(i); }
+        }
+        if (!pitems.empty()) {
+            const int np = (int)pitems.size();
+            if (int e = c->d_probe_items.ensure(sizeof(ScanItem) * (size_t)np)) return e;
+            if (int e = c->d_probe_orig.ensure(sizeof(int) * (size_t)np)) return e;
+            if (int e = c->d_probe_out.ensure(sizeof(uint32_t) * (size_t)np)) return e;
+            LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_probe_items.p, pitems.data(), sizeof(ScanItem) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
+            LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_probe_orig.p, porig.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
+            if (int e = launch_scan(c, c->d_probe_items.as<ScanItem>(), np, max_len, c->d_prof_ssw.as<uint32_t>(), nullptr,
+                                    c->d_probe_out.as<uint32_t>(), ti.jstar)) return e;
+            EpiArgs pa = ea;
+            pa.items = c->d_probe_items.as<ScanItem>(); pa.item_orig = c->d_probe_orig.as<int>(); pa.probe = c->d_probe_out.as<uint32_t>();
+            pa.n_items = np; pa.mode = 3;
+            k_epilogue<<<(np * 32 + 127) / 128, 128, 0, c->stream>>>(pa);
+            c->launches += 1;
+            LTG_CUDA_CHECK(cudaGetLastError());
+            LTG_CUDA_CHECK(cudaMemcpyAsync(hti.flags, ti.flags, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
+            LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // (also: `pitems` / `porig` are host memory of this scope)
+            c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
+            c->h2d_bytes += (int64_t)(sizeof(ScanItem) + sizeof(int)) * np;
+            c->n_probe_items += np;
+        }
+    }
     // kLitOnly: were all requested tasks already swept by the side stream (their literal column maxima wait in d_side_colmax)?
     bool from_side = (lit_mode == kLitOnly && only_rows && !only_rows->empty());
     if (from_side) for (int r : *only_rows) if (r < 0) from_side = false;
@@ -946,7 +1014,7 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
     if (!c || !out || (n_recs > 0 && !recs)) { set_error("null argument"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
     LTG_CUDA_CHECK(cudaStreamSynchronize(c->lit_stream));
-    const int64_t launches0 = c->launches, h2d0 = c->h2d_bytes, d2h0 = c->d2h_bytes;
+    const int64_t launches0 = c->launches, h2d0 = c->h2d_bytes, d2h0 = c->d2h_bytes, probed0 = c->n_probe_items;
     const bool trace_time = getenv("LTG_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
@@ -1079,6 +1147,7 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
     r->gpu_launches = c->launches - launches0;
     r->gpu_ms_scan_kernel = st.ms_scan_kernel; r->n_scan_launches = st.n_scan_launches;
     r->h2d_bytes = c->h2d_bytes - h2d0; r->d2h_bytes = c->d2h_bytes - d2h0;
+    r->n_q4_probed = c->n_probe_items - probed0;
     if (trace_time && len > 0)
         fprintf(stderr, "[ltg timing] prep %.1f ms, batches %.1f, last retire %.1f, record filter %.1f, strings %.1f, result %.1f (total %.1f)\n",
                 t_prep - t_begin, t_loop - t_prep, t_retire - t_loop, t_filter - t_retire, t_strings - t_filter, now() - t_strings, now() - t_begin);
@@ -1142,6 +1211,8 @@ int ltg_create(int device, ltg_context** out)
     if (const char* e = getenv("LTG_NO_DEAD")) c->dead_rule = atoi(e) == 0;
     // LTG_NO_SKIP=1 runs every window round of fastSIM's loop even when it provably repeats the previous result
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
+    if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
+    if (const char* e = getenv("LTG_LIT_OLD")) c->lit_col = atoi(e) == 0;
     *out = c;
     return LTG_OK;
 }
@@ -1297,7 +1368,7 @@ int ltg_result_append(ltg_result* dst, const ltg_result* src)
     dst->n_literal_windows += src->n_literal_windows; dst->gpu_ms_scan += src->gpu_ms_scan; dst->gpu_ms_window += src->gpu_ms_window;
     dst->gpu_launches += src->gpu_launches;
     dst->gpu_ms_scan_kernel += src->gpu_ms_scan_kernel; dst->n_scan_launches += src->n_scan_launches;
-    dst->h2d_bytes += src->h2d_bytes; dst->d2h_bytes += src->d2h_bytes;
+    dst->h2d_bytes += src->h2d_bytes; dst->d2h_bytes += src->d2h_bytes; dst->n_q4_probed += src->n_q4_probed;
     return LTG_OK;
 }
 

@@ -205,6 +205,208 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
     }
 }
 
+// ---- column-parallel variant ---------------------------------------------------------------------------------------
+// Same emulation, one CTA of 16 x CH threads per job: thread (lane, chunk) owns a chunk of the lane's stripe.  What is
+// sequential in the reference's stripe loop is only the F chain  F' = max(subs(F,4), subs(H,16)), and that is max-plus
+// linear: each chunk runs it from F = 0, the chunk ends are folded along the stripe, and a carried-in F that is still
+// positive is applied to the first offsets of a chunk afterwards (H = max(H, F_in - 4k), E' = max(E', subs(H,16)): the
+// values the sequential loop produces).  The lazy-F loop with the signed compare, the maximum bookkeeping, the overflow
+// break and the terminate test are run literally by the 16 threads of chunk 0.  Workspace: BYTE arrays [lane][offset] in
+// shared memory (H stored, H previous column, E, H at the best column, one-hot read codes); the profile value of a row is
+// derived from its one-hot code (match 9, mismatch 0, pad row 4 = the reference's score + bias).
+constexpr int kLitColMaxChunks = 32;
+constexpr int kLitColArrays = 5;
+
+__global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
+{
+    extern __shared__ uint32_t lit_smem[];
+    __shared__ int s_agg[16 * kLitColMaxChunks];     // [lane][chunk] F at the end of the chunk when it starts from 0
+    __shared__ int s_cmx[16 * kLitColMaxChunks];     // [lane][chunk] maximum of the chunk's H values in this column
+    __shared__ int s_ctl[4];                          // 0 copy H to the best-column array, 1 leave the column loop, 2 end_read, 3 max
+    const int tid = threadIdx.x, lam = tid & 15, ch = tid >> 4, CH = blockDim.x >> 4;
+    const unsigned hmask = 0x0000ffffu;
+    const int bias = 4;
+    const uint32_t kFF = 0x00FF00FFu, kM4 = 0xFFFCFFFCu, kM16 = 0xFFF0FFF0u;
+    const int n_jobs = a.n_jobs >= 0 ? a.n_jobs : *a.n_jobs_dev;
+    for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
+        __syncthreads();                                         // the previous job's readers are done with the workspace
+        const LiteralJob J = a.jobs[jb];
+        SegDesc sd;
+        if (a.segs) sd = a.segs[J.seg]; else { sd.start = J.seg_start; sd.len = J.seg_len; sd.flags = 0; }
+        const TaskDef td = c_tasks[J.tdef];
+        const int L = (J.read_len + 15) / 16;
+        const int P = a.pitch;                                   // bytes per (array, lane), 4 * odd
+        uint8_t* hs = reinterpret_cast<uint8_t*>(lit_smem) + (size_t)lam * P;
+        uint8_t* hl = hs + 16 * (size_t)P;
+        uint8_t* ev = hl + 16 * (size_t)P;
+        uint8_t* hm = ev + 16 * (size_t)P;
+        uint8_t* oh = hm + 16 * (size_t)P;
+        const int Lc = 4 * ((L + 4 * CH - 1) / (4 * CH));        // chunk length, a multiple of 4
+        const int tb = min(L, ch * Lc), te = min(L, tb + Lc);
+        const int tv = tb + ((te - tb) & ~3);                    // end of the part done four offsets at a time
+        for (int t = tb; t < te; ++t) {
+            hs[t] = 0; hl[t] = 0; ev[t] = 0; hm[t] = 0;
+            const int row = lam * L + t;
+            const bool real = row < J.read_len;
+            const int r = real ? a.rna_ssw[J.read_start + J.read_dir * row] : 5;
+            oh[t] = (uint8_t)(r < 4 ? (1 << r) : (r == 5 ? 0x10 : 0));
+        }
+        uint16_t* cmrow = nullptr;
+        if (J.kind == 0) {
+            cmrow = a.lit_colmax + (size_t)(a.row_base + jb) * a.max_len;
+            for (int j = tid; j < J.ref_len; j += blockDim.x) cmrow[j] = 0;
+            if (tid == 0 && a.task_litrow) a.task_litrow[J.task] = a.row_base + jb;
+        }
+        if (tid == 0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[2] = J.read_len - 1; s_ctl[3] = 0; }
+        __syncthreads();
+        int vMaxScore = 0, vMaxMark = 0, maxv = 0, end_ref = -1;          // live in the threads of chunk 0
+        bool overflow = false;
+        const int begin = J.ref_dir ? J.ref_len - 1 : 0, end = J.ref_dir ? -1 : J.ref_len, step = J.ref_dir ? -1 : 1;
+        for (int i = begin; i != end; i += step) {
+            const int q = J.ref_start + i;
+            const int c = td.img[a.codes[sd.start + (td.reversed ? (sd.len - 1 - q) : q)]];
+            const int csh = c < 4 ? c : 7;                       // bit 7 of a one-hot code is never set: no match
+            { uint8_t* tmp = hl; hl = hs; hs = tmp; }
+            // ---- sweep 1: the chunk from F = 0
+            uint32_t vH = 0;
+            if (tb > 0) vH = hl[tb - 1];
+            else if (lam > 0) vH = (hl - P)[L - 1];              // stripe start: last offset of the previous lane (the byte shift)
+            int vF = 0;
+            uint32_t vmax2 = 0;
+            for (int t0 = tb; t0 < tv; t0 += 4) {
+                const uint32_t h4 = *reinterpret_cast<const uint32_t*>(hl + t0);
+                const uint32_t e4 = *reinterpret_cast<const uint32_t*>(ev + t0);
+                const uint32_t o4 = *reinterpret_cast<const uint32_t*>(oh + t0);
+                const uint32_t p4 = ((o4 >> csh) & 0x01010101u) * 9u + ((o4 >> 4) & 0x01010101u) * 4u;
+                // H diagonal of offsets t0..t0+3 = H of the previous column at offsets t0-1..t0+2
+                const uint32_t dlo = __byte_perm(vH, h4, 0x1410), dhi = __byte_perm(vH, h4, 0x1615);
+                vH = h4 >> 24;
+                const uint32_t elo = __byte_perm(e4, 0u, 0x4140), ehi = __byte_perm(e4, 0u, 0x4342);
+                const uint32_t plo = __byte_perm(p4, 0u, 0x4140), phi = __byte_perm(p4, 0u, 0x4342);
+                const uint32_t hba = __vmaxs2(__viaddmax_s16x2(__vmins2(__vadd2(dlo, plo), kFF), kM4, 0u), elo);
+                const uint32_t hbb = __vmaxs2(__viaddmax_s16x2(__vmins2(__vadd2(dhi, phi), kFF), kM4, 0u), ehi);
+                const uint32_t ga = __viaddmax_s16x2(hba, kM16, 0u), gb = __viaddmax_s16x2(hbb, kM16, 0u);
+                const int f0 = vF;
+                const int f1 = __viaddmax_s32(f0, -kGapExt, (int)(ga & 0xffffu));
+                const int f2 = __viaddmax_s32(f1, -kGapExt, (int)(ga >> 16));
+                const int f3 = __viaddmax_s32(f2, -kGapExt, (int)(gb & 0xffffu));
+                vF = __viaddmax_s32(f3, -kGapExt, (int)(gb >> 16));
+                const uint32_t ha = __vmaxs2(hba, __byte_perm((uint32_t)f0, (uint32_t)f1, 0x5410));
+                const uint32_t hb = __vmaxs2(hbb, __byte_perm((uint32_t)f2, (uint32_t)f3, 0x5410));
+                vmax2 = __vimax3_s16x2(vmax2, ha, hb);
+                *reinterpret_cast<uint32_t*>(hs + t0) = __byte_perm(ha, hb, 0x6420);
+                const uint32_t ea = __viaddmax_s16x2(elo, kM4, __viaddmax_s16x2(ha, kM16, 0u));
+                const uint32_t eb = __viaddmax_s16x2(ehi, kM4, __viaddmax_s16x2(hb, kM16, 0u));
+                *reinterpret_cast<uint32_t*>(ev + t0) = __byte_perm(ea, eb, 0x6420);
+            }
+            int lmax = max((int)(vmax2 & 0xffffu), (int)(vmax2 >> 16));
+            for (int t = tv; t < te; ++t) {                      // the last (length mod 4) offsets of the stripe
+                const int o = oh[t];
+                const int pv = ((o >> csh) & 1) * 9 + ((o >> 4) & 1) * 4;
+                int h = sat8(sat8((int)vH + pv) - bias);
+                const int e = ev[t];
+                h = max(h, e); h = max(h, vF);
+                lmax = max(lmax, h);
+                hs[t] = (uint8_t)h;
+                const int open = sat8(h - kGapOpen);
+                ev[t] = (uint8_t)max(sat8(e - kGapExt), open);
+                vF = max(sat8(vF - kGapExt), open);
+                vH = hl[t];
+            }
+            s_agg[lam * kLitColMaxChunks + ch] = vF;
+            __syncthreads();
+            // ---- F carried into this chunk from the chunks before it, applied to the chunk's first offsets
+            int fin = 0;
+            for (int k = 0; k < ch; ++k) {
+                const int len = max(0, min(L, (k + 1) * Lc) - min(L, k * Lc));
+                fin = max(s_agg[lam * kLitColMaxChunks + k], max(fin - kGapExt * len, 0));
+            }
+            for (int t = tb, fv = fin; t < te && fv > 0; ++t, fv -= kGapExt) {
+                if (fv > (int)hs[t]) {
+                    hs[t] = (uint8_t)fv;
+                    ev[t] = (uint8_t)max((int)ev[t], sat8(fv - kGapOpen));
+                    lmax = max(lmax, fv);
+                }
+            }
+            s_cmx[lam * kLitColMaxChunks + ch] = lmax;
+            __syncthreads();
+            // ---- lazy-F loop and the per-column bookkeeping: the 16 threads of chunk 0, literally
+            if (ch == 0) {
+                int vMaxCol = 0;
+                vF = 0;
+                for (int k = 0; k < CH; ++k) {
+                    const int len = max(0, min(L, (k + 1) * Lc) - min(L, k * Lc));
+                    vF = max(s_agg[lam * kLitColMaxChunks + k], max(vF - kGapExt * len, 0));
+                    vMaxCol = max(vMaxCol, s_cmx[lam * kLitColMaxChunks + k]);
+                }
+                bool done = false;
+                for (int k = 0; k < 16 && !done; ++k) {
+                    vF = __shfl_up_sync(hmask, vF, 1, 16);
+                    if (lam == 0) vF = 0;
+                    for (int t = 0; t < L; ++t) {
+                        int h = hs[t];
+                        h = max(h, vF);
+                        vMaxCol = max(vMaxCol, h);
+                        hs[t] = (uint8_t)h;
+                        const int open = sat8(h - kGapOpen);
+                        vF = sat8(vF - kGapExt);
+                        const bool gt = (int)(int8_t)vF > (int)(int8_t)open;        // signed byte compare (Q4)
+                        if (!__any_sync(hmask, gt)) { done = true; break; }
+                    }
+                }
+                bool copy = false, leave = false;
+                vMaxScore = max(vMaxScore, vMaxCol);
+                const bool changed = __any_sync(hmask, vMaxScore != vMaxMark);
+                if (changed) {
+                    vMaxMark = vMaxScore;
+                    int temp = vMaxScore;
+#pragma unroll
+                    for (int o = 8; o; o >>= 1) temp = max(temp, __shfl_xor_sync(hmask, temp, o, 16));
+                    if (temp > maxv) {
+                        maxv = temp;
+                        if (maxv + bias >= 255) { overflow = true; leave = true; }
+                        else { end_ref = i; copy = true; }
+                    }
+                }
+                if (!leave) {
+                    int cm = vMaxCol;
+#pragma unroll
+                    for (int o = 8; o; o >>= 1) cm = max(cm, __shfl_xor_sync(hmask, cm, o, 16));
+                    if (cmrow && lam == 0) cmrow[i] = (uint16_t)cm;
+                    if (cm == J.terminate) leave = true;
+                }
+                if (lam == 0) { s_ctl[0] = copy ? 1 : 0; s_ctl[1] = leave ? 1 : 0; }
+            }
+            __syncthreads();
+            if (s_ctl[0]) for (int t = tb; t < te; ++t) hm[t] = hs[t];
+            if (s_ctl[1]) break;
+        }
+        if (J.kind == 0) continue;
+        if (tid == 0) s_ctl[3] = maxv;
+        __syncthreads();
+        {
+            const int mv = s_ctl[3];
+            int er = J.read_len;
+            for (int t = tb; t < te; ++t) if ((int)hm[t] == mv) er = min(er, t + lam * L);
+            if (er < J.read_len) atomicMin(&s_ctl[2], er);
+        }
+        __syncthreads();
+        if (tid != 0) continue;
+        // overflow (score marker 255) sends the reference to its exact 16-bit kernel: keep the exact fast-path result
+        if (overflow) continue;
+        const int end_read = s_ctl[2];
+        const int pk = J.peak;
+        if (J.kind == 1) {
+            a.w.res[pk] = make_int4(maxv, end_ref, end_read, 1);
+        } else {
+            const int fwd = a.w.fin_sw[pk];
+            a.w.fin_sw[pk] = end_ref < 0 ? 0 : min(maxv, fwd);
+            a.w.fin_rb[pk] = end_ref;
+            a.w.fin_qb[pk] = a.w.fin_qe[pk] - end_read;
+        }
+    }
+}
+
 // collect the windows whose exact score reaches the Q4 guard
 __global__ void k_lit_collect(const WinState w, int reverse, int round, LiteralJob* jobs, int* count, int* count_total)
 {

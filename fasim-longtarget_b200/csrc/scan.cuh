@@ -131,6 +131,12 @@ struct ScanArgs {
                                 // kGranRows RNA rows (n_strips * 32 * R / kGranRows granules per item)
     uint2* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F)
     int* counter;               // work queue head
+    // Q4 probe variant (k_scan<R, W, true>): no column maxima are written; per item the largest F value carried into a
+    // row that starts a stripe of the reference's 16-lane layout (rows k * stripe_len) within the recorded columns
+    uint32_t* probe_out;        // [item] packed (task 0 | task 1 << 16)
+    const int* task_jstar;      // [seg * T + task] first column the reference does not record any more (or n)
+    int tasks_per_seg;
+    int stripe_len;             // ceil(m / 16)
 };
 
 template <int R>
@@ -149,6 +155,7 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
 
 #define LTG_CELL(SV, RR)                                          \
     {                                                             \
+        if (PROBE && (bmask & (1u << (RR)))) fb = __vmaxs2(fb, f & vmask); \
         const uint32_t t_ = __viaddmax_s16x2_relu(d, (SV), E[RR]); \
         const uint32_t u_ = __vadd2(t_, kNegOpen);                \
         LTG_E_UPDATE(E[RR], u_);                                  \
@@ -157,7 +164,7 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
         d = Hd[RR];                                               \
         Hd[RR] = h_;                                              \
         tv[(RR) & 1] = t_;                                        \
-        if ((RR) & 1) cm = __vimax3_s16x2(cm, tv[0], tv[1]);      \
+        if (!PROBE && ((RR) & 1)) cm = __vimax3_s16x2(cm, tv[0], tv[1]); \
         hlast = h_;                                               \
     }
 
@@ -167,7 +174,7 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
 // skip RNA rows that cannot hold a window's best cell (window.cuh, "row pruning").
 constexpr int kGranRows = 128;                   // RNA rows per granule (kGranRows / R lanes; 32 * R / kGranRows granules per strip)
 
-template <int R, int WARPS>
+template <int R, int WARPS, bool PROBE = false>
 __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 {
     static_assert(R % 4 == 0, "R must be a multiple of 4");
@@ -202,7 +209,26 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
         uint32_t* cm_item = a.colmax + (size_t)item * a.n_strips * kGranPerStrip * a.max_len;
         const bool gran_head = (lane & (kGranLanes - 1)) == 0, gran_tail = (lane & (kGranLanes - 1)) == kGranLanes - 1;
 
+        uint32_t fb = 0;                                           // PROBE: running maximum of the carried F values
+        int jst0 = 0, jst1 = 0;
+        if (PROBE) {
+            const PairDef pd = c_pairs[it.pair];
+            // columns the reference processes: up to and including the one where it stops recording (Q2)
+            jst0 = min(a.task_jstar[it.seg * a.tasks_per_seg + pd.task[0]] + 1, n);
+            jst1 = min(a.task_jstar[it.seg * a.tasks_per_seg + pd.task[1]] + 1, n);
+        }
+
         for (int strip = 0; strip < a.n_strips; ++strip) {
+            // PROBE: which of this lane's rows start a stripe of the reference's layout (row = k * stripe_len, k = 1..15)
+            uint32_t bmask = 0, vmask = 0;
+            if (PROBE) {
+                const int row0 = (strip * 32 + lane) * R;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = row0 + r;
+                    if (row > 0 && row < 16 * a.stripe_len && row % a.stripe_len == 0) bmask |= 1u << r;
+                }
+            }
             const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
             __syncwarp();
             for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
@@ -257,6 +283,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                     if (first) { hin = 0; fin = 0; }                                                            \
                     else asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hin), "=r"(fin) : "r"(sa_ring + (K) * 8)); \
                 }                                                                                               \
+                if (PROBE) { const int j_ = (S) - lane; vmask = (j_ < jst0 ? 0xFFFFu : 0u) | (j_ < jst1 ? 0xFFFF0000u : 0u); } \
                 uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;                                              \
                 uint32_t tv[2];                                                                                 \
                 _Pragma("unroll") for (int k = 0; k < R / 4; ++k) {                                             \
@@ -269,10 +296,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 hdiag = hin;                                                                                    \
                 hout = hlast; fout = f; cmout = cm;                                                             \
                 if (GUARD) {                                                                                    \
-                    if (gran_tail && (S) >= lane && (S) - lane < n) cm_ptr[(K)] = cm;                           \
+                    if (!PROBE && gran_tail && (S) >= lane && (S) - lane < n) cm_ptr[(K)] = cm;                 \
                     if (st_bnd && (S) >= 31 && (S) - 31 < n) bnd_ptr[(K)] = make_uint2(hout, fout);             \
                 } else {                                                                                        \
-                    if (gran_tail) cm_ptr[(K)] = cm;                                                            \
+                    if (!PROBE && gran_tail) cm_ptr[(K)] = cm;                                                  \
                     if (st_bnd) bnd_ptr[(K)] = make_uint2(hout, fout);                                          \
                 }                                                                                               \
             }
@@ -297,6 +324,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             }
 #undef LTG_SCAN_STEP
         }
+        if (PROBE) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) fb = __vmaxs2(fb, __shfl_xor_sync(0xffffffffu, fb, o));
+            if (lane == 0) a.probe_out[item] = fb;
+        }
     }
 }
 #undef LTG_CELL
@@ -320,6 +352,8 @@ struct EpiArgs {
     int lit_pitch;
     const int* task_litrow;      // [task] row in lit_colmax (valid when the task carries kTaskLiteral)
     const ScanItem* items;
+    const int* item_orig;        // mode 3: [item] index of the item in the batch's full item list (rows of colmax_all)
+    const uint32_t* probe;       // mode 3: [item] packed carried-F maxima of the Q4 probe sweep
     const SegDesc* segs;
     int n_items;
     int max_len;
@@ -357,8 +391,9 @@ __global__ void k_epilogue(const EpiArgs a)
     const ScanItem it = a.items[warp];
     const SegDesc sd = a.segs[it.seg];
     const int n = sd.len;
-    const uint32_t* cm = a.colmax + (size_t)warp * a.n_gran * a.max_len;
-    uint32_t* cm_all = a.colmax_all + (size_t)warp * a.max_len;
+    const int row = (a.mode == 3) ? a.item_orig[warp] : warp;
+    const uint32_t* cm = a.colmax + (size_t)row * a.n_gran * a.max_len;
+    uint32_t* cm_all = a.colmax_all + (size_t)row * a.max_len;
     const PairDef pd = c_pairs[it.pair];
     if (a.mode == 0) {
         // column maximum over all granules, as the reference's scan reports it
@@ -392,14 +427,24 @@ __global__ void k_epilogue(const EpiArgs a)
             const int flags = (jstar < n ? kTaskOverflow : 0) | (mx >= kQ4Guard ? kTaskLiteral : 0) | (mx >= 32000 ? kTaskRange : 0);
             if (lane == 0) {
                 a.task_max[task] = score; a.task_thr[task] = thr; a.task_flags[task] = flags; a.task_npeaks[task] = 0;
-                a.task_jstar[task] = (flags & kTaskLiteral) ? n : jstar;     // literal maxima already carry the stop-recording zeros
+                a.task_jstar[task] = jstar;
             }
-            if (flags & kTaskLiteral) continue;      // counted in mode 1, from the literal re-run
+            if (flags & kTaskLiteral) continue;      // counted in mode 3 (cleared by the probe) or 1 (from the literal re-run)
+        } else if (a.mode == 3) {
+            // Q4 probe verdict: no F >= 132 was carried into a stripe start within the recorded columns, so the reference's
+            // signed lazy-F test behaves like an unsigned one and its column maxima are the exact ones: back to the fast path
+            const bool is_lit = (a.task_flags[task] & kTaskLiteral) != 0;
+            const uint32_t pv = a.probe[warp];
+            __syncwarp();
+            if (!is_lit || (h ? hi16(pv) : lo16(pv)) >= kQ4CarryF) continue;
+            if (lane == 0) a.task_flags[task] &= ~kTaskLiteral;
+            thr = a.task_thr[task];
+            jstar = a.task_jstar[task];
         } else {
             const bool is_lit = (a.task_flags[task] & kTaskLiteral) != 0;
             if (a.mode == 1 && !is_lit) continue;
             thr = a.task_thr[task];
-            jstar = a.task_jstar[task];
+            jstar = is_lit ? n : a.task_jstar[task];     // literal maxima already carry the stop-recording zeros
             if (is_lit && a.lit_colmax == nullptr) continue;      // deferred to a literal-only batch: no peaks here
             if (is_lit) lit = a.lit_colmax + (size_t)a.task_litrow[task] * a.lit_pitch;
         }

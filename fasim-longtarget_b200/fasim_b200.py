@@ -35,7 +35,7 @@ class Result(C.Structure):
                 ("n_peaks", C.c_int64), ("window_cells", C.c_int64), ("n_literal_tasks", C.c_int64),
                 ("n_literal_windows", C.c_int64), ("gpu_ms_scan", C.c_double), ("gpu_ms_window", C.c_double),
                 ("gpu_launches", C.c_int64), ("gpu_ms_scan_kernel", C.c_double), ("n_scan_launches", C.c_int64),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("n_q4_probed", C.c_int64)]
 
 
 class TaskProbe(C.Structure):

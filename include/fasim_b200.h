@@ -82,6 +82,7 @@ typedef struct ltg_result {
     int64_t n_scan_launches;    /* number of k_scan launches                                       */
     int64_t h2d_bytes;          /* bytes copied host -> device for this result (DNA, descriptors)   */
     int64_t d2h_bytes;          /* bytes copied device -> host (per-peak records, strings, counters) */
+    int64_t n_q4_probed;        /* task pairs swept a second time to decide whether the Q4 emulation is needed */
 } ltg_result;
 
 /* ---- context ---------------------------------------------------------------------------------- */

@@ -570,12 +570,14 @@ def test_row_pruning_is_exact(data_dir):
     os.environ["LTG_NO_PRUNE"] = "1"
     os.environ["LTG_NO_DEAD"] = "1"          # and trace every alignment, not only those that can still be reported
     os.environ["LTG_NO_SKIP"] = "1"          # and run every window round
+    os.environ["LTG_NO_Q4PROBE"] = "1"       # and send every task that reaches 148 through the literal emulation
     try:
         full = fb.Engine(0)
     finally:
         del os.environ["LTG_NO_PRUNE"]
         del os.environ["LTG_NO_DEAD"]
         del os.environ["LTG_NO_SKIP"]
+        del os.environ["LTG_NO_Q4PROBE"]
     pruned = fb.Engine(0)
     try:
         outs = []
@@ -602,6 +604,43 @@ def test_row_pruning_is_exact(data_dir):
     finally:
         full.close()
         pruned.close()
+
+
+def test_q4_probe_is_exact(engine):
+    """Tasks whose maximum reaches 148 are swept a second time to see whether an F >= 132 is carried into a stripe start of the
+    reference's layout; only those go through the literal emulation.  With LTG_NO_Q4PROBE=1 all of them do: same rows, on a
+    lncRNA with low-complexity tracts against repeat-rich DNA (most tasks reach 148), and far fewer literal tasks."""
+    import random
+    rng = random.Random(11)
+    mut = lambda s, rate: "".join(rng.choice("ACGT") if rng.random() < rate else c for c in s)
+    rna = list(splitmix_bases(2001, 2000))
+    for at, unit in ((300, "CT"), (900, "GA"), (1500, "GT")):
+        rna[at:at + 180] = mut(unit * 90, 0.08)
+    rna = "".join(rna)
+    dna = list(splitmix_bases(1001, 120_000))
+    for _ in range(60):
+        at = rng.randrange(0, len(dna) - 300)
+        L = rng.randrange(30, 220)
+        dna[at:at + L] = mut((rng.choice(["GA", "CT", "GAA", "CCT", "GGA", "TC"]) * L)[:L], rng.choice([0.0, 0.06, 0.12]))
+    dna = "".join(dna)
+    os.environ["LTG_NO_Q4PROBE"] = "1"
+    try:
+        plain = fb.Engine(0)
+    finally:
+        del os.environ["LTG_NO_Q4PROBE"]
+    try:
+        outs = []
+        for eng in (plain, engine):
+            eng.set_params(c_length=25)
+            eng.set_query("lnc", rna)
+            res = eng.scan_record(dna, "chr1", 1)
+            outs.append((fb.result_rows(res), res.contents.n_literal_tasks, res.contents.n_q4_probed))
+            eng.free(res)
+        assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 100
+        assert outs[0][2] == 0 and outs[1][2] > 0
+        assert 0 < outs[1][1] < outs[0][1]
+    finally:
+        plain.close()
 
 
 def test_error_behaviour(engine):
