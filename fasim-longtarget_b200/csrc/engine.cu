@@ -140,6 +140,7 @@ struct ltg_context {
     int num_sms = 0;
     int host_threads = 1;
     bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true;
+    int lit_rows_per_chunk = 24, lit_min_chunks = 0;      // tuning of the column-parallel literal kernel (LTG_LIT_ROWS / LTG_LIT_CH)
     int64_t n_probe_items = 0;          // pairs swept a second time by the Q4 probe (diagnostics)
     cudaStream_t stream = nullptr, copy_stream = nullptr, lit_stream = nullptr;
     cudaEvent_t lit_event = nullptr;
@@ -157,7 +158,8 @@ struct ltg_context {
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_colmax, d_bnd, d_counters;
-    DevBuf d_probe_items, d_probe_orig, d_probe_out;
+    DevBuf d_probe_items, d_probe_orig, d_probe_out, d_bnd_gran;
+    int n_bnd_gran = 0;                 // granules that hold the rows just above a stripe start (Q4 pre-filter)
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
     DevBuf d_w[20], d_pc[4], d_res64, d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
@@ -242,6 +244,23 @@ int build_profiles(ltg_context* c)
     }
     c->launches += 2;
     LTG_CUDA_CHECK(cudaGetLastError());
+    // Q4 pre-filter: the granules that hold one of the 28 rows above a stripe start of the reference's 16-lane layout (an F
+    // that enters such a row with >= 132 was opened below a cell >= 148 at most 26 rows up)
+    {
+        const int stripe = (c->m + 15) / 16, n_gran = c->n_strips * (32 * c->scan_r / kGranRows);
+        std::vector<char> mark((size_t)n_gran, 0);
+        for (int k = 1; k < 16; ++k) {
+            const int b = k * stripe;
+            if (b >= m16) break;
+            for (int g = std::max(0, b - 28) / kGranRows; g <= (b - 1) / kGranRows && g < n_gran; ++g) mark[g] = 1;
+        }
+        std::vector<int> list;
+        for (int g = 0; g < n_gran; ++g) if (mark[g]) list.push_back(g);
+        c->n_bnd_gran = (int)list.size();
+        if (int e = c->d_bnd_gran.ensure(sizeof(int) * std::max<size_t>(1, list.size()))) return e;
+        if (!list.empty()) LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_bnd_gran.p, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, c->stream));
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // `list` is host memory of this scope
+    }
     c->profiles_dirty = false;
     return LTG_OK;
 }
@@ -313,7 +332,8 @@ int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const i
     if (c->lit_col && max_read_len >= 256 && col_smem <= 220 * 1024) {
         const int L = (max_read_len + 15) / 16;
         int CH = 8;
-        while (CH < kLitColMaxChunks && L > 24 * CH) CH *= 2;
+        while (CH < kLitColMaxChunks && L > c->lit_rows_per_chunk * CH) CH *= 2;
+        if (c->lit_min_chunks > 0) CH = std::max(2, std::min(kLitColMaxChunks, c->lit_min_chunks & ~1));      // forced (tuning)
         const int threads = 16 * CH;
         const int per_sm = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, 2048 / threads), (220 * 1024) / col_smem));
         const int blocks = n_jobs >= 0 ? std::max(1, std::min(n_jobs, c->num_sms * per_sm)) : c->num_sms * per_sm;
@@ -599,6 +619,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     ea.colmax = c->d_colmax.as<uint32_t>(); ea.n_gran = n_gran; ea.colmax_all = c->d_colmax_all.as<uint32_t>(); ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
     ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
     ea.item_orig = nullptr; ea.probe = nullptr;
+    ea.bnd_gran = (c->q4_probe && c->n_bnd_gran > 0) ? c->d_bnd_gran.as<int>() : nullptr; ea.n_bnd_gran = c->n_bnd_gran;
     ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.stats_all = c->rna_plain ? 0 : 1; ea.mode = 0;
     ea.task_max = ti.max; ea.task_thr = ti.thr; ea.task_npeaks = ti.npk; ea.task_flags = ti.flags; ea.task_jstar = ti.jstar;
     ea.task_off = c->d_task_off.as<int>(); ea.pk_task = nullptr; ea.pk_pos = nullptr; ea.pk_score = nullptr;
@@ -1213,6 +1234,8 @@ int ltg_create(int device, ltg_context** out)
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
     if (const char* e = getenv("LTG_LIT_OLD")) c->lit_col = atoi(e) == 0;
+    if (const char* e = getenv("LTG_LIT_ROWS")) c->lit_rows_per_chunk = std::max(4, atoi(e));
+    if (const char* e = getenv("LTG_LIT_CH")) c->lit_min_chunks = atoi(e);
     *out = c;
     return LTG_OK;
 }

@@ -211,18 +211,21 @@ __global__ void __launch_bounds__(128) k_literal(const LiteralArgs a)
 // linear: each chunk runs it from F = 0, the chunk ends are folded along the stripe, and a carried-in F that is still
 // positive is applied to the first offsets of a chunk afterwards (H = max(H, F_in - 4k), E' = max(E', subs(H,16)): the
 // values the sequential loop produces).  The lazy-F loop with the signed compare, the maximum bookkeeping, the overflow
-// break and the terminate test are run literally by the 16 threads of chunk 0.  Workspace: BYTE arrays [lane][offset] in
-// shared memory (H stored, H previous column, E, H at the best column, one-hot read codes); the profile value of a row is
-// derived from its one-hot code (match 9, mismatch 0, pad row 4 = the reference's score + bias).
+// break and the terminate test are run literally by the 16 threads of chunk 0.  Workspace: three BYTE arrays
+// [lane][offset] in shared memory — H (updated in place: the diagonal input of an offset is kept in a register, the one
+// of a chunk's first offset is read before anyone writes), E, and the one-hot read codes from which the profile value of
+// a row is derived (match 9, mismatch 0, pad row 4 = the reference's score + bias).  The reference's copy of the best
+// column (pvHmax) is only used to find the smallest row that holds the maximum: that row is taken when the column
+// becomes the best one.
 constexpr int kLitColMaxChunks = 32;
-constexpr int kLitColArrays = 5;
+constexpr int kLitColArrays = 3;
 
 __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
 {
     extern __shared__ uint32_t lit_smem[];
-    __shared__ int s_agg[16 * kLitColMaxChunks];     // [lane][chunk] F at the end of the chunk when it starts from 0
-    __shared__ int s_cmx[16 * kLitColMaxChunks];     // [lane][chunk] maximum of the chunk's H values in this column
-    __shared__ int s_ctl[4];                          // 0 copy H to the best-column array, 1 leave the column loop, 2 end_read, 3 max
+    __shared__ uint8_t s_agg[16 * kLitColMaxChunks];  // [lane][chunk] F at the end of the chunk when it starts from 0
+    __shared__ uint8_t s_cmx[16 * kLitColMaxChunks];  // [lane][chunk] maximum of the chunk's H values in this column
+    __shared__ int s_ctl[4];                          // 0 new best column, 1 leave the column loop, 2 end_read, 3 max
     const int tid = threadIdx.x, lam = tid & 15, ch = tid >> 4, CH = blockDim.x >> 4;
     const unsigned hmask = 0x0000ffffu;
     const int bias = 4;
@@ -237,15 +240,13 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
         const int L = (J.read_len + 15) / 16;
         const int P = a.pitch;                                   // bytes per (array, lane), 4 * odd
         uint8_t* hs = reinterpret_cast<uint8_t*>(lit_smem) + (size_t)lam * P;
-        uint8_t* hl = hs + 16 * (size_t)P;
-        uint8_t* ev = hl + 16 * (size_t)P;
-        uint8_t* hm = ev + 16 * (size_t)P;
-        uint8_t* oh = hm + 16 * (size_t)P;
+        uint8_t* ev = hs + 16 * (size_t)P;
+        uint8_t* oh = ev + 16 * (size_t)P;
         const int Lc = 4 * ((L + 4 * CH - 1) / (4 * CH));        // chunk length, a multiple of 4
         const int tb = min(L, ch * Lc), te = min(L, tb + Lc);
         const int tv = tb + ((te - tb) & ~3);                    // end of the part done four offsets at a time
         for (int t = tb; t < te; ++t) {
-            hs[t] = 0; hl[t] = 0; ev[t] = 0; hm[t] = 0;
+            hs[t] = 0; ev[t] = 0;
             const int row = lam * L + t;
             const bool real = row < J.read_len;
             const int r = real ? a.rna_ssw[J.read_start + J.read_dir * row] : 5;
@@ -257,7 +258,8 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
             for (int j = tid; j < J.ref_len; j += blockDim.x) cmrow[j] = 0;
             if (tid == 0 && a.task_litrow) a.task_litrow[J.task] = a.row_base + jb;
         }
-        if (tid == 0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[2] = J.read_len - 1; s_ctl[3] = 0; }
+        // (no best column yet: like the reference's zero-filled pvHmax, row 0 "holds" a maximum of 0)
+        if (tid == 0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[2] = 0; s_ctl[3] = 0; }
         __syncthreads();
         int vMaxScore = 0, vMaxMark = 0, maxv = 0, end_ref = -1;          // live in the threads of chunk 0
         bool overflow = false;
@@ -266,15 +268,17 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
             const int q = J.ref_start + i;
             const int c = td.img[a.codes[sd.start + (td.reversed ? (sd.len - 1 - q) : q)]];
             const int csh = c < 4 ? c : 7;                       // bit 7 of a one-hot code is never set: no match
-            { uint8_t* tmp = hl; hl = hs; hs = tmp; }
-            // ---- sweep 1: the chunk from F = 0
+            // H diagonal of the chunk's first offset: the previous column's H one offset up — for a stripe start the last
+            // offset of the previous lane (the reference's byte shift) — read before this column overwrites anything
             uint32_t vH = 0;
-            if (tb > 0) vH = hl[tb - 1];
-            else if (lam > 0) vH = (hl - P)[L - 1];              // stripe start: last offset of the previous lane (the byte shift)
+            if (tb > 0) vH = hs[tb - 1];
+            else if (lam > 0) vH = (hs - P)[L - 1];
+            __syncthreads();
+            // ---- sweep 1: the chunk from F = 0
             int vF = 0;
             uint32_t vmax2 = 0;
             for (int t0 = tb; t0 < tv; t0 += 4) {
-                const uint32_t h4 = *reinterpret_cast<const uint32_t*>(hl + t0);
+                const uint32_t h4 = *reinterpret_cast<const uint32_t*>(hs + t0);
                 const uint32_t e4 = *reinterpret_cast<const uint32_t*>(ev + t0);
                 const uint32_t o4 = *reinterpret_cast<const uint32_t*>(oh + t0);
                 const uint32_t p4 = ((o4 >> csh) & 0x01010101u) * 9u + ((o4 >> 4) & 0x01010101u) * 4u;
@@ -303,6 +307,7 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
             for (int t = tv; t < te; ++t) {                      // the last (length mod 4) offsets of the stripe
                 const int o = oh[t];
                 const int pv = ((o >> csh) & 1) * 9 + ((o >> 4) & 1) * 4;
+                const int hold = hs[t];
                 int h = sat8(sat8((int)vH + pv) - bias);
                 const int e = ev[t];
                 h = max(h, e); h = max(h, vF);
@@ -311,15 +316,15 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
                 const int open = sat8(h - kGapOpen);
                 ev[t] = (uint8_t)max(sat8(e - kGapExt), open);
                 vF = max(sat8(vF - kGapExt), open);
-                vH = hl[t];
+                vH = hold;
             }
-            s_agg[lam * kLitColMaxChunks + ch] = vF;
+            s_agg[lam * kLitColMaxChunks + ch] = (uint8_t)vF;
             __syncthreads();
             // ---- F carried into this chunk from the chunks before it, applied to the chunk's first offsets
             int fin = 0;
             for (int k = 0; k < ch; ++k) {
                 const int len = max(0, min(L, (k + 1) * Lc) - min(L, k * Lc));
-                fin = max(s_agg[lam * kLitColMaxChunks + k], max(fin - kGapExt * len, 0));
+                fin = max((int)s_agg[lam * kLitColMaxChunks + k], max(fin - kGapExt * len, 0));
             }
             for (int t = tb, fv = fin; t < te && fv > 0; ++t, fv -= kGapExt) {
                 if (fv > (int)hs[t]) {
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
                     lmax = max(lmax, fv);
                 }
             }
-            s_cmx[lam * kLitColMaxChunks + ch] = lmax;
+            s_cmx[lam * kLitColMaxChunks + ch] = (uint8_t)lmax;
             __syncthreads();
             // ---- lazy-F loop and the per-column bookkeeping: the 16 threads of chunk 0, literally
             if (ch == 0) {
@@ -336,8 +341,8 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
                 vF = 0;
                 for (int k = 0; k < CH; ++k) {
                     const int len = max(0, min(L, (k + 1) * Lc) - min(L, k * Lc));
-                    vF = max(s_agg[lam * kLitColMaxChunks + k], max(vF - kGapExt * len, 0));
-                    vMaxCol = max(vMaxCol, s_cmx[lam * kLitColMaxChunks + k]);
+                    vF = max((int)s_agg[lam * kLitColMaxChunks + k], max(vF - kGapExt * len, 0));
+                    vMaxCol = max(vMaxCol, (int)s_cmx[lam * kLitColMaxChunks + k]);
                 }
                 bool done = false;
                 for (int k = 0; k < 16 && !done; ++k) {
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
                         if (!__any_sync(hmask, gt)) { done = true; break; }
                     }
                 }
-                bool copy = false, leave = false;
+                bool best = false, leave = false;
                 vMaxScore = max(vMaxScore, vMaxCol);
                 const bool changed = __any_sync(hmask, vMaxScore != vMaxMark);
                 if (changed) {
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
                     if (temp > maxv) {
                         maxv = temp;
                         if (maxv + bias >= 255) { overflow = true; leave = true; }
-                        else { end_ref = i; copy = true; }
+                        else { end_ref = i; best = true; }
                     }
                 }
                 if (!leave) {
@@ -375,23 +380,23 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
                     if (cmrow && lam == 0) cmrow[i] = (uint16_t)cm;
                     if (cm == J.terminate) leave = true;
                 }
-                if (lam == 0) { s_ctl[0] = copy ? 1 : 0; s_ctl[1] = leave ? 1 : 0; }
+                if (lam == 0) {
+                    s_ctl[0] = best ? 1 : 0; s_ctl[1] = leave ? 1 : 0;
+                    if (best) { s_ctl[2] = J.read_len - 1; s_ctl[3] = maxv; }
+                }
             }
             __syncthreads();
-            if (s_ctl[0]) for (int t = tb; t < te; ++t) hm[t] = hs[t];
+            // a new best column: the smallest row that holds the maximum (what the reference reads off its copy of the column)
+            if (s_ctl[0] && J.kind != 0) {
+                const int mv = s_ctl[3];
+                int er = J.read_len;
+                for (int t = tb; t < te; ++t) if ((int)hs[t] == mv) er = min(er, t + lam * L);
+                if (er < J.read_len) atomicMin(&s_ctl[2], er);
+            }
             if (s_ctl[1]) break;
         }
-        if (J.kind == 0) continue;
-        if (tid == 0) s_ctl[3] = maxv;
         __syncthreads();
-        {
-            const int mv = s_ctl[3];
-            int er = J.read_len;
-            for (int t = tb; t < te; ++t) if ((int)hm[t] == mv) er = min(er, t + lam * L);
-            if (er < J.read_len) atomicMin(&s_ctl[2], er);
-        }
-        __syncthreads();
-        if (tid != 0) continue;
+        if (J.kind == 0 || tid != 0) continue;
         // overflow (score marker 255) sends the reference to its exact 16-bit kernel: keep the exact fast-path result
         if (overflow) continue;
         const int end_read = s_ctl[2];

@@ -153,9 +153,9 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
 #define LTG_E_UPDATE(EV, U) EV = __viaddmax_s16x2(EV, kNegExt, (U))
 #endif
 
+#define LTG_PROBE_F(RR) if (bmask & (1u << (RR))) fb = __vmaxs2(fb, f & vmask);
 #define LTG_CELL(SV, RR)                                          \
     {                                                             \
-        if (PROBE && (bmask & (1u << (RR)))) fb = __vmaxs2(fb, f & vmask); \
         const uint32_t t_ = __viaddmax_s16x2_relu(d, (SV), E[RR]); \
         const uint32_t u_ = __vadd2(t_, kNegOpen);                \
         LTG_E_UPDATE(E[RR], u_);                                  \
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 
         for (int strip = 0; strip < a.n_strips; ++strip) {
             // PROBE: which of this lane's rows start a stripe of the reference's layout (row = k * stripe_len, k = 1..15)
-            uint32_t bmask = 0, vmask = 0;
+            uint32_t bmask = 0, vmask = 0, amask = 0;
             if (PROBE) {
                 const int row0 = (strip * 32 + lane) * R;
 #pragma unroll
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                     const int row = row0 + r;
                     if (row > 0 && row < 16 * a.stripe_len && row % a.stripe_len == 0) bmask |= 1u << r;
                 }
+                amask = __reduce_or_sync(0xffffffffu, bmask);
             }
             const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
             __syncwarp();
@@ -287,10 +288,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;                                              \
                 uint32_t tv[2];                                                                                 \
                 _Pragma("unroll") for (int k = 0; k < R / 4; ++k) {                                             \
-                    LTG_CELL(sc[k].x, 4 * k + 0)                                                                \
-                    LTG_CELL(sc[k].y, 4 * k + 1)                                                                \
-                    LTG_CELL(sc[k].z, 4 * k + 2)                                                                \
-                    LTG_CELL(sc[k].w, 4 * k + 3)                                                                \
+                    if (PROBE && ((amask >> (4 * k)) & 0xFu)) {     /* warp-uniform: some lane has a stripe start here */ \
+                        LTG_PROBE_F(4 * k + 0) LTG_CELL(sc[k].x, 4 * k + 0)                                     \
+                        LTG_PROBE_F(4 * k + 1) LTG_CELL(sc[k].y, 4 * k + 1)                                     \
+                        LTG_PROBE_F(4 * k + 2) LTG_CELL(sc[k].z, 4 * k + 2)                                     \
+                        LTG_PROBE_F(4 * k + 3) LTG_CELL(sc[k].w, 4 * k + 3)                                     \
+                    } else {                                                                                    \
+                        LTG_CELL(sc[k].x, 4 * k + 0)                                                            \
+                        LTG_CELL(sc[k].y, 4 * k + 1)                                                            \
+                        LTG_CELL(sc[k].z, 4 * k + 2)                                                            \
+                        LTG_CELL(sc[k].w, 4 * k + 3)                                                            \
+                    }                                                                                           \
                 }                                                                                               \
                 _Pragma("unroll") for (int k = 0; k < R / 4; ++k) sc[k] = scn[k];                               \
                 hdiag = hin;                                                                                    \
@@ -332,6 +340,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
     }
 }
 #undef LTG_CELL
+#undef LTG_PROBE_F
 #undef LTG_E_UPDATE
 
 // ---------------------------------------------------------------------------------------------
@@ -352,6 +361,8 @@ struct EpiArgs {
     int lit_pitch;
     const int* task_litrow;      // [task] row in lit_colmax (valid when the task carries kTaskLiteral)
     const ScanItem* items;
+    const int* bnd_gran;         // mode 0: granules that hold one of the 28 rows above a stripe start of the reference's layout
+    int n_bnd_gran;              //         (nullptr: every task that reaches 148 is flagged)
     const int* item_orig;        // mode 3: [item] index of the item in the batch's full item list (rows of colmax_all)
     const uint32_t* probe;       // mode 3: [item] packed carried-F maxima of the Q4 probe sweep
     const SegDesc* segs;
@@ -424,7 +435,22 @@ __global__ void k_epilogue(const EpiArgs a)
             }
             const int score = (a.stats_max && (a.stats_all || (sd.flags & kSegNonACGT))) ? a.stats_max[task] : mx;
             thr = (int)((double)score * 0.8);
-            const int flags = (jstar < n ? kTaskOverflow : 0) | (mx >= kQ4Guard ? kTaskLiteral : 0) | (mx >= 32000 ? kTaskRange : 0);
+            // Q4 can only fire where an F >= 132 enters a stripe start, i.e. below a cell >= 148 at most 26 rows up, in a column
+            // the reference still processes: without such a cell in the granules that hold those rows the task stays exact
+            bool q4 = mx >= kQ4Guard;
+            if (q4 && a.bnd_gran) {
+                int near = 0;
+                const int jend = min(jstar + 1, n);
+                for (int j = lane; j < jend; j += 32) {
+                    uint32_t v = 0;
+                    for (int k = 0; k < a.n_bnd_gran; ++k) v = __vmaxs2(v, cm[(size_t)a.bnd_gran[k] * a.max_len + j]);
+                    near = max(near, h ? hi16(v) : lo16(v));
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) near = max(near, __shfl_xor_sync(0xffffffffu, near, o));
+                q4 = near >= kQ4Guard;
+            }
+            const int flags = (jstar < n ? kTaskOverflow : 0) | (q4 ? kTaskLiteral : 0) | (mx >= 32000 ? kTaskRange : 0);
             if (lane == 0) {
                 a.task_max[task] = score; a.task_thr[task] = thr; a.task_flags[task] = flags; a.task_npeaks[task] = 0;
                 a.task_jstar[task] = jstar;
