@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
         const int Lc = 4 * ((L + 4 * CH - 1) / (4 * CH));        // chunk length, a multiple of 4
         const int tb = min(L, ch * Lc), te = min(L, tb + Lc);
         const int tv = tb + ((te - tb) & ~3);                    // end of the part done four offsets at a time
+        const int klast = (L - 1) / Lc;                          // last chunk that holds an offset (the ones after it are empty)
+        const int kfold = 60 / Lc + 2;                           // full chunks that span 60 offsets, plus one, plus the short last one
         for (int t = tb; t < te; ++t) {
             hs[t] = 0; ev[t] = 0;
             const int row = lam * L + t;
@@ -277,10 +279,19 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
             // ---- sweep 1: the chunk from F = 0
             int vF = 0;
             uint32_t vmax2 = 0;
+            uint32_t nh4 = 0, ne4 = 0, no4 = 0;                  // the next four offsets are loaded before the current ones are stored
+            if (tb < tv) {
+                nh4 = *reinterpret_cast<const uint32_t*>(hs + tb);
+                ne4 = *reinterpret_cast<const uint32_t*>(ev + tb);
+                no4 = *reinterpret_cast<const uint32_t*>(oh + tb);
+            }
             for (int t0 = tb; t0 < tv; t0 += 4) {
-                const uint32_t h4 = *reinterpret_cast<const uint32_t*>(hs + t0);
-                const uint32_t e4 = *reinterpret_cast<const uint32_t*>(ev + t0);
-                const uint32_t o4 = *reinterpret_cast<const uint32_t*>(oh + t0);
+                const uint32_t h4 = nh4, e4 = ne4, o4 = no4;
+                if (t0 + 4 < tv) {
+                    nh4 = *reinterpret_cast<const uint32_t*>(hs + t0 + 4);
+                    ne4 = *reinterpret_cast<const uint32_t*>(ev + t0 + 4);
+                    no4 = *reinterpret_cast<const uint32_t*>(oh + t0 + 4);
+                }
                 const uint32_t p4 = ((o4 >> csh) & 0x01010101u) * 9u + ((o4 >> 4) & 0x01010101u) * 4u;
                 // H diagonal of offsets t0..t0+3 = H of the previous column at offsets t0-1..t0+2
                 const uint32_t dlo = __byte_perm(vH, h4, 0x1410), dhi = __byte_perm(vH, h4, 0x1615);
@@ -321,8 +332,9 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
             s_agg[lam * kLitColMaxChunks + ch] = (uint8_t)vF;
             __syncthreads();
             // ---- F carried into this chunk from the chunks before it, applied to the chunk's first offsets
+            // (an F is at most 239 and loses 4 per offset: only the chunks within 60 offsets above this one can contribute)
             int fin = 0;
-            for (int k = 0; k < ch; ++k) {
+            for (int k = max(0, ch - kfold); k < ch; ++k) {
                 const int len = max(0, min(L, (k + 1) * Lc) - min(L, k * Lc));
                 fin = max((int)s_agg[lam * kLitColMaxChunks + k], max(fin - kGapExt * len, 0));
             }
@@ -338,11 +350,11 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
             // ---- lazy-F loop and the per-column bookkeeping: the 16 threads of chunk 0, literally
             if (ch == 0) {
                 int vMaxCol = 0;
-                vF = 0;
-                for (int k = 0; k < CH; ++k) {
+                for (int k = 0; k < CH; ++k) vMaxCol = max(vMaxCol, (int)s_cmx[lam * kLitColMaxChunks + k]);
+                vF = 0;                                          // F after the stripe's last offset
+                for (int k = max(0, klast - kfold); k <= klast; ++k) {
                     const int len = max(0, min(L, (k + 1) * Lc) - min(L, k * Lc));
                     vF = max((int)s_agg[lam * kLitColMaxChunks + k], max(vF - kGapExt * len, 0));
-                    vMaxCol = max(vMaxCol, (int)s_cmx[lam * kLitColMaxChunks + k]);
                 }
                 bool done = false;
                 for (int k = 0; k < 16 && !done; ++k) {
