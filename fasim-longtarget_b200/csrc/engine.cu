@@ -328,7 +328,7 @@ int launch_literal(ltg_context* c, const LiteralJob* d_jobs, int n_jobs, const i
 {
     const int pitch = literal_pitch(max_read_len);
     // column-parallel kernel (one CTA per job, byte workspace in shared memory) for all but short reads
-    const long long col_smem = (long long)kLitColArrays * 16 * pitch;
+    const long long col_smem = (long long)kLitColArrays * 16 * pitch + 16;     // + slack for the kernel's one-ahead loads
     if (c->lit_col && max_read_len >= 256 && col_smem <= 220 * 1024) {
         const int L = (max_read_len + 15) / 16;
         int CH = 8;

@@ -279,40 +279,44 @@ __global__ void __launch_bounds__(512) k_literal_col(const LiteralArgs a)
             // ---- sweep 1: the chunk from F = 0
             int vF = 0;
             uint32_t vmax2 = 0;
-            uint32_t nh4 = 0, ne4 = 0, no4 = 0;                  // the next four offsets are loaded before the current ones are stored
-            if (tb < tv) {
-                nh4 = *reinterpret_cast<const uint32_t*>(hs + tb);
-                ne4 = *reinterpret_cast<const uint32_t*>(ev + tb);
-                no4 = *reinterpret_cast<const uint32_t*>(oh + tb);
-            }
-            for (int t0 = tb; t0 < tv; t0 += 4) {
-                const uint32_t h4 = nh4, e4 = ne4, o4 = no4;
-                if (t0 + 4 < tv) {
-                    nh4 = *reinterpret_cast<const uint32_t*>(hs + t0 + 4);
-                    ne4 = *reinterpret_cast<const uint32_t*>(ev + t0 + 4);
-                    no4 = *reinterpret_cast<const uint32_t*>(oh + t0 + 4);
+            // Shared memory is addressed with explicit 32-bit shared addresses; the next four offsets are loaded before the
+            // current ones are stored (the arrays carry 16 bytes of slack, so the last, unused prefetch stays inside them).
+            {
+                const uint32_t sa_h = (uint32_t)__cvta_generic_to_shared(hs), sa_e = (uint32_t)__cvta_generic_to_shared(ev);
+                const uint32_t sa_o = (uint32_t)__cvta_generic_to_shared(oh);
+                uint32_t nh4, ne4, no4;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nh4) : "r"(sa_h + tb));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ne4) : "r"(sa_e + tb));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(no4) : "r"(sa_o + tb));
+                for (int t0 = tb; t0 < tv; t0 += 4) {
+                    const uint32_t h4 = nh4, e4 = ne4, o4 = no4;
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(nh4) : "r"(sa_h + t0));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(ne4) : "r"(sa_e + t0));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(no4) : "r"(sa_o + t0));
+                    const uint32_t p4 = ((o4 >> csh) & 0x01010101u) * 9u + ((o4 >> 4) & 0x01010101u) * 4u;
+                    // H diagonal of offsets t0..t0+3 = H of the previous column at offsets t0-1..t0+2
+                    const uint32_t dlo = __byte_perm(vH, h4, 0x1410), dhi = __byte_perm(vH, h4, 0x1615);
+                    vH = h4 >> 24;
+                    const uint32_t elo = __byte_perm(e4, 0u, 0x4140), ehi = __byte_perm(e4, 0u, 0x4342);
+                    const uint32_t plo = __byte_perm(p4, 0u, 0x4140), phi = __byte_perm(p4, 0u, 0x4342);
+                    // hbase = max(subs(adds(Hdiag, profile), bias), E): adds saturates at 255, subs at 0 (E >= 0 is the floor)
+                    const uint32_t hba = __viaddmax_s16x2_relu(__viaddmin_s16x2(dlo, plo, kFF), kM4, elo);
+                    const uint32_t hbb = __viaddmax_s16x2_relu(__viaddmin_s16x2(dhi, phi, kFF), kM4, ehi);
+                    const uint32_t ga = __viaddmax_s16x2_relu(hba, kM16, kM16), gb = __viaddmax_s16x2_relu(hbb, kM16, kM16);   // subs(hbase, 16)
+                    const int f0 = vF;
+                    const int f1 = __viaddmax_s32(f0, -kGapExt, (int)(ga & 0xffffu));
+                    const int f2 = __viaddmax_s32(f1, -kGapExt, (int)(ga >> 16));
+                    const int f3 = __viaddmax_s32(f2, -kGapExt, (int)(gb & 0xffffu));
+                    vF = __viaddmax_s32(f3, -kGapExt, (int)(gb >> 16));
+                    const uint32_t ha = __vmaxs2(hba, __byte_perm((uint32_t)f0, (uint32_t)f1, 0x5410));
+                    const uint32_t hb = __vmaxs2(hbb, __byte_perm((uint32_t)f2, (uint32_t)f3, 0x5410));
+                    vmax2 = __vimax3_s16x2(vmax2, ha, hb);
+                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(sa_h + t0), "r"(__byte_perm(ha, hb, 0x6420)) : "memory");
+                    // E' = max(subs(E, 4), subs(H, 16))
+                    const uint32_t ea = __viaddmax_s16x2_relu(elo, kM4, __vadd2(ha, kM16));
+                    const uint32_t eb = __viaddmax_s16x2_relu(ehi, kM4, __vadd2(hb, kM16));
+                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(sa_e + t0), "r"(__byte_perm(ea, eb, 0x6420)) : "memory");
                 }
-                const uint32_t p4 = ((o4 >> csh) & 0x01010101u) * 9u + ((o4 >> 4) & 0x01010101u) * 4u;
-                // H diagonal of offsets t0..t0+3 = H of the previous column at offsets t0-1..t0+2
-                const uint32_t dlo = __byte_perm(vH, h4, 0x1410), dhi = __byte_perm(vH, h4, 0x1615);
-                vH = h4 >> 24;
-                const uint32_t elo = __byte_perm(e4, 0u, 0x4140), ehi = __byte_perm(e4, 0u, 0x4342);
-                const uint32_t plo = __byte_perm(p4, 0u, 0x4140), phi = __byte_perm(p4, 0u, 0x4342);
-                const uint32_t hba = __vmaxs2(__viaddmax_s16x2(__vmins2(__vadd2(dlo, plo), kFF), kM4, 0u), elo);
-                const uint32_t hbb = __vmaxs2(__viaddmax_s16x2(__vmins2(__vadd2(dhi, phi), kFF), kM4, 0u), ehi);
-                const uint32_t ga = __viaddmax_s16x2(hba, kM16, 0u), gb = __viaddmax_s16x2(hbb, kM16, 0u);
-                const int f0 = vF;
-                const int f1 = __viaddmax_s32(f0, -kGapExt, (int)(ga & 0xffffu));
-                const int f2 = __viaddmax_s32(f1, -kGapExt, (int)(ga >> 16));
-                const int f3 = __viaddmax_s32(f2, -kGapExt, (int)(gb & 0xffffu));
-                vF = __viaddmax_s32(f3, -kGapExt, (int)(gb >> 16));
-                const uint32_t ha = __vmaxs2(hba, __byte_perm((uint32_t)f0, (uint32_t)f1, 0x5410));
-                const uint32_t hb = __vmaxs2(hbb, __byte_perm((uint32_t)f2, (uint32_t)f3, 0x5410));
-                vmax2 = __vimax3_s16x2(vmax2, ha, hb);
-                *reinterpret_cast<uint32_t*>(hs + t0) = __byte_perm(ha, hb, 0x6420);
-                const uint32_t ea = __viaddmax_s16x2(elo, kM4, __viaddmax_s16x2(ha, kM16, 0u));
-                const uint32_t eb = __viaddmax_s16x2(ehi, kM4, __viaddmax_s16x2(hb, kM16, 0u));
-                *reinterpret_cast<uint32_t*>(ev + t0) = __byte_perm(ea, eb, 0x6420);
             }
             int lmax = max((int)(vmax2 & 0xffffu), (int)(vmax2 >> 16));
             for (int t = tv; t < te; ++t) {                      // the last (length mod 4) offsets of the stripe
