@@ -3,6 +3,7 @@
 // Included at the end of engine.cu (same translation unit: it uses the anonymous-namespace helpers).
 #include <atomic>
 #include <fstream>
+#include <mutex>
 #include <getopt.h>
 #include <time.h>
 
@@ -272,7 +273,10 @@ int ltg_main(int argc, char* const* argv)
     std::vector<Unit> units;
     {
         const int64_t stride = P.cut_length - P.overlap;
-        const int64_t kUnitSegments = 2048, unit_bases = kUnitSegments * (stride > 0 ? stride : 1);
+        // (with at least two lncRNAs per GPU the queue is balanced by the lncRNAs themselves: whole records per job, so that a
+        //  call's pipeline drains once per lncRNA and not once per 10 Mbp)
+        const bool by_query = queries.size() >= 2 * devs.size() && devs.size() > 1;
+        const int64_t kUnitSegments = by_query ? (1ll << 40) / 5000 : 2048, unit_bases = kUnitSegments * (stride > 0 ? stride : 1);
         if (stride <= 0) { fprintf(stderr, "fasim: cut length (%d) must exceed the overlap (%d)\n", P.cut_length, P.overlap); return 2; }
         size_t i = 0;
         while (i < recs.size()) {
@@ -301,6 +305,12 @@ int ltg_main(int argc, char* const* argv)
     std::vector<ltg_result*> results(n_jobs, nullptr);
     std::vector<std::atomic<size_t> > remaining(queries.size());
     for (auto& r : remaining) r.store(n_units);
+    std::vector<size_t> q_order(queries.size());              // longest lncRNA first: the queue's tail is made of short jobs
+    for (size_t q = 0; q < q_order.size(); ++q) q_order[q] = q;
+    std::stable_sort(q_order.begin(), q_order.end(), [&](size_t a, size_t b) { return queries[a].second.size() > queries[b].second.size(); });
+    std::vector<std::thread> finishers;                       // merge / cluster / write of a finished lncRNA, off the GPU threads
+    std::mutex finishers_mu;
+    std::vector<std::string> finish_errors;
     std::atomic<size_t> next_job(0);
     std::atomic<int> failed(0);
     std::vector<std::string> errors(devs.size());
@@ -311,7 +321,7 @@ int ltg_main(int argc, char* const* argv)
         int rc = ltg_result_new(&all);
         for (size_t u = 0; rc == LTG_OK && u < n_units; ++u) {
             ltg_result* part = results[q * n_units + u];
-            if (!part) { rc = LTG_ERR_STATE; break; }
+            if (!part) { set_error("internal: a work unit of %s has no result", queries[q].first.c_str()); rc = LTG_ERR_STATE; break; }
             for (int64_t k = 0; k < part->n_triplex; ++k) part->triplex[k].record += (int32_t)units[u].r0;
             rc = ltg_result_append(all, part);
         }
@@ -336,14 +346,14 @@ int ltg_main(int argc, char* const* argv)
         while (rc == LTG_OK && !failed.load()) {
             const size_t job = next_job.fetch_add(1);
             if (job >= n_jobs) break;
-            const size_t q = job / n_units, u = job % n_units;
+            const size_t q = q_order[job / n_units], u = job % n_units;
             if (q != cur_q) {
                 rc = ltg_set_query(ctx, queries[q].first.c_str(), queries[q].second.c_str(), (int64_t)queries[q].second.size());
                 if (rc != LTG_OK) break;
                 cur_q = q;
             }
             const Unit& U = units[u];
-            ltg_result** out = &results[job];
+            ltg_result** out = &results[q * n_units + u];
             if (U.n_seg >= 0) {                                  // shard of one long record
                 const FastaRecord& R = recs[U.r0];
                 const int64_t stride = P.cut_length - P.overlap, lo = U.first_seg * stride;
@@ -358,7 +368,13 @@ int ltg_main(int argc, char* const* argv)
                 }
                 rc = ltg_scan_records(ctx, (int64_t)(U.r1 - U.r0), dna.data(), len.data(), chr.data(), start.data(), out);
             }
-            if (rc == LTG_OK && remaining[q].fetch_sub(1) == 1) rc = finish_query(q);
+            if (rc == LTG_OK && remaining[q].fetch_sub(1) == 1) {
+                if (queries.size() == 1) rc = finish_query(q);
+                else {
+                    std::lock_guard<std::mutex> lk(finishers_mu);
+                    finishers.emplace_back([&, q]() { if (finish_query(q) != LTG_OK) { std::lock_guard<std::mutex> lk2(finishers_mu); finish_errors.push_back(ltg_last_error()); failed.store(1); } });
+                }
+            }
         }
         if (rc != LTG_OK) { errors[w] = ltg_last_error(); failed.store(1); }
         if (ctx) ltg_destroy(ctx);
@@ -369,6 +385,8 @@ int ltg_main(int argc, char* const* argv)
         gpu_worker(0);
         for (std::thread& t : pool) t.join();
     }
+    for (std::thread& t : finishers) t.join();
+    for (const std::string& e : finish_errors) errors.push_back(e);
     lap("scan+write");
     for (ltg_result* r : results) if (r) ltg_result_free(r);
     if (failed.load()) {
