@@ -340,7 +340,10 @@ int ltg_main(int argc, char* const* argv)
     };
     auto gpu_worker = [&](size_t w) {
         ltg_context* ctx = nullptr;
+        auto tnow = []() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
+        double t_create = tnow(), t_query = 0, t_scan = 0;
         int rc = ltg_create(devs[w], &ctx);
+        t_create = tnow() - t_create;
         if (rc == LTG_OK) rc = ltg_set_params(ctx, &P);
         size_t cur_q = (size_t)-1;
         while (rc == LTG_OK && !failed.load()) {
@@ -348,10 +351,13 @@ int ltg_main(int argc, char* const* argv)
             if (job >= n_jobs) break;
             const size_t q = q_order[job / n_units], u = job % n_units;
             if (q != cur_q) {
+                const double t0q = tnow();
                 rc = ltg_set_query(ctx, queries[q].first.c_str(), queries[q].second.c_str(), (int64_t)queries[q].second.size());
+                t_query += tnow() - t0q;
                 if (rc != LTG_OK) break;
                 cur_q = q;
             }
+            const double t0s = tnow();
             const Unit& U = units[u];
             ltg_result** out = &results[q * n_units + u];
             if (U.n_seg >= 0) {                                  // shard of one long record
@@ -368,6 +374,7 @@ int ltg_main(int argc, char* const* argv)
                 }
                 rc = ltg_scan_records(ctx, (int64_t)(U.r1 - U.r0), dna.data(), len.data(), chr.data(), start.data(), out);
             }
+            t_scan += tnow() - t0s;
             if (rc == LTG_OK && remaining[q].fetch_sub(1) == 1) {
                 if (queries.size() == 1) rc = finish_query(q);
                 else {
@@ -377,7 +384,10 @@ int ltg_main(int argc, char* const* argv)
             }
         }
         if (rc != LTG_OK) { errors[w] = ltg_last_error(); failed.store(1); }
+        const double t0d = tnow();
         if (ctx) ltg_destroy(ctx);
+        if (timing) fprintf(stderr, "[fasim timing] device %d: create %.3f s, set_query %.3f s, scan calls %.3f s, destroy %.3f s\n",
+                            devs[w], t_create, t_query, t_scan, tnow() - t0d);
     };
     {
         std::vector<std::thread> pool;
