@@ -628,9 +628,14 @@ def test_q4_probe_is_exact(engine):
         plain = fb.Engine(0)
     finally:
         del os.environ["LTG_NO_Q4PROBE"]
+    os.environ["LTG_LIT_OLD"] = "1"              # and the one-half-warp-per-job literal kernel instead of the column-parallel one
+    try:
+        old_kernel = fb.Engine(0)
+    finally:
+        del os.environ["LTG_LIT_OLD"]
     try:
         outs = []
-        for eng in (plain, engine):
+        for eng in (plain, engine, old_kernel):
             eng.set_params(c_length=25)
             eng.set_query("lnc", rna)
             res = eng.scan_record(dna, "chr1", 1)
@@ -639,8 +644,10 @@ def test_q4_probe_is_exact(engine):
         assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 100
         assert outs[0][2] == 0 and outs[1][2] > 0
         assert 0 < outs[1][1] < outs[0][1]
+        assert outs[2] == outs[1]
     finally:
         plain.close()
+        old_kernel.close()
 
 
 def test_error_behaviour(engine):
