@@ -66,7 +66,7 @@ void usage()
            "  -f1 also takes a gzip/bgzip-compressed FASTA and a UCSC .2bit file; for .2bit:\n"
            "  --seq name[:start-end][,...]   sequences / 1-based inclusive regions to scan (default: every sequence, whole)\n"
            "  --species S                    species field of the output file name (default: the .2bit file's base name)\n"
-           "  --list-records   print the DNA records -f1 yields (species, chr, start, length, CRC-32) and exit (no GPU needed)\n"
+           "  --list-records   print the DNA records -f1 and the lncRNAs -f2 yield (name, start, length, CRC-32) and exit (no GPU needed)\n"
            "  --queries   -f2 holds several lncRNAs (one per '>' record): every lncRNA is scanned against -f1 and gets its own\n"
            "              output files; the (lncRNA, chunk) pairs go through the same queue\n");
 }
@@ -237,7 +237,6 @@ int ltg_main(int argc, char* const* argv)
         for (const FastaRecord& r : recs)
             printf("record\t%s\t%s\t%ld\t%zu\t%08lx\n", r.species.c_str(), r.chr.c_str(), r.start, r.seq.size(),
                    (unsigned long)crc32(0L, (const Bytef*)r.seq.data(), (uInt)r.seq.size()));
-        return 0;
     }
     std::vector<std::pair<std::string, std::string> > queries;            // (name, sequence); one entry unless --queries
     if (multi_query) {
@@ -249,6 +248,11 @@ int ltg_main(int argc, char* const* argv)
     }
     if (queries.empty()) { fprintf(stderr, "fasim: cannot read RNA file %s\n", f2.c_str()); return 2; }
     for (const auto& q : queries) printf("%s\n", q.first.c_str());
+    if (list_records) {                                             // ... and the lncRNAs -f2 yields; nothing is scanned
+        for (const auto& q : queries)
+            printf("query\t%s\t%zu\t%08lx\n", q.first.c_str(), q.second.size(), (unsigned long)crc32(0L, (const Bytef*)q.second.data(), (uInt)q.second.size()));
+        return 0;
+    }
     lap("read");
 
     // devices: --device N, or --devices a,b,.. / all (one context + one host thread per entry; an entry may repeat)

@@ -49,11 +49,20 @@ def write_twobit(path, seqs, byteswap=False):
     open(path, "wb").write(header + index + b"".join(recs))
 
 
-def list_records(args, cwd):
-    r = fb.run_cli(list(args) + ["--list-records"], cwd=cwd)
+def list_records(args, cwd, rna=None):
+    if rna is None:
+        rna = "_q.fa"
+        open(os.path.join(cwd, rna), "w").write(">q\nACGT\n")
+    r = fb.run_cli(list(args) + ["-f2", rna, "--list-records"], cwd=cwd)
     assert r.returncode == 0, r.stdout + r.stderr
     rows = [l.split("\t")[1:] for l in r.stdout.splitlines() if l.startswith("record\t")]
     return [(sp, ch, int(st), int(n), crc) for sp, ch, st, n, crc in rows]
+
+
+def list_queries(args, cwd):
+    r = fb.run_cli(list(args) + ["--list-records"], cwd=cwd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return [tuple(l.split("\t")[1:]) for l in r.stdout.splitlines() if l.startswith("query\t")]
 
 
 def crc(s):
@@ -96,3 +105,20 @@ def test_twobit_whole_sequences_and_regions(tmp_path, seqs, byteswap):
                    ("hg38", "chr1", 9399, len(a) - 9398, crc(a[9398:]))]
     r = fb.run_cli(["-f1", "mini.2bit", "--seq", "chrZ", "--list-records"], cwd=d)
     assert r.returncode != 0 and "chrZ" in r.stderr
+
+
+def test_rna_readers(tmp_path):
+    """-f2 as the reference reads it (first line = name with every '>' removed, every other line appended: readRna,
+    Fasim-LongTarget.cpp:174-200) and with --queries (one lncRNA per '>' record, empty records dropped)."""
+    fb.build()
+    d = str(tmp_path)
+    open(os.path.join(d, "dna.fa"), "w").write(">sp|chr1|1-8\nACGTACGT\n")
+    a, b = splitmix_bases(4001, 150), splitmix_bases(4002, 77)
+    open(os.path.join(d, "two.fa"), "w").write(">lncA extra>words\r\n%s\r\n%s\n>lncB\n%s\n>empty\n\n" % (a[:60], a[60:], b))
+    multi = list_queries(["-f1", "dna.fa", "-f2", "two.fa", "--queries"], d)
+    assert multi == [("lncA extrawords", "150", crc(a)), ("lncB", "77", crc(b))]
+    # without --queries the file is ONE lncRNA, later header lines and all (what the reference does with such a file)
+    single = list_queries(["-f1", "dna.fa", "-f2", "two.fa"], d)
+    assert single == [("lncA extrawords", str(150 + len(">lncB") + 77 + len(">empty")), crc(a + ">lncB" + b + ">empty"))]
+    r = fb.run_cli(["-f1", "dna.fa", "-f2", "missing.fa", "--list-records"], cwd=d)
+    assert r.returncode != 0 and "missing.fa" in r.stderr
