@@ -11,59 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from _harness import ref_side
 from test_q4_theory_cpu import exact_colmax_and_carried_f, make_case
-MATCH, MISMATCH, OPEN, EXT = 10, -8, 32, 8            # doubled scores: bit 0 is the "untainted" flag
-
-
-def certify(rna, dna):
-    m, n = len(rna), len(dna)
-    L = (m + 15) // 16; m16 = 16 * L
-    code = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 0}
-    d = np.array([code.get(c, 4) for c in dna])
-    idx = np.arange(n)
-    one = np.ones(n, dtype=np.int64)
-    H = one.copy(); Hmain_prev = one.copy()
-    fin = one.copy(); fcar = one.copy()
-    cut = np.zeros(n, dtype=bool)            # the chain of this column has passed through [132, 143]
-    colmax = one.copy()
-    giveup = False
-    for i in range(m16):
-        if i > 0:
-            fend = np.maximum(np.maximum(fin - EXT, Hmain_prev - OPEN), 1)
-            if i % L == 0:
-                old = np.maximum(fcar - EXT, 1)
-                newer = (fend >> 1) >= (old >> 1)
-                fcar = np.where(newer, fend, old)
-                cut = np.where(newer, False, cut_next)
-                fin = one.copy()
-                if np.any(((fcar & 1) == 0) & ((fcar >> 1) >= 132)):
-                    giveup = True            # a chain that may itself be lower in the reference: its failing rows are unknown
-            else:
-                fin = fend
-                fcar = np.maximum(fcar - EXT, 1)
-                cut = cut_next
-        v = fcar >> 1
-        cut_next = cut | ((v >= 132) & (v <= 143))
-        if i < m:
-            r = code.get(rna[i], 4)
-            s = np.where((d == r) & (d < 4), MATCH, MISMATCH) if r < 4 else np.full(n, MISMATCH)
-        else:
-            s = np.zeros(n, dtype=np.int64)
-        diag = np.concatenate(([1], H[:-1]))
-        t0 = np.maximum(diag + s, 1)
-        pm = np.maximum.accumulate(t0 + EXT * idx)
-        E = np.maximum(np.concatenate(([1], pm[:-1] - OPEN - EXT * (idx[1:] - 1))), 1)
-        T = np.maximum(t0, E)
-        Hmain = np.maximum(T, fin)
-        contrib = np.where(cut, fcar & ~1, fcar)
-        H = np.maximum(Hmain, contrib)
-        Hmain_prev = Hmain
-        colmax = np.maximum(colmax, H)
-    val = colmax >> 1
-    over = np.nonzero(val >= 251)[0]
-    jstar = int(over[0]) if len(over) else n
-    je = min(jstar + 1, n)
-    clean = bool(np.all((colmax[:je] & 1) == 1))
-    return clean and not giveup
+from test_q4_theory_cpu import certify
 
 
 def run(cases):
