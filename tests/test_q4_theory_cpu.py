@@ -297,3 +297,98 @@ def test_taint_certification_is_sound():
         certified += int(ok); different += int(differs); certified_kernel += int(ok_kernel)
     assert flagged > 200 and certified > flagged // 2 and certified_kernel > flagged // 2 and different >= 5
     print("flagged %d, certified %d (kernel-shaped rule %d), really different %d" % (flagged, certified, certified_kernel, different))
+
+
+# the same certification for Aligner::Align: both passes' column maxima up to the column where the pass ends, and the cell that
+# gives the end row, must be untainted
+def h_matrix_taint(read, ref):
+    m, n = len(read), len(ref)
+    L = (m + 15) // 16; m16 = 16 * L
+    d = np.asarray(ref); idx = np.arange(n)
+    one = np.ones(n, dtype=np.int64)
+    H = one.copy(); Hmain_prev = one.copy(); fin = one.copy(); fcar = one.copy()
+    orig = np.zeros(n, dtype=bool)
+    rows = np.ones((m16, n), dtype=np.int64)
+    giveup = np.zeros(n, dtype=bool)         # per column: a tainted chain >= 132 was seen there
+    for i in range(m16):
+        if i > 0:
+            fend = np.maximum(np.maximum(fin - EXT2, Hmain_prev - OPEN2), 1)
+            if i % L == 0:
+                old = np.maximum(fcar - EXT2, 1)
+                newer = (fend >> 1) >= (old >> 1)
+                fcar = np.where(newer, fend, old)
+                orig = np.where(newer, (fend >> 1) >= 132, orig)
+                fin = one.copy()
+                giveup |= ((fcar & 1) == 0) & ((fcar >> 1) >= 132)
+            else:
+                fin = fend
+                fcar = np.maximum(fcar - EXT2, 1)
+        v = fcar >> 1
+        cut = orig & (v <= 139)
+        if i < m:
+            r = read[i]
+            s = np.where((d == r) & (d < 4), MATCH2, MISMATCH2) if r < 4 else np.full(n, MISMATCH2)
+        else:
+            s = np.zeros(n, dtype=np.int64)
+        diag = np.concatenate(([1], H[:-1]))
+        t0 = np.maximum(diag + s, 1)
+        pm = np.maximum.accumulate(t0 + EXT2 * idx)
+        E = np.maximum(np.concatenate(([1], pm[:-1] - OPEN2 - EXT2 * (idx[1:] - 1))), 1)
+        T = np.maximum(t0, E)
+        Hmain = np.maximum(T, fin)
+        H = np.maximum(Hmain, np.where(cut, fcar & ~1, fcar))
+        Hmain_prev = Hmain
+        rows[i] = H
+    return rows, giveup
+
+def pass_ok(read, ref, terminate):
+    """-> (best, end_ref, end_read, certified)"""
+    rows, giveup = h_matrix_taint(read, ref)
+    colmax = rows.max(axis=0)
+    best, end_ref, last = 0, -1, len(ref)
+    for j in range(len(ref)):
+        if (colmax[j] >> 1) > best:
+            best, end_ref = int(colmax[j] >> 1), j
+        if (colmax[j] >> 1) == terminate:
+            last = j + 1
+            break
+    if best >= 251 or end_ref < 0:
+        return None
+    ok = bool(np.all((colmax[:last] & 1) == 1)) and not bool(giveup[:last].any())
+    col = rows[:len(read), end_ref]
+    hit = np.nonzero((col >> 1) == best)[0]
+    end_read = len(read) - 1
+    if len(hit):
+        end_read = min(end_read, int(hit[0]))
+        ok = ok and bool(col[hit[0]] & 1)
+    return best, end_ref, end_read, ok
+
+def certify_align(rna, win):
+    code = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 0}
+    read = [code.get(c, 4) for c in rna]; ref = [code.get(c, 4) for c in win]
+    f = pass_ok(read, ref, 255)
+    if f is None: return None
+    score, re_, qe, okf = f
+    r = pass_ok(read[qe::-1], ref[re_::-1], score)
+    if r is None: return None
+    return okf and r[3]
+
+
+def test_taint_certification_of_window_alignments_is_sound():
+    S = ref_side() if have_ref_shim() else oracle_side()
+    rng = random.Random(77)
+    flagged = certified = different = 0
+    for _ in range(400):
+        rna, win = make_case(rng)
+        win = win[:196]
+        ex = exact_align(rna, win)
+        if ex is None or ex[1] < 132:
+            continue
+        flagged += 1
+        got, _ = S.align(rna, win)
+        differs = tuple(got) != tuple(ex[0])
+        ok = bool(certify_align(rna, win))
+        assert not (ok and differs), (rna, win)
+        certified += int(ok); different += int(differs)
+    assert flagged > 150 and certified > flagged // 2 and different >= 5
+    print("windows flagged %d, certified %d, really different %d" % (flagged, certified, different))
