@@ -14,7 +14,10 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <new>
 #include <numeric>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -149,6 +152,7 @@ struct ltg_context {
     std::vector<TaskDef> tasks;
     std::vector<PairDef> pairs;
     bool tables_dirty = true;
+    bool params_changed = true;     // rule / strand changed since the profiles were built
     // query
     std::string rna_name, rna;
     bool rna_plain = true;          // only ACGT (any case): the SSW-side and Farrar-side scorings coincide
@@ -173,6 +177,56 @@ struct ltg_context {
 };
 
 namespace {
+
+// The task / pair tables are __constant__ symbols, i.e. one copy per DEVICE, while rule / strand selections belong to a
+// context.  Contexts that share a device (`--devices 0,0`) may therefore only coexist with identical tables; the registry
+// below (per device: content of the uploaded tables and the contexts that rely on it) refuses anything else loudly
+// instead of letting one context's kernels run with another one's rule images.
+struct DeviceTables { std::vector<unsigned char> bytes; std::vector<const ltg_context*> users; };
+std::mutex g_tables_mu;
+DeviceTables g_tables[64];
+
+std::vector<unsigned char> table_bytes(const std::vector<TaskDef>& t, const std::vector<PairDef>& p)
+{
+    std::vector<unsigned char> b(t.size() * sizeof(TaskDef) + p.size() * sizeof(PairDef));
+    if (!t.empty()) memcpy(b.data(), t.data(), t.size() * sizeof(TaskDef));
+    if (!p.empty()) memcpy(b.data() + t.size() * sizeof(TaskDef), p.data(), p.size() * sizeof(PairDef));
+    return b;
+}
+// claims the device's tables for `c` with content `bytes`; false if another live context relies on different content
+bool claim_tables(const ltg_context* c, int device, const std::vector<unsigned char>& bytes)
+{
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    DeviceTables& d = g_tables[device & 63];
+    bool others = false;
+    for (const ltg_context* u : d.users) if (u != c) others = true;
+    if (others && d.bytes != bytes) return false;
+    d.bytes = bytes;
+    if (std::find(d.users.begin(), d.users.end(), c) == d.users.end()) d.users.push_back(c);
+    return true;
+}
+void release_tables(const ltg_context* c, int device)
+{
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    DeviceTables& d = g_tables[device & 63];
+    d.users.erase(std::remove(d.users.begin(), d.users.end(), c), d.users.end());
+    if (d.users.empty()) d.bytes.clear();
+}
+bool tables_current(const ltg_context* c, int device, const std::vector<unsigned char>& bytes)
+{
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    const DeviceTables& d = g_tables[device & 63];
+    return d.bytes == bytes && std::find(d.users.begin(), d.users.end(), c) != d.users.end();
+}
+
+// No exception may cross the C ABI: every extern "C" entry point runs its body through this.
+template <class F> int guarded(F&& body)
+{
+    try { return body(); }
+    catch (const std::bad_alloc&) { set_error("out of host memory"); return LTG_ERR_LIMIT; }
+    catch (const std::exception& e) { set_error("internal error: %s", e.what()); return LTG_ERR_STATE; }
+    catch (...) { set_error("internal error (unknown exception)"); return LTG_ERR_STATE; }
+}
 
 // per-task scalars of the scan stage, one row of 5 ints per array: [max | thr | npeaks | flags | jstar][n_tasks]
 struct TaskInfo {
@@ -201,6 +255,10 @@ int upload_tables(ltg_context* c)
             for (int h = 1; h >= 0; --h) { c->tasks[p.task[h]].pair = (int8_t)c->pairs.size(); c->tasks[p.task[h]].half = (int8_t)h; }
             c->pairs.push_back(p);
         }
+    }
+    if (!claim_tables(c, c->device, table_bytes(c->tasks, c->pairs))) {
+        set_error("another context on device %d uses a different rule/strand selection: contexts that share a GPU must share it", c->device);
+        return LTG_ERR_STATE;
     }
     LTG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tasks, c->tasks.data(), sizeof(TaskDef) * c->tasks.size(), 0, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pairs, c->pairs.data(), sizeof(PairDef) * c->pairs.size(), 0, cudaMemcpyHostToDevice, c->stream));
@@ -268,7 +326,8 @@ int build_profiles(ltg_context* c)
 int prepare(ltg_context* c)
 {
     LTG_CUDA_CHECK(cudaSetDevice(c->device));
-    if (c->tables_dirty) if (int e = upload_tables(c)) return e;
+    if (!c->tables_dirty && !tables_current(c, c->device, table_bytes(c->tasks, c->pairs))) c->tables_dirty = true;
+    if (c->tables_dirty) { const bool keep_profiles = !c->profiles_dirty && !c->params_changed; if (int e = upload_tables(c)) return e; if (keep_profiles) c->profiles_dirty = false; c->params_changed = false; }
     if (c->profiles_dirty) if (int e = build_profiles(c)) return e;
     if (int e = c->d_counters.ensure(sizeof(int) * kCntTotal)) return e;
     return LTG_OK;
@@ -1084,7 +1143,12 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
         // host phase of one overlaps the device phase of the next
         const size_t per_seg = (size_t)c->pairs.size() * c->n_strips * (32 * c->scan_r / kGranRows) * (size_t)((c->params.cut_length + 3) & ~3) * 4;
         size_t bs = std::max<size_t>(16, std::min<size_t>(kBatchSegments, kStripBytesPerBatch / std::max<size_t>(1, per_seg)));
-        if (active.size() > 256 && active.size() < 2 * bs) bs = (active.size() + 1) / 2;
+        // equal-sized batches (a short last batch would expose its drain and host tail): 2551 segments -> 3 x 851, not 1024 + 1024 + 503
+        if (!active.empty()) {
+            size_t nbatch = (active.size() + bs - 1) / bs;
+            if (active.size() > 256 && nbatch < 2) nbatch = 2;
+            bs = (active.size() + nbatch - 1) / nbatch;
+        }
         std::vector<ltg_host::Triplex> record_list;
         int rc = LTG_OK;
         size_t nb = 0;
@@ -1199,6 +1263,7 @@ void ltg_default_params(ltg_params* p)
 
 int ltg_create(int device, ltg_context** out)
 {
+    return guarded([&]() -> int {
     if (!out) { set_error("null argument"); return LTG_ERR_ARG; }
     int n = 0;
     cudaError_t ce = cudaGetDeviceCount(&n);
@@ -1208,18 +1273,24 @@ int ltg_create(int device, ltg_context** out)
     cudaDeviceProp prop;
     LTG_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { set_error("device %s is sm_%d%d; this build contains sm_100a code only", prop.name, prop.major, prop.minor); return LTG_ERR_CUDA; }
+    *out = nullptr;
     ltg_context* c = new ltg_context();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     ltg_default_params(&c->params);
-    LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->lit_stream, cudaStreamNonBlocking));
-    LTG_CUDA_CHECK(cudaEventCreateWithFlags(&c->lit_event, cudaEventDisableTiming));
-    for (HostBatch& hb : c->hb) {
-        LTG_CUDA_CHECK(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
-        for (int i = 0; i < 6; ++i) LTG_CUDA_CHECK(cudaEventCreate(&hb.ev[i]));
-    }
+    // streams and events; on any failure the half-built context is torn down again (ltg_destroy copes with null handles)
+    auto make = [&]() -> int {
+        LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        LTG_CUDA_CHECK(cudaStreamCreateWithFlags(&c->lit_stream, cudaStreamNonBlocking));
+        LTG_CUDA_CHECK(cudaEventCreateWithFlags(&c->lit_event, cudaEventDisableTiming));
+        for (HostBatch& hb : c->hb) {
+            LTG_CUDA_CHECK(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
+            for (int i = 0; i < 6; ++i) LTG_CUDA_CHECK(cudaEventCreate(&hb.ev[i]));
+        }
+        return LTG_OK;
+    };
+    if (int e = make()) { ltg_destroy(c); return e; }
     // host-phase worker threads: LTG_HOST_THREADS, else the host cores divided among the visible GPUs (one process
     // per GPU is the deployment model), capped at 16
     int threads = 0;
@@ -1238,13 +1309,15 @@ int ltg_create(int device, ltg_context** out)
     if (const char* e = getenv("LTG_LIT_CH")) c->lit_min_chunks = atoi(e);
     *out = c;
     return LTG_OK;
+    });
 }
 
 void ltg_destroy(ltg_context* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    release_tables(c, c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (HostBatch& hb : c->hb) {
         if (hb.worker.joinable()) hb.worker.join();
         for (PinBuf* b : {&hb.task_off, &hb.jobs, &hb.tout, &hb.task_info, &hb.scalars, &hb.c_task, &hb.c_poff}) b->release();
@@ -1278,18 +1351,21 @@ void ltg_debug_stats(ltg_context* c, int64_t* out30, int reset)
 
 int ltg_set_params(ltg_context* c, const ltg_params* p)
 {
+    return guarded([&]() -> int {
     if (!c || !p) { set_error("null argument"); return LTG_ERR_ARG; }
     if (p->cut_length <= 0 || p->cut_length - p->overlap <= 0) { set_error("cut length (%d) must be positive and exceed the overlap (%d)", p->cut_length, p->overlap); return LTG_ERR_ARG; }
     if (p->cut_length > 6500) { set_error("cut length %d exceeds the 16-bit score envelope of this build (max 6500)", p->cut_length); return LTG_ERR_LIMIT; }
     std::vector<TaskDef> probe;
     if (!ltg_host::enumerate_tasks(*p, probe)) { set_error("invalid rule/strand selection (rule=%d strand=%d)", p->rule, p->strand); return LTG_ERR_ARG; }
-    if (p->rule != c->params.rule || p->strand != c->params.strand) c->tables_dirty = true;
+    if (p->rule != c->params.rule || p->strand != c->params.strand) { c->tables_dirty = true; c->params_changed = true; }
     c->params = *p;
     return LTG_OK;
+    });
 }
 
 int ltg_set_query(ltg_context* c, const char* name, const char* rna, int64_t len)
 {
+    return guarded([&]() -> int {
     if (!c || !rna || len <= 0) { set_error("empty lncRNA"); return LTG_ERR_ARG; }
     if (len > (1 << 24)) { set_error("lncRNA longer than 16 Mnt is not supported"); return LTG_ERR_LIMIT; }
     LTG_CUDA_CHECK(cudaSetDevice(c->device));
@@ -1319,18 +1395,22 @@ int ltg_set_query(ltg_context* c, const char* name, const char* rna, int64_t len
     LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->profiles_dirty = true;
     return prepare(c);
+    });
 }
 
 int ltg_scan_record(ltg_context* c, const char* dna, int64_t len, const char* chr, int64_t record_start, ltg_result** out)
 {
+    return guarded([&]() -> int {
     if (!dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
     RecordIn R; R.h_dna = dna; R.len = len; R.chr = chr; R.record_start = record_start;
     return scan_impl(c, &R, 1, out);
+    });
 }
 
 int ltg_scan_records(ltg_context* c, int64_t n_records, const char* const* dna, const int64_t* len, const char* const* chr,
                      const int64_t* record_start, ltg_result** out)
 {
+    return guarded([&]() -> int {
     if (n_records < 0 || (n_records > 0 && (!dna || !len))) { set_error("null argument"); return LTG_ERR_ARG; }
     std::vector<RecordIn> recs((size_t)n_records);
     for (int64_t r = 0; r < n_records; ++r) {
@@ -1338,31 +1418,53 @@ int ltg_scan_records(ltg_context* c, int64_t n_records, const char* const* dna, 
         recs[r].h_dna = dna[r]; recs[r].len = len[r]; recs[r].chr = chr ? chr[r] : nullptr; recs[r].record_start = record_start ? record_start[r] : 0;
     }
     return scan_impl(c, recs.data(), n_records, out);
+    });
+}
+
+int ltg_scan_records_at(ltg_context* c, int64_t n_records, const void* const* dna, int dna_on_device, const int64_t* len, const char* const* chr,
+                        const int64_t* record_start, ltg_result** out)
+{
+    return guarded([&]() -> int {
+        if (n_records < 0 || (n_records > 0 && (!dna || !len))) { set_error("null argument"); return LTG_ERR_ARG; }
+        std::vector<RecordIn> recs((size_t)n_records);
+        for (int64_t r = 0; r < n_records; ++r) {
+            if (!dna[r] && len[r] > 0) { set_error("null DNA in record %lld", (long long)r); return LTG_ERR_ARG; }
+            if (dna_on_device) recs[r].d_dna = (const unsigned char*)dna[r]; else recs[r].h_dna = (const char*)dna[r];
+            recs[r].len = len[r]; recs[r].chr = chr ? chr[r] : nullptr; recs[r].record_start = record_start ? record_start[r] : 0;
+        }
+        return scan_impl(c, recs.data(), n_records, out);
+    });
 }
 
 int ltg_scan_device(ltg_context* c, const void* d_dna, int64_t len, const char* chr, int64_t record_start, ltg_result** out)
 {
+    return guarded([&]() -> int {
     if (!d_dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
     RecordIn R; R.d_dna = (const unsigned char*)d_dna; R.len = len; R.chr = chr; R.record_start = record_start;
     return scan_impl(c, &R, 1, out);
+    });
 }
 
 int ltg_scan_shard(ltg_context* c, const void* dna, int dna_on_device, int64_t len, const char* chr, int64_t record_start,
                    int64_t record_len, int64_t first_segment, int64_t n_segments, ltg_result** out)
 {
+    return guarded([&]() -> int {
     if (!dna && len > 0) { set_error("null DNA"); return LTG_ERR_ARG; }
     RecordIn R;
     if (dna_on_device) R.d_dna = (const unsigned char*)dna; else R.h_dna = (const char*)dna;
     R.len = len; R.chr = chr; R.record_start = record_start; R.record_len = record_len; R.first_seg = first_segment; R.n_seg = n_segments;
     return scan_impl(c, &R, 1, out);
+    });
 }
 
 int ltg_result_new(ltg_result** out)
 {
+    return guarded([&]() -> int {
     if (!out) return LTG_ERR_ARG;
     ResultBuilder rb;
     *out = finish_result(rb);
     return LTG_OK;
+    });
 }
 
 void ltg_result_free(ltg_result* r)
@@ -1375,11 +1477,17 @@ void ltg_result_free(ltg_result* r)
 
 int ltg_result_append(ltg_result* dst, const ltg_result* src)
 {
+    return guarded([&]() -> int {
     if (!dst || !src) { set_error("null argument"); return LTG_ERR_ARG; }
     const int64_t n0 = dst->n_triplex, t0 = dst->text_bytes;
-    dst->triplex = (ltg_triplex*)realloc(dst->triplex, sizeof(ltg_triplex) * (size_t)std::max<int64_t>(1, n0 + src->n_triplex));
-    dst->text = (char*)realloc(dst->text, (size_t)std::max<int64_t>(1, t0 + src->text_bytes));
-    memcpy(dst->text + t0, src->text, (size_t)src->text_bytes);
+    // grow both blocks before touching anything: on failure dst stays as it was (a successful first realloc only moved a block)
+    ltg_triplex* nt = (ltg_triplex*)realloc(dst->triplex, sizeof(ltg_triplex) * (size_t)std::max<int64_t>(1, n0 + src->n_triplex));
+    if (!nt) { set_error("out of memory appending %lld triplexes", (long long)src->n_triplex); return LTG_ERR_LIMIT; }
+    dst->triplex = nt;
+    char* tx = (char*)realloc(dst->text, (size_t)std::max<int64_t>(1, t0 + src->text_bytes));
+    if (!tx) { set_error("out of memory appending %lld text bytes", (long long)src->text_bytes); return LTG_ERR_LIMIT; }
+    dst->text = tx;
+    if (src->text_bytes > 0) memcpy(dst->text + t0, src->text, (size_t)src->text_bytes);
     for (int64_t i = 0; i < src->n_triplex; ++i) {
         ltg_triplex t = src->triplex[i];
         t.tfo_off += t0; t.tts_off += t0; t.chr_off += t0;
@@ -1393,21 +1501,25 @@ int ltg_result_append(ltg_result* dst, const ltg_result* src)
     dst->gpu_ms_scan_kernel += src->gpu_ms_scan_kernel; dst->n_scan_launches += src->n_scan_launches;
     dst->h2d_bytes += src->h2d_bytes; dst->d2h_bytes += src->d2h_bytes; dst->n_q4_probed += src->n_q4_probed;
     return LTG_OK;
+    });
 }
 
 int ltg_cluster(ltg_result* r, const ltg_params* p)
 {
+    return guarded([&]() -> int {
     if (!r || !p) { set_error("null argument"); return LTG_ERR_ARG; }
     std::vector<ltg_triplex> v(r->triplex, r->triplex + r->n_triplex);
     ltg_host::cluster(v, p->c_distance, p->c_length, nullptr);
     std::sort(v.begin(), v.end(), [](const ltg_triplex& a, const ltg_triplex& b) { return a.motif < b.motif; });   // :813, :847
     if (!v.empty()) memcpy(r->triplex, v.data(), sizeof(ltg_triplex) * v.size());
     return LTG_OK;
+    });
 }
 
 int ltg_probe_segment(ltg_context* c, const char* seg, int32_t seg_len, ltg_task_probe* tasks, int32_t n_tasks, int32_t* colmax,
                       int32_t* peak_score, int32_t* peak_pos, int32_t peak_cap)
 {
+    return guarded([&]() -> int {
     if (!c || !seg || seg_len <= 0 || !tasks) { set_error("bad argument"); return LTG_ERR_ARG; }
     if (seg_len > c->params.cut_length) { set_error("segment longer than the cut length"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
@@ -1456,6 +1568,7 @@ int ltg_probe_segment(ltg_context* c, const char* seg, int32_t seg_len, ltg_task
         }
     }
     return LTG_OK;
+    });
 }
 
 
@@ -1464,6 +1577,7 @@ int ltg_probe_segment(ltg_context* c, const char* seg, int32_t seg_len, ltg_task
 int ltg_probe_align(ltg_context* c, const char* const* windows, const int32_t* window_len, int32_t n, int32_t* out6, uint32_t* cigar,
                     int32_t cigar_cap)
 {
+    return guarded([&]() -> int {
     if (!c || !windows || !window_len || n <= 0 || !out6) { set_error("bad argument"); return LTG_ERR_ARG; }
     if (int e = prepare(c)) return e;
     // identity task table (restored afterwards by marking the tables dirty)
@@ -1472,6 +1586,10 @@ int ltg_probe_align(ltg_context* c, const char* const* windows, const int32_t* w
     for (int k = 0; k < 5; ++k) id.img[k] = (int8_t)k;
     PairDef pd; pd.task[0] = pd.task[1] = 0; pd.reversed = 0; pd.pad_ = 0;
     id.pair = 0; id.half = 0;
+    if (!claim_tables(c, c->device, table_bytes(std::vector<TaskDef>(1, id), std::vector<PairDef>(1, pd)))) {
+        set_error("ltg_probe_align replaces the device's task tables: not available while another context uses device %d", c->device);
+        return LTG_ERR_STATE;
+    }
     LTG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tasks, &id, sizeof id, 0, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pairs, &pd, sizeof pd, 0, cudaMemcpyHostToDevice, c->stream));
     c->tables_dirty = true;
@@ -1537,6 +1655,7 @@ int ltg_probe_align(ltg_context* c, const char* const* windows, const int32_t* w
         o[5] = nc;
     }
     return LTG_OK;
+    });
 }
 
 }  // extern "C"

@@ -439,7 +439,9 @@ __global__ void k_lit_collect(const WinState w, int reverse, int round, LiteralJ
     if (!reverse) {
         if (w.w_done[i] || w.w_next[i] != round) return;       // only the windows swept in this round
         const int4 v = w.res[i];
-        if (v.x < kQ4Guard || v.x >= kOverflowU8) return;
+        // (no upper bound: with the Q4 quirk the reference's byte kernel can stay below 251 where exact SW reaches it and then
+        //  keeps its own, lower result; the literal kernels detect a real overflow themselves and leave the exact result alone)
+        if (v.x < kQ4Guard) return;
         const int cut = w.w_len[i];
         J.kind = 1; J.ref_start = w.pk_pos[i] - cut + 1; J.ref_len = cut; J.ref_dir = 0;
         J.read_start = 0; J.read_len = w.m; J.read_dir = 1; J.terminate = 255;

@@ -44,7 +44,7 @@ class TaskProbe(C.Structure):
 
 
 EXPORTS = ["ltg_create", "ltg_destroy", "ltg_last_error", "ltg_default_params", "ltg_set_params", "ltg_set_query",
-           "ltg_scan_record", "ltg_scan_records", "ltg_scan_device", "ltg_scan_shard", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
+           "ltg_scan_record", "ltg_scan_records", "ltg_scan_records_at", "ltg_scan_device", "ltg_scan_shard", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
            "ltg_write_tfosorted", "ltg_write_tfoclass", "ltg_main", "ltg_probe_segment", "ltg_probe_align", "ltg_stream", "ltg_debug_stats",
            "ltg_device_count"]
 
@@ -75,6 +75,8 @@ def lib():
         L.ltg_scan_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.POINTER(Result))]
         L.ltg_scan_records.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_char_p),
                                        C.POINTER(C.c_int64), C.POINTER(C.POINTER(Result))]
+        L.ltg_scan_records_at.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_char_p),
+                                          C.POINTER(C.c_int64), C.POINTER(C.POINTER(Result))]
         L.ltg_scan_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                      C.POINTER(C.POINTER(Result))]
         L.ltg_result_free.argtypes = [C.POINTER(Result)]

@@ -15,6 +15,26 @@ namespace ltg_host {
 
 struct FastaRecord { std::string species, chr; long start = 0; std::string header, seq; };
 
+// Lower-case (soft-masked) bases.  The reference's transferString scores every byte outside "ATGCN" as N while its
+// complement() silently DROPS such bytes (rules.h:82-83, 308-311), so a soft-masked genome loses every
+// repeat and gets shifted TTS strings.  This build makes the choice explicit (--softmask): upper-case them (default, with
+// a notice on stderr), score them as N like the reference's scan does, or refuse the input.
+enum SoftMask { kSoftUpper = 0, kSoftAsN = 1, kSoftError = 2 };
+
+// applies the policy to one record; returns the number of lower-case letters found
+inline int64_t apply_softmask(std::string& seq, int policy)
+{
+    int64_t n = 0;
+    for (char& ch : seq) {
+        if (ch >= 'a' && ch <= 'z') {
+            ++n;
+            if (policy == kSoftUpper) ch = (char)(ch - 'a' + 'A');
+            else if (policy == kSoftAsN) ch = 'N';
+        }
+    }
+    return n;
+}
+
 // Header ">species|chr|start-end" (Fasim-LongTarget.cpp:211-248): the first two '|' close species and chr, the first '-'
 // after them closes the start (atoi); everything else is ignored.
 inline void parse_dna_header(const std::string& line, FastaRecord& cur)
@@ -98,32 +118,48 @@ public:
     {
         f_ = fopen(path.c_str(), "rb");
         if (!f_) { err = "cannot open " + path; return false; }
+        if (fseeko(f_, 0, SEEK_END) != 0) { err = "cannot seek in " + path; return false; }
+        file_size_ = (int64_t)ftello(f_);
+        rewind(f_);
         uint32_t sig = 0, version = 0, count = 0, reserved = 0;
         if (fread(&sig, 4, 1, f_) != 1) { err = "truncated .2bit header"; return false; }
         if (sig == 0x4327411Au) swap_ = true;
         else if (sig != 0x1A412743u) { err = "not a .2bit file"; return false; }
         if (!u32(version) || !u32(count) || !u32(reserved)) { err = "truncated .2bit header"; return false; }
         if (version != 0) { err = ".2bit version " + std::to_string(version) + " is not supported (only version 0)"; return false; }
+        // every index entry takes at least 5 bytes: a count the file cannot hold is a corrupt header, not an allocation size
+        if ((int64_t)count * 5 > file_size_) { err = "corrupt .2bit header (sequence count exceeds the file size)"; return false; }
         for (uint32_t i = 0; i < count; ++i) {
             unsigned char len = 0;
             if (fread(&len, 1, 1, f_) != 1) { err = "truncated .2bit index"; return false; }
             std::string name(len, '\0');
             uint32_t off = 0;
             if ((len && fread(&name[0], 1, len, f_) != len) || !u32(off)) { err = "truncated .2bit index"; return false; }
+            if ((int64_t)off + 16 > file_size_) { err = "corrupt .2bit index (offset of '" + name + "' is outside the file)"; return false; }
             seqs.push_back(TwoBitSeq{name, off});
         }
         return true;
     }
     // bases [lo, hi) of sequence `idx` (0-based, half open; hi < 0 or beyond the end = to the end)
-    bool fetch(size_t idx, int64_t lo, int64_t hi, std::string& out, int64_t& dna_size, std::string& err)
+    bool fetch(size_t idx, int64_t lo, int64_t hi, std::string& out, int64_t& dna_size, std::string& err, int softmask = kSoftUpper,
+               int64_t* n_masked = nullptr)
     {
         if (fseeko(f_, (off_t)seqs[idx].offset, SEEK_SET) != 0) { err = "bad .2bit offset"; return false; }
         uint32_t size = 0, nb = 0, mb = 0, reserved = 0;
         if (!u32(size) || !u32(nb)) { err = "truncated .2bit record"; return false; }
+        // counts come from the file: check them against what the file can hold before they size an allocation or a seek
+        const int64_t left = file_size_ - (int64_t)ftello(f_);
+        if ((int64_t)nb * 8 > left) { err = "corrupt .2bit record (N-block count exceeds the file size)"; return false; }
         std::vector<uint32_t> nstart(nb), nsize(nb);
         for (uint32_t& v : nstart) if (!u32(v)) { err = "truncated .2bit record"; return false; }
         for (uint32_t& v : nsize) if (!u32(v)) { err = "truncated .2bit record"; return false; }
-        if (!u32(mb) || fseeko(f_, (off_t)mb * 8, SEEK_CUR) != 0 || !u32(reserved)) { err = "truncated .2bit record"; return false; }
+        if (!u32(mb)) { err = "truncated .2bit record"; return false; }
+        if ((int64_t)mb * 8 > file_size_ - (int64_t)ftello(f_)) { err = "corrupt .2bit record (mask-block count exceeds the file size)"; return false; }
+        std::vector<uint32_t> mstart(mb), msize(mb);
+        for (uint32_t& v : mstart) if (!u32(v)) { err = "truncated .2bit record"; return false; }
+        for (uint32_t& v : msize) if (!u32(v)) { err = "truncated .2bit record"; return false; }
+        if (!u32(reserved)) { err = "truncated .2bit record"; return false; }
+        if (((int64_t)size + 3) / 4 > file_size_ - (int64_t)ftello(f_)) { err = "corrupt .2bit record (sequence size exceeds the file size)"; return false; }
         dna_size = size;
         if (lo < 0) lo = 0;
         if (hi < 0 || hi > (int64_t)size) hi = size;
@@ -143,6 +179,16 @@ public:
             const int64_t a = std::max<int64_t>(nstart[k], lo), e = std::min<int64_t>((int64_t)nstart[k] + nsize[k], hi);
             for (int64_t i = a; i < e; ++i) out[(size_t)(i - lo)] = 'N';
         }
+        // soft-mask blocks = the lower-case stretches of the FASTA view
+        int64_t masked = 0;
+        for (uint32_t k = 0; k < mb; ++k) {
+            const int64_t a = std::max<int64_t>(mstart[k], lo), e = std::min<int64_t>((int64_t)mstart[k] + msize[k], hi);
+            if (e <= a) continue;
+            masked += e - a;
+            if (softmask == kSoftAsN) for (int64_t i = a; i < e; ++i) out[(size_t)(i - lo)] = 'N';
+        }
+        if (n_masked) *n_masked += masked;
+        if (masked > 0 && softmask == kSoftError) { err = "sequence '" + seqs[idx].name + "' holds soft-masked (lower-case) bases; choose --softmask upper or --softmask n"; return false; }
         return true;
     }
     std::vector<TwoBitSeq> seqs;
@@ -156,12 +202,13 @@ private:
     }
     FILE* f_ = nullptr;
     bool swap_ = false;
+    int64_t file_size_ = 0;
 };
 
 // `.2bit` records for the scan.  `regions` = "", or a comma-separated list of  name | name:start-end  (1-based, inclusive,
 // the convention of the FASTA header's start field).  No list = every sequence of the file, whole.
 inline bool read_dna_twobit(const std::string& path, const std::string& regions, const std::string& species,
-                            std::vector<FastaRecord>& out, std::string& err)
+                            std::vector<FastaRecord>& out, std::string& err, int softmask = kSoftUpper, int64_t* n_masked = nullptr)
 {
     TwoBitFile tb;
     if (!tb.open(path, err)) return false;
@@ -200,7 +247,7 @@ inline bool read_dna_twobit(const std::string& path, const std::string& regions,
     for (const Want& w : wants) {
         FastaRecord r;
         int64_t size = 0;
-        if (!tb.fetch(w.idx, w.lo, w.hi, r.seq, size, err)) return false;
+        if (!tb.fetch(w.idx, w.lo, w.hi, r.seq, size, err, softmask, n_masked)) return false;
         r.species = species;
         r.chr = tb.seqs[w.idx].name;
         r.start = (long)w.lo + 1;

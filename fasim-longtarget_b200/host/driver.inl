@@ -66,6 +66,8 @@ void usage()
            "  -f1 also takes a gzip/bgzip-compressed FASTA and a UCSC .2bit file; for .2bit:\n"
            "  --seq name[:start-end][,...]   sequences / 1-based inclusive regions to scan (default: every sequence, whole)\n"
            "  --species S                    species field of the output file name (default: the .2bit file's base name)\n"
+           "  --softmask upper|n|error       lower-case (soft-masked) bases of -f1: upper-case them (default; a notice is printed),\n"
+           "                                 score them as N (what the reference's scan does), or refuse the input\n"
            "  --list-records   print the DNA records -f1 and the lncRNAs -f2 yield (name, start, length, CRC-32) and exit (no GPU needed)\n"
            "  --queries   -f2 holds several lncRNAs (one per '>' record): every lncRNA is scanned against -f1 and gets its own\n"
            "              output files; the (lncRNA, chunk) pairs go through the same queue\n");
@@ -77,6 +79,7 @@ extern "C" {
 
 int ltg_write_tfosorted(const ltg_result* r, const char* path)
 {
+    return guarded([&]() -> int {
     if (!r || !path) { set_error("null argument"); return LTG_ERR_ARG; }
     FILE* f = fopen(path, "w");
     if (!f) { set_error("cannot write %s", path); return LTG_ERR_IO; }
@@ -95,6 +98,7 @@ int ltg_write_tfosorted(const ltg_result* r, const char* path)
     }
     fclose(f);
     return LTG_OK;
+    });
 }
 
 // print_cluster — Fasim-LongTarget.cpp:694-795 for class levels 1 and 2 (called from printResult :831-836
@@ -102,6 +106,7 @@ int ltg_write_tfosorted(const ltg_result* r, const char* path)
 int ltg_write_tfoclass(const ltg_result* r, const ltg_params* p, const char* sorted_path, const char* chr, int64_t record_start,
                        int64_t dna_size, const char* rna_name)
 {
+    return guarded([&]() -> int {
     if (!r || !p || !sorted_path) { set_error("null argument"); return LTG_ERR_ARG; }
     // rebuild the per-class coverage maps exactly as cluster_triplex fills class1[] (:661-672)
     std::map<size_t, size_t> cov[6];
@@ -151,10 +156,12 @@ int ltg_write_tfoclass(const ltg_result* r, const ltg_params* p, const char* sor
         fclose(f);
     }
     return LTG_OK;
+    });
 }
 
 int ltg_main(int argc, char* const* argv)
 {
+    return guarded([&]() -> int {
     ltg_params P;
     ltg_default_params(&P);
     std::string f1 = "./", f2 = "./", outdir = "./", devices_arg;
@@ -168,12 +175,14 @@ int ltg_main(int argc, char* const* argv)
         {"cn", required_argument, nullptr, 'C'}, {"ds", required_argument, nullptr, 'D'}, {"lg", required_argument, nullptr, 'E'},
         {"device", required_argument, nullptr, 1000}, {"devices", required_argument, nullptr, 1001}, {"queries", no_argument, nullptr, 1002},
         {"seq", required_argument, nullptr, 1003}, {"species", required_argument, nullptr, 1004}, {"list-records", no_argument, nullptr, 1005},
+        {"softmask", required_argument, nullptr, 1006},
         {nullptr, 0, nullptr, 0}};
     if (argc <= 1) { usage(); return 1; }
     optind = 1;
     int opt;
     bool want_sim = false, multi_query = false, list_records = false;
     std::string seq_arg, species_arg;
+    int softmask = ltg_host::kSoftUpper;
     while ((opt = getopt_long_only(argc, argv, optstring, long_options, nullptr)) != -1) {
         switch (opt) {
         case 'f': f1 = optarg; break;
@@ -199,6 +208,12 @@ int ltg_main(int argc, char* const* argv)
         case 1003: seq_arg = seq_arg.empty() ? std::string(optarg) : seq_arg + "," + optarg; break;
         case 1004: species_arg = optarg; break;
         case 1005: list_records = true; break;
+        case 1006:
+            if (!strcmp(optarg, "upper")) softmask = ltg_host::kSoftUpper;
+            else if (!strcmp(optarg, "n") || !strcmp(optarg, "N")) softmask = ltg_host::kSoftAsN;
+            else if (!strcmp(optarg, "error")) softmask = ltg_host::kSoftError;
+            else { fprintf(stderr, "fasim: --softmask takes upper, n or error\n"); return 2; }
+            break;
         default: break;
         }
     }
@@ -221,17 +236,28 @@ int ltg_main(int argc, char* const* argv)
     }
     auto ends_with = [](const std::string& s, const char* suf) { const size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; };
     std::vector<FastaRecord> recs;
+    int64_t n_lower = 0;                      // soft-masked (lower-case) bases met in -f1
     if (ltg_host::TwoBitFile::is_twobit(f1)) {
         if (ends_with(base, ".2bit")) base = base.substr(0, base.size() - 5);
         std::string err;
-        if (!ltg_host::read_dna_twobit(f1, seq_arg, species_arg.empty() ? base : species_arg, recs, err)) { fprintf(stderr, "fasim: %s\n", err.c_str()); return 2; }
+        if (!ltg_host::read_dna_twobit(f1, seq_arg, species_arg.empty() ? base : species_arg, recs, err, softmask, &n_lower)) { fprintf(stderr, "fasim: %s\n", err.c_str()); return 2; }
     } else {
         if (!seq_arg.empty()) { fprintf(stderr, "fasim: --seq needs a .2bit file as -f1\n"); return 2; }
         if (!read_dna_fasta(f1, recs)) recs.clear();
         if (ends_with(base, ".gz")) base = base.substr(0, base.size() - 3);
         base = base.substr(0, base.size() >= 3 ? base.size() - 3 : 0);
         if (!species_arg.empty()) for (FastaRecord& r : recs) r.species = species_arg;
+        for (FastaRecord& r : recs) n_lower += ltg_host::apply_softmask(r.seq, softmask);
+        if (n_lower > 0 && softmask == ltg_host::kSoftError) {
+            fprintf(stderr, "fasim: %s holds %lld lower-case (soft-masked) bases; choose --softmask upper or --softmask n\n", f1.c_str(), (long long)n_lower);
+            return 2;
+        }
     }
+    if (n_lower > 0 && softmask == ltg_host::kSoftUpper)
+        fprintf(stderr, "fasim: note: %lld lower-case (soft-masked) bases of %s were upper-cased (--softmask upper, the default); the reference "
+                        "scores them as N (--softmask n)\n", (long long)n_lower, f1.c_str());
+    else if (n_lower > 0 && softmask == ltg_host::kSoftAsN)
+        fprintf(stderr, "fasim: note: %lld lower-case (soft-masked) bases of %s are scored as N (--softmask n)\n", (long long)n_lower, f1.c_str());
     if (recs.empty()) { fprintf(stderr, "fasim: cannot read DNA file %s\n", f1.c_str()); return 2; }
     if (list_records) {
         for (const FastaRecord& r : recs)
@@ -277,10 +303,14 @@ int ltg_main(int argc, char* const* argv)
     std::vector<Unit> units;
     {
         const int64_t stride = P.cut_length - P.overlap;
-        // (with at least two lncRNAs per GPU the queue is balanced by the lncRNAs themselves: whole records per job, so that a
-        //  call's pipeline drains once per lncRNA and not once per 10 Mbp)
-        const bool by_query = queries.size() >= 2 * devs.size() && devs.size() > 1;
-        const int64_t kUnitSegments = by_query ? (1ll << 40) / 5000 : 2048, unit_bases = kUnitSegments * (stride > 0 ? stride : 1);
+        // Unit size: large enough that a call's pipeline fill / drain (~10 ms) is noise, small enough that every GPU gets
+        // at least ~8 jobs, so the tail of the queue (the last job of the slowest GPU) stays a small fraction of the run:
+        // 1024 .. 16384 segments (5 .. 80 Mbp), chosen from the total work of the run.
+        int64_t total_segs = 0;
+        if (stride > 0) for (const FastaRecord& r : recs) total_segs += ((int64_t)r.seq.size() + stride - 1) / stride;
+        const int64_t want = total_segs * (int64_t)queries.size() / ((int64_t)devs.size() * 8);
+        const int64_t kUnitSegments = devs.size() > 1 ? std::max<int64_t>(1024, std::min<int64_t>(16384, want)) : 2048;
+        const int64_t unit_bases = kUnitSegments * (stride > 0 ? stride : 1);
         if (stride <= 0) { fprintf(stderr, "fasim: cut length (%d) must exceed the overlap (%d)\n", P.cut_length, P.overlap); return 2; }
         size_t i = 0;
         while (i < recs.size()) {
@@ -411,6 +441,7 @@ int ltg_main(int argc, char* const* argv)
     const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     printf("finished normally\nRunning time is %g\n", secs);
     return 0;
+    });
 }
 
 }  // extern "C"

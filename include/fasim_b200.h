@@ -109,6 +109,11 @@ int ltg_scan_record(ltg_context* ctx, const char* dna, int64_t len, const char* 
 int ltg_scan_records(ltg_context* ctx, int64_t n_records, const char* const* dna, const int64_t* len, const char* const* chr,
                      const int64_t* record_start, ltg_result** out);
 
+/* ltg_scan_records with every record given by a pointer that is either host memory (dna_on_device = 0) or device memory
+ * (1: the records are already resident in HBM — bench.py's device-resident figure for the multi-record example sets).   */
+int ltg_scan_records_at(ltg_context* ctx, int64_t n_records, const void* const* dna, int dna_on_device, const int64_t* len,
+                        const char* const* chr, const int64_t* record_start, ltg_result** out);
+
 /* Same computation with the DNA already resident in HBM (device pointer to `len` ASCII bytes). Used by
  * bench.py for the device-resident throughput figure.                                                  */
 int ltg_scan_device(ltg_context* ctx, const void* d_dna, int64_t len, const char* chr, int64_t record_start,

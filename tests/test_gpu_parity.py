@@ -497,6 +497,98 @@ def test_reference_binary_repeat_rich_chunks(tmp_path):
     assert rows > 1500
 
 
+def _run_reference_and_cli(d, rna_files, chunk_files, flags, extra_cli=()):
+    """Runs the unmodified reference binary (host cores, all (lncRNA, chunk) pairs in parallel) and this build's CLI on the
+    same files; returns ({name: text} reference, {name: text} this build).  One reference process per (lncRNA, chunk)."""
+    from _harness import ref_binary
+    os.makedirs(os.path.join(d, "ref"))
+    os.makedirs(os.path.join(d, "gpu"))
+    procs = [subprocess.Popen([ref_binary(), "-f1", c, "-f2", r, "-O", "ref/"] + flags, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+             for r in rna_files for c in chunk_files]
+    for r in rna_files:
+        for c in chunk_files:
+            out = fb.run_cli(["-f1", c, "-f2", r, "-O", "gpu/"] + flags + list(extra_cli), cwd=d)
+            assert out.returncode == 0, out.stdout + out.stderr
+    for pr in procs:
+        assert pr.wait(timeout=1500) == 0
+    rd = lambda sub: {f: open(os.path.join(d, sub, f)).read() for f in sorted(os.listdir(os.path.join(d, sub)))}
+    return rd("ref"), rd("gpu")
+
+
+def test_reference_binary_planted_bench_chunks(tmp_path):
+    """The PLANTED variant of the headline workload: the bench's 100 Mbp region (seed 1001) with 160 bp of
+    (GA)n carrying 10 % substitutions (SplitMix64 stream 3001) written over offset 500 000 of every Mbp, against the bench's
+    3 kb lncRNA with three 200-nt (CT) / (GA) / (GT) tracts at 500 / 1500 / 2500 -> overflows >= 251, long runs of hits, top-50
+    truncation.  Six 250 kb chunks centred on planted sites, every output file byte-equal to the unmodified reference."""
+    from _harness import ref_binary
+    if not os.path.exists(ref_binary()):
+        pytest.skip("oracle/_ref/fasim not built")
+    import bench
+    rna = list(splitmix_bases(2001, 3000))
+    for at, unit in ((500, "CT"), (1500, "GA"), (2500, "GT")):
+        rna[at:at + 200] = unit * 100
+    rna = "".join(rna)
+    sub = splitmix_bases(3001, 160 * 100)
+    d = str(tmp_path)
+    open(os.path.join(d, "rna.fa"), "w").write(">synRNA3kP\n%s\n" % rna)
+    chunk_files = []
+    for k, mbp in enumerate((0, 17, 38, 55, 76, 99)):
+        lo = mbp * 1_000_000 + 375_000
+        dna = list(bench.splitmix_bases(1001, 250_000, lo).tobytes().decode())
+        tract = list("GA" * 80)
+        for i in range(160):
+            z = sub[mbp * 160 + i]
+            if (ord(z) * 7 + i) % 10 == 0:                   # ~10 % substitutions, deterministic
+                tract[i] = z
+        at = mbp * 1_000_000 + 500_000 - lo
+        dna[at:at + 160] = tract
+        name = "p%02d.fa" % k
+        open(os.path.join(d, name), "w").write(">syn|chr1|%d-%d\n%s\n" % (lo + 1, lo + 250_000, "".join(dna)))
+        chunk_files.append(name)
+    ref, got = _run_reference_and_cli(d, ["rna.fa"], chunk_files, [])
+    assert sorted(ref) == sorted(got) and len(ref) == 3 * len(chunk_files)
+    rows = 0
+    for f in ref:
+        assert got[f] == ref[f], f
+        rows += len(ref[f].splitlines()) - 1 if f.endswith("TFOsorted") else 0
+    assert rows > 300
+
+
+def test_reference_binary_multi_query_inputs(tmp_path):
+    """BASELINE.json configs[4] inputs (DNA seed 1002, lncRNAs of 1000 + z % 9001 nt from seeds 4001..4004)
+    through the multi-query work-queue path (`--queries --devices 0,0`): every lncRNA's files equal the unmodified reference
+    run on that lncRNA alone (one reference process per lncRNA; the reference reads one lncRNA per run)."""
+    from _harness import ref_binary
+    if not os.path.exists(ref_binary()):
+        pytest.skip("oracle/_ref/fasim not built")
+    import bench
+    qs = bench.synthetic_queries(4)
+    dna = list(bench.splitmix_bases(1002, 120_000, 7 * 4900).tobytes().decode())
+    for k, (_, r) in enumerate(qs):                        # one planted target per lncRNA so that every output has rows
+        at = 9_000 + 27_000 * k
+        dna[at:at + 90] = r[200:290].translate(str.maketrans("TG", "AT"))
+    d = str(tmp_path)
+    open(os.path.join(d, "dna.fa"), "w").write(">syn|chr1|%d-%d\n%s\n" % (7 * 4900 + 1, 7 * 4900 + len(dna), "".join(dna)))
+    open(os.path.join(d, "all.fa"), "w").write("".join(">%s\n%s\n" % (n, r) for n, r in qs))
+    os.makedirs(os.path.join(d, "ref"))
+    os.makedirs(os.path.join(d, "gpu"))
+    procs = []
+    for n, r in qs:
+        open(os.path.join(d, n + ".fa"), "w").write(">%s\n%s\n" % (n, r))
+        procs.append(subprocess.Popen([ref_binary(), "-f1", "dna.fa", "-f2", n + ".fa", "-O", "ref/", "-lg", "30"], cwd=d,
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    out = fb.run_cli(["-f1", "dna.fa", "-f2", "all.fa", "-O", "gpu/", "-lg", "30", "--queries", "--devices", "0,0"], cwd=d)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for pr in procs:
+        assert pr.wait(timeout=1500) == 0
+    names = sorted(os.listdir(os.path.join(d, "ref")))
+    assert len(names) == 3 * len(qs) and names == sorted(os.listdir(os.path.join(d, "gpu")))
+    for f in names:
+        assert open(os.path.join(d, "gpu", f)).read() == open(os.path.join(d, "ref", f)).read(), f
+        if f.endswith("TFOsorted"):
+            assert len(open(os.path.join(d, "ref", f)).read().splitlines()) > 1, f
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_1mbp(engine):
     """Size-independent properties at bench scale (1 Mbp x 3 kb): determinism, shard-invariance (scanning the region as

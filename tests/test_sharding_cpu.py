@@ -85,3 +85,67 @@ def test_two_rank_gloo_gather_and_reductions():
     assert [r["start"] for r in merged] == [s for s, _ in segs]              # rank order == segment order
     assert tmax == 11.0
     assert cells == float(sum(l for _, l in segs))
+
+
+def _queue_worker(rank, world, port, n_jobs, q):
+    """bench.py's multi-query path on CPU: every rank pulls (lncRNA, DNA part) jobs from ONE atomic counter (the c10d
+    store's fetch-and-add) and ships its result blobs to rank 0 through gather_object on a gloo group."""
+    import pickle
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    queue = bench.JobQueue(dist)
+    seen = []
+    for epoch in range(2):                      # two "steps": the counter restarts under a new key
+        queue.reset()
+        mine = []
+        while True:
+            j = queue.next()
+            if j >= n_jobs:
+                break
+            mine.append(j)
+        payload = pickle.dumps([(b"x" * bench.TRI_BYTES * len(mine), bytes(mine))])
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(payload, gathered, dst=0)
+        if rank == 0:
+            jobs = sorted(j for pl in gathered for _, text in pickle.loads(pl) for j in text)
+            seen.append(jobs)
+        dist.barrier()
+    if rank == 0:
+        q.put(seen)
+    dist.destroy_process_group()
+
+
+def test_two_rank_atomic_job_queue():
+    n_jobs, world = 37, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_queue_worker, args=(r, world, port, n_jobs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    seen = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert seen == [list(range(n_jobs))] * 2                                 # every job exactly once per step
+
+
+def test_bench_workload_definitions():
+    """The synthetic workloads are the ones SURVEY.md 8(d) pins: generator, seeds, lncRNA lengths, cell counts."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from _harness import splitmix_bases
+    assert bench.splitmix_bases(1001, 64).tobytes().decode() == splitmix_bases(1001, 64)
+    assert bench.splitmix_bases(1001, 10, 54).tobytes().decode() == splitmix_bases(1001, 64)[54:]
+    qs = bench.synthetic_queries(64)
+    assert len(qs) == 64 and all(1000 <= len(s) <= 10000 for _, s in qs)
+    assert abs(sum(len(s) for _, s in qs) - 3.5e5) < 0.5e5                   # SURVEY: sum of m ~ 3.5e5
+    assert bench.region_cells(100_000_000, 3000) == 102_040_800 * 3000 * 48  # 20 408 full segments + one of 800 bp
+    for name in ("demo", "meg3", "h19", "malat1", "neat1"):
+        wl, rn, rna, recs, flags, params = bench.real_config(name)
+        assert len(rna) > 1000 and len(recs) in (1, 532)
