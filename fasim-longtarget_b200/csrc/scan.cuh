@@ -127,8 +127,12 @@ struct ScanArgs {
     const uint32_t* profiles;   // [pair][strip][5*32*R]
     int n_strips;
     int max_len;                // row pitch of colmax / bnd (>= longest segment)
-    uint32_t* colmax;           // [item][granule][max_len] packed column maxima of the two tasks, one row per granule of
-                                // kGranRows RNA rows (n_strips * 32 * R / kGranRows granules per item)
+    uint32_t* colmax_all;       // [item][max_len] packed column maxima of the two tasks over ALL RNA rows (exact, what ssw_pre_align
+                                // reports before the Q2 truncation)
+    uint16_t* blkmax;           // [item][granule][blk_pitch] per granule of kGranRows RNA rows (n_strips * 32 * R / kGranRows per item) and
+                                // per block of kBlkCols wavefront steps: the maxima of the two tasks, saturated to 8 bits each
+                                // (task 0 in the low byte) — upper bounds for the window stage's row pruning and the Q4 pre-filter
+    int blk_pitch;
     uint2* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F)
     int* counter;               // work queue head
     // Q4 probe variant (k_scan<R, W, true>): no column maxima are written; per item the largest F value carried into a
@@ -139,10 +143,25 @@ struct ScanArgs {
     int stripe_len;             // ceil(m / 16)
 };
 
+// The column maxima are kept PER GRANULE of kGranRows / R lanes (kGranRows RNA rows; the running maximum that travels
+// along the lanes restarts at every granule head and the granule's last lane — its "tail" — holds the granule's maximum of
+// a column).  Nothing of that is written per cell column any more: the tail lanes park the values in a shared-memory ring;
+// once per 32 steps the warp folds the granules of the 32 columns that just became complete into the exact whole-column
+// maximum (one coalesced 128-byte row update), and each tail lane keeps a running maximum over blocks of kBlkCols steps
+// that it stores as two saturated bytes.  Block b of the granule whose tail is lane t covers the columns
+// [kBlkCols * b - t, kBlkCols * b - t + kBlkCols) (the wavefront skew), see blk_of().
+constexpr int kGranRows = 128;                   // RNA rows per granule (kGranRows / R lanes; 32 * R / kGranRows granules per strip)
+constexpr int kBlkCols = 16;
+__host__ __device__ inline int blk_pitch_for(int max_len) { return (max_len + 31 + kBlkCols - 1) / kBlkCols + 1; }
+// tail lane of granule g of an item (the lane layout repeats in every strip)
+__host__ __device__ inline int gran_tail_lane(int g, int scan_r) { const int gl = kGranRows / scan_r, gps = 32 / gl; return (g % gps) * gl + gl - 1; }
+// block that holds column j of a granule with tail lane t
+__host__ __device__ inline int blk_of(int j, int tail_lane) { return (j + tail_lane) / kBlkCols; }
+
 template <int R>
 __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
 {
-    return 5 * 32 * R * 4 + 32 * 8 + ((max_len + 64 + 15) / 16) * 16;
+    return 5 * 32 * R * 4 + 32 * 8 + (32 / (kGranRows / R)) * 64 * 4 + ((max_len + 64 + 15) / 16) * 16;
 }
 
 // E update: fused VIADDMNMX (2 ALU-pipe slots) or VIADD on the FMA pipe + VIMNMX (1 ALU-pipe slot); the split form
@@ -168,12 +187,6 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
         hlast = h_;                                               \
     }
 
-// The column maxima are kept PER GRANULE of kGranRows / R lanes (kGranRows RNA rows; the running maximum that
-// travels along the lanes restarts at every granule head and the granule's last lane stores it): the epilogue
-// combines them into the reference's per-column maximum, and the window stage uses them as upper bounds to
-// skip RNA rows that cannot hold a window's best cell (window.cuh, "row pruning").
-constexpr int kGranRows = 128;                   // RNA rows per granule (kGranRows / R lanes; 32 * R / kGranRows granules per strip)
-
 template <int R, int WARPS, bool PROBE = false>
 __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 {
@@ -183,7 +196,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
     const int warp_bytes = scan_warp_smem_bytes<R>(a.max_len);
     uint4* s_prof = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(smem_u4) + (size_t)wib * warp_bytes);
     uint2* s_ring = reinterpret_cast<uint2*>(s_prof + 5 * (R / 4) * 32);
-    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_ring + 32);
+    constexpr int kGranLanes = kGranRows / R, kGranPerStrip = 32 / kGranLanes;
+    static_assert(kGranLanes >= 1 && kGranLanes * R == kGranRows, "R must divide the granule");
+    uint32_t* s_cring = reinterpret_cast<uint32_t*>(s_ring + 32);          // [granule of the strip][step & 63] granule maxima in flight
+    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_cring + kGranPerStrip * 64);
     uint2* bnd = a.bnd + (size_t)(blockIdx.x * WARPS + wib) * a.max_len;
     const uint32_t kNegOpen = 0xFFF0FFF0u, kNegExt = 0xFFFCFFFCu;
     constexpr int PLANE = (R / 4) * 32;     // uint4 per base-code plane
@@ -204,9 +220,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             const int j = i - 32;
             s_codes[i] = (j < 0 || j >= n) ? (uint8_t)kBaseOther : gcodes[rev ? (n - 1 - j) : j];
         }
-        constexpr int kGranLanes = kGranRows / R, kGranPerStrip = 32 / kGranLanes;
-        static_assert(kGranLanes >= 1 && kGranLanes * R == kGranRows, "R must divide the granule");
-        uint32_t* cm_item = a.colmax + (size_t)item * a.n_strips * kGranPerStrip * a.max_len;
+        uint32_t* cm_all = a.colmax_all + (size_t)item * a.max_len;
+        uint16_t* blk_item = a.blkmax + (size_t)item * a.n_strips * kGranPerStrip * a.blk_pitch;
         const bool gran_head = (lane & (kGranLanes - 1)) == 0, gran_tail = (lane & (kGranLanes - 1)) == kGranLanes - 1;
 
         uint32_t fb = 0;                                           // PROBE: running maximum of the carried F values
@@ -235,8 +250,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
             __syncwarp();
             const bool first = (strip == 0), last = (strip == a.n_strips - 1);
-            // this lane's granule row, biased so that cm_lane[s] is the slot of the column it finishes at step s
-            uint32_t* cm_lane = cm_item + ((size_t)strip * kGranPerStrip + (lane / kGranLanes)) * a.max_len - lane;
+            // this lane's granule: its row of block maxima, and its row of the ring
+            uint16_t* blk_row = blk_item + ((size_t)strip * kGranPerStrip + (lane / kGranLanes)) * a.blk_pitch;
+            uint32_t blk = 0;
             uint32_t Hd[R], E[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
@@ -250,6 +266,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             const uint32_t sa_prof = (uint32_t)__cvta_generic_to_shared(s_prof) + lane * 16;
             const uint32_t sa_code = (uint32_t)__cvta_generic_to_shared(s_codes) + (32 - lane);
             const uint32_t sa_ring = (uint32_t)__cvta_generic_to_shared(s_ring);
+            const uint32_t sa_cring = (uint32_t)__cvta_generic_to_shared(s_cring);
+            const uint32_t sa_cmine = sa_cring + (lane / kGranLanes) * 256;        // this lane's granule row of the ring
             uint4 sc[R / 4];
             uint32_t xn;
             {
@@ -261,7 +279,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sc[k].x), "=r"(sc[k].y), "=r"(sc[k].z), "=r"(sc[k].w) : "r"(ad + k * 512));
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(xn) : "r"(sa_code + 1));
             }
-            uint32_t* cm_ptr = cm_lane;                           // cm_ptr[0] is this lane's slot for step s
             uint2* bnd_ptr = bnd - 31;                            // bnd_ptr[0] is lane 31's slot for step s
             const bool st_bnd = (lane == 31) && !last;
 
@@ -304,12 +321,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 hdiag = hin;                                                                                    \
                 hout = hlast; fout = f; cmout = cm;                                                             \
                 if (GUARD) {                                                                                    \
-                    if (!PROBE && gran_tail && (S) >= lane && (S) - lane < n) cm_ptr[(K)] = cm;                 \
+                    if (!PROBE) {                                                                               \
+                        const uint32_t cmv = ((S) >= lane && (S) - lane < n) ? cm : 0u;                         \
+                        if (gran_tail) asm volatile("st.shared.u32 [%0], %1;" :: "r"(sa_cmine + (((S) & 63) << 2)), "r"(cmv) : "memory"); \
+                        blk = __vmaxs2(blk, cmv);                                                               \
+                    }                                                                                           \
                     if (st_bnd && (S) >= 31 && (S) - 31 < n) bnd_ptr[(K)] = make_uint2(hout, fout);             \
                 } else {                                                                                        \
-                    if (!PROBE && gran_tail) cm_ptr[(K)] = cm;                                                  \
+                    if (!PROBE) {                                                                               \
+                        if (gran_tail) asm volatile("st.shared.u32 [%0], %1;" :: "r"(sa_cmine + (((S) & 63) << 2)), "r"(cm) : "memory"); \
+                        blk = __vmaxs2(blk, cm);                                                                \
+                    }                                                                                           \
                     if (st_bnd) bnd_ptr[(K)] = make_uint2(hout, fout);                                          \
                 }                                                                                               \
+            }
+            // block maximum of the last kBlkCols steps: two saturated bytes (task 0 low)
+#define LTG_BLK_STORE(S)                                                                                        \
+            if (!PROBE) {                                                                                       \
+                if (gran_tail) blk_row[(S) / kBlkCols] = (uint16_t)__byte_perm(__vminu2(blk, 0x00FF00FFu), 0u, 0x4420); \
+                blk = 0;                                                                                        \
             }
 
             for (int s0 = 0; s0 < steps; s0 += 32) {
@@ -322,15 +352,42 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                     __syncwarp();
                 }
                 if (s0 >= 32 && s0 + 33 < n) {
+                    static_assert(kBlkCols == 16, "two blocks per 32 steps");
 #pragma unroll 4
-                    for (int k = 0; k < 32; ++k) LTG_SCAN_STEP(false, s0 + k, k)
+                    for (int k = 0; k < 16; ++k) LTG_SCAN_STEP(false, s0 + k, k)
+                    LTG_BLK_STORE(s0)
+#pragma unroll 4
+                    for (int k = 16; k < 32; ++k) LTG_SCAN_STEP(false, s0 + k, k)
+                    LTG_BLK_STORE(s0 + 16)
                 } else {
                     const int cnt = min(32, steps - s0);
-                    for (int k = 0; k < cnt; ++k) LTG_SCAN_STEP(true, s0 + k, k)
+                    for (int k = 0; k < cnt; ++k) {
+                        LTG_SCAN_STEP(true, s0 + k, k)
+                        if ((k & (kBlkCols - 1)) == kBlkCols - 1 || k == cnt - 1) { LTG_BLK_STORE(s0 + k) }
+                    }
                 }
-                cm_ptr += 32; bnd_ptr += 32;
+                bnd_ptr += 32;
+                if (!PROBE) {
+                    // the 32 columns s0-31 .. s0 are complete in this strip (every granule tail has passed them): fold the
+                    // granules into the whole-column maximum; one column per lane, one coalesced row update
+                    __syncwarp();
+                    const int j = s0 - 31 + lane;
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int q = 0; q < kGranPerStrip; ++q) {
+                        uint32_t x;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(sa_cring + q * 256 + (((j + q * kGranLanes + kGranLanes - 1) & 63) << 2)));
+                        v = __vmaxs2(v, x);
+                    }
+                    if (j >= 0 && j < n) {
+                        if (!first) v = __vmaxs2(v, cm_all[j]);
+                        cm_all[j] = v;
+                    }
+                    __syncwarp();
+                }
             }
 #undef LTG_SCAN_STEP
+#undef LTG_BLK_STORE
         }
         if (PROBE) {
 #pragma unroll

@@ -12,4 +12,4 @@ for cfg in demo meg3 h19 malat1 neat1; do
 done
 timeout 900 python bench.py --queries 8 --region-mbp 10 --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_mq8.json 2> gpurun_out/${TAG}_bench_mq8.err; echo "bench mq8 rc=$?"
 cat gpurun_out/${TAG}_bench*.json | cut -c1-1500
-tail -3 gpurun_out/${TAG}_bench*.err
+for f in gpurun_out/${TAG}_bench*.err; do tail -n 3 $f; done
