@@ -94,8 +94,11 @@ inline int choose_scan_r(int m)
     return pad32 * 100 <= pad16 * 104 ? 32 : 16;      // R = 32 is ~4.5 % faster per row
 #endif
 }
-constexpr int kBatchSegments = 1024;
-constexpr size_t kStripBytesPerBatch = 16ull << 30;     // cap of the granule-maxima buffer of one batch
+#ifndef LTG_BATCH_SEGMENTS
+#define LTG_BATCH_SEGMENTS 2048
+#endif
+constexpr int kBatchSegments = LTG_BATCH_SEGMENTS;
+constexpr size_t kStripBytesPerBatch = 8ull << 30;      // cap of the column-maxima buffers (whole-column rows + block maxima) of one batch
 
 struct HostSeg {
     int64_t start;      // offset in the device DNA buffer of this call (records are laid out back to back)
@@ -142,7 +145,8 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
-    bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true;
+    bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true, floor_s = true;
+    int batch_segments = kBatchSegments;                  // segments per device batch (LTG_BATCH_SEGMENTS)
     int lit_rows_per_chunk = 24, lit_min_chunks = 0;      // tuning of the column-parallel literal kernel (LTG_LIT_ROWS / LTG_LIT_CH)
     int64_t n_probe_items = 0;          // pairs swept a second time by the Q4 probe (diagnostics)
     cudaStream_t stream = nullptr, copy_stream = nullptr, lit_stream = nullptr;
@@ -161,7 +165,7 @@ struct ltg_context {
     bool profiles_dirty = true;
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
     // record / batch buffers
-    DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_colmax, d_bnd, d_counters;
+    DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_blkmax, d_bnd, d_counters;
     DevBuf d_probe_items, d_probe_orig, d_probe_out, d_bnd_gran;
     int n_bnd_gran = 0;                 // granules that hold the rows just above a stripe start (Q4 pre-filter)
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
@@ -344,7 +348,7 @@ struct ProbeOut {
 };
 
 // probe_out != nullptr: the Q4 probe variant (no column maxima; per item the largest F carried into a stripe start)
-int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax,
+int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax_all, uint16_t* blkmax,
                 uint32_t* probe_out = nullptr, const int* task_jstar = nullptr)
 {
     const int R = c->scan_r;
@@ -357,7 +361,8 @@ int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_le
     ScanArgs a;
     a.codes = c->d_codes.as<uint8_t>(); a.segs = c->d_segs.as<SegDesc>(); a.items = d_items;
     a.n_items = n_items; a.profiles = prof; a.n_strips = c->n_strips; a.max_len = max_len;
-    a.colmax = colmax; a.bnd = c->d_bnd.as<uint2>(); a.counter = counters + kCntScan;
+    a.colmax_all = colmax_all; a.blkmax = blkmax; a.blk_pitch = blk_pitch_for(max_len);
+    a.bnd = c->d_bnd.as<uint2>(); a.counter = counters + kCntScan;
     a.probe_out = probe_out; a.task_jstar = task_jstar; a.tasks_per_seg = (int)c->tasks.size(); a.stripe_len = (c->m + 15) / 16;
     if (probe_out) {
         if (R == 32) {
@@ -451,7 +456,7 @@ int literal_windows(ltg_context* c, const WinState& w, bool reverse, int round)
 }
 
 // ---------------- window stage: peaks (device-resident pool) -> chosen alignments -> traceback pass 1 ----------------
-int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint32_t* gran_colmax, int max_len, HostBatch* hb, bool dead_rule)
+int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint16_t* gran_blk, int max_len, HostBatch* hb, bool dead_rule)
 {
     for (int k = 0; k < 20; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
     const int pc_cap = 4 * n_peaks;          // kMaxRuns pieces per peak at most
@@ -477,7 +482,8 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.rna_ssw = c->d_rna_ssw.as<uint8_t>(); w.rna_sel = c->d_rna_sel.as<uint16_t>(); w.m = c->m; w.cut_table = c->d_cut.as<int>();
     w.cell_counter = reinterpret_cast<long long*>(counters + kCntCells);
     w.forced_cut = forced_cut;
-    w.gran_colmax = c->prune ? gran_colmax : nullptr; w.n_gran = c->n_strips * (32 * c->scan_r / kGranRows); w.gran_rows = kGranRows; w.max_len = max_len;
+    w.gran_blk = c->prune ? gran_blk : nullptr; w.n_gran = c->n_strips * (32 * c->scan_r / kGranRows); w.gran_rows = kGranRows;
+    w.blk_pitch = blk_pitch_for(max_len); w.scan_r = c->scan_r; w.floor_s = c->floor_s ? 1 : 0;
     w.n_pairs = (int)c->pairs.size();
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntCells, 0, 8, c->stream));
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntLitTotal, 0, sizeof(int), c->stream));
@@ -502,7 +508,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
         c->launches += 2;
     };
     for (int round = 0; round < 4; ++round) {
-        for (int retry = 0; retry < (w.gran_colmax ? 2 : 1); ++retry) {
+        for (int retry = 0; retry < (w.gran_blk ? 2 : 1); ++retry) {
             schedule(round, retry);
             sweep(false);
         }
@@ -630,7 +636,8 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     if (int e = c->d_segs.ensure(sizeof(SegDesc) * S)) return e;
     if (int e = c->d_items.ensure(sizeof(ScanItem) * n_items)) return e;
     const int n_gran = c->n_strips * (32 * c->scan_r / kGranRows);
-    if (int e = c->d_colmax.ensure((size_t)n_items * n_gran * max_len * 4)) return e;
+    const int blk_pitch = blk_pitch_for(max_len);
+    if (int e = c->d_blkmax.ensure((size_t)n_items * n_gran * blk_pitch * sizeof(uint16_t))) return e;
     if (int e = c->d_colmax_all.ensure((size_t)n_items * max_len * 4)) return e;
     if (int e = c->d_task_info.ensure(sizeof(int) * 5 * (size_t)n_tasks)) return e;
     if (int e = c->d_task_off.ensure(sizeof(int) * ((size_t)n_tasks + 1))) return e;
@@ -662,20 +669,23 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
         const int ns = (int)sitems.size();
         if (int e = c->d_items_stats.ensure(sizeof(ScanItem) * (size_t)std::max(ns, 1))) return e;
         LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_items_stats.p, sitems.data(), sizeof(ScanItem) * (size_t)ns, cudaMemcpyHostToDevice, c->stream));
-        if (int e = launch_scan(c, c->d_items_stats.as<ScanItem>(), ns, max_len, c->d_prof_stats.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
-        k_rowmax<<<(ns * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_colmax.as<uint32_t>(), c->d_items_stats.as<ScanItem>(), c->d_segs.as<SegDesc>(),
-                                                              ns, n_gran, max_len, T, c->d_stats_max.as<int>());
+        if (int e = launch_scan(c, c->d_items_stats.as<ScanItem>(), ns, max_len, c->d_prof_stats.as<uint32_t>(), c->d_colmax_all.as<uint32_t>(),
+                                c->d_blkmax.as<uint16_t>())) return e;
+        k_rowmax<<<(ns * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_colmax_all.as<uint32_t>(), c->d_items_stats.as<ScanItem>(), c->d_segs.as<SegDesc>(),
+                                                              ns, 1, max_len, T, c->d_stats_max.as<int>());
         c->launches += 1;
         stats_max = c->d_stats_max.as<int>();
         LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));          // `sitems` is host memory of this scope
     }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[4], c->stream));
-    if (int e = launch_scan(c, c->d_items.as<ScanItem>(), n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax.as<uint32_t>())) return e;
+    if (int e = launch_scan(c, c->d_items.as<ScanItem>(), n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax_all.as<uint32_t>(),
+                            c->d_blkmax.as<uint16_t>())) return e;
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[5], c->stream));
 
     // peaks: statistics + count, literal re-runs, count of those, exclusive scan, write
     EpiArgs ea;
-    ea.colmax = c->d_colmax.as<uint32_t>(); ea.n_gran = n_gran; ea.colmax_all = c->d_colmax_all.as<uint32_t>(); ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
+    ea.blkmax = c->d_blkmax.as<uint16_t>(); ea.n_gran = n_gran; ea.blk_pitch = blk_pitch; ea.scan_r = c->scan_r;
+    ea.colmax_all = c->d_colmax_all.as<uint32_t>(); ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
     ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
     ea.item_orig = nullptr; ea.probe = nullptr;
     ea.bnd_gran = (c->q4_probe && c->n_bnd_gran > 0) ? c->d_bnd_gran.as<int>() : nullptr; ea.n_bnd_gran = c->n_bnd_gran;
@@ -709,7 +719,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
             if (int e = c->d_probe_out.ensure(sizeof(uint32_t) * (size_t)np)) return e;
             LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_probe_items.p, pitems.data(), sizeof(ScanItem) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
             LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_probe_orig.p, porig.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
-            if (int e = launch_scan(c, c->d_probe_items.as<ScanItem>(), np, max_len, c->d_prof_ssw.as<uint32_t>(), nullptr,
+            if (int e = launch_scan(c, c->d_probe_items.as<ScanItem>(), np, max_len, c->d_prof_ssw.as<uint32_t>(), nullptr, nullptr,
                                     c->d_probe_out.as<uint32_t>(), ti.jstar)) return e;
             EpiArgs pa = ea;
             pa.items = c->d_probe_items.as<ScanItem>(); pa.item_orig = c->d_probe_orig.as<int>(); pa.probe = c->d_probe_out.as<uint32_t>();
@@ -823,7 +833,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     }
     if (want_alignments && n_peaks > 0) {
         LTG_CUDA_CHECK(cudaEventRecord(hb.ev[2], c->stream));
-        if (int e = run_windows(c, n_peaks, T, nullptr, lit_mode == kLitOnly ? nullptr : c->d_colmax.as<uint32_t>(), max_len, &hb, true)) return e;
+        if (int e = run_windows(c, n_peaks, T, nullptr, lit_mode == kLitOnly ? nullptr : c->d_blkmax.as<uint16_t>(), max_len, &hb, true)) return e;
         if (int e = run_traceback(c, c->d_jobs.as<TraceJob>(), n_peaks, c->d_tout.as<TraceOut>(), nullptr, true)) return e;
         LTG_CUDA_CHECK(cudaEventRecord(hb.ev[3], c->stream));
         hb.timed_windows = true;
@@ -1141,8 +1151,9 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
 
         // batch size: bounded by the strip-maxima buffer; at least two batches when there is enough work so that the
         // host phase of one overlaps the device phase of the next
-        const size_t per_seg = (size_t)c->pairs.size() * c->n_strips * (32 * c->scan_r / kGranRows) * (size_t)((c->params.cut_length + 3) & ~3) * 4;
-        size_t bs = std::max<size_t>(16, std::min<size_t>(kBatchSegments, kStripBytesPerBatch / std::max<size_t>(1, per_seg)));
+        const int cutp = (c->params.cut_length + 3) & ~3;
+        const size_t per_seg = (size_t)c->pairs.size() * ((size_t)c->n_strips * (32 * c->scan_r / kGranRows) * blk_pitch_for(cutp) * sizeof(uint16_t) + (size_t)cutp * 4);
+        size_t bs = std::max<size_t>(16, std::min<size_t>((size_t)c->batch_segments, kStripBytesPerBatch / std::max<size_t>(1, per_seg)));
         // equal-sized batches (a short last batch would expose its drain and host tail): 2551 segments -> 3 x 851, not 1024 + 1024 + 503
         if (!active.empty()) {
             size_t nbatch = (active.size() + bs - 1) / bs;
@@ -1304,6 +1315,9 @@ int ltg_create(int device, ltg_context** out)
     // LTG_NO_SKIP=1 runs every window round of fastSIM's loop even when it provably repeats the previous result
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
+    // LTG_NO_FLOORS=1: the first window sweep tracks every cell above the pruning bound, not only those reaching the peak score
+    if (const char* e = getenv("LTG_NO_FLOORS")) c->floor_s = atoi(e) == 0;
+    if (const char* e = getenv("LTG_BATCH_SEGMENTS")) c->batch_segments = std::max(16, atoi(e));
     if (const char* e = getenv("LTG_LIT_OLD")) c->lit_col = atoi(e) == 0;
     if (const char* e = getenv("LTG_LIT_ROWS")) c->lit_rows_per_chunk = std::max(4, atoi(e));
     if (const char* e = getenv("LTG_LIT_CH")) c->lit_min_chunks = atoi(e);
@@ -1326,7 +1340,7 @@ void ltg_destroy(ltg_context* c)
         for (int i = 0; i < 6; ++i) if (hb.ev[i]) cudaEventDestroy(hb.ev[i]);
     }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_rna_sel, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
-                      &c->d_segs, &c->d_items, &c->d_items_stats, &c->d_colmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
+                      &c->d_segs, &c->d_items, &c->d_items_stats, &c->d_blkmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
                       &c->d_stats_max, &c->d_task_litrow, &c->d_cand, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs, &c->d_side_jobs, &c->d_side_colmax})

@@ -405,15 +405,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 // 8-bit "stop recording" truncation (Q2), threshold-hit compaction and run merge to peaks
 // (ssw_cpp.cpp:446-572).  One warp per item; hits are found with __ballot_sync and consumed in column
 // order.  Three passes:
-//   mode 0  granule maxima -> per-column maximum (one compact row per item), statistics of every task + peak COUNT of
-//           the tasks that stay on the exact path
+//   mode 0  statistics of every task (maximum, threshold, first overflow column, Q4 pre-filter) + peak COUNT of the tasks
+//           that stay on the exact path
 //   mode 1  peak count of the tasks re-run by the literal emulation (Q4 guard)
 //   (exclusive scan of the counts -> one contiguous, position-ordered slice of the peak pool per task)
 //   mode 2  peaks written, 32 at a time, one lane per peak
 struct EpiArgs {
-    const uint32_t* colmax;      // [item][granule][max_len]
+    const uint16_t* blkmax;      // [item][granule][blk_pitch] saturated block maxima of the scan (Q4 pre-filter)
     int n_gran;                  // granule rows per item
-    uint32_t* colmax_all;        // [item][max_len] maximum over the granules (written by mode 0, read by modes 1 and 2)
+    int blk_pitch, scan_r;
+    const uint32_t* colmax_all;  // [item][max_len] exact column maxima over all rows (written by the scan)
     const uint16_t* lit_colmax;  // [literal row][lit_pitch] column maxima of the literal re-runs
     int lit_pitch;
     const int* task_litrow;      // [task] row in lit_colmax (valid when the task carries kTaskLiteral)
@@ -460,18 +461,9 @@ __global__ void k_epilogue(const EpiArgs a)
     const SegDesc sd = a.segs[it.seg];
     const int n = sd.len;
     const int row = (a.mode == 3) ? a.item_orig[warp] : warp;
-    const uint32_t* cm = a.colmax + (size_t)row * a.n_gran * a.max_len;
-    uint32_t* cm_all = a.colmax_all + (size_t)row * a.max_len;
+    const uint16_t* blk = a.blkmax + (size_t)row * a.n_gran * a.blk_pitch;
+    const uint32_t* cm_all = a.colmax_all + (size_t)row * a.max_len;
     const PairDef pd = c_pairs[it.pair];
-    if (a.mode == 0) {
-        // column maximum over all granules, as the reference's scan reports it
-        for (int j = lane; j < n; j += 32) {
-            uint32_t v = cm[j];
-            for (int k = 1; k < a.n_gran; ++k) v = __vmaxs2(v, cm[(size_t)k * a.max_len + j]);
-            cm_all[j] = v;
-        }
-        __syncwarp();
-    }
     for (int h = 0; h < 2; ++h) {
         if (h == 1 && pd.task[1] == pd.task[0]) break;
         const int task = it.seg * a.tasks_per_seg + pd.task[h];
@@ -496,12 +488,16 @@ __global__ void k_epilogue(const EpiArgs a)
             // the reference still processes: without such a cell in the granules that hold those rows the task stays exact
             bool q4 = mx >= kQ4Guard;
             if (q4 && a.bnd_gran) {
+                // (block maxima: upper bounds over 16-column blocks, saturated at 255 — coarser than per column, never smaller)
                 int near = 0;
                 const int jend = min(jstar + 1, n);
-                for (int j = lane; j < jend; j += 32) {
-                    uint32_t v = 0;
-                    for (int k = 0; k < a.n_bnd_gran; ++k) v = __vmaxs2(v, cm[(size_t)a.bnd_gran[k] * a.max_len + j]);
-                    near = max(near, h ? hi16(v) : lo16(v));
+                for (int k = 0; k < a.n_bnd_gran; ++k) {
+                    const int g = a.bnd_gran[k], tl = gran_tail_lane(g, a.scan_r);
+                    const uint16_t* rowp = blk + (size_t)g * a.blk_pitch;
+                    for (int b = blk_of(0, tl) + lane; b <= blk_of(jend - 1, tl); b += 32) {
+                        const int v = rowp[b];
+                        near = max(near, h ? (v >> 8) : (v & 0xff));
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) near = max(near, __shfl_xor_sync(0xffffffffu, near, o));

@@ -95,8 +95,11 @@ struct WinState {
     const int* cut_table;   // [256][4]  cut length per (peak score, round) — fastsim.h:210 evaluated in float32 on the host
     long long* cell_counter;
     const int* forced_cut;  // probe path: explicit window length per peak (nullptr in the product path)
-    // granule maxima of the scan stage (nullptr: no pruning, every window streams the whole lncRNA)
-    const uint32_t* gran_colmax; int n_gran; int gran_rows; int max_len; int n_pairs;
+    // saturated block maxima per granule of the scan stage (scan.cuh; nullptr: no pruning, every window streams the whole lncRNA)
+    const uint16_t* gran_blk; int n_gran; int gran_rows; int blk_pitch; int n_pairs; int scan_r;
+    // 1: the first sweep of round 0 only tracks cells that reach the peak score (what an accepted window needs, fastsim.h:218);
+    // a window that stays below it gets its position from the re-planned sweep (fewer slow-path trips of the tracker)
+    int floor_s;
 };
 
 // rows spanned by a positive-score local alignment over `cols` columns: < 2.25 * cols + 1
@@ -114,16 +117,17 @@ __device__ inline int win_key(int len, int rows)
 // round >= 0, retry 0: forward plan for round `round` (row range from the bound L = peak score);
 // round >= 0, retry 1: windows whose pruned result fell short of the value that proves it exact, re-planned with
 //                      L = that result; round < 0: reverse plan over the chosen alignments.
-// 8 threads cooperate on one peak (the granule-bound scan reads n_gran * cut column maxima).
+// 8 threads cooperate on one peak (each reads the block maxima of every eighth granule).
 __global__ void k_win_plan(const WinState w, int round, int retry)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 3, sub = gt & 7;
     bool active = i < w.n_peaks;
-    int len = 0, rows = 0, bound = 0, proven = 0;
+    int len = 0, rows = 0, bound = 0, proven = 0, accept_floor = 0;
     if (active) {
         if (round >= 0) {
             const int sc = w.pk_score[i], pos = w.pk_pos[i];
+            if (round == 0 && !retry && w.floor_s && w.gran_blk != nullptr) accept_floor = sc - 1;
             if (!retry) {
                 if (round == 0) { if (sub == 0) { w.w_done[i] = 0; w.best_sw[i] = 0; w.fin_sw[i] = 0; w.w_next[i] = 0; w.w_probe[i] = 0; } }
                 else if (w.w_done[i] || w.w_next[i] != round) active = false;
@@ -136,7 +140,8 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
                 if (round > 0) { const int prev = w.res[i].x; if (prev > 0 && prev < bound) bound = prev; }
             } else {
                 const int4 v = w.res[i];
-                if (w.w_done[i] || w.w_next[i] != round || v.x >= w.w_bound[i]) active = false;      // not in flight / exact already
+                // not in flight / exact already (value proven and position known; a zero needs no position)
+                if (w.w_done[i] || w.w_next[i] != round || (v.x >= w.w_bound[i] && (v.y != 0x7fffffff || v.x <= 0))) active = false;
                 len = w.w_len[i];
                 bound = max(v.x, 0);
                 proven = bound;              // a cell with this value exists: anything below it is irrelevant now
@@ -158,39 +163,43 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
     const int gq = (w.n_gran + 63) >> 6;                // granules per mask bit (1 up to 8192 rows; long lncRNAs share bits)
     const int bit_rows = gq * w.gran_rows;
     const int join = (win_margin(len) + bit_rows - 1) / bit_rows;           // a gap this short would be covered by the next margin anyway
-    if (round >= 0 && w.gran_colmax != nullptr) {
+    if (round >= 0 && w.gran_blk != nullptr) {
         const bool scan = active && bound > 0;
         int task = 0, pos = 0;
         if (scan) { task = w.pk_task[i]; pos = w.pk_pos[i]; }
         const TaskDef td = c_tasks[task % w.tasks_per_seg];
-        const uint32_t* base = w.gran_colmax + ((size_t)(task / w.tasks_per_seg) * w.n_pairs + td.pair) * w.n_gran * w.max_len;
+        const uint16_t* base = w.gran_blk + ((size_t)(task / w.tasks_per_seg) * w.n_pairs + td.pair) * w.n_gran * w.blk_pitch;
+        const int lo_col = pos - len + 1;
+        const int grp = (threadIdx.x & 31) & ~7;       // first lane of this peak's 8 threads
         int pending = 0;        // largest bound among the non-qualifying granules after the last qualifying one
-        for (int k = 0; k < w.n_gran; ++k) {
-            int b = 0;
-            if (scan) {
-                const uint32_t* row = base + (size_t)k * w.max_len;
-                uint32_t v = 0;
-                for (int j = pos - len + 1 + sub; j <= pos; j += 8) v = __vmaxs2(v, row[j]);
-                b = td.half ? hi16(v) : lo16(v);
+        for (int k0 = 0; k0 < w.n_gran; k0 += 8) {
+            // thread `sub` reads the bound of granule k0 + sub: the maximum of the (skewed) 16-column blocks that cover the window
+            int mine_b = 0;
+            if (scan && k0 + sub < w.n_gran) {
+                const int tl = gran_tail_lane(k0 + sub, w.scan_r);
+                const uint16_t* row = base + (size_t)(k0 + sub) * w.blk_pitch;
+                for (int b = blk_of(lo_col, tl); b <= blk_of(pos, tl); ++b) { const int x = row[b]; mine_b = max(mine_b, td.half ? (x >> 8) : (x & 0xff)); }
             }
-            b = max(b, __shfl_xor_sync(0xffffffffu, b, 1));
-            b = max(b, __shfl_xor_sync(0xffffffffu, b, 2));
-            b = max(b, __shfl_xor_sync(0xffffffffu, b, 4));
-            if (scan && b >= bound) {
-                // the granules since the previous qualifying one are left out unless the gap is short enough to be joined
-                if (klo < 0) { klo = k; outside = pending; }
-                else if (k / gq - khi / gq - 1 > join) outside = max(outside, pending);
-                pending = 0;
-                khi = k;
-                qmask |= 1ull << (k / gq);
-            } else pending = max(pending, b);
+            // ... and all eight walk the granules in order
+            for (int q = 0; q < 8 && k0 + q < w.n_gran; ++q) {
+                const int k = k0 + q;
+                const int b = __shfl_sync(0xffffffffu, mine_b, grp + q);
+                if (scan && b >= bound) {
+                    // the granules since the previous qualifying one are left out unless the gap is short enough to be joined
+                    if (klo < 0) { klo = k; outside = pending; }
+                    else if (k / gq - khi / gq - 1 > join) outside = max(outside, pending);
+                    pending = 0;
+                    khi = k;
+                    qmask |= 1ull << (k / gq);
+                } else pending = max(pending, b);
+            }
         }
         outside = max(outside, pending);
     }
     // From here on one thread per peak works (sub == 0 of an active peak); the others only take part in the warp-wide
     // reservation of piece slots (one atomic per warp instead of one per peak).
     const bool mine = active && sub == 0;
-    int floor_v = max(proven - 1, 0);
+    int floor_v = max(max(proven - 1, 0), accept_floor);
     // only cells above `outside` matter (a result r > outside is exact), and their alignments span at most `margin` rows
     const int margin = win_margin_for(len, outside + 1);
     // walks the runs of qualifying granules (gaps <= join joined, at most 4 runs); f(lo, rows) per run; returns their number
