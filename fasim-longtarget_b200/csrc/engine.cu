@@ -145,7 +145,7 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
-    bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true, floor_s = true;
+    bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true, floor_s = false;
     int batch_segments = kBatchSegments;                  // segments per device batch (LTG_BATCH_SEGMENTS)
     int lit_rows_per_chunk = 24, lit_min_chunks = 0;      // tuning of the column-parallel literal kernel (LTG_LIT_ROWS / LTG_LIT_CH)
     int64_t n_probe_items = 0;          // pairs swept a second time by the Q4 probe (diagnostics)
@@ -1315,8 +1315,9 @@ int ltg_create(int device, ltg_context** out)
     // LTG_NO_SKIP=1 runs every window round of fastSIM's loop even when it provably repeats the previous result
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
-    // LTG_NO_FLOORS=1: the first window sweep tracks every cell above the pruning bound, not only those reaching the peak score
-    if (const char* e = getenv("LTG_NO_FLOORS")) c->floor_s = atoi(e) == 0;
+    // LTG_FLOORS=1: the first window sweep only tracks cells that reach the peak score (fewer slow-path trips of the tracker, more
+    // re-planned sweeps; measured neutral on the headline workload, profiles/README.md)
+    if (const char* e = getenv("LTG_FLOORS")) c->floor_s = atoi(e) != 0;
     if (const char* e = getenv("LTG_BATCH_SEGMENTS")) c->batch_segments = std::max(16, atoi(e));
     if (const char* e = getenv("LTG_LIT_OLD")) c->lit_col = atoi(e) == 0;
     if (const char* e = getenv("LTG_LIT_ROWS")) c->lit_rows_per_chunk = std::max(4, atoi(e));

@@ -45,10 +45,12 @@ constexpr int kWinKeys = 32 * kWinRowBuckets;
 // (class c = g - 1); a warp carries floor(32 / g) groups in each 16-bit half.  Windows are counting-sorted by
 // (g, stream length descending), so the windows that share a warp stream about the same number of RNA rows and the
 // short bins come last in the queue.
+constexpr int kWinCopies = 16;      // the key histogram is kept in this many copies (chosen per block): millions of pieces fall on a few
+                                    // dozen keys, and same-address atomics serialise
 struct WinSched {
-    int hist[kWinKeys];        // windows per key
-    int off[kWinKeys];         // exclusive prefix of hist
-    int fill[kWinKeys];
+    int hist[kWinCopies][kWinKeys];        // pieces per (copy, key)
+    int off[kWinCopies][kWinKeys];         // first list slot of every (copy, key): keys ascending, the copies of a key back to back
+    int fill[kWinCopies][kWinKeys];
     int cls_count[32];         // windows per class
     int cls_off[32];           // first list slot of the class
     int bin_start[32];         // first bin (warp work unit) of the class
@@ -229,14 +231,23 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
             if (total < w.m) { pruned = true; np = nr; }
         }
     }
-    // reserve np slots per thread: warp-inclusive scan, one atomicAdd by the last lane
-    const int lane = threadIdx.x & 31;
+    // reserve np slots per thread: warp-inclusive scan, then one atomicAdd per BLOCK (every warp's total goes through shared memory)
+    __shared__ int s_wtot[32], s_wbase[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
     int incl = np;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    int base = 0;
-    if (lane == 31 && incl > 0) base = atomicAdd(&w.sched->n_pieces, incl);      // (pc_cap = 4 * n_peaks: cannot overflow)
-    base = __shfl_sync(0xffffffffu, base, 31);
+    if (lane == 31) s_wtot[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < nwarps; ++k) { s_wbase[k] = tot; tot += s_wtot[k]; }
+        const int b0 = tot > 0 ? atomicAdd(&w.sched->n_pieces, tot) : 0;      // (pc_cap = 4 * n_peaks: cannot overflow)
+        for (int k = 0; k < nwarps; ++k) s_wbase[k] += b0;
+    }
+    __syncthreads();
+    const int base = s_wbase[wid];
+    const int copy = blockIdx.x & (kWinCopies - 1);
     unsigned long long cells = 0;
     if (mine) {
         int p = base + incl - np;
@@ -245,9 +256,9 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
         w.res64[i] = 0ull;
         auto emit = [&](int lo, int rows) {
             const int key = win_key(len, rows);
-            w.pc_peak[p] = i; w.pc_lo[p] = lo; w.pc_rows[p] = rows; w.pc_key[p] = key;
+            w.pc_peak[p] = i; w.pc_lo[p] = lo; w.pc_rows[p] = rows; w.pc_key[p] = key | (copy << 16);
             ++p;
-            atomicAdd(&w.sched->hist[key], 1);
+            atomicAdd(&w.sched->hist[copy][key], 1);
             cells += (unsigned long long)len * (unsigned long long)rows;
         };
         if (round < 0) emit(0, min(w.fin_qe[i] + 1, win_margin(len)));
@@ -257,15 +268,20 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
             w.w_bound[i] = bound; w.w_floor[i] = floor_v;
         }
     }
-    // statistics: one atomic per warp
+    // statistics: one set of global atomics per block
+    __shared__ unsigned long long s_cells, s_cnt;
+    if (threadIdx.x == 0) { s_cells = 0ull; s_cnt = 0ull; }
+    __syncthreads();
     unsigned long long cnt = mine ? 1ull : 0ull;
 #pragma unroll
     for (int o = 16; o; o >>= 1) { cells += __shfl_xor_sync(0xffffffffu, cells, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if (lane == 0 && cnt) {
+    if (lane == 0 && cnt) { atomicAdd(&s_cells, cells); atomicAdd(&s_cnt, cnt); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) {
         const int slot = round >= 0 ? round * 2 + retry : (round == -1 ? 8 : 9);
-        atomicAdd(&w.sched->st_windows[slot], cnt);
-        atomicAdd(&w.sched->st_cells[slot], cells);
-        if (round >= 0 && w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, cells);
+        atomicAdd(&w.sched->st_windows[slot], s_cnt);
+        atomicAdd(&w.sched->st_cells[slot], s_cells);
+        if (round >= 0 && w.cell_counter) atomicAdd((unsigned long long*)w.cell_counter, s_cells);
     }
 }
 
@@ -275,7 +291,8 @@ __global__ void __launch_bounds__(1024) k_win_offsets(WinSched* sc)
     __shared__ int s_warp[32];
     __shared__ int s_cls[32];
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const int v0 = sc->hist[2 * tid], v1 = sc->hist[2 * tid + 1];
+    int v0 = 0, v1 = 0;
+    for (int c = 0; c < kWinCopies; ++c) { v0 += sc->hist[c][2 * tid]; v1 += sc->hist[c][2 * tid + 1]; }
     int x = v0 + v1;
     const int mine = x;
 #pragma unroll
@@ -292,9 +309,12 @@ __global__ void __launch_bounds__(1024) k_win_offsets(WinSched* sc)
     }
     __syncthreads();
     const int excl = s_warp[wp] + x - mine;
-    sc->off[2 * tid] = excl; sc->off[2 * tid + 1] = excl + v0;
-    sc->fill[2 * tid] = 0; sc->fill[2 * tid + 1] = 0;
-    sc->hist[2 * tid] = 0; sc->hist[2 * tid + 1] = 0;       // ready for the next plan
+    for (int c = 0, a0 = excl, a1 = excl + v0; c < kWinCopies; ++c) {
+        sc->off[c][2 * tid] = a0; sc->off[c][2 * tid + 1] = a1;
+        a0 += sc->hist[c][2 * tid]; a1 += sc->hist[c][2 * tid + 1];
+        sc->fill[c][2 * tid] = 0; sc->fill[c][2 * tid + 1] = 0;
+        sc->hist[c][2 * tid] = 0; sc->hist[c][2 * tid + 1] = 0;       // ready for the next plan
+    }
     if (wp == 0) {
         const int cnt = s_cls[lane];
         const int g = lane + 1, wpw = 2 * (32 / g);
@@ -313,8 +333,8 @@ __global__ void k_win_place(const WinState w)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= w.sched->n_pieces) return;
-    const int key = w.pc_key[p];
-    w.list[w.sched->off[key] + atomicAdd(&w.sched->fill[key], 1)] = p;
+    const int key = w.pc_key[p] & 0xFFFF, copy = w.pc_key[p] >> 16;
+    w.list[w.sched->off[copy][key] + atomicAdd(&w.sched->fill[copy][key], 1)] = p;
 }
 
 // best cell of every peak that had pieces in the launch: unpack res64 into res
@@ -327,6 +347,16 @@ __global__ void k_win_combine(const WinState w)
     const int val = (int)(v >> 36);
     if ((v & 0xFFFFFFFFFull) == 0) w.res[i] = make_int4(val, 0x7fffffff, 0, 0);       // nothing above the floor: value only
     else w.res[i] = make_int4(val, 0xFFF - (int)((v >> 24) & 0xFFF), 0xFFFFFF - (int)(v & 0xFFFFFF), 0);
+}
+
+// signed 16-bit half of a packed register, extracted with one opaque bit-field instruction: written with C casts the
+// compiler types the packed value as a pair of shorts and then pays an identity PRMT for every packed-SIMD use of it
+__device__ __forceinline__ int half_s16(uint32_t v, int h)
+{
+    int r;
+    if (h) asm("bfe.s32 %0, %1, 16, 16;" : "=r"(r) : "r"(v));
+    else asm("bfe.s32 %0, %1, 0, 16;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 // TAB: score lookup with one PRMT per cell pair (needs an lncRNA made of A/C/G/T/U only); otherwise XNOR + VIADDMNMX.
@@ -430,23 +460,21 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
         // sign bytes, i.e. a score of -1 or 0, which like -4 can never raise a maximum.
         const uint32_t kNoneLo = TAB ? 0x88u : 64u, kNoneHi = TAB ? 0xCCu : 64u;
         uint32_t hout = 0, fout = 0, xout = kNoneLo | (kNoneHi << (TAB ? 8 : 16)), hdiag = 0;
-        // leader prefetch of the stream symbol
+        // leader prefetch of the stream symbol: only group leaders have a stream (length 0 elsewhere), so the loads are plain
+        // predicated instructions — no divergent branch per step
+        const int ln0 = leader ? slen[0] : 0, ln1 = leader ? slen[1] : 0;
         auto fetch = [&](int s) -> uint32_t {
             if (TAB) {
                 // both selector bytes of a row are precomputed (rna_sel); the low half takes byte 0 of its row's entry, the high
                 // half byte 1 of its own row's entry; past the end of a stream the "none" selector stays
                 uint32_t v0 = 0xCC88u, v1 = 0xCC88u;
-                if (leader) {
-                    if (s < slen[0]) v0 = w.rna_sel[sbase[0] + sdir[0] * s];
-                    if (s < slen[1]) v1 = w.rna_sel[sbase[1] + sdir[1] * s];
-                }
-                return (v0 & 0xFFu) | (v1 & 0xFF00u);
+                if (s < ln0) v0 = __ldg(w.rna_sel + (uint32_t)(sbase[0] + sdir[0] * s));       // (unsigned index: one wide multiply-add)
+                if (s < ln1) v1 = __ldg(w.rna_sel + (uint32_t)(sbase[1] + sdir[1] * s));
+                return __byte_perm(v0, v1, 0x4450);           // byte 0 of v0, byte 1 of v1
             }
             uint32_t c0 = kNoneLo, c1 = kNoneHi;
-            if (leader) {
-                if (s < slen[0]) { const uint32_t q = w.rna_ssw[sbase[0] + sdir[0] * s]; c0 = q < 4 ? q * 16 : 64u; }
-                if (s < slen[1]) { const uint32_t q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = q < 4 ? q * 16 : 64u; }
-            }
+            if (s < ln0) { const uint32_t q = w.rna_ssw[sbase[0] + sdir[0] * s]; c0 = q < 4 ? q * 16 : 64u; }
+            if (s < ln1) { const uint32_t q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = q < 4 ? q * 16 : 64u; }
             return c0 | (c1 << 16);
         };
         uint32_t xnext = fetch(0);
@@ -488,7 +516,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int cc = lig * R + r - off;
-                        const int v = h ? hi16(t[r]) : lo16(t[r]);
+                        const int v = half_s16(t[r], h);
                         if (cc >= 0 && (v > best[h] || (v == best[h] && cc < bcol[h]))) { best[h] = v; bcol[h] = cc; brow[h] = row; }
                     }
                 }
@@ -501,7 +529,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
         // group reduction: highest value, then smallest column (lower lanes own smaller columns)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            int rmx = h ? hi16(runmax) : lo16(runmax);
+            int rmx = half_s16(runmax, h);
             for (int o = 1; o < g; o <<= 1) {
                 const int ob = __shfl_down_sync(0xffffffffu, best[h], o);
                 const int oc = __shfl_down_sync(0xffffffffu, bcol[h], o);

@@ -812,6 +812,381 @@ static std::string format_sorted(std::vector<Triplex>& v, const Params& P)
     return o;
 }
 
+// =====================================================================================
+// -F mode: SIM() — sim.h:410-1143.  Huang & Miller's k best non-intersecting local alignments in linear space as the
+// reference carries it: scores x10 (match +50, mismatch -40, gap of k columns 120 + 40k), a list of at most K = 50
+// candidate nodes keyed by the START of their alignment (addnode :99-148), the best node aligned by the Myers-Miller
+// divide-and-conquer (diff :171-348) with the cells of earlier alignments forbidden (the per-row `row` lists), then the
+// scores of the region the new alignment may have invalidated recomputed (reverse sweep that grows the rectangle until
+// no start point inside depends on the outside, no_cross :150-169, forward sweep that re-enters nodes).
+// Quirks kept because they decide the output: cells enter the node list when their x10 score exceeds the UNSCALED
+// threshold (:549), the loop ends at the first alignment whose score/10 is not above the threshold (:591), Nt(bp) is the
+// number of lncRNA bases spanned (:589), the ParaMinus coordinates are off by two (:724-727).  The substitution matrix
+// V[128][128] is only initialised for A/C/G/T there: any other letter reads indeterminate stack memory in the reference;
+// this restatement scores it as a mismatch.
+// =====================================================================================
+namespace sim {
+
+constexpr int kNodes = 50;                 // sim.h:17 (#define K 50)
+
+struct Cand { long s, i, j; };             // a score and the start point of the alignment that achieves it
+struct Node { long score, stari, starj, endi, endj, top, bot, left, right; };
+
+// ORDER — sim.h:483-495: the better candidate stays in `a`; equal scores prefer the larger start row, then column
+static inline void keep_better(Cand& a, const Cand& b)
+{
+    if (a.s < b.s) a = b;
+    else if (a.s == b.s) {
+        if (a.i < b.i) { a.i = b.i; a.j = b.j; }
+        else if (a.i == b.i && a.j < b.j) a.j = b.j;
+    }
+}
+
+struct Sim {
+    const std::string& rna; const std::string& seq2;
+    long M, N, Q = 120, R = 40;
+    std::vector<Cand> CC, DD, HH, WW;       // C / D candidates per column (CC,RR,EE / DD,SS,FF) and per row (HH,II,JJ / WW,XX,YY)
+    std::vector<std::vector<long> > used;   // used[i] = columns of row i taken by earlier alignments (the `row` lists)
+    std::vector<Node> list;                 // LIST[0..numnode)
+    long floor_min = 0;                     // `min` of sim.h:416
+    std::vector<long> script;               // S: 0 = aligned pair, +k = k DNA-only columns, -k = k RNA-only columns
+    long I = 0, J = 0, last = 0;            // state of the script writer while diff() runs
+
+    Sim(const std::string& a, const std::string& b) : rna(a), seq2(b), M((long)a.size()), N((long)b.size()),
+        CC(N + 2), DD(N + 2), HH(M + 2), WW(M + 2), used(M + 2) {}
+    char A(long i) const { return rna[i - 1]; }
+    char B(long j) const { return seq2[j - 1]; }
+    static bool base(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+    long V(char a, char b) const { return (a == b && base(a)) ? 50 : -40; }
+    bool taken(long i, long j) const { for (long c : used[i]) if (c == j) return true; return false; }
+    long gap(long k) const { return k <= 0 ? 0 : Q + R * k; }
+
+    // One cell of the sweep (sim.h:512-547 and its four siblings :866-896, :921-956, :977-1012, :1060-1093): c / f run along
+    // the sweep line, lc / ld are the stored candidates of the neighbouring line at this position, p the diagonal
+    // predecessor, (i, j) the cell (= the start point of an alignment that begins right after it).
+    void cell(Cand& c, Cand& f, Cand& lc, Cand& ld, Cand& p, long sub, bool blocked, long i, long j) const
+    {
+        f.s -= R; c.s -= Q + R; keep_better(f, c);
+        Cand d = ld; d.s -= R;
+        Cand up = lc; up.s -= Q + R;
+        keep_better(d, up);
+        long v = 0;
+        if (!blocked) v = p.s + sub;
+        Cand n;
+        if (v <= 0) n = Cand{0, i, j}; else n = Cand{v, p.i, p.j};
+        keep_better(n, d); keep_better(n, f);
+        p = lc; lc = n; ld = d; c = n;
+    }
+
+    // addnode — sim.h:99-148
+    long addnode(long c, long ci, long cj, long i, long j)
+    {
+        size_t at = list.size();
+        for (size_t d = 0; d < list.size(); ++d) if (list[d].stari == ci && list[d].starj == cj) { at = d; break; }
+        if (at < list.size()) {
+            Node& n = list[at];
+            if (n.score < c) { n.score = c; n.endi = i; n.endj = j; }
+            if (n.top > i) n.top = i;
+            if (n.bot < i) n.bot = i;
+            if (n.left > j) n.left = j;
+            if (n.right < j) n.right = j;
+        } else {
+            Node n{c, ci, cj, i, j, i, i, j, j};
+            if ((int)list.size() == kNodes) {
+                size_t low = 0;
+                for (size_t d = 1; d < list.size(); ++d) if (list[d].score < list[low].score) low = d;
+                list[low] = n;
+            } else list.push_back(n);
+        }
+        return 1;
+    }
+
+    // no_cross — sim.h:150-169
+    bool no_cross(long m1, long mm, long n1, long nn, long& rl, long& cl) const
+    {
+        for (const Node& n : list) {
+            if (n.stari <= mm && n.starj <= nn && n.bot >= m1 - 1 && n.right >= n1 - 1 && (n.stari < rl || n.starj < cl)) {
+                if (n.stari < rl) rl = n.stari;
+                if (n.starj < cl) cl = n.starj;
+                return false;
+            }
+        }
+        return true;
+    }
+
+    // script writer — the DEL / INS / REP macros of sim.h:176-197
+    void del(long k) { I += k; if (last < 0) { script.back() -= k; last = script.back(); } else { script.push_back(-k); last = -k; } }
+    void ins(long k) { J += k; if (last < 0) { script.back() = k; script.push_back(last); } else { script.push_back(k); last = k; } }
+    void rep() { script.push_back(0); last = 0; }
+
+    // diff — sim.h:171-348: optimal global alignment of a[1..m] with b[1..n] (a = rna + oa, b = seq2 + ob) in linear space,
+    // gap-open charges tb at the top and te at the bottom boundary; pairs already used by earlier alignments are forbidden.
+    long diff(long oa, long ob, long m, long n, long tb, long te, std::vector<long>& c1, std::vector<long>& d1, std::vector<long>& c2,
+              std::vector<long>& d2)
+    {
+        auto a = [&](long i) { return A(oa + i); };
+        auto b = [&](long j) { return B(ob + j); };
+        if (n <= 0) { if (m > 0) del(m); return -gap(m); }
+        if (m <= 1) {
+            if (m <= 0) { ins(n); return -gap(n); }
+            if (tb > te) tb = te;
+            long midc = -(tb + R + gap(n)), midj = 0;
+            for (long j = 1; j <= n; ++j) {
+                if (taken(I + 1, j + J)) continue;
+                const long c = V(a(1), b(j)) - (gap(j - 1) + gap(n - j));
+                if (c > midc) { midc = c; midj = j; }
+            }
+            if (midj == 0) { ins(n); del(1); }
+            else {
+                if (midj > 1) ins(midj - 1);
+                rep();
+                ++I; ++J;
+                used[I].push_back(J);
+                if (midj < n) ins(n - midj);
+            }
+            return midc;
+        }
+        const long midi = m / 2;
+        // forward half: rows 1..midi
+        c1[0] = 0;
+        long t = -Q;
+        for (long j = 1; j <= n; ++j) { c1[j] = t = t - R; d1[j] = t - Q; }
+        t = -tb;
+        for (long i = 1; i <= midi; ++i) {
+            long s = c1[0], c, e, d;
+            c1[0] = c = t = t - R;
+            e = t - Q;
+            for (long j = 1; j <= n; ++j) {
+                if ((c = c - Q - R) > (e = e - R)) e = c;
+                if ((c = c1[j] - Q - R) > (d = d1[j] - R)) d = c;
+                if (!taken(i + I, j + J)) c = s + V(a(i), b(j));
+                if (c < d) c = d;
+                if (c < e) c = e;
+                s = c1[j]; c1[j] = c; d1[j] = d;
+            }
+        }
+        d1[0] = c1[0];
+        // reverse half: rows m-1..midi
+        c2[n] = 0;
+        t = -Q;
+        for (long j = n - 1; j >= 0; --j) { c2[j] = t = t - R; d2[j] = t - Q; }
+        t = -te;
+        for (long i = m - 1; i >= midi; --i) {
+            long s = c2[n], c, e, d;
+            c2[n] = c = t = t - R;
+            e = t - Q;
+            for (long j = n - 1; j >= 0; --j) {
+                if ((c = c - Q - R) > (e = e - R)) e = c;
+                if ((c = c2[j] - Q - R) > (d = d2[j] - R)) d = c;
+                if (!taken(i + 1 + I, j + 1 + J)) c = s + V(a(i + 1), b(j + 1));
+                if (c < d) c = d;
+                if (c < e) c = e;
+                s = c2[j]; c2[j] = c; d2[j] = d;
+            }
+        }
+        d2[n] = c2[n];
+        // where the two halves meet (sim.h:319-332)
+        long midc = c1[0] + c2[0], midj = 0, type = 1;
+        for (long j = 0; j <= n; ++j) {
+            const long c = c1[j] + c2[j];
+            if (c >= midc && (c > midc || (c1[j] != d1[j] && c2[j] == d2[j]))) { midc = c; midj = j; }
+        }
+        for (long j = n; j >= 0; --j) {
+            const long c = d1[j] + d2[j] + Q;
+            if (c > midc) { midc = c; midj = j; type = 2; }
+        }
+        if (type == 1) {
+            diff(oa, ob, midi, midj, tb, Q, c1, d1, c2, d2);
+            diff(oa + midi, ob + midj, m - midi, n - midj, Q, te, c1, d1, c2, d2);
+        } else {
+            diff(oa, ob, midi - 1, midj, tb, 0, c1, d1, c2, d2);
+            del(2);
+            diff(oa + midi + 1, ob + midj, m - midi - 1, n - midj, 0, te, c1, d1, c2, d2);
+        }
+        return midc;
+    }
+};
+
+// display — sim.h:350-388: script -> gapped strings (RNA side, translated-DNA side) and identity
+static float expand(const Sim& S, long stari, long starj, long m, long n, const std::vector<long>& script, std::string& sa, std::string& sb)
+{
+    long i = 0, j = 0, match = 0, mis = 0;
+    size_t at = 0;
+    sa.clear(); sb.clear();
+    while (i < m || j < n) {
+        while (i < m && j < n && at < script.size() && script[at] == 0) {
+            ++i; ++j;
+            const char x = S.A(stari - 1 + i), y = S.B(starj - 1 + j);
+            if (x == y) ++match; else ++mis;
+            sa += x; sb += y;
+            ++at;
+        }
+        if (i < m || j < n) {
+            const long op = at < script.size() ? script[at] : 0;
+            ++at;
+            if (op > 0) for (long f = 0; f < op; ++f) { sa += '-'; sb += S.B(starj - 1 + (++j)); ++mis; }
+            else for (long f = 0; f < -op; ++f) { sb += '-'; sa += S.A(stari - 1 + (++i)); ++mis; }
+        }
+    }
+    return (float)(100 * match) / (float)(match + mis);
+}
+
+// SIM() — sim.h:410-1143
+static void run(const std::string& rna, const std::string& seq2, const std::string& src, long dnaStartPos, long min_score,
+                std::vector<Triplex>& out, long strand, long Para, long rule, int ntMin, int ntMax, int penaltyT, int penaltyC)
+{
+    Sim S(rna, seq2);
+    const long M = S.M, N = S.N, Q = S.Q;
+    if (M == 0 || N == 0) return;
+    std::vector<long> c1(N + 2), d1(N + 2), c2(N + 2), d2(N + 2);
+    // ---- first pass over the whole matrix (:498-553)
+    for (long j = 1; j <= N; ++j) { S.CC[j] = Cand{0, 0, j}; S.DD[j] = Cand{-Q, 0, j}; }
+    for (long i = 1; i <= M; ++i) {
+        Cand c{0, i, 0}, f{-Q, i, 0}, p{0, i - 1, 0};
+        for (long j = 1; j <= N; ++j) {
+            S.cell(c, f, S.CC[j], S.DD[j], p, S.V(S.A(i), S.B(j)), S.taken(i, j), i, j);
+            if (c.s > min_score) S.addnode(c.s, c.i, c.j, i, j);
+        }
+    }
+    // ---- the k best alignments (:554-1142)
+    for (long count = (long)S.list.size() - 1; count >= 0; --count) {
+        size_t best = 0;
+        for (size_t i = 1; i < S.list.size(); ++i) if (S.list[i].score > S.list[best].score) best = i;
+        Node cur = S.list[best];
+        if (best != S.list.size() - 1) S.list[best] = S.list.back();
+        S.list.pop_back();
+        const long score = cur.score;
+        long stari = ++cur.stari, starj = ++cur.starj;
+        const long endi = cur.endi, endj = cur.endj;
+        long m1 = cur.top, mm = cur.bot, n1 = cur.left, nn = cur.right;
+        long rl = endi - stari + 1, cl = endj - starj + 1;
+        S.I = stari - 1; S.J = starj - 1; S.last = 0; S.script.clear();
+        const int nt = (int)(endi - stari + 1);
+        S.diff(stari - 1, starj - 1, rl, cl, Q, Q, c1, d1, c2, d2);
+        if (score / 10.0 <= min_score) break;
+        std::string stri_align, strj_align;
+        const float identity = expand(S, stari, starj, rl, cl, S.script, stri_align, strj_align);
+        if (nt >= ntMin && nt <= ntMax) {
+            // stability along the alignment (:678-710), same arithmetic as convertMyTriplex
+            float tri_score = 0.0f, hashvalue = 0, prescore = 0;
+            char prechar = 0, curchar = 0;
+            std::string tts;
+            long j = 0;
+            for (size_t i = 0; i < strj_align.size(); ++i) {
+                if (strj_align[i] == '-') { curchar = '-'; hashvalue = triplex_score(curchar, stri_align[i], (int)Para); tts += '-'; }
+                else {
+                    curchar = src[starj + j - 1];
+                    hashvalue = triplex_score(curchar, stri_align[i], (int)Para);
+                    tts += curchar;
+                    ++j;
+                }
+                if (curchar == prechar && curchar == 'T') { tri_score = tri_score - prescore + penaltyT; hashvalue = penaltyT; }
+                if (curchar == prechar && curchar == 'C') { tri_score = tri_score - prescore + penaltyC; hashvalue = penaltyC; }
+                prescore = hashvalue;
+                if (strj_align[i] != '-') prechar = curchar;
+                tri_score += hashvalue;
+            }
+            const long score10 = score / 10;
+            tri_score /= nt;
+            int refStart, refEnd;
+            if (Para < 0 && strand == 0) { refStart = (int)(N - endj + 1); refEnd = (int)(N - starj + 1); }
+            else if (Para > 0 && strand == 1) { refStart = (int)(N - endj - 1); refEnd = (int)(N - starj - 1); }
+            else { refStart = (int)starj; refEnd = (int)endj; }
+            Triplex t;
+            t.stari = (int)stari; t.endi = (int)endi; t.starj = (int)(refStart + dnaStartPos); t.endj = (int)(refEnd + dnaStartPos);
+            t.strand = (int)strand; t.reverse = (int)Para; t.rule = (int)rule; t.nt = nt; t.score = (float)score10; t.identity = identity;
+            t.tri_score = tri_score; t.stri_align = stri_align; t.strj_align = tts;
+            out.push_back(t);
+        }
+        if (!count) continue;
+        // ---- scores the new alignment may have changed (:853-1140)
+        bool flag = false;
+        for (long j = nn; j >= n1; --j) { S.CC[j] = Cand{0, mm + 1, j}; S.DD[j] = Cand{-Q, mm + 1, j}; }
+        for (long i = mm; i >= m1; --i) {
+            Cand c{0, i, nn + 1}, f{-Q, i, nn + 1}, p{0, i + 1, nn + 1};
+            for (long j = nn; j >= n1; --j) {
+                S.cell(c, f, S.CC[j], S.DD[j], p, S.V(S.A(i), S.B(j)), S.taken(i, j), i, j);
+                if (c.s > S.floor_min) flag = true;
+            }
+            S.HH[i] = S.CC[n1]; S.WW[i] = f;
+        }
+        auto inside = [&](const Cand& x) { return x.i > rl && x.j > cl; };
+        for (rl = m1, cl = n1;;) {
+            for (bool rflag = true, cflag = true; (rflag && m1 > 1) || (cflag && n1 > 1);) {
+                if (rflag && m1 > 1) {                    // one more row on top
+                    rflag = false;
+                    --m1;
+                    Cand c{0, m1, nn + 1}, f{-Q, m1, nn + 1}, p{0, m1 + 1, nn + 1};
+                    bool hit = false;
+                    for (long j = nn; j >= n1; --j) {
+                        S.cell(c, f, S.CC[j], S.DD[j], p, S.V(S.A(m1), S.B(j)), S.taken(m1, j), m1, j);
+                        if (c.s > S.floor_min) flag = true;
+                        hit = inside(c) || inside(S.DD[j]) || inside(f);
+                        if (!rflag && hit) rflag = true;
+                    }
+                    S.HH[m1] = S.CC[n1]; S.WW[m1] = f;
+                    if (!cflag && hit) cflag = true;
+                }
+                if (cflag && n1 > 1) {                    // one more column on the left
+                    cflag = false;
+                    --n1;
+                    Cand c{0, mm + 1, n1}, f{-Q, mm + 1, n1}, p{0, mm + 1, n1 + 1};
+                    bool hit = false;
+                    for (long i = mm; i >= m1; --i) {
+                        S.cell(c, f, S.HH[i], S.WW[i], p, S.V(S.B(n1), S.A(i)), S.taken(i, n1), i, n1);
+                        if (c.s > S.floor_min) flag = true;
+                        hit = inside(c) || inside(S.WW[i]) || inside(f);
+                        if (!cflag && hit) cflag = true;
+                    }
+                    S.CC[n1] = S.HH[m1]; S.DD[n1] = f;
+                    if (!rflag && hit) rflag = true;
+                }
+            }
+            if ((m1 == 1 && n1 == 1) || S.no_cross(m1, mm, n1, nn, rl, cl)) break;
+        }
+        --m1; --n1;
+        if (flag) {
+            for (long j = n1 + 1; j <= nn; ++j) { S.CC[j] = Cand{0, m1, j}; S.DD[j] = Cand{-Q, m1, j}; }
+            for (long i = m1 + 1; i <= mm; ++i) {
+                Cand c{0, i, n1}, f{-Q, i, n1}, p{0, i - 1, n1};
+                for (long j = n1 + 1; j <= nn; ++j) {
+                    S.cell(c, f, S.CC[j], S.DD[j], p, S.V(S.A(i), S.B(j)), S.taken(i, j), i, j);
+                    if (c.s > S.floor_min) S.floor_min = S.addnode(c.s, c.i, c.j, i, j);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace sim
+
+// One task in -F mode — Fasim-LongTarget.cpp:419-426
+static void run_task_sim(const std::string& rna, const std::string& seg, long dnaStart, int para, int strand, int rule,
+                         const Params& P, std::vector<Triplex>& out, int* minscore_out)
+{
+    std::string seq2, src;
+    task_strings(seg, para, strand, rule, seq2, src);
+    const int minscore = (int)(threshold_score(rna, seq2) * 0.8);
+    if (minscore_out) *minscore_out = minscore;
+    sim::run(rna, seq2, src, dnaStart, minscore, out, strand, para, rule, P.ntMin, P.ntMax, P.penaltyT, P.penaltyC);
+}
+
+static void run_record_sim(const std::string& rna, const std::string& dna, const Params& P, std::vector<Triplex>& out)
+{
+    std::vector<Triplex> all;
+    const std::vector<TaskId> order = task_order(P);
+    unsigned pos = 0;
+    while (pos < dna.size()) {
+        std::string seg = dna.substr(pos, P.cutLength);
+        long start = pos;
+        pos += P.cutLength; pos -= P.overlap;
+        if (same_seq(seg)) continue;
+        for (const TaskId& t : order) run_task_sim(rna, seg, start, t.para, t.strand, t.rule, P, all, nullptr);
+    }
+    for (const Triplex& t : all)
+        if (t.score >= 0.0f && t.identity >= P.minIdentity && t.tri_score >= P.minStability && t.nt >= P.cLength) out.push_back(t);
+}
+
 static unsigned fbits(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static void append_text(std::string& out, const Triplex& t)
 {
@@ -923,6 +1298,28 @@ int orc_longtarget(const char* rna, const char* dna, const int* params, char* ou
     orc::Params P = orc::params_from(params);
     std::vector<orc::Triplex> list;
     orc::run_record(rna, dna, P, list);
+    std::string txt;
+    for (auto& t : list) orc::append_text(txt, t);
+    return orc::emit(txt, out, cap);
+}
+
+// -F mode (SIM): one task / one record
+int orc_sim_task(const char* rna, const char* seg, long dna_start, int para, int strand, int rule, const int* params,
+                 int* minscore_out, char* out, long cap)
+{
+    orc::Params P = orc::params_from(params);
+    std::vector<orc::Triplex> list;
+    orc::run_task_sim(rna, seg, dna_start, para, strand, rule, P, list, minscore_out);
+    std::string txt;
+    for (auto& t : list) orc::append_text(txt, t);
+    return orc::emit(txt, out, cap);
+}
+
+int orc_sim_longtarget(const char* rna, const char* dna, const int* params, char* out, long cap)
+{
+    orc::Params P = orc::params_from(params);
+    std::vector<orc::Triplex> list;
+    orc::run_record_sim(rna, dna, P, list);
     std::string txt;
     for (auto& t : list) orc::append_text(txt, t);
     return orc::emit(txt, out, cap);

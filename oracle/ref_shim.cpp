@@ -188,6 +188,37 @@ int ref_longtarget(const char* rna, const char* dna, const int* params, char* ou
     return emit(txt, out, cap);
 }
 
+// One task through calc_score_once + SIM (the -F path, Fasim-LongTarget.cpp:419-426; sim.h:410).
+int ref_sim_task(const char* rna, const char* seg, long dna_start, int para_, int strand, int rule, const int* params,
+                 int* minscore_out, char* out, long cap)
+{
+    std::vector<char> s2(strlen(seg) + 1), sr(strlen(seg) + 1);
+    ref_task_strings(seg, para_, strand, rule, s2.data(), sr.data());
+    std::string A(rna), B(s2.data()), S(sr.data());
+    para pl = make_para(params);
+    int minscore = calc_score_once(A, B, dna_start, pl.rule) * 0.8;
+    if (minscore_out) *minscore_out = minscore;
+    std::vector<triplex> list;
+    SIM(A, B, S, dna_start, minscore, 5, -4, -12, -4, list, strand, para_, rule, pl.ntMin, pl.ntMax, pl.penaltyT, pl.penaltyC);
+    std::string txt;
+    for (size_t i = 0; i < list.size(); ++i) append_triplex(txt, list[i]);
+    return emit(txt, out, cap);
+}
+
+// One DNA record through LongTarget() with doFastSim = false (-F).
+int ref_sim_longtarget(const char* rna, const char* dna, const int* params, char* out, long cap)
+{
+    para pl = make_para(params);
+    pl.doFastSim = false;
+    std::vector<triplex> list;
+    std::streambuf* old = std::cout.rdbuf(nullptr);
+    LongTarget(pl, std::string(rna), std::string(dna), list);
+    std::cout.rdbuf(old);
+    std::string txt;
+    for (size_t i = 0; i < list.size(); ++i) append_triplex(txt, list[i]);
+    return emit(txt, out, cap);
+}
+
 // cluster_triplex on (stari, endi, nt) triples; returns middle/center/motif per element.
 int ref_cluster(int n, const int* stari, const int* endi, const int* nt, int dd, int length, int* middle, int* center,
                 int* motif)

@@ -6,7 +6,7 @@ timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 
 tail -4 gpurun_out/${TAG}_pytest.log
 B="python bench.py --steps 2 --warmup 1 --region-mbp 20 --no-cpu-baseline --debug-stats"
 timeout 600 $B > gpurun_out/${TAG}_ab_default.json 2> gpurun_out/${TAG}_ab_default.err; echo "default rc=$?"
-LTG_NO_FLOORS=1 timeout 600 $B > gpurun_out/${TAG}_ab_nofloors.json 2> gpurun_out/${TAG}_ab_nofloors.err; echo "nofloors rc=$?"
+LTG_FLOORS=1 timeout 600 $B > gpurun_out/${TAG}_ab_floors.json 2> gpurun_out/${TAG}_ab_floors.err; echo "floors rc=$?"
 LTG_BATCH_SEGMENTS=1024 timeout 600 $B > gpurun_out/${TAG}_ab_bs1024.json 2> gpurun_out/${TAG}_ab_bs1024.err; echo "bs1024 rc=$?"
 LTG_BATCH_SEGMENTS=4096 timeout 600 $B > gpurun_out/${TAG}_ab_bs4096.json 2> gpurun_out/${TAG}_ab_bs4096.err; echo "bs4096 rc=$?"
 timeout 900 python bench.py --steps 3 --warmup 2 --debug-stats > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
