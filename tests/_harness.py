@@ -108,6 +108,27 @@ class Side:
         assert k >= 0
         return ms.value, buf.value.decode()
 
+    def sim_task(self, rna, seg, dna_start, para, strand, rule, **kw):
+        """one task in -F mode: calc_score_once + SIM (Fasim-LongTarget.cpp:419-426, sim.h:410)"""
+        cap = 1 << 22
+        buf = C.create_string_buffer(cap)
+        ms = C.c_int(0)
+        f = self._f("sim_task")
+        f.argtypes = [C.c_char_p, C.c_char_p, C.c_long, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                      C.c_char_p, C.c_long]
+        k = f(rna.encode(), seg.encode(), dna_start, para, strand, rule, params_array(**kw), C.byref(ms), buf, cap)
+        assert k >= 0
+        return ms.value, buf.value.decode()
+
+    def sim_longtarget(self, rna, dna, **kw):
+        cap = 1 << 26
+        buf = C.create_string_buffer(cap)
+        f = self._f("sim_longtarget")
+        f.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_long]
+        k = f(rna.encode(), dna.encode(), params_array(**kw), buf, cap)
+        assert k >= 0
+        return buf.value.decode()
+
     def longtarget(self, rna, dna, **kw):
         cap = 1 << 26
         buf = C.create_string_buffer(cap)
