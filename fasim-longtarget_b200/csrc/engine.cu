@@ -27,8 +27,10 @@
 #include "scan.cuh"
 #include "window.cuh"
 #include "literal.cuh"
+#include "sim.cuh"
 #include "../host/rules_table.hpp"
 #include "../host/triplex_host.hpp"
+#include "../host/sim_host.hpp"
 
 namespace ltg {
 
@@ -145,6 +147,7 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
+    bool sim_mode = false;              // -F: SIM() instead of fastSIM() per task (ltg_set_sim_mode)
     bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true, floor_s = false;
     int batch_segments = kBatchSegments;                  // segments per device batch (LTG_BATCH_SEGMENTS)
     int lit_rows_per_chunk = 24, lit_min_chunks = 0;      // tuning of the column-parallel literal kernel (LTG_LIT_ROWS / LTG_LIT_CH)
@@ -164,6 +167,7 @@ struct ltg_context {
     int m = 0, n_strips = 0, scan_r = 32;
     bool profiles_dirty = true;
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
+    DevBuf d_rna_sim, d_sim_scratch, d_sim_hdr, d_sim_pool, d_sim_tasks;      // -F mode (sim.cuh)
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_blkmax, d_bnd, d_counters;
     DevBuf d_probe_items, d_probe_orig, d_probe_out, d_bnd_gran;
@@ -603,7 +607,7 @@ int run_traceback(ltg_context* c, const TraceJob* d_jobs, int n_jobs, TraceOut* 
 //   kLitDefer   leave them out (no peaks) and report them in `deferred`; the record collects them ...
 //   kLitOnly    ... and runs them together in batches of this kind: only the pairs that carry a task of `only_tasks`
 //               are scanned, and the host phase keeps the rows of exactly those tasks
-enum LitMode { kLitInline, kLitDefer, kLitOnly };
+enum LitMode { kLitInline, kLitDefer, kLitOnly, kLitSkip /* thresholds only (-F mode): the Q4 flags are ignored */ };
 
 constexpr int kSideCap = 4096;      // literal scan jobs a call may park on the side stream
 
@@ -704,7 +708,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
     // Q4 probe: a second sweep of the pairs that carry a flagged task finds the largest F carried into a stripe start of the
     // reference's layout; below 132 the signed compare cannot misfire and the task returns to the exact path (mode 3)
-    if (c->q4_probe) {
+    if (c->q4_probe && lit_mode != kLitSkip) {
         std::vector<ScanItem> pitems;
         std::vector<int> porig;
         for (int i = 0; i < n_items; ++i) {
@@ -740,7 +744,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     std::vector<LiteralJob> jobs, side_jobs;
     for (int t = 0; t < n_tasks; ++t) {
         if (hti.flags[t] & kTaskRange) { set_error("alignment score exceeds the 16-bit range (segment too long for this build)"); return LTG_ERR_LIMIT; }
-        if (hti.flags[t] & kTaskLiteral) {
+        if ((hti.flags[t] & kTaskLiteral) && lit_mode != kLitSkip) {
             LiteralJob j; memset(&j, 0, sizeof j);
             j.kind = 0; j.task = t; j.seg = t / T; j.tdef = t % T; j.ref_start = 0; j.ref_len = segs[t / T].len;
             j.read_start = 0; j.read_len = c->m; j.read_dir = 1; j.ref_dir = 0; j.terminate = 255; j.peak = -1;
@@ -1099,6 +1103,92 @@ struct RecordIn {
     int64_t record_len = -1, first_seg = 0, n_seg = -1;     // shard geometry (ltg_scan_shard); defaults: the whole record
 };
 
+// -F mode: every task goes through SIM() (sim.h:410) instead of fastSIM().  Per batch of segments: the scan stage yields the
+// thresholds (calc_score_once * 0.8, Fasim-LongTarget.cpp:421), k_sim the alignments of every task (coordinates + edit scripts),
+// and the host turns them into rows in the reference's order (segment, task, alignment) — sim_host.hpp.
+constexpr int kSimBatchSegments = 64;
+constexpr long long kSimPoolInts = 32LL << 20;           // 128 MB of alignment records + scripts per batch
+
+int run_sim_batches(ltg_context* c, const std::vector<HostSeg>& active, const RecordIn* recs, ResultBuilder& rb, RecordStats& st)
+{
+    if (c->m >= simk::kMaxRows) { set_error("-F (SIM) mode supports lncRNAs up to %d nt", simk::kMaxRows - 1); return LTG_ERR_LIMIT; }
+    if (c->params.cut_length >= (1 << simk::kColBits) - 2) { set_error("-F (SIM) mode supports cut lengths below %d", (1 << simk::kColBits) - 2); return LTG_ERR_LIMIT; }
+    const int T = (int)c->tasks.size();
+    int* counters = c->d_counters.as<int>();
+    for (size_t b0 = 0; b0 < active.size(); b0 += kSimBatchSegments) {
+        std::vector<HostSeg> batch(active.begin() + b0, active.begin() + std::min(active.size(), b0 + (size_t)kSimBatchSegments));
+        HostBatch& hb = c->hb[0];
+        const int rc = run_batch_device(c, batch, hb, false, nullptr, kLitSkip);
+        hb.timed = false;
+        if (rc != LTG_OK) return rc;
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const int S = (int)batch.size(), n_tasks = S * T;
+        int max_len = 1;
+        for (const HostSeg& sg : batch) max_len = std::max(max_len, sg.len);
+        std::vector<int> ids(n_tasks);
+        for (int t = 0; t < n_tasks; ++t) ids[t] = t;
+        // one warp per task; few tasks (a single record of the demo's size) spread one warp per block over the SMs
+        const int wpb = n_tasks <= c->num_sms * 8 ? 1 : 4;
+        const int blocks = std::max(1, std::min(c->num_sms * (wpb == 1 ? 8 : 4), (n_tasks + wpb - 1) / wpb));
+        const long long per_warp = sim_scratch_bytes(c->m, max_len);
+        if (int e = c->d_sim_scratch.ensure((size_t)blocks * wpb * (size_t)per_warp)) return e;
+        if (int e = c->d_sim_hdr.ensure(sizeof(SimHeader) * (size_t)n_tasks)) return e;
+        if (int e = c->d_sim_pool.ensure(sizeof(int) * (size_t)kSimPoolInts)) return e;
+        if (int e = c->d_sim_tasks.ensure(sizeof(int) * (size_t)n_tasks)) return e;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_sim_tasks.p, ids.data(), sizeof(int) * (size_t)n_tasks, cudaMemcpyHostToDevice, c->stream));
+        LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntScan, 0, 2 * sizeof(int), c->stream));        // queue head, pool fill
+        SimArgs sa;
+        sa.task_ids = c->d_sim_tasks.as<int>(); sa.n_tasks = n_tasks; sa.tasks_per_seg = T;
+        sa.codes = c->d_codes.as<uint8_t>(); sa.segs = c->d_segs.as<SegDesc>();
+        sa.rna_codes = c->d_rna_sim.as<uint8_t>(); sa.m = c->m;
+        sa.task_thr = TaskInfo(c->d_task_info.as<int>(), n_tasks).thr;
+        sa.scratch = c->d_sim_scratch.as<unsigned char>(); sa.scratch_per_warp = per_warp; sa.max_len = max_len;
+        sa.counter = counters + kCntScan; sa.hdr = c->d_sim_hdr.as<SimHeader>();
+        sa.pool = c->d_sim_pool.as<int>(); sa.pool_cap = (int)kSimPoolInts; sa.pool_used = counters + kCntPeaks;
+        k_sim<<<blocks, 32 * wpb, 0, c->stream>>>(sa);
+        c->launches += 1;
+        LTG_CUDA_CHECK(cudaGetLastError());
+        std::vector<SimHeader> hdr(n_tasks);
+        int used = 0;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(hdr.data(), c->d_sim_hdr.p, sizeof(SimHeader) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(&used, counters + kCntPeaks, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int t = 0; t < n_tasks; ++t)
+            if (hdr[t].error) { set_error("SIM kernel: task %d failed with code %d (1 script pool, 2 used-cell pool, 3 alignment table, 4 diff stack, 5 batch pool)", t, hdr[t].error); return LTG_ERR_LIMIT; }
+        used = std::min<long long>(used, kSimPoolInts);
+        std::vector<int> pool((size_t)std::max(used, 1));
+        // the batch's DNA bytes for the TTS strings (host copy of the device buffer: the input may be device resident)
+        const int64_t lo = batch.front().start, hi = batch.back().start + batch.back().len;
+        std::vector<char> dna((size_t)(hi - lo));
+        if (used > 0) LTG_CUDA_CHECK(cudaMemcpyAsync(pool.data(), c->d_sim_pool.p, sizeof(int) * (size_t)used, cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(dna.data(), c->d_dna.as<unsigned char>() + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->stream));
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += (int64_t)sizeof(SimHeader) * n_tasks + (int64_t)sizeof(int) * used + (hi - lo);
+        c->h2d_bytes += (int64_t)sizeof(int) * n_tasks;
+        std::vector<ltg_host::SimRow> rows;
+        for (int t = 0; t < n_tasks; ++t) {
+            const HostSeg& sg = batch[t / T];
+            const TaskDef& td = c->tasks[t % T];
+            rows.clear();
+            for (int k = 0; k < hdr[t].n_aln; ++k) {
+                simk::Aln al;
+                memcpy(&al, pool.data() + hdr[t].aln_off + 8 * k, sizeof al);
+                const int* script = pool.data() + hdr[t].aln_off + 8 * hdr[t].n_aln + al.script_off;
+                ltg_host::sim_convert(al, script, c->rna.c_str(), td, dna.data() + (sg.start - lo), sg.len, (long)sg.coord, c->params, rows);
+            }
+            for (ltg_host::SimRow& r : rows) {
+                if (!ltg_host::passes_record_filter(r.t, c->params)) continue;            // Fasim-LongTarget.cpp:589-597
+                r.t.record = sg.record;
+                rb.add(r.t, r.tfo.c_str(), r.tts.c_str(), recs[sg.record].chr, recs[sg.record].record_start, sg.record);
+            }
+        }
+        st.n_segments += S; st.n_tasks += n_tasks;
+        for (const HostSeg& sg : batch) st.scan_cells += (int64_t)sg.len * c->m * T;
+    }
+    return LTG_OK;
+}
+
+
 int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result** out)
 {
     if (!c || !out || (n_recs > 0 && !recs)) { set_error("null argument"); return LTG_ERR_ARG; }
@@ -1149,6 +1239,16 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
             for (int s = 0; s < NS; ++s) { segs[s].flags = hs[s].flags; if (!(hs[s].flags & kSegSkip)) active.push_back(segs[s]); }
         }
 
+        if (c->sim_mode) {
+            t_prep = now();
+            if (int e = run_sim_batches(c, active, recs, rb, st)) return e;
+            ltg_result* r = finish_result(rb);
+            r->n_segments = st.n_segments; r->n_tasks = st.n_tasks; r->scan_cells = st.scan_cells; r->dna_bases = len;
+            r->gpu_launches = c->launches - launches0; r->h2d_bytes = c->h2d_bytes - h2d0; r->d2h_bytes = c->d2h_bytes - d2h0;
+            if (trace_time) fprintf(stderr, "[ltg timing] -F mode: prep %.1f ms, SIM batches %.1f ms\n", t_prep - t_begin, now() - t_prep);
+            *out = r;
+            return LTG_OK;
+        }
         // batch size: bounded by the strip-maxima buffer; at least two batches when there is enough work so that the
         // host phase of one overlaps the device phase of the next
         const int cutp = (c->params.cut_length + 3) & ~3;
@@ -1346,6 +1446,7 @@ void ltg_destroy(ltg_context* c)
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs, &c->d_side_jobs, &c->d_side_colmax})
         b->release();
+    for (DevBuf* b : {&c->d_rna_sim, &c->d_sim_scratch, &c->d_sim_hdr, &c->d_sim_pool, &c->d_sim_tasks}) b->release();
     for (int k = 0; k < 20; ++k) c->d_w[k].release();
     for (int k = 0; k < 4; ++k) c->d_pc[k].release();
     c->d_res64.release();
@@ -1378,6 +1479,13 @@ int ltg_set_params(ltg_context* c, const ltg_params* p)
     });
 }
 
+int ltg_set_sim_mode(ltg_context* c, int on)
+{
+    if (!c) { set_error("null argument"); return LTG_ERR_ARG; }
+    c->sim_mode = on != 0;
+    return LTG_OK;
+}
+
 int ltg_set_query(ltg_context* c, const char* name, const char* rna, int64_t len)
 {
     return guarded([&]() -> int {
@@ -1402,6 +1510,11 @@ int ltg_set_query(ltg_context* c, const char* name, const char* rna, int64_t len
         const unsigned q = q1[i] & 3u;
         sel[i] = (uint16_t)((q | ((q | 8u) << 4)) | (((4u + q) | ((12u + q) << 4)) << 8));
     }
+    // -F mode: plain letter codes (A0 C1 G2 T3, anything else 4 — SIM's substitution matrix knows no U, sim.h:468-472)
+    std::vector<uint8_t> q3(len);
+    for (int64_t i = 0; i < len; ++i) q3[i] = (uint8_t)dna_code((unsigned char)rna[i]);
+    if (int e = c->d_rna_sim.ensure((size_t)len)) return e;
+    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_sim.p, q3.data(), (size_t)len, cudaMemcpyHostToDevice, c->stream));
     if (int e = c->d_rna_sel.ensure(sizeof(uint16_t) * (size_t)len)) return e;
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_sel.p, sel.data(), sizeof(uint16_t) * (size_t)len, cudaMemcpyHostToDevice, c->stream));
     LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_rna_raw.p, rna, (size_t)len, cudaMemcpyHostToDevice, c->stream));

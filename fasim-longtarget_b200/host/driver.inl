@@ -167,7 +167,7 @@ int ltg_main(int argc, char* const* argv)
     std::string f1 = "./", f2 = "./", outdir = "./", devices_arg;
     int device = 0;
     // same option table as initEnv (Fasim-LongTarget.cpp:271-283); -m, -d, -cn, -F are accepted and ignored
-    // (-F selects the SIM path, which this build does not provide: it is reported as an error)
+    // (-F selects the SIM path: ltg_set_sim_mode)
     const char* optstring = "f:s:r:O:c:m:t:i:S:z:Y:Z:h:C:D:E:o:y:Fd";
     static const struct option long_options[] = {
         {"f1", required_argument, nullptr, 'f'}, {"f2", required_argument, nullptr, 's'}, {"ni", required_argument, nullptr, 'y'},
@@ -217,7 +217,6 @@ int ltg_main(int argc, char* const* argv)
         default: break;
         }
     }
-    if (want_sim) { fprintf(stderr, "fasim: -F (SIM mode) is not available in the B200 build\n"); return 2; }
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     const bool timing = getenv("LTG_TIMING") != nullptr;
@@ -226,7 +225,7 @@ int ltg_main(int argc, char* const* argv)
         struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
         fprintf(stderr, "[fasim timing] %-10s at %.3f s\n", what, (t.tv_sec - t0.tv_sec) + 1e-9 * (t.tv_nsec - t0.tv_nsec));
     };
-    printf("Searching triplexes using Fasim\n");
+    printf(want_sim ? "Searching triplexes using Sim\n" : "Searching triplexes using Fasim\n");        // Fasim-LongTarget.cpp:105-108
     // base name of -f1: the reference drops the last 3 characters (".fa", Fasim-LongTarget.cpp:800); the new input kinds
     // drop their own extension (".2bit"; ".gz" and then 3 more)
     std::string base = f1;
@@ -379,6 +378,7 @@ int ltg_main(int argc, char* const* argv)
         int rc = ltg_create(devs[w], &ctx);
         t_create = tnow() - t_create;
         if (rc == LTG_OK) rc = ltg_set_params(ctx, &P);
+        if (rc == LTG_OK && want_sim) rc = ltg_set_sim_mode(ctx, 1);
         size_t cur_q = (size_t)-1;
         while (rc == LTG_OK && !failed.load()) {
             const size_t job = next_job.fetch_add(1);

@@ -92,6 +92,11 @@ const char* ltg_last_error(void);
 void ltg_default_params(ltg_params* p);                        /* initEnv defaults — Fasim-LongTarget.cpp:284-303 */
 int ltg_set_params(ltg_context* ctx, const ltg_params* p);
 
+/* replaces the -F switch (paraList.doFastSim = false, Fasim-LongTarget.cpp:360-362): with on != 0 every task is aligned by
+ * SIM() — sim.h:410-1143, Huang & Miller's k best non-intersecting local alignments — instead of fastSIM(); the scan calls
+ * then return SIM's rows (dispatch at Fasim-LongTarget.cpp:419-426 and its 15 sibling call sites).                          */
+int ltg_set_sim_mode(ltg_context* ctx, int on);
+
 /* replaces readRna + the per-call RNA preparation (TranslateBase ssw_cpp.cpp:323, cg_str stats.h:306,
  * ssw_init/qP_byte sswNew.cpp:1274/176, init_work stats.h:386): uploads the lncRNA once and builds the
  * device-resident packed query profiles for every task pair.                                          */

@@ -589,6 +589,65 @@ def test_reference_binary_multi_query_inputs(tmp_path):
             assert len(open(os.path.join(d, "ref", f)).read().splitlines()) > 1, f
 
 
+# ------------------------------------------------------------------------------------------------ -F mode (SIM)
+def test_sim_mode_vs_oracle(engine):
+    """-F: every task through SIM() (sim.h:410).  k_sim's wavefront first pass + in-order node-list replay + the shared k-best
+    core against the oracle restatement (itself pinned to the unmodified sim.h by tests/test_sim_cpu.py): planted targets on
+    random DNA (several segments incl. a tail), and a repeat-rich record where the 50-node list overflows."""
+    rnd = random.Random(23)
+    try:
+        engine.set_sim_mode(True)
+        rna = splitmix_bases(2001, 333)
+        dna = list(splitmix_bases(1001, 2300))
+        for at in (150, 900, 1400, 2100):
+            L = rnd.randrange(30, 70)
+            a = rnd.randrange(0, len(rna) - L)
+            dna[at:at + L] = rna[a:a + L].translate(str.maketrans("TG", "AT"))
+        dna = "".join(dna)
+        for kw, ekw in ((dict(c_length=20, cut_length=1000, overlap=100), dict(cLength=20, cutLength=1000, overlap=100)),
+                        (dict(c_length=25, nt_min=22, nt_max=60, penalty_t=-3, penalty_c=2, cut_length=2500, overlap=50),
+                         dict(cLength=25, ntMin=22, ntMax=60, penaltyT=-3, penaltyC=2, cutLength=2500, overlap=50))):
+            engine.set_params(**kw)
+            engine.set_query("r", rna)
+            rows = engine.LongTarget(dna, "chrS", 1)
+            assert rows_as_oracle_text(rows) == oracle_text_rows(O.sim_longtarget(rna, dna, **ekw)), kw
+            assert len(rows) > 5
+
+        def noisy(unit, n, rate):
+            s = list((unit * (n // len(unit) + 1))[:n])
+            for i in range(n):
+                if rnd.random() < rate:
+                    s[i] = rnd.choice("ACGT")
+            return "".join(s)
+        rna = splitmix_bases(2001, 60) + noisy("CT", 70, 0.08) + splitmix_bases(2002, 40) + noisy("GA", 50, 0.05)
+        dna = splitmix_bases(1001, 150) + noisy("GA", 260, 0.1) + splitmix_bases(1002, 100) + noisy("TC", 150, 0.06)
+        engine.set_params(c_length=15, nt_min=10, cut_length=400, overlap=60)
+        engine.set_query("rr", rna)
+        rows = engine.LongTarget(dna, "chrR", 1)
+        assert rows_as_oracle_text(rows) == oracle_text_rows(O.sim_longtarget(rna, dna, cLength=15, ntMin=10, cutLength=400, overlap=60))
+        assert len(rows) > 100
+        # a 35-row lncRNA (one partial strip), a 1-column segment, an empty record
+        engine.set_params(c_length=10, nt_min=5)
+        engine.set_query("tiny", splitmix_bases(7, 35))
+        for d in (splitmix_bases(8, 1), splitmix_bases(9, 90), ""):
+            assert rows_as_oracle_text(engine.LongTarget(d)) == oracle_text_rows(O.sim_longtarget(splitmix_bases(7, 35), d, cLength=10, ntMin=5)) if d else engine.LongTarget(d) == []
+    finally:
+        engine.set_sim_mode(False)
+        engine.set_params()
+
+
+def test_cli_sim_mode_demo_byte_equal(tmp_path, data_dir):
+    """`fasim -F` on the H19 / testDNA demo (-lg 40): byte-equal to the unmodified reference's -F run (120 s on a CPU core;
+    golden generated by tests/golden/make_golden.py --sim)."""
+    files = run_cli_files(tmp_path, "testDNA.fa", open(os.path.join(data_dir, "testDNA.fa")).read(), "H19.fa",
+                          open(os.path.join(data_dir, "H19.fa")).read(), ["-F", "-lg", "40"])
+    names = [f for f in os.listdir(GOLDEN) if f.startswith("demo_F_lg40__")]
+    assert len(names) == 3
+    for g in names:
+        assert files[g.split("__", 1)[1]] == open(os.path.join(GOLDEN, g)).read(), g
+    assert len(files["hg19-H19-testDNA-TFOsorted"].splitlines()) > 100
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_1mbp(engine):
     """Size-independent properties at bench scale (1 Mbp x 3 kb): determinism, shard-invariance (scanning the region as
