@@ -148,6 +148,7 @@ struct ltg_context {
     int num_sms = 0;
     int host_threads = 1;
     bool sim_mode = false;              // -F: SIM() instead of fastSIM() per task (ltg_set_sim_mode)
+    bool compat = false;                // window loop / per-task tail of the older variant (ltg_set_compat)
     bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true, floor_s = false;
     int batch_segments = kBatchSegments;                  // segments per device batch (LTG_BATCH_SEGMENTS)
     int lit_rows_per_chunk = 24, lit_min_chunks = 0;      // tuning of the column-parallel literal kernel (LTG_LIT_ROWS / LTG_LIT_CH)
@@ -174,7 +175,7 @@ struct ltg_context {
     int n_bnd_gran = 0;                 // granules that hold the rows just above a stripe start (Q4 pre-filter)
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
-    DevBuf d_w[20], d_pc[4], d_res64, d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
+    DevBuf d_w[24], d_pc[4], d_res64, d_win_list, d_win_sched, d_res, d_colmax_all, d_ovf_list;
     DevBuf d_jobs, d_tout, d_strpool, d_scratch, d_scratch_big;
     DevBuf d_lit_colmax, d_lit_work, d_lit_jobs;
     DevBuf d_side_jobs, d_side_colmax;       // literal scan jobs running on the side stream while the main batches compute
@@ -462,7 +463,7 @@ int literal_windows(ltg_context* c, const WinState& w, bool reverse, int round)
 // ---------------- window stage: peaks (device-resident pool) -> chosen alignments -> traceback pass 1 ----------------
 int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const uint16_t* gran_blk, int max_len, HostBatch* hb, bool dead_rule)
 {
-    for (int k = 0; k < 20; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
+    for (int k = 0; k < 24; ++k) if (int e = c->d_w[k].ensure(sizeof(int) * (size_t)n_peaks)) return e;
     const int pc_cap = 4 * n_peaks;          // kMaxRuns pieces per peak at most
     if (int e = c->d_win_list.ensure(sizeof(int) * (size_t)pc_cap)) return e;
     for (int k = 0; k < 4; ++k) if (int e = c->d_pc[k].ensure(sizeof(int) * (size_t)pc_cap)) return e;
@@ -480,6 +481,9 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.w_bound = c->d_w[14].as<int>(); w.w_flight = c->d_w[15].as<int>(); w.w_floor = c->d_w[16].as<int>();
     w.pc_peak = c->d_pc[0].as<int>(); w.pc_lo = c->d_pc[1].as<int>(); w.pc_rows = c->d_pc[2].as<int>(); w.pc_key = c->d_pc[3].as<int>(); w.pc_cap = pc_cap;
     w.res64 = c->d_res64.as<unsigned long long>(); w.w_next = c->d_w[17].as<int>(); w.w_probe = c->d_w[18].as<int>();
+    w.w_ws = c->d_w[12].as<int>(); w.fin_ws = c->d_w[13].as<int>(); w.w_shift = c->d_w[19].as<int>(); w.best_ws = c->d_w[20].as<int>();
+    w.fin_shift = c->d_w[21].as<int>();
+    w.compat = (c->compat && forced_cut == nullptr) ? 1 : 0;
     w.sched = c->d_win_sched.as<WinSched>(); w.list = c->d_win_list.as<int>();
     w.res = c->d_res.as<int4>();
     w.codes = c->d_codes.as<uint8_t>(); w.segs = c->d_segs.as<SegDesc>(); w.tasks_per_seg = T;
@@ -520,7 +524,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
         if (int e = literal_windows(c, w, /*reverse=*/false, round)) return e;
         k_win_decide<<<pb, 256, 0, c->stream>>>(w, round);
         c->launches += 1;
-        if (round < 3 && c->skip_rounds) {
+        if (round < 3 && c->skip_rounds && !w.compat) {
             // reverse probe of the rounds that failed without a candidate: may skip later rounds or finish the peak
             schedule(-2, 0);
             sweep(true);
@@ -920,13 +924,13 @@ void host_phase(const ltg_context* c, HostBatch& hb, int threads)
                 if (J.score <= 0) continue;                     // fastsim.h:253 (sw_score == 0 -> skipped)
                 if (tout[i].status != 1 && tout[i].status != 4) continue;       // banded_sw failed -> sw_score 0 (ssw_cpp.cpp:627-633)
                 ltg_host::DeviceAlignment al;
-                al.sw_score = J.score; al.ws = J.ws; al.rb = J.rb; al.re = J.re; al.query_begin = J.qb; al.query_end = J.qe;
+                al.sw_score = J.score; al.ws = J.ws; al.shift = J.tdef >> 8; al.rb = J.rb; al.re = J.re; al.query_begin = J.qb; al.query_end = J.qe;
                 al.nt = tout[i].nt; al.identity = tout[i].identity; al.tri_score = tout[i].tri;
                 // dead alignment (window.cuh DeadRule): de-duplicates like any other, fails every output filter
                 if (tout[i].status == 4) { al.identity = -INFINITY; al.tri_score = -INFINITY; }
                 ltg_host::make_triplex(al, task % T, sg.len, (long)sg.start, (long)sg.coord, sg.record, td.para, td.strand, td.rule, c->params, mine);
             }
-            if (!mine.empty()) ltg_host::finish_task(mine, c->params, part[k]);
+            if (!mine.empty()) ltg_host::finish_task(mine, c->params, part[k], c->compat);
         }
     };
     if (threads == 1) work(0);
@@ -983,8 +987,10 @@ struct ResultBuilder {
     std::vector<ltg_triplex> tri;
     std::string text;
     std::vector<int64_t> chr_off;       // per record: offset of its chromosome tag in `text` (-1: not stored yet)
-    void add(const ltg_host::Triplex& t, const char* tfo, const char* tts, const char* chr, int64_t record_start, int record)
+    // text_len: columns of the alignment strings (= t.nt for fastSIM rows; SIM rows report the lncRNA span as Nt(bp), sim.h:589)
+    void add(const ltg_host::Triplex& t, const char* tfo, const char* tts, const char* chr, int64_t record_start, int record, int64_t text_len = -1)
     {
+        if (text_len < 0) text_len = t.nt;
         if ((size_t)record >= chr_off.size()) chr_off.resize((size_t)record + 1, -1);
         if (chr_off[record] < 0) { chr_off[record] = (int64_t)text.size(); text += (chr ? chr : ""); text += '\0'; }
         ltg_triplex o;
@@ -994,8 +1000,8 @@ struct ResultBuilder {
         o.rule = t.rule; o.nt = t.nt; o.score = t.score; o.identity = t.identity; o.tri_score = t.tri_score;
         o.genomestart = o.starj + record_start - 1;         // Fasim-LongTarget.cpp:146-147
         o.genomeend = o.endj + record_start - 1;
-        o.tfo_off = (int64_t)text.size(); text.append(tfo, (size_t)t.nt); text += '\0';
-        o.tts_off = (int64_t)text.size(); text.append(tts, (size_t)t.nt); text += '\0';
+        o.tfo_off = (int64_t)text.size(); text.append(tfo, (size_t)text_len); text += '\0';
+        o.tts_off = (int64_t)text.size(); text.append(tts, (size_t)text_len); text += '\0';
         o.chr_off = chr_off[record];
         o.record = record;
         tri.push_back(o);
@@ -1026,7 +1032,7 @@ int fetch_strings(ltg_context* c, const std::vector<ltg_host::Triplex>& rows, st
     for (size_t i = 0; i < n; ++i) {
         const ltg_host::Triplex& t = rows[i];
         TraceJob& J = jobs[i];
-        J.seg_start = t.seg_start; J.seg_len = t.seg_len; J.tdef = t.tdef; J.ws = t.ws; J.rb = t.rb; J.re = t.re; J.qb = t.qb; J.qe = t.qe;
+        J.seg_start = t.seg_start; J.seg_len = t.seg_len; J.tdef = t.tdef | (t.shift << 8); J.ws = t.ws; J.rb = t.rb; J.re = t.re; J.qb = t.qb; J.qe = t.qe;
         J.score = (int)t.score; J.out_off = total;
         offs[i] = total;
         total += 2 * ((int64_t)t.nt + 1);
@@ -1179,7 +1185,7 @@ int run_sim_batches(ltg_context* c, const std::vector<HostSeg>& active, const Re
             for (ltg_host::SimRow& r : rows) {
                 if (!ltg_host::passes_record_filter(r.t, c->params)) continue;            // Fasim-LongTarget.cpp:589-597
                 r.t.record = sg.record;
-                rb.add(r.t, r.tfo.c_str(), r.tts.c_str(), recs[sg.record].chr, recs[sg.record].record_start, sg.record);
+                rb.add(r.t, r.tfo.c_str(), r.tts.c_str(), recs[sg.record].chr, recs[sg.record].record_start, sg.record, (int64_t)r.tfo.size());
             }
         }
         st.n_segments += S; st.n_tasks += n_tasks;
@@ -1447,7 +1453,7 @@ void ltg_destroy(ltg_context* c)
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs, &c->d_side_jobs, &c->d_side_colmax})
         b->release();
     for (DevBuf* b : {&c->d_rna_sim, &c->d_sim_scratch, &c->d_sim_hdr, &c->d_sim_pool, &c->d_sim_tasks}) b->release();
-    for (int k = 0; k < 20; ++k) c->d_w[k].release();
+    for (int k = 0; k < 24; ++k) c->d_w[k].release();
     for (int k = 0; k < 4; ++k) c->d_pc[k].release();
     c->d_res64.release();
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1477,6 +1483,13 @@ int ltg_set_params(ltg_context* c, const ltg_params* p)
     c->params = *p;
     return LTG_OK;
     });
+}
+
+int ltg_set_compat(ltg_context* c, int lowercase_variant)
+{
+    if (!c) { set_error("null argument"); return LTG_ERR_ARG; }
+    c->compat = lowercase_variant != 0;
+    return LTG_OK;
 }
 
 int ltg_set_sim_mode(ltg_context* c, int on)

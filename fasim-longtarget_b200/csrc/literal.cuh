@@ -443,12 +443,12 @@ __global__ void k_lit_collect(const WinState w, int reverse, int round, LiteralJ
         //  keeps its own, lower result; the literal kernels detect a real overflow themselves and leave the exact result alone)
         if (v.x < kQ4Guard) return;
         const int cut = w.w_len[i];
-        J.kind = 1; J.ref_start = w.pk_pos[i] - cut + 1; J.ref_len = cut; J.ref_dir = 0;
+        J.kind = 1; J.ref_start = w.w_ws[i]; J.ref_len = cut; J.ref_dir = 0;
         J.read_start = 0; J.read_len = w.m; J.read_dir = 1; J.terminate = 255;
     } else {
         const int sw = w.fin_sw[i];
         if (sw < kQ4Guard || sw >= kOverflowU8) return;
-        J.kind = 2; J.ref_start = w.pk_pos[i] - w.fin_cut[i] + 1; J.ref_len = w.fin_re[i] + 1; J.ref_dir = 1;
+        J.kind = 2; J.ref_start = w.fin_ws[i]; J.ref_len = w.fin_re[i] + 1; J.ref_dir = 1;
         J.read_start = w.fin_qe[i]; J.read_len = w.fin_qe[i] + 1; J.read_dir = -1; J.terminate = sw & 0xff;
     }
     jobs[atomicAdd(count, 1)] = J;

@@ -71,6 +71,9 @@ struct WinState {
     const int* pk_score;
     // per peak
     int* w_len;        // columns of the window in flight (cut, or re+1 in the reverse pass)
+    int* w_ws;         // first column (translated-segment coordinates) of the forward window in flight
+    int* w_shift;      // lowercase compat only: columns by which that window starts right of pos - cut + 1 (the start clamp the older
+                       // variant applies to the substring but not to the reported coordinates, fastSim.h:204-212); 0 otherwise
     int* w_bound;      // a result >= w_bound is exact (row pruning, see the header comment); 0: all rows were streamed
     int* w_floor;      // cells <= w_floor cannot matter for this sweep (they neither prove exactness nor beat a proven
                        // lower bound), so the per-lane result tracker starts there
@@ -78,8 +81,9 @@ struct WinState {
     int* w_done;       // 1: final alignment chosen
     int* w_next;       // next forward round this peak takes part in (rounds in between are provably no-ops, see k_win_probe)
     int* w_probe;      // 1: the round's result waits for its reverse probe; 2: fin_rb / fin_qb are final already
-    int* best_sw; int* best_cut; int* best_re; int* best_qe;
-    int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb;
+    int* best_sw; int* best_cut; int* best_re; int* best_qe; int* best_ws;
+    int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb; int* fin_ws; int* fin_shift;
+    int compat;        // 1: window loop of the older variant (fastSim.h:194-226): no start clamp, accept on equality only, no best candidate
     WinSched* sched;
     // Work items ("pieces") of a launch: a peak's window swept over one range of RNA rows.  First sweeps and reverse
     // sweeps have one piece per peak; a re-planned forward sweep has one piece per run of qualifying granules.
@@ -125,7 +129,7 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt >> 3, sub = gt & 7;
     bool active = i < w.n_peaks;
-    int len = 0, rows = 0, bound = 0, proven = 0, accept_floor = 0;
+    int len = 0, rows = 0, bound = 0, proven = 0, accept_floor = 0, ws = 0, shift = 0;
     if (active) {
         if (round >= 0) {
             const int sc = w.pk_score[i], pos = w.pk_pos[i];
@@ -134,8 +138,17 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
                 if (round == 0) { if (sub == 0) { w.w_done[i] = 0; w.best_sw[i] = 0; w.fin_sw[i] = 0; w.w_next[i] = 0; w.w_probe[i] = 0; } }
                 else if (w.w_done[i] || w.w_next[i] != round) active = false;
                 int cut = w.forced_cut ? w.forced_cut[i] : w.cut_table[min(sc, 255) * 4 + round];
-                if (pos - cut + 1 <= 0) cut = pos + 1;                 // fastsim.h:211
-                len = cut;
+                if (w.compat) {
+                    // fastSim.h:204-205: substr(max(pos - cut + 1, 0), cut) — a clamped window keeps its length (cut short only by
+                    // the end of the segment) and so reaches beyond the peak column
+                    ws = max(pos - cut + 1, 0);
+                    shift = ws - (pos - cut + 1);
+                    len = min(cut, w.segs[w.pk_task[i] / w.tasks_per_seg].len - ws);
+                } else {
+                    if (pos - cut + 1 <= 0) cut = pos + 1;             // fastsim.h:211
+                    len = cut;
+                    ws = pos - cut + 1;
+                }
                 bound = sc;
                 // rounds >= 1 look at a shorter window with the same right end: its best score cannot exceed the previous
                 // round's (exact) one, which is therefore the better first guess (any guess is safe, exactness is verified)
@@ -145,6 +158,7 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
                 // not in flight / exact already (value proven and position known; a zero needs no position)
                 if (w.w_done[i] || w.w_next[i] != round || (v.x >= w.w_bound[i] && (v.y != 0x7fffffff || v.x <= 0))) active = false;
                 len = w.w_len[i];
+                ws = w.w_ws[i]; shift = w.w_shift[i];
                 bound = max(v.x, 0);
                 proven = bound;              // a cell with this value exists: anything below it is irrelevant now
             }
@@ -167,11 +181,11 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
     const int join = (win_margin(len) + bit_rows - 1) / bit_rows;           // a gap this short would be covered by the next margin anyway
     if (round >= 0 && w.gran_blk != nullptr) {
         const bool scan = active && bound > 0;
-        int task = 0, pos = 0;
-        if (scan) { task = w.pk_task[i]; pos = w.pk_pos[i]; }
+        int task = 0;
+        if (scan) task = w.pk_task[i];
         const TaskDef td = c_tasks[task % w.tasks_per_seg];
         const uint16_t* base = w.gran_blk + ((size_t)(task / w.tasks_per_seg) * w.n_pairs + td.pair) * w.n_gran * w.blk_pitch;
-        const int lo_col = pos - len + 1;
+        const int lo_col = ws, pos = ws + len - 1;
         const int grp = (threadIdx.x & 31) & ~7;       // first lane of this peak's 8 threads
         int pending = 0;        // largest bound among the non-qualifying granules after the last qualifying one
         for (int k0 = 0; k0 < w.n_gran; k0 += 8) {
@@ -252,6 +266,7 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
     if (mine) {
         int p = base + incl - np;
         w.w_len[i] = len;
+        if (round >= 0) { w.w_ws[i] = ws; w.w_shift[i] = shift; }
         w.w_flight[i] = 1;
         w.res64[i] = 0ull;
         auto emit = [&](int lo, int rows) {
@@ -409,8 +424,7 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
                 const TaskDef td = c_tasks[task % w.tasks_per_seg];
                 const int L = w.w_len[i];
                 len[h] = L;
-                const int cutw = REV ? w.fin_cut[i] : L;
-                const int ws = w.pk_pos[i] - cutw + 1;                    // window start in seq2 coordinates
+                const int ws = REV ? w.fin_ws[i] : w.w_ws[i];              // window start in seq2 coordinates
                 if (REV) { slen[h] = min(w.fin_qe[i] + 1, win_margin(L)); sbase[h] = w.fin_qe[i]; sdir[h] = -1; }
                 else { slen[h] = w.pc_rows[piece]; sbase[h] = w.pc_lo[piece]; sdir[h] = 1; }
                 const int off = g * R - L;
@@ -565,33 +579,43 @@ __global__ void k_win_decide(const WinState w, int round)
     int sw = 0, re = 0, qe = 0;
     if (v.x > 0) { sw = v.x; re = v.y; qe = v.z; }
     const int S = w.pk_score[i];
+    const int ws = w.w_ws[i];
+    if (w.compat) {
+        // fastSim.h:203-210: the loop only stops on equality; whatever the last window gave is converted (an exact 0 stays 0 in
+        // every nested window)
+        if (sw == S || round == 3 || (sw == 0 && v.w == 0)) {
+            w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.fin_ws[i] = ws; w.fin_shift[i] = w.w_shift[i]; w.w_done[i] = 1;
+        } else w.w_next[i] = round + 1;
+        return;
+    }
+    w.fin_shift[i] = 0;
     if (sw >= S) {
-        w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.w_done[i] = 1;
+        w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.fin_ws[i] = ws; w.w_done[i] = 1;
         return;
     }
     if (sw > w.best_sw[i] && re == cut - 1) {
-        w.best_sw[i] = sw; w.best_cut[i] = cut; w.best_re[i] = re; w.best_qe[i] = qe;
+        w.best_sw[i] = sw; w.best_cut[i] = cut; w.best_re[i] = re; w.best_qe[i] = qe; w.best_ws[i] = ws;
         // The later rounds look at nested, shorter windows with the same right end, so their exact scores cannot exceed
         // this one: they can neither reach S (> sw) nor replace this candidate (needs a strictly larger score), and the
         // loop ends with this candidate (fastsim.h:236-249).  Only when this score came from the literal emulation (which may
         // report less than exact SW, res.w = 1) a later round could still overtake it, so those keep going.
         if (v.w == 0) {
-            w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.w_done[i] = 1;
+            w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.fin_ws[i] = ws; w.w_done[i] = 1;
             return;
         }
     }
     // an exact score of 0 stays 0 in every nested window: nothing will be accepted or become a candidate any more
     const bool dead_end = (sw == 0 && v.w == 0);
     if (round == 3 || dead_end) {
-        if (w.best_sw[i] > 0) { w.fin_sw[i] = w.best_sw[i]; w.fin_cut[i] = w.best_cut[i]; w.fin_re[i] = w.best_re[i]; w.fin_qe[i] = w.best_qe[i]; }
-        else { w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; }
+        if (w.best_sw[i] > 0) { w.fin_sw[i] = w.best_sw[i]; w.fin_cut[i] = w.best_cut[i]; w.fin_re[i] = w.best_re[i]; w.fin_qe[i] = w.best_qe[i]; w.fin_ws[i] = w.best_ws[i]; }
+        else { w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.fin_ws[i] = ws; }
         w.w_done[i] = 1;
         return;
     }
     w.w_next[i] = round + 1;
     // exact result, no candidate so far: park it in fin_* for the reverse probe (k_win_probe) that may skip rounds
     if (v.w == 0 && w.best_sw[i] == 0) {
-        w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe;
+        w.fin_sw[i] = sw; w.fin_cut[i] = cut; w.fin_re[i] = re; w.fin_qe[i] = qe; w.fin_ws[i] = ws;
         w.w_probe[i] = 1;
     }
 }
@@ -612,7 +636,7 @@ __global__ void k_win_probe(const WinState w, int round)
     if (v.x != S) return;                        // (cannot happen for an exact forward score) take every round
     const int rb = w.fin_re[i] - v.y, qb = w.fin_qe[i] - v.z;
     const int pos = w.pk_pos[i], sc = w.pk_score[i];
-    const int start_col = pos - w.fin_cut[i] + 1 + rb;       // in translated-segment coordinates
+    const int start_col = w.fin_ws[i] + rb;                  // in translated-segment coordinates
     int k = round + 1;
     for (; k <= 3; ++k) {
         int cut = w.forced_cut ? w.forced_cut[i] : w.cut_table[min(sc, 255) * 4 + k];
@@ -654,7 +678,7 @@ __global__ void k_win_finish(const WinState w)
 // with a large scratch.
 struct TraceJob {
     long long seg_start;       // segment offset in the record
-    int seg_len, tdef;         // segment length, index into the task table
+    int seg_len, tdef;         // segment length; index into the task table (bits 0..7) | lowercase compat: the coordinate shift << 8
     int ws;                    // window start in seq2 (translated-segment) coordinates
     int rb, re, qb, qe;        // alignment box: window-relative columns, lncRNA rows
     int score;                 // sw_score (<= 0: nothing to do)
@@ -708,10 +732,11 @@ __global__ void k_make_trace_jobs(const WinState w, TraceJob* jobs, TraceOut* to
     J.ws = 0; J.rb = J.re = J.qb = J.qe = 0; J.out_off = 0;
     TraceOut o; o.status = 0; o.nt = 0; o.identity = 0.0f; o.tri = 0.0f;
     if (J.score > 0) {
-        J.ws = w.pk_pos[i] - w.fin_cut[i] + 1;
+        J.ws = w.fin_ws[i];
+        J.tdef |= w.fin_shift[i] << 8;
         J.rb = w.fin_rb[i]; J.re = w.fin_re[i]; J.qb = w.fin_qb[i]; J.qe = w.fin_qe[i];
         const int refLen = J.re - J.rb + 1, readLen = J.qe - J.qb + 1;
-        if (dr.dna != nullptr && max(refLen, readLen) >= dr.nt_min) {
+        if (dr.dna != nullptr && w.fin_shift[i] == 0 && max(refLen, readLen) >= dr.nt_min) {
             bool dead = refLen + readLen - (J.score + 4) / 5 < dr.need_nt;
             if (!dead && dr.penalty_t < 0 && refLen + readLen <= dr.nt_max) {     // (nt > ntMax would zero the stability instead)
                 const float pcf = (float)dr.penalty_c;
@@ -771,7 +796,8 @@ __global__ void k_traceback(const TraceArgs a)
         const TraceJob J = a.jobs[i];
         if (J.score <= 0) continue;
 
-        const TaskDef td = c_tasks[J.tdef];
+        const TaskDef td = c_tasks[J.tdef & 0xFF];
+        const int shift = J.tdef >> 8;      // lowercase compat: the strings are read `shift` columns left of the aligned ones (fastSim.h:211-212)
         const int ws = J.ws, rb = J.rb, re = J.re, qb = J.qb, qe = J.qe;
         const int refLen = re - rb + 1, readLen = qe - qb + 1, score = J.score;
         const uint8_t* gc = a.codes + J.seg_start;
@@ -850,17 +876,20 @@ __global__ void k_traceback(const TraceArgs a)
         ops[--wp] = 0;      // closing rule (:1220-1238): the alignment always starts with one more M column
         const int nt = ntmax + 2 - wp;
         // expansion from the front exactly like getAlignment: q walks the translated DNA from ref_begin, p the RNA
-        int q = ws + rb, p = qb, match = 0;
+        int q = ws + rb - shift, p = qb, match = 0;
         for (int k = 0; k < nt; ++k) {
             const int op = ops[wp + k];
             char rch = '-', sch = '-', tch = '-';
             if (op != 2) rch = (char)a.rna_raw[p++];
             if (op != 1) {
-                const int gi = gidx(q++);
-                const unsigned char raw = a.dna[J.seg_start + gi];
-                sch = td.comp_src ? comp_char(raw) : (char)raw;
-                const int dcode = td.img[gc[gi]];
-                tch = dcode < 4 ? "ACGT"[dcode] : 'N';
+                if (q >= 0 && q < J.seg_len) {
+                    const int gi = gidx(q);
+                    const unsigned char raw = a.dna[J.seg_start + gi];
+                    sch = td.comp_src ? comp_char(raw) : (char)raw;
+                    const int dcode = td.img[gc[gi]];
+                    tch = dcode < 4 ? "ACGT"[dcode] : 'N';
+                } else { sch = 'N'; tch = 'N'; }          // (shifted outside the segment: the reference reads out of bounds there)
+                ++q;
             }
             tfo[k] = rch; tts[k] = sch;
             if (tch == rch) ++match;
@@ -921,7 +950,8 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         }
         const TraceJob J = a.jobs[i];
         if (J.score <= 0) continue;
-        const TaskDef td = c_tasks[J.tdef];
+        const TaskDef td = c_tasks[J.tdef & 0xFF];
+        const int shift = J.tdef >> 8;
         const int ws = J.ws, rb = J.rb, qb = J.qb;
         const int refLen = J.re - rb + 1, readLen = J.qe - qb + 1, score = J.score;
         const uint8_t* gc = a.codes + J.seg_start;
@@ -1034,7 +1064,7 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
         const float pt = __int2float_rn(a.penalty_t), pc = __int2float_rn(a.penalty_c);
         char* o_tfo = a.strpool ? a.strpool + J.out_off : nullptr;
         char* o_tts = o_tfo ? o_tfo + nt + 1 : nullptr;
-        int q = ws + rb, p = qb, match = 0;
+        int q = ws + rb - shift, p = qb, match = 0;
         float tri = 0.0f, prev_val = 0.0f;
         char prev_ch = 0;
         for (int k = 0; k < nt; ++k) {
@@ -1042,11 +1072,14 @@ __global__ void __launch_bounds__(TPB) k_traceback_fast(const TraceArgs a)
             char rch = '-', sch = '-', tch = '-';
             if (op != 2) rch = (char)a.rna_raw[p++];
             if (op != 1) {
-                const int gi = gidx(q++);
-                const unsigned char raw = a.dna[J.seg_start + gi];
-                sch = td.comp_src ? comp_char(raw) : (char)raw;
-                const int dcode = td.img[gc[gi]];
-                tch = dcode < 4 ? "ACGT"[dcode] : 'N';
+                if (q >= 0 && q < J.seg_len) {
+                    const int gi = gidx(q);
+                    const unsigned char raw = a.dna[J.seg_start + gi];
+                    sch = td.comp_src ? comp_char(raw) : (char)raw;
+                    const int dcode = td.img[gc[gi]];
+                    tch = dcode < 4 ? "ACGT"[dcode] : 'N';
+                } else { sch = 'N'; tch = 'N'; }
+                ++q;
             }
             if (tch == rch) ++match;
             if (with_tri) {

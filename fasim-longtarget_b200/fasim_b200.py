@@ -43,7 +43,7 @@ class TaskProbe(C.Structure):
                 ("n_peaks", C.c_int32), ("literal", C.c_int32), ("pad_", C.c_int32)]
 
 
-EXPORTS = ["ltg_create", "ltg_destroy", "ltg_last_error", "ltg_default_params", "ltg_set_params", "ltg_set_sim_mode", "ltg_set_query",
+EXPORTS = ["ltg_create", "ltg_destroy", "ltg_last_error", "ltg_default_params", "ltg_set_params", "ltg_set_sim_mode", "ltg_set_compat", "ltg_set_query",
            "ltg_scan_record", "ltg_scan_records", "ltg_scan_records_at", "ltg_scan_device", "ltg_scan_shard", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
            "ltg_write_tfosorted", "ltg_write_tfoclass", "ltg_main", "ltg_probe_segment", "ltg_probe_align", "ltg_stream", "ltg_debug_stats",
            "ltg_device_count"]
@@ -71,6 +71,7 @@ def lib():
         L.ltg_destroy.argtypes = [C.c_void_p]
         L.ltg_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.ltg_set_sim_mode.argtypes = [C.c_void_p, C.c_int]
+        L.ltg_set_compat.argtypes = [C.c_void_p, C.c_int]
         L.ltg_set_query.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int64]
         L.ltg_scan_record.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.POINTER(Result))]
         L.ltg_scan_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.POINTER(Result))]
@@ -160,6 +161,10 @@ class Engine:
     def set_sim_mode(self, on=True):
         """-F of the reference (Fasim-LongTarget.cpp:360): SIM() instead of fastSIM() per task."""
         _check(lib().ltg_set_sim_mode(self._h, 1 if on else 0))
+
+    def set_compat(self, lowercase=True):
+        """the older variant's per-task pipeline (fasim-LongTarget.cpp / fastSim.h)"""
+        _check(lib().ltg_set_compat(self._h, 1 if lowercase else 0))
 
     def set_query(self, name, rna):
         self.rna = rna

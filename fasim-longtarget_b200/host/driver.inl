@@ -68,6 +68,8 @@ void usage()
            "  --species S                    species field of the output file name (default: the .2bit file's base name)\n"
            "  --softmask upper|n|error       lower-case (soft-masked) bases of -f1: upper-case them (default; a notice is printed),\n"
            "                                 score them as N (what the reference's scan does), or refuse the input\n"
+           "  --compat lowercase   behave like the older fasim-LongTarget.cpp / fastSim.h variant (window loop without start clamp, no\n"
+           "                       per-task filter) and write <species>-<lncRNA>-fastSim-TFOsorted only\n"
            "  --list-records   print the DNA records -f1 and the lncRNAs -f2 yield (name, start, length, CRC-32) and exit (no GPU needed)\n"
            "  --queries   -f2 holds several lncRNAs (one per '>' record): every lncRNA is scanned against -f1 and gets its own\n"
            "              output files; the (lncRNA, chunk) pairs go through the same queue\n");
@@ -175,12 +177,12 @@ int ltg_main(int argc, char* const* argv)
         {"cn", required_argument, nullptr, 'C'}, {"ds", required_argument, nullptr, 'D'}, {"lg", required_argument, nullptr, 'E'},
         {"device", required_argument, nullptr, 1000}, {"devices", required_argument, nullptr, 1001}, {"queries", no_argument, nullptr, 1002},
         {"seq", required_argument, nullptr, 1003}, {"species", required_argument, nullptr, 1004}, {"list-records", no_argument, nullptr, 1005},
-        {"softmask", required_argument, nullptr, 1006},
+        {"softmask", required_argument, nullptr, 1006}, {"compat", required_argument, nullptr, 1007},
         {nullptr, 0, nullptr, 0}};
     if (argc <= 1) { usage(); return 1; }
     optind = 1;
     int opt;
-    bool want_sim = false, multi_query = false, list_records = false;
+    bool want_sim = false, multi_query = false, list_records = false, compat_lc = false;
     std::string seq_arg, species_arg;
     int softmask = ltg_host::kSoftUpper;
     while ((opt = getopt_long_only(argc, argv, optstring, long_options, nullptr)) != -1) {
@@ -208,6 +210,10 @@ int ltg_main(int argc, char* const* argv)
         case 1003: seq_arg = seq_arg.empty() ? std::string(optarg) : seq_arg + "," + optarg; break;
         case 1004: species_arg = optarg; break;
         case 1005: list_records = true; break;
+        case 1007:
+            if (!strcmp(optarg, "lowercase")) compat_lc = true;
+            else if (strcmp(optarg, "canonical")) { fprintf(stderr, "fasim: --compat takes canonical or lowercase\n"); return 2; }
+            break;
         case 1006:
             if (!strcmp(optarg, "upper")) softmask = ltg_host::kSoftUpper;
             else if (!strcmp(optarg, "n") || !strcmp(optarg, "N")) softmask = ltg_host::kSoftAsN;
@@ -361,9 +367,11 @@ int ltg_main(int argc, char* const* argv)
         for (size_t u = 0; u < n_units; ++u) if (results[q * n_units + u]) { ltg_result_free(results[q * n_units + u]); results[q * n_units + u] = nullptr; }
         if (rc == LTG_OK) rc = ltg_cluster(all, &P);
         const std::string& lnc_name = queries[q].first;
-        const std::string out_path = outdir + "/" + recs[0].species + "-" + lnc_name + "-" + base + "-TFOsorted";
+        // (the older variant: <species>-<lncName>-fastSim-TFOsorted and no -TFOclass files, fasim-LongTarget.cpp:883)
+        const std::string out_path = compat_lc ? outdir + "/" + recs[0].species + "-" + lnc_name + "-fastSim-TFOsorted"
+                                               : outdir + "/" + recs[0].species + "-" + lnc_name + "-" + base + "-TFOsorted";
         if (rc == LTG_OK) rc = ltg_write_tfosorted(all, out_path.c_str());
-        if (rc == LTG_OK) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, (int64_t)recs[0].seq.size(), lnc_name.c_str());
+        if (rc == LTG_OK && !compat_lc) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, (int64_t)recs[0].seq.size(), lnc_name.c_str());
         if (rc == LTG_OK && all->scan_cells > 0)
             printf("[b200] %s: segments=%ld tasks=%ld peaks=%ld scan_cells=%.3e gpu_scan_ms=%.2f gpu_window_ms=%.2f literal_tasks=%ld literal_windows=%ld\n",
                    lnc_name.c_str(), (long)all->n_segments, (long)all->n_tasks, (long)all->n_peaks, (double)all->scan_cells, all->gpu_ms_scan,
@@ -379,6 +387,7 @@ int ltg_main(int argc, char* const* argv)
         t_create = tnow() - t_create;
         if (rc == LTG_OK) rc = ltg_set_params(ctx, &P);
         if (rc == LTG_OK && want_sim) rc = ltg_set_sim_mode(ctx, 1);
+        if (rc == LTG_OK && compat_lc) rc = ltg_set_compat(ctx, 1);
         size_t cur_q = (size_t)-1;
         while (rc == LTG_OK && !failed.load()) {
             const size_t job = next_job.fetch_add(1);

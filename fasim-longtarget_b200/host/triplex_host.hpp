@@ -23,12 +23,14 @@ struct Triplex {
     float score = 0, identity = 0, tri_score = 0;
     // where the alignment lives: input of the string pass (window.cuh TraceJob)
     int tdef = 0, seg_len = 0, ws = 0, rb = 0, re = 0, qb = 0, qe = 0;
+    int shift = 0;          // lowercase compat: reported coordinates and strings lie `shift` columns left of the aligned ones
     long seg_start = 0;     // offset of the segment in the device DNA buffer of the call
     int record = 0;         // record index within the call
 };
 
 struct DeviceAlignment {        // one chosen alignment as it comes back from the GPU (pass 1 of the traceback)
     int sw_score, ws, rb, re, query_begin, query_end;   // ws + rb / ws + re = ref_begin / ref_end in translated-segment coordinates
+    int shift = 0;              // ... minus this in the older variant's reporting (fastSim.h:211-212), 0 otherwise
     int nt;
     float identity, tri_score;  // evaluated on the device exactly as fastsim.h:323-383 does (float32, same order)
 };
@@ -38,7 +40,7 @@ inline void make_triplex(const DeviceAlignment& al, int tdef, int seg_len, long 
                          int rule, const ltg_params& P, std::vector<Triplex>& out)
 {
     if (al.nt < P.nt_min) return;
-    const int ref_begin = al.ws + al.rb, ref_end = al.ws + al.re;
+    const int ref_begin = al.ws + al.rb - al.shift, ref_end = al.ws + al.re - al.shift;
     int a, b;
     if ((para > 0 && strand == 1) || (para < 0 && strand == 0)) { a = seg_len - ref_end - 1; b = seg_len - ref_begin - 1; }
     else { a = ref_begin + 1; b = ref_end + 1; }
@@ -48,7 +50,7 @@ inline void make_triplex(const DeviceAlignment& al, int tdef, int seg_len, long 
     t.strand = strand; t.reverse = para; t.rule = rule; t.nt = al.nt;
     t.score = (float)al.sw_score; t.identity = al.identity; t.tri_score = al.tri_score;
     t.tdef = tdef; t.seg_len = seg_len; t.seg_start = seg_start; t.record = record;
-    t.ws = al.ws; t.rb = al.rb; t.re = al.re; t.qb = al.query_begin; t.qe = al.query_end;
+    t.ws = al.ws; t.shift = al.shift; t.rb = al.rb; t.re = al.re; t.qb = al.query_begin; t.qe = al.query_end;
     out.push_back(t);
 }
 
@@ -72,7 +74,8 @@ inline bool redundant(const Triplex& a, const Triplex& b)
 }
 
 // tail of fastSIM — fastsim.h:273-288: two sort/unique rounds, sort by score, first 50, per-task filter
-inline void finish_task(std::vector<Triplex>& mine, const ltg_params& P, std::vector<Triplex>& out)
+// (compat: the older variant keeps the first 50 without the identity / stability / nt filter, fastSim.h:311-313)
+inline void finish_task(std::vector<Triplex>& mine, const ltg_params& P, std::vector<Triplex>& out, bool compat = false)
 {
     std::sort(mine.begin(), mine.end(), by_start);
     mine.erase(std::unique(mine.begin(), mine.end(), redundant), mine.end());
@@ -82,7 +85,7 @@ inline void finish_task(std::vector<Triplex>& mine, const ltg_params& P, std::ve
     const size_t lim = std::min<size_t>(mine.size(), 50);
     const float min_id = (float)P.min_identity, min_st = (float)P.min_stability;
     for (size_t i = 0; i < lim; ++i)
-        if (mine[i].identity >= min_id && mine[i].tri_score >= min_st && mine[i].nt >= P.nt_min) out.push_back(mine[i]);
+        if (compat || (mine[i].identity >= min_id && mine[i].tri_score >= min_st && mine[i].nt >= P.nt_min)) out.push_back(mine[i]);
 }
 
 // final filter of LongTarget — Fasim-LongTarget.cpp:589-597

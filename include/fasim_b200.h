@@ -92,6 +92,12 @@ const char* ltg_last_error(void);
 void ltg_default_params(ltg_params* p);                        /* initEnv defaults — Fasim-LongTarget.cpp:284-303 */
 int ltg_set_params(ltg_context* ctx, const ltg_params* p);
 
+/* lowercase_variant != 0 selects the behaviour of the OLDER driver that ships next to the canonical one (fasim-LongTarget.cpp +
+ * fastSim.h): per-peak window loop of fastSim.h:194-226 (no start clamp, acceptance only on equality, no best-candidate
+ * tracking, the last window's alignment is always converted) and no per-task identity / stability filter (:311-313).  The
+ * `fasim --compat lowercase` command line adds that variant's output naming (fasim-LongTarget.cpp:883).                    */
+int ltg_set_compat(ltg_context* ctx, int lowercase_variant);
+
 /* replaces the -F switch (paraList.doFastSim = false, Fasim-LongTarget.cpp:360-362): with on != 0 every task is aligned by
  * SIM() — sim.h:410-1143, Huang & Miller's k best non-intersecting local alignments — instead of fastSIM(); the scan calls
  * then return SIM's rows (dispatch at Fasim-LongTarget.cpp:419-426 and its 15 sibling call sites).                          */

@@ -589,6 +589,10 @@ struct Params {
     int rule = 0, cutLength = 5000, strand = 0, overlap = 100, ntMin = 20, ntMax = 100000;
     float minIdentity = 60, minStability = 1;
     int penaltyT = -1000, penaltyC = 0, cDistance = 15, cLength = 50;
+    // 1: the older driver / pipeline that ships next to the canonical one (fasim-LongTarget.cpp + fastSim.h): window loop without
+    // the start clamp, acceptance only on equality, no best-candidate tracking, no per-task identity / stability filter
+    int lowercase = 0;
+    long oob = 0;        // compat mode: alignment columns whose shifted coordinates fall outside the segment (the reference reads out of bounds there)
 };
 
 static void convert_triplex(const Alignment& al, std::vector<Triplex>& list, const std::string& rna, const std::string& seq2,
@@ -597,12 +601,15 @@ static void convert_triplex(const Alignment& al, std::vector<Triplex>& list, con
     // CIGAR expansion (fastsim.h:416-560; the 60-column chunking there only wraps printing)
     std::string ref_align, read_align, src_align;
     int q = al.ref_begin, p = al.query_begin;
+    // (canonical mode: q always lies inside the segment.  Lowercase compat: the unclamped window offset can shift it left of
+    //  the segment, where the reference reads whatever precedes its string buffers; those columns read as 'N' here and are counted)
+    auto at = [&](const std::string& str, int k) -> char { if (k >= 0 && k < (int)str.size()) return str[k]; ++const_cast<Params&>(P).oob; return 'N'; };
     for (uint32_t c : al.cigar) {
         const uint32_t len = c >> 4, op = c & 15u;
         for (uint32_t k = 0; k < len; ++k) {
             if (op == 1) { ref_align += '-'; src_align += '-'; read_align += rna[p++]; }             // I
-            else if (op == 2) { ref_align += seq2[q]; src_align += src[q]; ++q; read_align += '-'; }    // D
-            else { ref_align += seq2[q]; src_align += src[q]; ++q; read_align += rna[p++]; }            // M
+            else if (op == 2) { ref_align += at(seq2, q); src_align += at(src, q); ++q; read_align += '-'; }    // D
+            else { ref_align += at(seq2, q); src_align += at(src, q); ++q; read_align += rna[p++]; }            // M
         }
     }
     const int nt = (int)ref_align.size();
@@ -677,6 +684,24 @@ static void run_task(const std::string& rna, const std::string& seg, long dnaSta
     for (size_t i = 0; i < seq2.size(); ++i) refc[i] = ssw_code(seq2[i]);
     std::vector<Triplex> mine;
     for (const Peak& pk : peaks) {
+        if (P.lowercase) {                                    // fastSim.h:194-226
+            float Iden = 0.6;
+            int cut = 0;
+            Alignment al;
+            while (Iden <= 1) {
+                cut = (int)(pk.score + 24) / (9 * Iden - 4) + 1;
+                const int ws = pk.pos - cut + 1 > 0 ? pk.pos - cut + 1 : 0;          // substr(start clamped to 0, cut): the window keeps its
+                const int len = std::min(cut, (int)seq2.size() - ws);                // length and then reaches beyond the peak column
+                al = align_window(read, refc.data() + ws, len);
+                if (trace) trace->push_back({pk.score, pk.pos, cut, al.sw_score, al.ref_begin, al.ref_end, al.query_begin, al.query_end});
+                if (al.sw_score == pk.score) break;
+                Iden += 0.1;
+            }
+            al.ref_begin += pk.pos - cut + 1;                 // (unclamped: a clamped window reports coordinates shifted to the left)
+            al.ref_end += pk.pos - cut + 1;
+            convert_triplex(al, mine, rna, seq2, src, dnaStart, rule, strand, para, P);
+            continue;
+        }
         float Iden = 0.6;
         int cut = 0, bestcut = 0, flag = 0;
         Alignment al, best;
@@ -705,7 +730,7 @@ static void run_task(const std::string& rna, const std::string& seg, long dnaSta
     const size_t lim = mine.size() > 50 ? 50 : mine.size();
     for (size_t i = 0; i < lim; ++i) {
         const Triplex& t = mine[i];
-        if (t.identity >= P.minIdentity && t.tri_score >= P.minStability && t.nt >= P.ntMin) out.push_back(t);
+        if (P.lowercase || (t.identity >= P.minIdentity && t.tri_score >= P.minStability && t.nt >= P.ntMin)) out.push_back(t);     // fastSim.h:311-313: no filter
     }
 }
 
@@ -1366,6 +1391,30 @@ int orc_run_tfosorted_multi(const char* rna, int n_records, const char* const* d
             all.push_back(t);
         }
     }
+    std::string txt = orc::format_sorted(all, P);
+    return orc::emit(txt, out, cap);
+}
+
+// The older variant's whole run (fasim-LongTarget.cpp:86-141 main, :869-905 printResult): multi-record -f1, one output file
+// <species>-<lncName>-fastSim-TFOsorted, no -TFOclass files.  *oob_out receives the number of alignment columns the
+// reference would have read out of bounds (results are not comparable when it is not 0).
+int orc_run_lowercase(const char* rna, int n_records, const char* const* dnas, const char* const* chrs, const long* starts,
+                      const int* params, char* out, long cap, long* oob_out)
+{
+    orc::Params P = orc::params_from(params);
+    P.lowercase = 1;
+    std::vector<orc::Triplex> all;
+    for (int r = 0; r < n_records; ++r) {
+        std::vector<orc::Triplex> list;
+        orc::run_record(rna, dnas[r], P, list);
+        for (auto& t : list) {
+            t.chr = chrs[r];
+            t.genomestart = t.starj + starts[r] - 1;
+            t.genomeend = t.endj + starts[r] - 1;
+            all.push_back(t);
+        }
+    }
+    if (oob_out) *oob_out = P.oob;
     std::string txt = orc::format_sorted(all, P);
     return orc::emit(txt, out, cap);
 }

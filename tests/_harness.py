@@ -138,6 +138,21 @@ class Side:
         assert k >= 0
         return buf.value.decode()
 
+    def run_lowercase(self, rna, records, **kw):
+        """oracle only: the older variant's whole run (fasim-LongTarget.cpp) -> (text of -fastSim-TFOsorted, out-of-bounds columns);
+        records = [(dna, chr, start)]"""
+        n = len(records)
+        cap = 1 << 26
+        buf = C.create_string_buffer(cap)
+        oob = C.c_long(0)
+        f = self._f("run_lowercase")
+        f.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_long), C.POINTER(C.c_int), C.c_char_p,
+                      C.c_long, C.POINTER(C.c_long)]
+        k = f(rna.encode(), n, (C.c_char_p * n)(*[d.encode() for d, _, _ in records]), (C.c_char_p * n)(*[c.encode() for _, c, _ in records]),
+              (C.c_long * n)(*[int(s) for _, _, s in records]), params_array(**kw), buf, cap, C.byref(oob))
+        assert k >= 0
+        return buf.value.decode(), oob.value
+
     def cluster(self, stari, endi, nt, dd, length):
         n = len(stari)
         arr = lambda v: (C.c_int * n)(*[int(x) for x in v])

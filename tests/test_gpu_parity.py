@@ -589,6 +589,49 @@ def test_reference_binary_multi_query_inputs(tmp_path):
             assert len(open(os.path.join(d, "ref", f)).read().splitlines()) > 1, f
 
 
+# ------------------------------------------------------------------------------------------------ --compat lowercase
+def test_cli_compat_lowercase_byte_equal(tmp_path, data_dir):
+    """`fasim --compat lowercase`: the older variant that ships next to the canonical one (fasim-LongTarget.cpp + fastSim.h;
+    window loop without start clamp, acceptance on equality, no per-task filter, -fastSim-TFOsorted naming).  Byte-equal to the
+    UNMODIFIED older binary (tests/golden/make_golden_lowercase.py) on the demo and on the first 12 MEG3 regions (multi-record)."""
+    files = run_cli_files(tmp_path, "testDNA.fa", open(os.path.join(data_dir, "testDNA.fa")).read(), "H19.fa",
+                          open(os.path.join(data_dir, "H19.fa")).read(), ["-lg", "40", "--compat", "lowercase"])
+    assert list(files) == ["hg19-H19-fastSim-TFOsorted"]
+    assert files["hg19-H19-fastSim-TFOsorted"] == open(os.path.join(GOLDEN, "demo_lc_lg40__hg19-H19-fastSim-TFOsorted")).read()
+    d2 = tmp_path / "m"
+    d2.mkdir()
+    files = run_cli_files(d2, "MEG3-12.fa", open(os.path.join(data_dir, "MEG3-DNAseq-first12.fa")).read(), "MEG3.fa",
+                          open(os.path.join(data_dir, "MEG3-ENST00000451743.fa")).read(), ["-lg", "60", "--compat", "lowercase"])
+    (name, text), = files.items()
+    assert text == open(os.path.join(GOLDEN, "meg3_first12_lc__" + name)).read() and len(text.splitlines()) > 30
+
+
+def test_compat_lowercase_vs_oracle(engine):
+    """The same mode through the C ABI against the oracle's restatement of the older variant (pinned to its binary by
+    tests/test_oracle_golden.py): planted targets right at segment starts, where the unclamped window offset matters."""
+    rna = splitmix_bases(2001, 700)
+    dna = list(splitmix_bases(1001, 9000))
+    for at, (a, L) in zip((3, 40, 1500, 2980, 3010, 5990, 8950), ((50, 60), (200, 45), (300, 70), (400, 66), (90, 50), (500, 58), (610, 40))):
+        dna[at:at + L] = rna[a:a + L].translate(str.maketrans("TG", "AT"))
+    dna = "".join(dna)
+    try:
+        engine.set_compat(True)
+        for kw, ekw in ((dict(c_length=20, cut_length=3000, overlap=100), dict(cLength=20, cutLength=3000, overlap=100)),
+                        (dict(c_length=15, nt_min=30, min_identity=40, min_stability=0, penalty_t=-2), dict(cLength=15, ntMin=30, minIdentity=40, minStability=0, penaltyT=-2))):
+            engine.set_params(**kw)
+            engine.set_query("r", rna)
+            res = engine.scan_record(dna, "chrL", 5)
+            engine.cluster_triplex(res)
+            engine.printResult(res, "/tmp/_lc_TFOsorted")
+            engine.free(res)
+            want, oob = O.run_lowercase(rna, [(dna, "chrL", 5)], **ekw)
+            assert open("/tmp/_lc_TFOsorted").read() == want, kw
+            assert len(want.splitlines()) > 5
+    finally:
+        engine.set_compat(False)
+        engine.set_params()
+
+
 # ------------------------------------------------------------------------------------------------ -F mode (SIM)
 def test_sim_mode_vs_oracle(engine):
     """-F: every task through SIM() (sim.h:410).  k_sim's wavefront first pass + in-order node-list replay + the shared k-best

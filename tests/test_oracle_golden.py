@@ -121,3 +121,24 @@ def test_cluster_restatement():
     mid, cen, mot = O.cluster(stari, endi, nt, 15, 50)
     assert mid[6] == 0 and mot[6] == 0            # nt == length is not counted
     assert mot[0] == mot[1] == mot[2] and len(set(mot) - {0}) >= 3
+
+
+def test_oracle_lowercase_variant_equals_its_binary():
+    """The oracle's restatement of the OLDER variant (fasim-LongTarget.cpp + fastSim.h: Params::lowercase) against files written
+    by that variant's unmodified binary (tests/golden/make_golden_lowercase.py): demo, and 12 MEG3 regions as one multi-record run."""
+    import os
+    from _harness import GOLDEN, oracle_side, read_fasta
+    O = oracle_side()
+    data = os.path.join(GOLDEN, "data")
+    rna = read_fasta(os.path.join(data, "H19.fa"))[0][1]
+    hdr, dna = read_fasta(os.path.join(data, "testDNA.fa"))[0]
+    sp, ch, rng = hdr.split("|")
+    got, oob = O.run_lowercase(rna, [(dna, ch, int(rng.split("-")[0]))], cLength=40)
+    assert got == open(os.path.join(GOLDEN, "demo_lc_lg40__hg19-H19-fastSim-TFOsorted")).read()
+    rna = read_fasta(os.path.join(data, "MEG3-ENST00000451743.fa"))[0][1]
+    recs = []
+    for h, s in read_fasta(os.path.join(data, "MEG3-DNAseq-first12.fa")):
+        sp, ch, rng = h.split("|")
+        recs.append((s, ch, int(rng.split("-")[0])))
+    got, oob = O.run_lowercase(rna, recs, cLength=60)
+    assert got == open(os.path.join(GOLDEN, "meg3_first12_lc__MACS_pk13559-MEG3-ENST00000451743-fastSim-TFOsorted")).read()
