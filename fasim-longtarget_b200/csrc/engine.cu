@@ -168,6 +168,7 @@ struct ltg_context {
     int m = 0, n_strips = 0, scan_r = 32;
     bool profiles_dirty = true;
     DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
+    DevBuf d_packed, d_nblocks;         // 2-bit packed input staged for the device-side expansion
     DevBuf d_rna_sim, d_sim_scratch, d_sim_hdr, d_sim_pool, d_sim_tasks;      // -F mode (sim.cuh)
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_blkmax, d_bnd, d_counters;
@@ -1107,6 +1108,9 @@ struct RecordIn {
     const char* chr = nullptr;
     int64_t record_start = 0;
     int64_t record_len = -1, first_seg = 0, n_seg = -1;     // shard geometry (ltg_scan_shard); defaults: the whole record
+    // 2-bit packed input (ltg_scan_packed): `len` bases starting at base index packed_first of the packed bytes
+    const unsigned char* packed = nullptr; int packed_on_device = 0; int64_t packed_first = 0;
+    const uint32_t* n_start = nullptr; const uint32_t* n_size = nullptr; int n_blocks = 0;
 };
 
 // -F mode: every task goes through SIM() (sim.h:410) instead of fastSIM().  Per batch of segments: the scan stage yields the
@@ -1210,7 +1214,7 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
     std::vector<int64_t> base((size_t)n_recs + 1, 0);
     for (int64_t r = 0; r < n_recs; ++r) {
         const RecordIn& R = recs[r];
-        if (R.first_seg < 0 || R.len < 0 || (R.len > 0 && !R.h_dna && !R.d_dna)) { set_error("bad record %lld", (long long)r); return LTG_ERR_ARG; }
+        if (R.first_seg < 0 || R.len < 0 || (R.len > 0 && !R.h_dna && !R.d_dna && !R.packed)) { set_error("bad record %lld", (long long)r); return LTG_ERR_ARG; }
         if (int e = cut_segments(R.len, R.record_len < 0 ? R.len : R.record_len, R.first_seg, R.n_seg, c->params, base[r], (int)r, segs)) return e;
         base[r + 1] = base[r] + R.len;
     }
@@ -1220,11 +1224,35 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
     if (len > 0) {
         if (int e = c->d_dna.ensure((size_t)len)) return e;
         if (int e = c->d_codes.ensure((size_t)len)) return e;
+        bool any_packed = false;
         for (int64_t r = 0; r < n_recs; ++r) {
             const RecordIn& R = recs[r];
             if (R.len == 0) continue;
             unsigned char* dst = c->d_dna.as<unsigned char>() + base[r];
-            if (R.h_dna) { LTG_CUDA_CHECK(cudaMemcpyAsync(dst, R.h_dna, (size_t)R.len, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += R.len; }
+            if (R.packed) {
+                // 2-bit packed record: 0.25 B/base over PCIe (or none: the packed store may already sit in HBM), expanded on the device
+                const int64_t b0 = R.packed_first >> 2, b1 = (R.packed_first + R.len + 3) >> 2;
+                const unsigned char* dpk = R.packed + b0;
+                if (!R.packed_on_device) {
+                    if (int e = c->d_packed.ensure((size_t)(b1 - b0))) return e;
+                    LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_packed.p, R.packed + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->stream));
+                    c->h2d_bytes += b1 - b0;
+                    dpk = c->d_packed.as<unsigned char>();
+                }
+                if (int e = c->d_nblocks.ensure(sizeof(uint32_t) * 2 * (size_t)std::max(R.n_blocks, 1))) return e;
+                uint32_t* dn = c->d_nblocks.as<uint32_t>();
+                if (R.n_blocks > 0) {
+                    LTG_CUDA_CHECK(cudaMemcpyAsync(dn, R.n_start, sizeof(uint32_t) * (size_t)R.n_blocks, cudaMemcpyHostToDevice, c->stream));
+                    LTG_CUDA_CHECK(cudaMemcpyAsync(dn + R.n_blocks, R.n_size, sizeof(uint32_t) * (size_t)R.n_blocks, cudaMemcpyHostToDevice, c->stream));
+                    c->h2d_bytes += (int64_t)sizeof(uint32_t) * 2 * R.n_blocks;
+                }
+                k_unpack_2bit<<<(int)std::min<int64_t>((R.len + 255) / 256, 148 * 16), 256, 0, c->stream>>>(
+                    dpk, R.packed_first - (b0 << 2), R.len, dn, dn + R.n_blocks, R.n_blocks, dst, c->d_codes.as<uint8_t>() + base[r]);
+                c->launches += 1;
+                // (the staging buffers are reused by the next packed record of the call)
+                LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                any_packed = true;
+            } else if (R.h_dna) { LTG_CUDA_CHECK(cudaMemcpyAsync(dst, R.h_dna, (size_t)R.len, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += R.len; }
             else LTG_CUDA_CHECK(cudaMemcpyAsync(dst, R.d_dna, (size_t)R.len, cudaMemcpyDeviceToDevice, c->stream));
         }
         k_encode<<<(int)std::min<int64_t>((len + 255) / 256, 148 * 16), 256, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_codes.as<uint8_t>(), len);
@@ -1236,13 +1264,34 @@ int scan_impl(ltg_context* c, const RecordIn* recs, int64_t n_recs, ltg_result**
         for (int s = 0; s < NS; ++s) { hs[s].start = segs[s].start; hs[s].len = segs[s].len; hs[s].flags = 0; }
         std::vector<HostSeg> active;
         if (NS > 0) {
-            LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_segs.p, hs.data(), sizeof(SegDesc) * NS, cudaMemcpyHostToDevice, c->stream));
+            if (n_recs <= 16) {
+                // cutSequence on the device (k_cut_segments): the descriptors of a record's segments are arithmetic in (record length,
+                // cut length, overlap), so nothing but those numbers crosses PCIe; calls with many short records upload the list instead
+                int at = 0;
+                for (int64_t r = 0; r < n_recs; ++r) {
+                    int cnt = 0;
+                    while (at + cnt < NS && segs[at + cnt].record == (int)r) ++cnt;
+                    if (cnt > 0)
+                        k_cut_segments<<<(cnt + 255) / 256, 256, 0, c->stream>>>(c->d_segs.as<SegDesc>() + at, cnt, base[r], recs[r].first_seg,
+                                                                                  c->params.cut_length - c->params.overlap, c->params.cut_length,
+                                                                                  recs[r].record_len < 0 ? recs[r].len : recs[r].record_len);
+                    c->launches += cnt > 0 ? 1 : 0;
+                    at += cnt;
+                }
+            } else {
+                LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_segs.p, hs.data(), sizeof(SegDesc) * NS, cudaMemcpyHostToDevice, c->stream));
+                c->h2d_bytes += (int64_t)sizeof(SegDesc) * NS;
+            }
             k_seg_flags<<<(NS * 32 + 127) / 128, 128, 0, c->stream>>>(c->d_dna.as<unsigned char>(), c->d_segs.as<SegDesc>(), NS);
             c->launches += 1;
             LTG_CUDA_CHECK(cudaMemcpyAsync(hs.data(), c->d_segs.p, sizeof(SegDesc) * NS, cudaMemcpyDeviceToHost, c->stream));
             LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            c->h2d_bytes += (int64_t)sizeof(SegDesc) * NS; c->d2h_bytes += (int64_t)sizeof(SegDesc) * NS;
-            for (int s = 0; s < NS; ++s) { segs[s].flags = hs[s].flags; if (!(hs[s].flags & kSegSkip)) active.push_back(segs[s]); }
+            c->d2h_bytes += (int64_t)sizeof(SegDesc) * NS;
+            for (int s = 0; s < NS; ++s) {
+                if (hs[s].start != segs[s].start || hs[s].len != segs[s].len) { set_error("device segmenter disagrees with the host geometry (segment %d)", s); return LTG_ERR_STATE; }
+                segs[s].flags = hs[s].flags;
+                if (!(hs[s].flags & kSegSkip)) active.push_back(segs[s]);
+            }
         }
 
         if (c->sim_mode) {
@@ -1452,7 +1501,7 @@ void ltg_destroy(ltg_context* c)
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs, &c->d_side_jobs, &c->d_side_colmax})
         b->release();
-    for (DevBuf* b : {&c->d_rna_sim, &c->d_sim_scratch, &c->d_sim_hdr, &c->d_sim_pool, &c->d_sim_tasks}) b->release();
+    for (DevBuf* b : {&c->d_packed, &c->d_nblocks, &c->d_rna_sim, &c->d_sim_scratch, &c->d_sim_hdr, &c->d_sim_pool, &c->d_sim_tasks}) b->release();
     for (int k = 0; k < 24; ++k) c->d_w[k].release();
     for (int k = 0; k < 4; ++k) c->d_pc[k].release();
     c->d_res64.release();
@@ -1595,6 +1644,20 @@ int ltg_scan_shard(ltg_context* c, const void* dna, int dna_on_device, int64_t l
     if (dna_on_device) R.d_dna = (const unsigned char*)dna; else R.h_dna = (const char*)dna;
     R.len = len; R.chr = chr; R.record_start = record_start; R.record_len = record_len; R.first_seg = first_segment; R.n_seg = n_segments;
     return scan_impl(c, &R, 1, out);
+    });
+}
+
+int ltg_scan_packed(ltg_context* c, const void* packed, int packed_on_device, int64_t first_base, int64_t len, const uint32_t* n_start,
+                    const uint32_t* n_size, int32_t n_blocks, const char* chr, int64_t record_start, int64_t record_len, int64_t first_segment,
+                    int64_t n_segments, ltg_result** out)
+{
+    return guarded([&]() -> int {
+        if ((!packed && len > 0) || first_base < 0 || n_blocks < 0 || (n_blocks > 0 && (!n_start || !n_size))) { set_error("bad argument"); return LTG_ERR_ARG; }
+        RecordIn R;
+        R.packed = (const unsigned char*)packed; R.packed_on_device = packed_on_device; R.packed_first = first_base; R.len = len;
+        R.n_start = n_start; R.n_size = n_size; R.n_blocks = n_blocks;
+        R.chr = chr; R.record_start = record_start; R.record_len = record_len; R.first_seg = first_segment; R.n_seg = n_segments;
+        return scan_impl(c, &R, 1, out);
     });
 }
 

@@ -52,6 +52,41 @@ __global__ void k_encode(const unsigned char* __restrict__ dna, uint8_t* __restr
     for (; i < n; i += stride) codes[i] = (uint8_t)dna_code(dna[i]);
 }
 
+// 2-bit packed DNA (UCSC .2bit coding: 4 bases per byte, the first base in the two high bits, T0 C1 A2 G3) -> ASCII + base codes.
+// `first` = index of the record's first base inside `packed` (any value: regions need not start on a byte); the N runs of the
+// record come as sorted (start, size) blocks relative to that first base, like the nBlock arrays of a .2bit record.
+__global__ void k_unpack_2bit(const uint8_t* __restrict__ packed, int64_t first, int64_t n, const uint32_t* __restrict__ nstart,
+                              const uint32_t* __restrict__ nsize, int n_blocks, unsigned char* __restrict__ dna, uint8_t* __restrict__ codes)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t g = first + i;
+        const unsigned b = (packed[g >> 2] >> (6 - 2 * (int)(g & 3))) & 3u;
+        // last block that starts at or before i (binary search), then the range test
+        int lo = 0, hi = n_blocks;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)nstart[mid] <= i) lo = mid + 1; else hi = mid; }
+        const bool is_n = lo > 0 && i < (int64_t)nstart[lo - 1] + (int64_t)nsize[lo - 1];
+        const unsigned char ch = is_n ? 'N' : (unsigned char)"TCAG"[b];
+        dna[i] = ch;
+        codes[i] = (uint8_t)dna_code(ch);
+    }
+}
+
+// cutSequence on the device (fastsim.h:71-90): descriptor k of a shard = segment first_seg + k of a record of record_len bases
+// whose bytes start at `base` in the call's DNA buffer; the flags follow from k_seg_flags
+__global__ void k_cut_segments(SegDesc* __restrict__ segs, int n_segs, int64_t base, int64_t first_seg, int64_t stride, int cut, int64_t record_len)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_segs) return;
+    SegDesc sd;
+    sd.start = base + (int64_t)k * stride;
+    const int64_t left = record_len - (first_seg + k) * stride;
+    sd.len = (int32_t)(left < cut ? left : cut);
+    sd.flags = 0;
+    segs[k] = sd;
+}
+
 // per-segment flags: homopolymer test of same_seq (all bytes equal and one of A C G T U N) and
 // "has a byte outside ACGT" (needs the second, N-aware threshold scoring — SURVEY App. B Q3)
 __global__ void k_seg_flags(const unsigned char* __restrict__ dna, SegDesc* __restrict__ segs, int n_segs)

@@ -44,7 +44,7 @@ class TaskProbe(C.Structure):
 
 
 EXPORTS = ["ltg_create", "ltg_destroy", "ltg_last_error", "ltg_default_params", "ltg_set_params", "ltg_set_sim_mode", "ltg_set_compat", "ltg_set_query",
-           "ltg_scan_record", "ltg_scan_records", "ltg_scan_records_at", "ltg_scan_device", "ltg_scan_shard", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
+           "ltg_scan_record", "ltg_scan_records", "ltg_scan_records_at", "ltg_scan_device", "ltg_scan_shard", "ltg_scan_packed", "ltg_result_append", "ltg_result_new", "ltg_result_free", "ltg_cluster",
            "ltg_write_tfosorted", "ltg_write_tfoclass", "ltg_main", "ltg_probe_segment", "ltg_probe_align", "ltg_stream", "ltg_debug_stats",
            "ltg_device_count"]
 
@@ -81,6 +81,8 @@ def lib():
                                           C.POINTER(C.c_int64), C.POINTER(C.POINTER(Result))]
         L.ltg_scan_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                      C.POINTER(C.POINTER(Result))]
+        L.ltg_scan_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32,
+                                      C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.POINTER(Result))]
         L.ltg_result_free.argtypes = [C.POINTER(Result)]
         L.ltg_result_new.argtypes = [C.POINTER(C.POINTER(Result))]
         L.ltg_result_append.argtypes = [C.POINTER(Result), C.POINTER(Result)]
@@ -257,6 +259,22 @@ class Engine:
             b = dna.encode() if isinstance(dna, str) else dna
             _check(lib().ltg_scan_shard(self._h, C.cast(C.c_char_p(b), C.c_void_p), 0, len(b), chr_tag.encode(), record_start, record_len,
                                         first_segment, n_segments, C.byref(res)))
+        return res
+
+    def scan_packed(self, packed, first_base, n_bases, n_blocks=(), chr_tag="", record_start=0, record_len=-1, first_segment=0, n_segments=-1,
+                    device_ptr=None):
+        """2-bit packed DNA (UCSC coding) from host bytes or a device pointer; n_blocks = [(start, size)] relative to first_base."""
+        res = C.POINTER(Result)()
+        nb = len(n_blocks)
+        ns = (C.c_uint32 * max(nb, 1))(*[int(a) for a, _ in n_blocks])
+        nz = (C.c_uint32 * max(nb, 1))(*[int(b) for _, b in n_blocks])
+        if device_ptr is not None:
+            ptr, on_dev = C.c_void_p(device_ptr), 1
+        else:
+            self._packed_keep = bytes(packed)
+            ptr, on_dev = C.cast(C.c_char_p(self._packed_keep), C.c_void_p), 0
+        _check(lib().ltg_scan_packed(self._h, ptr, on_dev, first_base, n_bases, ns, nz, nb, chr_tag.encode(), record_start,
+                                     n_bases if record_len < 0 else record_len, first_segment, n_segments, C.byref(res)))
         return res
 
     def LongTarget(self, dna, chr_tag="", record_start=0):

@@ -13,7 +13,28 @@
 
 namespace ltg_host {
 
-struct FastaRecord { std::string species, chr; long start = 0; std::string header, seq; };
+// A DNA record of -f1: its bases as text (FASTA), or — for .2bit input — still 2-bit packed, the way the file stores them: the
+// expansion then happens on the GPU (ltg_scan_packed) and PCIe carries 0.25 B/base.
+struct FastaRecord {
+    std::string species, chr; long start = 0; std::string header, seq;
+    std::vector<unsigned char> packed;          // .2bit coding, covering bases [packed_first, packed_first + n_packed) of the bytes
+    int64_t packed_first = 0, n_packed = 0;
+    std::vector<uint32_t> n_start, n_size;      // N runs, sorted, relative to the record's first base
+    bool is_packed() const { return n_packed > 0; }
+    int64_t length() const { return is_packed() ? n_packed : (int64_t)seq.size(); }
+    // text of bases [lo, hi) (packed records only; used by --list-records)
+    std::string expand(int64_t lo, int64_t hi) const
+    {
+        static const char kBase[4] = {'T', 'C', 'A', 'G'};
+        std::string out((size_t)(hi - lo), 'N');
+        for (int64_t i = lo; i < hi; ++i) { const int64_t g = packed_first + i; out[(size_t)(i - lo)] = kBase[(packed[(size_t)(g >> 2)] >> (6 - 2 * (int)(g & 3))) & 3]; }
+        for (size_t k = 0; k < n_start.size(); ++k) {
+            const int64_t a = std::max<int64_t>(n_start[k], lo), e = std::min<int64_t>((int64_t)n_start[k] + n_size[k], hi);
+            for (int64_t i = a; i < e; ++i) out[(size_t)(i - lo)] = 'N';
+        }
+        return out;
+    }
+};
 
 // Lower-case (soft-masked) bases.  The reference's transferString scores every byte outside "ATGCN" as N while its
 // complement() silently DROPS such bytes (rules.h:82-83, 308-311), so a soft-masked genome loses every
@@ -191,6 +212,60 @@ public:
         if (masked > 0 && softmask == kSoftError) { err = "sequence '" + seqs[idx].name + "' holds soft-masked (lower-case) bases; choose --softmask upper or --softmask n"; return false; }
         return true;
     }
+    // the same region kept packed: the file's own bytes plus the N blocks (and, with --softmask n, the mask blocks) clipped to it
+    bool fetch_packed(size_t idx, int64_t lo, int64_t hi, FastaRecord& rec, int64_t& dna_size, std::string& err, int softmask = kSoftUpper,
+                      int64_t* n_masked = nullptr)
+    {
+        if (fseeko(f_, (off_t)seqs[idx].offset, SEEK_SET) != 0) { err = "bad .2bit offset"; return false; }
+        uint32_t size = 0, nb = 0, mb = 0, reserved = 0;
+        if (!u32(size) || !u32(nb)) { err = "truncated .2bit record"; return false; }
+        if ((int64_t)nb * 8 > file_size_ - (int64_t)ftello(f_)) { err = "corrupt .2bit record (N-block count exceeds the file size)"; return false; }
+        std::vector<uint32_t> nstart(nb), nsize(nb);
+        for (uint32_t& v : nstart) if (!u32(v)) { err = "truncated .2bit record"; return false; }
+        for (uint32_t& v : nsize) if (!u32(v)) { err = "truncated .2bit record"; return false; }
+        if (!u32(mb)) { err = "truncated .2bit record"; return false; }
+        if ((int64_t)mb * 8 > file_size_ - (int64_t)ftello(f_)) { err = "corrupt .2bit record (mask-block count exceeds the file size)"; return false; }
+        std::vector<uint32_t> mstart(mb), msize(mb);
+        for (uint32_t& v : mstart) if (!u32(v)) { err = "truncated .2bit record"; return false; }
+        for (uint32_t& v : msize) if (!u32(v)) { err = "truncated .2bit record"; return false; }
+        if (!u32(reserved)) { err = "truncated .2bit record"; return false; }
+        if (((int64_t)size + 3) / 4 > file_size_ - (int64_t)ftello(f_)) { err = "corrupt .2bit record (sequence size exceeds the file size)"; return false; }
+        dna_size = size;
+        if (lo < 0) lo = 0;
+        if (hi < 0 || hi > (int64_t)size) hi = size;
+        if (lo > hi) lo = hi;
+        const int64_t first_byte = lo / 4, last_byte = (hi + 3) / 4;
+        rec.packed.resize((size_t)(last_byte - first_byte));
+        if (fseeko(f_, (off_t)first_byte, SEEK_CUR) != 0 || (!rec.packed.empty() && fread(rec.packed.data(), 1, rec.packed.size(), f_) != rec.packed.size())) {
+            err = "truncated .2bit sequence data"; return false;
+        }
+        rec.packed_first = lo - first_byte * 4;
+        rec.n_packed = hi - lo;
+        // N blocks (and mask blocks scored as N) clipped to [lo, hi), relative to lo, merged into one sorted list
+        std::vector<std::pair<int64_t, int64_t> > blocks;
+        for (uint32_t k = 0; k < nb; ++k) {
+            const int64_t a = std::max<int64_t>(nstart[k], lo), e = std::min<int64_t>((int64_t)nstart[k] + nsize[k], hi);
+            if (e > a) blocks.emplace_back(a - lo, e - lo);
+        }
+        int64_t masked = 0;
+        for (uint32_t k = 0; k < mb; ++k) {
+            const int64_t a = std::max<int64_t>(mstart[k], lo), e = std::min<int64_t>((int64_t)mstart[k] + msize[k], hi);
+            if (e <= a) continue;
+            masked += e - a;
+            if (softmask == kSoftAsN) blocks.emplace_back(a - lo, e - lo);
+        }
+        if (n_masked) *n_masked += masked;
+        if (masked > 0 && softmask == kSoftError) { err = "sequence '" + seqs[idx].name + "' holds soft-masked (lower-case) bases; choose --softmask upper or --softmask n"; return false; }
+        std::sort(blocks.begin(), blocks.end());
+        rec.n_start.clear(); rec.n_size.clear();
+        for (const auto& b : blocks) {
+            if (!rec.n_start.empty() && b.first <= (int64_t)rec.n_start.back() + rec.n_size.back()) {
+                const int64_t end = std::max<int64_t>((int64_t)rec.n_start.back() + rec.n_size.back(), b.second);
+                rec.n_size.back() = (uint32_t)(end - rec.n_start.back());
+            } else { rec.n_start.push_back((uint32_t)b.first); rec.n_size.push_back((uint32_t)(b.second - b.first)); }
+        }
+        return true;
+    }
     std::vector<TwoBitSeq> seqs;
 
 private:
@@ -208,7 +283,8 @@ private:
 // `.2bit` records for the scan.  `regions` = "", or a comma-separated list of  name | name:start-end  (1-based, inclusive,
 // the convention of the FASTA header's start field).  No list = every sequence of the file, whole.
 inline bool read_dna_twobit(const std::string& path, const std::string& regions, const std::string& species,
-                            std::vector<FastaRecord>& out, std::string& err, int softmask = kSoftUpper, int64_t* n_masked = nullptr)
+                            std::vector<FastaRecord>& out, std::string& err, int softmask = kSoftUpper, int64_t* n_masked = nullptr,
+                            bool keep_packed = false)
 {
     TwoBitFile tb;
     if (!tb.open(path, err)) return false;
@@ -247,11 +323,12 @@ inline bool read_dna_twobit(const std::string& path, const std::string& regions,
     for (const Want& w : wants) {
         FastaRecord r;
         int64_t size = 0;
-        if (!tb.fetch(w.idx, w.lo, w.hi, r.seq, size, err, softmask, n_masked)) return false;
+        if (keep_packed) { if (!tb.fetch_packed(w.idx, w.lo, w.hi, r, size, err, softmask, n_masked)) return false; }
+        else if (!tb.fetch(w.idx, w.lo, w.hi, r.seq, size, err, softmask, n_masked)) return false;
         r.species = species;
         r.chr = tb.seqs[w.idx].name;
         r.start = (long)w.lo + 1;
-        r.header = species + "|" + r.chr + "|" + std::to_string(r.start) + "-" + std::to_string((long)(w.lo + (int64_t)r.seq.size()));
+        r.header = species + "|" + r.chr + "|" + std::to_string(r.start) + "-" + std::to_string((long)(w.lo + r.length()));
         out.push_back(std::move(r));
     }
     return true;

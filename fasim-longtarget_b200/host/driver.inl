@@ -245,7 +245,7 @@ int ltg_main(int argc, char* const* argv)
     if (ltg_host::TwoBitFile::is_twobit(f1)) {
         if (ends_with(base, ".2bit")) base = base.substr(0, base.size() - 5);
         std::string err;
-        if (!ltg_host::read_dna_twobit(f1, seq_arg, species_arg.empty() ? base : species_arg, recs, err, softmask, &n_lower)) { fprintf(stderr, "fasim: %s\n", err.c_str()); return 2; }
+        if (!ltg_host::read_dna_twobit(f1, seq_arg, species_arg.empty() ? base : species_arg, recs, err, softmask, &n_lower, /*keep_packed=*/true)) { fprintf(stderr, "fasim: %s\n", err.c_str()); return 2; }
     } else {
         if (!seq_arg.empty()) { fprintf(stderr, "fasim: --seq needs a .2bit file as -f1\n"); return 2; }
         if (!read_dna_fasta(f1, recs)) recs.clear();
@@ -266,8 +266,12 @@ int ltg_main(int argc, char* const* argv)
     if (recs.empty()) { fprintf(stderr, "fasim: cannot read DNA file %s\n", f1.c_str()); return 2; }
     if (list_records) {
         for (const FastaRecord& r : recs)
-            printf("record\t%s\t%s\t%ld\t%zu\t%08lx\n", r.species.c_str(), r.chr.c_str(), r.start, r.seq.size(),
-                   (unsigned long)crc32(0L, (const Bytef*)r.seq.data(), (uInt)r.seq.size()));
+        {
+            const std::string text = r.is_packed() ? r.expand(0, r.length()) : std::string();
+            const std::string& sq = r.is_packed() ? text : r.seq;
+            printf("record\t%s\t%s\t%ld\t%zu\t%08lx\n", r.species.c_str(), r.chr.c_str(), r.start, sq.size(),
+                   (unsigned long)crc32(0L, (const Bytef*)sq.data(), (uInt)sq.size()));
+        }
     }
     std::vector<std::pair<std::string, std::string> > queries;            // (name, sequence); one entry unless --queries
     if (multi_query) {
@@ -312,14 +316,14 @@ int ltg_main(int argc, char* const* argv)
         // at least ~8 jobs, so the tail of the queue (the last job of the slowest GPU) stays a small fraction of the run:
         // 1024 .. 16384 segments (5 .. 80 Mbp), chosen from the total work of the run.
         int64_t total_segs = 0;
-        if (stride > 0) for (const FastaRecord& r : recs) total_segs += ((int64_t)r.seq.size() + stride - 1) / stride;
+        if (stride > 0) for (const FastaRecord& r : recs) total_segs += (r.length() + stride - 1) / stride;
         const int64_t want = total_segs * (int64_t)queries.size() / ((int64_t)devs.size() * 8);
         const int64_t kUnitSegments = devs.size() > 1 ? std::max<int64_t>(1024, std::min<int64_t>(16384, want)) : 2048;
         const int64_t unit_bases = kUnitSegments * (stride > 0 ? stride : 1);
         if (stride <= 0) { fprintf(stderr, "fasim: cut length (%d) must exceed the overlap (%d)\n", P.cut_length, P.overlap); return 2; }
         size_t i = 0;
         while (i < recs.size()) {
-            const int64_t n = (int64_t)recs[i].seq.size();
+            const int64_t n = recs[i].length();
             if (n > unit_bases + stride && devs.size() > 1) {                 // a long record: shards of whole segments
                 const int64_t n_seg = (n + stride - 1) / stride;
                 for (int64_t s0 = 0; s0 < n_seg; s0 += kUnitSegments) units.push_back(Unit{i, i + 1, s0, std::min(kUnitSegments, n_seg - s0)});
@@ -329,9 +333,9 @@ int ltg_main(int argc, char* const* argv)
             size_t j = i;
             int64_t bytes = 0;
             const int64_t cap = devs.size() > 1 ? unit_bases : (256ll << 20);
-            for (; j < recs.size() && (j == i || bytes + (int64_t)recs[j].seq.size() <= cap); ++j) {
-                if (j > i && (int64_t)recs[j].seq.size() > unit_bases + stride && devs.size() > 1) break;
-                bytes += (int64_t)recs[j].seq.size();
+            for (; j < recs.size() && (j == i || bytes + recs[j].length() <= cap); ++j) {
+                if (j > i && recs[j].length() > unit_bases + stride && devs.size() > 1) break;
+                bytes += recs[j].length();
             }
             units.push_back(Unit{i, j, 0, -1});
             i = j;
@@ -371,13 +375,23 @@ int ltg_main(int argc, char* const* argv)
         const std::string out_path = compat_lc ? outdir + "/" + recs[0].species + "-" + lnc_name + "-fastSim-TFOsorted"
                                                : outdir + "/" + recs[0].species + "-" + lnc_name + "-" + base + "-TFOsorted";
         if (rc == LTG_OK) rc = ltg_write_tfosorted(all, out_path.c_str());
-        if (rc == LTG_OK && !compat_lc) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, (int64_t)recs[0].seq.size(), lnc_name.c_str());
+        if (rc == LTG_OK && !compat_lc) rc = ltg_write_tfoclass(all, &P, out_path.c_str(), recs[0].chr.c_str(), recs[0].start, recs[0].length(), lnc_name.c_str());
         if (rc == LTG_OK && all->scan_cells > 0)
             printf("[b200] %s: segments=%ld tasks=%ld peaks=%ld scan_cells=%.3e gpu_scan_ms=%.2f gpu_window_ms=%.2f literal_tasks=%ld literal_windows=%ld\n",
                    lnc_name.c_str(), (long)all->n_segments, (long)all->n_tasks, (long)all->n_peaks, (double)all->scan_cells, all->gpu_ms_scan,
                    all->gpu_ms_window, (long)all->n_literal_tasks, (long)all->n_literal_windows);
         if (all) ltg_result_free(all);
         return rc;
+    };
+    // bases [lo, hi) of a packed record as one ltg_scan_packed call (segments first_seg .. of the whole record)
+    auto scan_packed_range = [&](ltg_context* ctx, const FastaRecord& R, int64_t lo, int64_t hi, int64_t first_seg, int64_t n_seg, ltg_result** out) -> int {
+        std::vector<uint32_t> ns, nz;
+        for (size_t k = 0; k < R.n_start.size(); ++k) {
+            const int64_t a = std::max<int64_t>(R.n_start[k], lo), e = std::min<int64_t>((int64_t)R.n_start[k] + R.n_size[k], hi);
+            if (e > a) { ns.push_back((uint32_t)(a - lo)); nz.push_back((uint32_t)(e - a)); }
+        }
+        return ltg_scan_packed(ctx, R.packed.data(), 0, R.packed_first + lo, hi - lo, ns.data(), nz.data(), (int32_t)ns.size(), R.chr.c_str(), R.start,
+                               R.length(), first_seg, n_seg, out);
     };
     auto gpu_worker = [&](size_t w) {
         ltg_context* ctx = nullptr;
@@ -406,16 +420,30 @@ int ltg_main(int argc, char* const* argv)
             if (U.n_seg >= 0) {                                  // shard of one long record
                 const FastaRecord& R = recs[U.r0];
                 const int64_t stride = P.cut_length - P.overlap, lo = U.first_seg * stride;
-                const int64_t hi = std::min<int64_t>((int64_t)R.seq.size(), (U.first_seg + U.n_seg - 1) * stride + P.cut_length);
-                rc = ltg_scan_shard(ctx, R.seq.data() + lo, 0, hi - lo, R.chr.c_str(), R.start, (int64_t)R.seq.size(), U.first_seg, U.n_seg, out);
+                const int64_t hi = std::min<int64_t>(R.length(), (U.first_seg + U.n_seg - 1) * stride + P.cut_length);
+                if (R.is_packed()) rc = scan_packed_range(ctx, R, lo, hi, U.first_seg, U.n_seg, out);
+                else rc = ltg_scan_shard(ctx, R.seq.data() + lo, 0, hi - lo, R.chr.c_str(), R.start, R.length(), U.first_seg, U.n_seg, out);
             } else {
-                std::vector<const char*> dna, chr;
-                std::vector<int64_t> len, start;
-                for (size_t r = U.r0; r < U.r1; ++r) {
-                    dna.push_back(recs[r].seq.data()); len.push_back((int64_t)recs[r].seq.size());
-                    chr.push_back(recs[r].chr.c_str()); start.push_back(recs[r].start);
+                bool any_packed = false;
+                for (size_t r = U.r0; r < U.r1; ++r) any_packed |= recs[r].is_packed();
+                if (any_packed) {
+                    // .2bit records: one ltg_scan_packed call per record, results appended in record order
+                    rc = ltg_result_new(out);
+                    for (size_t r = U.r0; rc == LTG_OK && r < U.r1; ++r) {
+                        ltg_result* one = nullptr;
+                        rc = scan_packed_range(ctx, recs[r], 0, recs[r].length(), 0, -1, &one);
+                        if (rc == LTG_OK) { for (int64_t k = 0; k < one->n_triplex; ++k) one->triplex[k].record = (int32_t)(r - U.r0); rc = ltg_result_append(*out, one); }
+                        if (one) ltg_result_free(one);
+                    }
+                } else {
+                    std::vector<const char*> dna, chr;
+                    std::vector<int64_t> len, start;
+                    for (size_t r = U.r0; r < U.r1; ++r) {
+                        dna.push_back(recs[r].seq.data()); len.push_back((int64_t)recs[r].seq.size());
+                        chr.push_back(recs[r].chr.c_str()); start.push_back(recs[r].start);
+                    }
+                    rc = ltg_scan_records(ctx, (int64_t)(U.r1 - U.r0), dna.data(), len.data(), chr.data(), start.data(), out);
                 }
-                rc = ltg_scan_records(ctx, (int64_t)(U.r1 - U.r0), dna.data(), len.data(), chr.data(), start.data(), out);
             }
             t_scan += tnow() - t0s;
             if (rc == LTG_OK && remaining[q].fetch_sub(1) == 1) {

@@ -138,6 +138,16 @@ int ltg_scan_device(ltg_context* ctx, const void* d_dna, int64_t len, const char
 int ltg_scan_shard(ltg_context* ctx, const void* dna, int dna_on_device, int64_t len, const char* chr, int64_t record_start,
                    int64_t record_len, int64_t first_segment, int64_t n_segments, ltg_result** out);
 
+/* ltg_scan_shard for DNA kept 2-bit packed (chromosome-scale stores).  `packed` holds bases in UCSC .2bit
+ * coding (4 per byte, the first in the two high bits, T0 C1 A2 G3) in host memory or — the packed genome store resident in HBM,
+ * 0.25 B/base — in device memory; the shard's first base has index `first_base` in it, `len` bases are readable.  N runs come as
+ * sorted (start, size) blocks RELATIVE to first_base (the nBlock arrays of a .2bit record).  The bases are expanded on the
+ * device, the segment descriptors of cutSequence (fastsim.h:71-90) and the same_seq flags (Fasim-LongTarget.cpp:873) are
+ * produced there too.  Replaces readDna + cutSequence for such inputs; results equal ltg_scan_shard on the expanded text.     */
+int ltg_scan_packed(ltg_context* ctx, const void* packed, int packed_on_device, int64_t first_base, int64_t len,
+                    const uint32_t* n_start, const uint32_t* n_size, int32_t n_blocks, const char* chr, int64_t record_start,
+                    int64_t record_len, int64_t first_segment, int64_t n_segments, ltg_result** out);
+
 /* concatenates src into dst (dst may be empty); triplex order is preserved (main() :150-163)          */
 int ltg_result_append(ltg_result* dst, const ltg_result* src);
 int ltg_result_new(ltg_result** out);

@@ -589,6 +589,49 @@ def test_reference_binary_multi_query_inputs(tmp_path):
             assert len(open(os.path.join(d, "ref", f)).read().splitlines()) > 1, f
 
 
+def test_scan_packed_equals_text(engine):
+    """ltg_scan_packed: DNA kept 2-bit packed (host bytes, or a packed store resident in HBM), expanded and cut into segments on
+    the device.  Same rows as the text path, for a region that starts inside a byte, with N runs, as whole record and as shards."""
+    import torch
+    rna = splitmix_bases(2001, 800)
+    chrom = list(splitmix_bases(1001, 26000))
+    for at in (3000, 9000, 17000, 23000):
+        chrom[at:at + 70] = rna[100:170].translate(str.maketrans("TG", "AT"))
+    nruns = [(5000, 37), (12001, 1), (20000, 300)]
+    for a, n in nruns:
+        chrom[a:a + n] = "N" * n
+    chrom = "".join(chrom)
+    code = {"T": 0, "C": 1, "A": 2, "G": 3, "N": 0}
+    packed = bytearray((len(chrom) + 3) // 4)
+    for i, c in enumerate(chrom):
+        packed[i // 4] |= code[c] << (6 - 2 * (i % 4))
+    lo, hi = 1003, 25001                                        # region [lo, hi): starts 3 bases into a byte
+    blocks = [(max(a, lo) - lo, min(a + n, hi) - max(a, lo)) for a, n in nruns if min(a + n, hi) > max(a, lo)]
+    engine.set_params(c_length=20)
+    engine.set_query("q", rna)
+    want = engine.LongTarget(chrom[lo:hi], "chrP", lo + 1)
+    assert len(want) > 3
+    res = engine.scan_packed(bytes(packed), lo, hi - lo, blocks, "chrP", lo + 1)
+    got = fb.result_rows(res)
+    h2d = res.contents.h2d_bytes
+    engine.free(res)
+    assert got == want
+    assert h2d < (hi - lo) // 3                                  # a quarter byte per base crossed PCIe, not one
+    dev = torch.frombuffer(packed, dtype=torch.uint8).cuda()     # the packed store resident in HBM
+    parts = []
+    for r in range(3):
+        first, count, first_byte, n_bytes = fb.shard_segments(hi - lo, 3, r)
+        sb = [(max(a, first_byte) - first_byte, min(a + n, first_byte + n_bytes) - max(a, first_byte)) for a, n in blocks
+              if min(a + n, first_byte + n_bytes) > max(a, first_byte)]
+        res = engine.scan_packed(None, lo + first_byte, n_bytes, sb, "chrP", lo + 1, record_len=hi - lo, first_segment=first, n_segments=count,
+                                 device_ptr=dev.data_ptr())
+        parts.append(fb.result_rows(res))
+        assert res.contents.h2d_bytes < 4096                     # only descriptors: the bases were already on the device
+        engine.free(res)
+    assert fb.merge_shard_rows(parts) == want
+    engine.set_params()
+
+
 # ------------------------------------------------------------------------------------------------ --compat lowercase
 def test_cli_compat_lowercase_byte_equal(tmp_path, data_dir):
     """`fasim --compat lowercase`: the older variant that ships next to the canonical one (fasim-LongTarget.cpp + fastSim.h;

@@ -122,3 +122,36 @@ def test_rna_readers(tmp_path):
     assert single == [("lncA extrawords", str(150 + len(">lncB") + 77 + len(">empty")), crc(a + ">lncB" + b + ">empty"))]
     r = fb.run_cli(["-f1", "dna.fa", "-f2", "missing.fa", "--list-records"], cwd=d)
     assert r.returncode != 0 and "missing.fa" in r.stderr
+
+
+def test_softmask_policies_and_corrupt_twobit(tmp_path, seqs):
+    """--softmask: lower-case (soft-masked) bases are upper-cased (default, with a notice), scored as N, or refused — in FASTA and
+    in .2bit (mask blocks) alike.  A .2bit file whose counts do not fit the file is reported as corrupt, not allocated for."""
+    fb.build()
+    d = str(tmp_path)
+    a = seqs[0][1]                                             # holds a lower-case stretch and N runs
+    open(os.path.join(d, "m.fa"), "w").write(">hg|chr1|1-%d\n%s\n" % (len(a), a))
+    write_twobit(os.path.join(d, "m.2bit"), [("chr1", a)])
+    as_n = "".join("N" if c.islower() else c for c in a)
+    for f1 in ("m.fa", "m.2bit"):
+        sp = "hg" if f1 == "m.fa" else "m"
+        assert list_records(["-f1", f1], d) == [(sp, "chr1", 1, len(a), crc(a.upper()))]
+        assert list_records(["-f1", f1, "--softmask", "n"], d) == [(sp, "chr1", 1, len(a), crc(as_n))]
+        r = fb.run_cli(["-f1", f1, "-f2", "_q.fa", "--list-records", "--softmask", "error"], cwd=d)
+        assert r.returncode != 0 and "soft-masked" in r.stderr
+        r = fb.run_cli(["-f1", f1, "-f2", "_q.fa", "--list-records"], cwd=d)
+        assert "upper-cased" in r.stderr
+    # a region that does not start on a byte boundary of the packed data
+    assert list_records(["-f1", "m.2bit", "--seq", "chr1:7-3001", "--softmask", "n"], d) == [("m", "chr1", 7, 2995, crc(as_n[6:3001]))]
+    raw = bytearray(open(os.path.join(d, "m.2bit"), "rb").read())
+    off = struct.unpack("<I", raw[16 + 1 + 4:16 + 1 + 4 + 4])[0]                     # header 16, index entry: size byte, "chr1", offset
+    bad = bytearray(raw)
+    bad[off + 4:off + 8] = struct.pack("<I", 0x7FFFFFF0)                            # nBlockCount
+    open(os.path.join(d, "bad.2bit"), "wb").write(bytes(bad))
+    r = fb.run_cli(["-f1", "bad.2bit", "-f2", "_q.fa", "--list-records"], cwd=d)
+    assert r.returncode != 0 and "corrupt" in r.stderr
+    bad = bytearray(raw)
+    bad[8:12] = struct.pack("<I", 0x7FFFFFFF)                                        # sequenceCount
+    open(os.path.join(d, "bad2.2bit"), "wb").write(bytes(bad))
+    r = fb.run_cli(["-f1", "bad2.2bit", "-f2", "_q.fa", "--list-records"], cwd=d)
+    assert r.returncode != 0 and "corrupt" in r.stderr

@@ -29,8 +29,8 @@ cells = sum(float(x) for x in re.findall(r"scan_cells=([0-9.e+]+)", r.stdout))
 laps = dict((m.group(1), float(m.group(2))) for m in re.finditer(r"\[fasim timing\] (\S+)\s+at ([0-9.]+) s", r.stderr))
 scan_s = laps.get("scan+write", wall) - laps.get("read", 0.0)
 rows = sum(len(open(os.path.join(d, "out", f)).read().splitlines()) - 1 for f in os.listdir(os.path.join(d, "out")) if f.endswith("TFOsorted"))
-if os.environ.get("MQ_SHOW_TIMING"):
-    print("\n".join(l for l in r.stderr.splitlines() if l.startswith("[ltg timing]") or l.startswith("[fasim timing]")))
+# per-device breakdown of the one-process run: context creation, query switches, time inside the scan calls, destruction
+print("\n".join(l for l in r.stderr.splitlines() if l.startswith("[fasim timing]")))
 print({"queries": nq, "mbp": mbp, "devices": devs, "wall_s": round(wall, 2), "read_s": laps.get("read"), "scan_and_write_s": round(scan_s, 2),
        "scan_cells": cells, "gcups_scan_phase": round(cells / scan_s / 1e9, 1), "gcups_wall": round(cells / wall / 1e9, 1),
        "output_files": len(os.listdir(os.path.join(d, "out"))), "rows": rows})
