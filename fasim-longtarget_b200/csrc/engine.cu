@@ -96,6 +96,7 @@ inline int choose_scan_r(int m)
     return pad32 * 100 <= pad16 * 104 ? 32 : 16;      // R = 32 is ~4.5 % faster per row
 #endif
 }
+constexpr int kMaxCutLength = 24000;       // shared memory: the segment's base codes sit next to the strip profile (scan.cuh)
 #ifndef LTG_BATCH_SEGMENTS
 #define LTG_BATCH_SEGMENTS 2048
 #endif
@@ -340,6 +341,13 @@ int prepare(ltg_context* c)
     if (c->tables_dirty) { const bool keep_profiles = !c->profiles_dirty && !c->params_changed; if (int e = upload_tables(c)) return e; if (keep_profiles) c->profiles_dirty = false; c->params_changed = false; }
     if (c->profiles_dirty) if (int e = build_profiles(c)) return e;
     if (int e = c->d_counters.ensure(sizeof(int) * kCntTotal)) return e;
+    // 16-bit cells: a score never exceeds 5 * min(rows, columns).  Cut lengths beyond 6500 are therefore fine for lncRNAs up to
+    // 6399 nt (the reference accepts any -c); a long lncRNA AND a long cut would overflow and is refused here, before any work
+    if (c->m > 0 && 5LL * std::min<long long>(16LL * ((c->m + 15) / 16), c->params.cut_length) >= 32000) {
+        set_error("cut length %d with a lncRNA of %d nt exceeds the 16-bit score envelope of this build (min(lncRNA, cut) must stay below 6400)",
+                  c->params.cut_length, c->m);
+        return LTG_ERR_LIMIT;
+    }
     return LTG_OK;
 }
 
@@ -1525,7 +1533,7 @@ int ltg_set_params(ltg_context* c, const ltg_params* p)
     return guarded([&]() -> int {
     if (!c || !p) { set_error("null argument"); return LTG_ERR_ARG; }
     if (p->cut_length <= 0 || p->cut_length - p->overlap <= 0) { set_error("cut length (%d) must be positive and exceed the overlap (%d)", p->cut_length, p->overlap); return LTG_ERR_ARG; }
-    if (p->cut_length > 6500) { set_error("cut length %d exceeds the 16-bit score envelope of this build (max 6500)", p->cut_length); return LTG_ERR_LIMIT; }
+    if (p->cut_length > kMaxCutLength) { set_error("cut length %d exceeds this build's limit of %d", p->cut_length, kMaxCutLength); return LTG_ERR_LIMIT; }
     std::vector<TaskDef> probe;
     if (!ltg_host::enumerate_tasks(*p, probe)) { set_error("invalid rule/strand selection (rule=%d strand=%d)", p->rule, p->strand); return LTG_ERR_ARG; }
     if (p->rule != c->params.rule || p->strand != c->params.strand) { c->tables_dirty = true; c->params_changed = true; }
