@@ -148,6 +148,7 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
+    bool scan_shared = true;            // k_scan: one profile copy per CTA, 3 warps per scheduler (LTG_SCAN_SHARED=0: one copy per warp)
     bool sim_mode = false;              // -F: SIM() instead of fastSIM() per task (ltg_set_sim_mode)
     bool compat = false;                // window loop / per-task tail of the older variant (ltg_set_compat)
     bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true, floor_s = false;
@@ -173,7 +174,7 @@ struct ltg_context {
     DevBuf d_rna_sim, d_sim_scratch, d_sim_hdr, d_sim_pool, d_sim_tasks;      // -F mode (sim.cuh)
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_blkmax, d_bnd, d_counters;
-    DevBuf d_probe_items, d_probe_orig, d_probe_out, d_bnd_gran;
+    DevBuf d_probe_items, d_probe_orig, d_probe_out, d_bnd_gran, d_scan_order;
     int n_bnd_gran = 0;                 // granules that hold the rows just above a stripe start (Q4 pre-filter)
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
@@ -362,22 +363,63 @@ struct ProbeOut {
 };
 
 // probe_out != nullptr: the Q4 probe variant (no column maxima; per item the largest F carried into a stripe start)
+constexpr int kScanSharedWarps = 6;         // warps per CTA of the shared-profile scan (2 CTAs per SM: 3 warps per scheduler)
+// probe_out != nullptr: the Q4 probe variant (no column maxima; per item the largest F carried into a stripe start).
+// h_items (host copy of the item list) enables the shared-profile variant: the items are grouped by task pair, kScanSharedWarps to a
+// group, and a CTA keeps ONE copy of the pair's profiles for its six warps — what lifts the scan from 2 to 3 warps per scheduler.
 int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax_all, uint16_t* blkmax,
-                uint32_t* probe_out = nullptr, const int* task_jstar = nullptr)
+                uint32_t* probe_out = nullptr, const int* task_jstar = nullptr, const std::vector<ScanItem>* h_items = nullptr)
 {
     const int R = c->scan_r;
-    const int blocks = c->num_sms * scan_ctas_per_sm(R);
-    const size_t smem = (size_t)kScanWarps * (R == 32 ? scan_warp_smem_bytes<32>(max_len) : scan_warp_smem_bytes<16>(max_len));
-    if (smem > 227 * 1024) { set_error("segment length %d needs %zu bytes of shared memory per CTA", max_len, smem); return LTG_ERR_LIMIT; }
-    if (int e = c->d_bnd.ensure((size_t)blocks * kScanWarps * max_len * sizeof(uint2))) return e;
     int* counters = c->d_counters.as<int>();
     LTG_CUDA_CHECK(cudaMemsetAsync(counters + kCntScan, 0, sizeof(int), c->stream));
     ScanArgs a;
     a.codes = c->d_codes.as<uint8_t>(); a.segs = c->d_segs.as<SegDesc>(); a.items = d_items;
     a.n_items = n_items; a.profiles = prof; a.n_strips = c->n_strips; a.max_len = max_len;
     a.colmax_all = colmax_all; a.blkmax = blkmax; a.blk_pitch = blk_pitch_for(max_len);
-    a.bnd = c->d_bnd.as<uint2>(); a.counter = counters + kCntScan;
+    a.counter = counters + kCntScan;
+    a.order = nullptr; a.group_pair = nullptr; a.n_groups = 0;
     a.probe_out = probe_out; a.task_jstar = task_jstar; a.tasks_per_seg = (int)c->tasks.size(); a.stripe_len = (c->m + 15) / 16;
+    // shared-profile variant when the pair's profiles (all strips) and six warps' private parts fit twice into an SM
+    const size_t prof_bytes = (size_t)c->n_strips * 5 * 32 * R * 4;
+    const size_t smem_shared = prof_bytes + (size_t)kScanSharedWarps * (R == 32 ? scan_warp_smem_bytes_shared<32>(max_len) : scan_warp_smem_bytes_shared<16>(max_len));
+    if (c->scan_shared && !probe_out && h_items && n_items >= 4 * kScanSharedWarps && smem_shared <= 112 * 1024) {
+        const int W = kScanSharedWarps, P = (int)c->pairs.size();
+        std::vector<std::vector<int> > by_pair((size_t)P);
+        for (int i = 0; i < n_items; ++i) by_pair[(*h_items)[i].pair].push_back(i);
+        std::vector<int> order, gpair;
+        for (int p = 0; p < P; ++p)
+            for (size_t k = 0; k < by_pair[p].size(); k += W) {
+                gpair.push_back(p);
+                for (int w = 0; w < W; ++w) order.push_back(k + w < by_pair[p].size() ? by_pair[p][k + w] : -1);
+            }
+        const int n_groups = (int)gpair.size();
+        if (int e = c->d_scan_order.ensure(sizeof(int) * (order.size() + gpair.size()))) return e;
+        int* d_order = c->d_scan_order.as<int>();
+        LTG_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
+        LTG_CUDA_CHECK(cudaMemcpyAsync(d_order + order.size(), gpair.data(), sizeof(int) * gpair.size(), cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += (int64_t)sizeof(int) * (order.size() + gpair.size());
+        a.order = d_order; a.group_pair = d_order + order.size(); a.n_groups = n_groups;
+        const int blocks = std::min(n_groups, c->num_sms * 2);
+        if (int e = c->d_bnd.ensure((size_t)blocks * W * max_len * sizeof(uint2))) return e;
+        a.bnd = c->d_bnd.as<uint2>();
+        if (R == 32) {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanSharedWarps, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shared));
+            k_scan<32, kScanSharedWarps, false, true><<<blocks, W * 32, smem_shared, c->stream>>>(a);
+        } else {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<16, kScanSharedWarps, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shared));
+            k_scan<16, kScanSharedWarps, false, true><<<blocks, W * 32, smem_shared, c->stream>>>(a);
+        }
+        c->launches += 1;
+        LTG_CUDA_CHECK(cudaGetLastError());
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));          // `order` / `gpair` are host memory of this scope
+        return LTG_OK;
+    }
+    const int blocks = c->num_sms * scan_ctas_per_sm(R);
+    const size_t smem = (size_t)kScanWarps * (R == 32 ? scan_warp_smem_bytes<32>(max_len) : scan_warp_smem_bytes<16>(max_len));
+    if (smem > 227 * 1024) { set_error("segment length %d needs %zu bytes of shared memory per CTA", max_len, smem); return LTG_ERR_LIMIT; }
+    if (int e = c->d_bnd.ensure((size_t)blocks * kScanWarps * max_len * sizeof(uint2))) return e;
+    a.bnd = c->d_bnd.as<uint2>();
     if (probe_out) {
         if (R == 32) {
             LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -696,7 +738,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[4], c->stream));
     if (int e = launch_scan(c, c->d_items.as<ScanItem>(), n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax_all.as<uint32_t>(),
-                            c->d_blkmax.as<uint16_t>())) return e;
+                            c->d_blkmax.as<uint16_t>(), nullptr, nullptr, &items)) return e;
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[5], c->stream));
 
     // peaks: statistics + count, literal re-runs, count of those, exclusive scan, write
@@ -1478,6 +1520,7 @@ int ltg_create(int device, ltg_context** out)
     // LTG_NO_SKIP=1 runs every window round of fastSIM's loop even when it provably repeats the previous result
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
+    if (const char* e = getenv("LTG_SCAN_SHARED")) c->scan_shared = atoi(e) != 0;
     // LTG_FLOORS=1: the first window sweep only tracks cells that reach the peak score (fewer slow-path trips of the tracker, more
     // re-planned sweeps; measured neutral on the headline workload, profiles/README.md)
     if (const char* e = getenv("LTG_FLOORS")) c->floor_s = atoi(e) != 0;
@@ -1505,7 +1548,7 @@ void ltg_destroy(ltg_context* c)
     }
     for (DevBuf* b : {&c->d_rna_raw, &c->d_rna_ssw, &c->d_rna_stats, &c->d_rna_sel, &c->d_prof_ssw, &c->d_prof_stats, &c->d_cut, &c->d_dna, &c->d_codes,
                       &c->d_segs, &c->d_items, &c->d_items_stats, &c->d_blkmax, &c->d_bnd, &c->d_counters, &c->d_task_info, &c->d_task_off,
-                      &c->d_stats_max, &c->d_task_litrow, &c->d_cand, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
+                      &c->d_scan_order, &c->d_stats_max, &c->d_task_litrow, &c->d_cand, &c->d_pk_task, &c->d_pk_pos, &c->d_pk_score, &c->d_win_list, &c->d_win_sched, &c->d_res, &c->d_colmax_all, &c->d_ovf_list,
                       &c->d_jobs, &c->d_tout, &c->d_strpool, &c->d_scratch, &c->d_scratch_big,
                       &c->d_lit_colmax, &c->d_lit_work, &c->d_lit_jobs, &c->d_side_jobs, &c->d_side_colmax})
         b->release();

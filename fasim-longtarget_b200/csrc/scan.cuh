@@ -170,6 +170,11 @@ struct ScanArgs {
     int blk_pitch;
     uint2* bnd;                 // [persistent warp][max_len] strip boundary packets (H, F)
     int* counter;               // work queue head
+    // shared-profile variant (k_scan<R, W, false, true>): the CTA's warps work on items of ONE task pair and share one copy of
+    // that pair's profiles (all strips) in shared memory; work comes in groups of W items of the same pair
+    const int* order;           // [group][W] item index, or -1
+    const int* group_pair;      // [group]
+    int n_groups;
     // Q4 probe variant (k_scan<R, W, true>): no column maxima are written; per item the largest F value carried into a
     // row that starts a stripe of the reference's 16-lane layout (rows k * stripe_len) within the recorded columns
     uint32_t* probe_out;        // [item] packed (task 0 | task 1 << 16)
@@ -193,16 +198,25 @@ __host__ __device__ inline int gran_tail_lane(int g, int scan_r) { const int gl 
 // block that holds column j of a granule with tail lane t
 __host__ __device__ inline int blk_of(int j, int tail_lane) { return (j + tail_lane) / kBlkCols; }
 
+constexpr int kCringPitch = 68;                  // words per granule row of the ring: 64 slots + 4 (rows land in different banks, rows stay 16-byte aligned)
 template <int R>
 __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
 {
-    return 5 * 32 * R * 4 + 32 * 8 + (32 / (kGranRows / R)) * 64 * 4 + ((max_len + 64 + 15) / 16) * 16;
+    return 5 * 32 * R * 4 + 32 * 8 + (32 / (kGranRows / R)) * kCringPitch * 4 + ((max_len + 64 + 15) / 16) * 16;
+}
+// shared-profile variant: per warp only the rings and the base codes; the profiles (n_strips * 5 * 32 * R * 4 bytes) once per CTA
+template <int R>
+__host__ __device__ constexpr int scan_warp_smem_bytes_shared(int max_len)
+{
+    return 32 * 8 + (32 / (kGranRows / R)) * kCringPitch * 4 + ((max_len + 64 + 15) / 16) * 16;
 }
 
 // E update: fused VIADDMNMX (2 ALU-pipe slots) or VIADD on the FMA pipe + VIMNMX (1 ALU-pipe slot); the split form
 // trades one issue slot for one ALU-pipe slot (measured rates: profiles/int_simd_peak.json)
 #ifdef LTG_SCAN_SPLIT_E
-#define LTG_E_UPDATE(EV, U) EV = __vmaxs2(__vadd2(EV, kNegExt), (U))
+// (the empty asm keeps the compiler from fusing the add and the max back into one VIADDMNMX — without it this variant compiles to
+//  the very same SASS as the fused form, which is what round 1 unknowingly measured)
+#define LTG_E_UPDATE(EV, U) { uint32_t e_ = __vadd2(EV, kNegExt); asm volatile("" : "+r"(e_)); EV = __vmaxs2(e_, (U)); }
 #else
 #define LTG_E_UPDATE(EV, U) EV = __viaddmax_s16x2(EV, kNegExt, (U))
 #endif
@@ -222,28 +236,52 @@ __host__ __device__ constexpr int scan_warp_smem_bytes(int max_len)
         hlast = h_;                                               \
     }
 
-template <int R, int WARPS, bool PROBE = false>
+template <int R, int WARPS, bool PROBE = false, bool SHARED = false>
 __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 {
     static_assert(R % 4 == 0, "R must be a multiple of 4");
+    static_assert(!(PROBE && SHARED), "the probe sweep keeps per-warp profiles");
     extern __shared__ uint4 smem_u4[];
+    __shared__ int s_group;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int warp_bytes = scan_warp_smem_bytes<R>(a.max_len);
-    uint4* s_prof = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(smem_u4) + (size_t)wib * warp_bytes);
-    uint2* s_ring = reinterpret_cast<uint2*>(s_prof + 5 * (R / 4) * 32);
+    constexpr int PLANE = (R / 4) * 32;     // uint4 per base-code plane
+    const int warp_bytes = SHARED ? scan_warp_smem_bytes_shared<R>(a.max_len) : scan_warp_smem_bytes<R>(a.max_len);
+    // SHARED: [profiles of every strip][per warp: rings, codes]; otherwise per warp: [profile of the strip in flight, rings, codes]
+    uint4* const s_prof_all = smem_u4;
+    unsigned char* const warp_base = reinterpret_cast<unsigned char*>(smem_u4) + (SHARED ? (size_t)a.n_strips * 5 * PLANE * 16 : 0) + (size_t)wib * warp_bytes;
+    uint4* s_prof = reinterpret_cast<uint4*>(warp_base);
+    uint2* s_ring = SHARED ? reinterpret_cast<uint2*>(warp_base) : reinterpret_cast<uint2*>(s_prof + 5 * PLANE);
     constexpr int kGranLanes = kGranRows / R, kGranPerStrip = 32 / kGranLanes;
     static_assert(kGranLanes >= 1 && kGranLanes * R == kGranRows, "R must divide the granule");
     uint32_t* s_cring = reinterpret_cast<uint32_t*>(s_ring + 32);          // [granule of the strip][step & 63] granule maxima in flight
-    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_cring + kGranPerStrip * 64);
+    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_cring + kGranPerStrip * kCringPitch);
     uint2* bnd = a.bnd + (size_t)(blockIdx.x * WARPS + wib) * a.max_len;
     const uint32_t kNegOpen = 0xFFF0FFF0u, kNegExt = 0xFFFCFFFCu;
-    constexpr int PLANE = (R / 4) * 32;     // uint4 per base-code plane
+    int cur_pair = -1;
 
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(a.counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= a.n_items) break;
+        if (SHARED) {
+            // one group of WARPS items of the same task pair per round; the pair's profiles are (re)loaded when the pair changes
+            if (threadIdx.x == 0) s_group = atomicAdd(a.counter, 1);
+            __syncthreads();
+            const int g = s_group;
+            __syncthreads();                          // everyone holds g (and has left the previous group's profiles) before either changes
+            if (g >= a.n_groups) break;
+            const int pair = a.group_pair[g];
+            if (pair != cur_pair) {
+                const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + (size_t)pair * a.n_strips * (5 * PLANE);
+                for (int i = threadIdx.x; i < a.n_strips * 5 * PLANE; i += WARPS * 32) s_prof_all[i] = gp[i];
+                cur_pair = pair;
+                __syncthreads();
+            }
+            item = a.order[g * WARPS + wib];
+            if (item < 0) continue;                   // a short group: this warp idles until the next round's barrier
+        } else {
+            if (lane == 0) item = atomicAdd(a.counter, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= a.n_items) break;
+        }
         const ScanItem it = a.items[item];
         const SegDesc sd = a.segs[it.seg];
         const int n = sd.len;
@@ -280,10 +318,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 }
                 amask = __reduce_or_sync(0xffffffffu, bmask);
             }
-            const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
-            __syncwarp();
-            for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
-            __syncwarp();
+            if (SHARED) s_prof = s_prof_all + (size_t)strip * (5 * PLANE);
+            else {
+                const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
+                __syncwarp();
+                for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
+                __syncwarp();
+            }
             const bool first = (strip == 0), last = (strip == a.n_strips - 1);
             // this lane's granule: its row of block maxima, and its row of the ring
             uint16_t* blk_row = blk_item + ((size_t)strip * kGranPerStrip + (lane / kGranLanes)) * a.blk_pitch;
@@ -302,7 +343,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             const uint32_t sa_code = (uint32_t)__cvta_generic_to_shared(s_codes) + (32 - lane);
             const uint32_t sa_ring = (uint32_t)__cvta_generic_to_shared(s_ring);
             const uint32_t sa_cring = (uint32_t)__cvta_generic_to_shared(s_cring);
-            const uint32_t sa_cmine = sa_cring + (lane / kGranLanes) * 256;        // this lane's granule row of the ring
+            const uint32_t sa_cmine = sa_cring + (lane / kGranLanes) * (kCringPitch * 4);        // this lane's granule row of the ring
             uint4 sc[R / 4];
             uint32_t xn;
             {
@@ -411,7 +452,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 #pragma unroll
                     for (int q = 0; q < kGranPerStrip; ++q) {
                         uint32_t x;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(sa_cring + q * 256 + (((j + q * kGranLanes + kGranLanes - 1) & 63) << 2)));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(sa_cring + q * (kCringPitch * 4) + (((j + q * kGranLanes + kGranLanes - 1) & 63) << 2)));
                         v = __vmaxs2(v, x);
                     }
                     if (j >= 0 && j < n) {
