@@ -156,6 +156,18 @@ struct ltg_context {
     int batch_segments = kBatchSegments;                  // segments per device batch (LTG_BATCH_SEGMENTS)
     int lit_rows_per_chunk = 24, lit_min_chunks = 0;      // tuning of the column-parallel literal kernel (LTG_LIT_ROWS / LTG_LIT_CH)
     int64_t n_probe_items = 0;          // pairs swept a second time by the Q4 probe (diagnostics)
+    // Fused carried-F recording (k_scan FREC): the main sweep records what the probe sweep would find.  It costs the main sweep
+    // frec_cost (fraction of its instructions, from the stripe geometry of the lncRNA) for EVERY item, the probe costs one more
+    // sweep of the pairs that carry a flagged task: a context starts with the probe and switches a query to the fused form
+    // once a batch had to probe a larger share of its pairs than that (LTG_FREC=0 never, 1 always).
+    bool q4_taint = true;               // the flagged pairs are swept by the taint variant (certifies tasks) instead of the probe variant
+                                        // (LTG_Q4_TAINT=0: probe); with it the recording sweep is only used on request (LTG_FREC=1)
+    int64_t n_certified = 0;            // tasks the taint sweep returned to the exact path (diagnostics)
+    int frec_mode = -1;                 // -1 auto, 0 off, 1 on
+    bool frec_on = false;               // current query: main sweeps record the carried F
+    bool litonly_old = false;           // LTG_LITONLY_OLD=1 (diagnostics): literal-only batches take the Q4 verdict again instead of being told
+    double frec_cost = 0.0;
+    int64_t n_frec_batches = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, lit_stream = nullptr;
     cudaEvent_t lit_event = nullptr;
     ltg_params params;
@@ -170,12 +182,12 @@ struct ltg_context {
     bool rna_acgt = true;           // every SSW code of the lncRNA is 0..3 (A/C/G/T, U counts as A): table lookup scoring applies
     int m = 0, n_strips = 0, scan_r = 32;
     bool profiles_dirty = true;
-    DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_cut;
+    DevBuf d_rna_raw, d_rna_ssw, d_rna_stats, d_rna_sel, d_prof_ssw, d_prof_stats, d_prof_ssw2, d_cut;
     DevBuf d_packed, d_nblocks;         // 2-bit packed input staged for the device-side expansion
     DevBuf d_rna_sim, d_sim_scratch, d_sim_hdr, d_sim_pool, d_sim_tasks;      // -F mode (sim.cuh)
     // record / batch buffers
     DevBuf d_dna, d_codes, d_segs, d_items, d_items_stats, d_blkmax, d_bnd, d_counters;
-    DevBuf d_probe_items, d_probe_orig, d_probe_out, d_bnd_gran, d_scan_order;
+    DevBuf d_probe_items, d_probe_orig, d_probe_out, d_bnd_gran, d_scan_order, d_frec, d_taint_colmax;
     int n_bnd_gran = 0;                 // granules that hold the rows just above a stripe start (Q4 pre-filter)
     DevBuf d_task_info, d_task_off, d_stats_max, d_task_litrow, d_cand;
     DevBuf d_pk_task, d_pk_pos, d_pk_score;
@@ -305,15 +317,16 @@ int build_profiles(ltg_context* c)
     const size_t words = (size_t)c->pairs.size() * c->n_strips * 5 * 32 * c->scan_r;
     if (int e = c->d_prof_ssw.ensure(words * 4)) return e;
     if (int e = c->d_prof_stats.ensure(words * 4)) return e;
+    if (int e = c->d_prof_ssw2.ensure(words * 4)) return e;
     const int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 8);
-    for (int kind = 0; kind < 2; ++kind) {
-        uint32_t* dst = kind ? c->d_prof_stats.as<uint32_t>() : c->d_prof_ssw.as<uint32_t>();
+    for (int kind = 0; kind < 3; ++kind) {
+        uint32_t* dst = kind == 1 ? c->d_prof_stats.as<uint32_t>() : kind == 2 ? c->d_prof_ssw2.as<uint32_t>() : c->d_prof_ssw.as<uint32_t>();
         if (c->scan_r == 32)
             k_build_profiles<32><<<blocks, 256, 0, c->stream>>>(c->d_rna_ssw.as<uint8_t>(), c->d_rna_stats.as<uint8_t>(), c->m, (int)c->pairs.size(), c->n_strips, kind, dst);
         else
             k_build_profiles<16><<<blocks, 256, 0, c->stream>>>(c->d_rna_ssw.as<uint8_t>(), c->d_rna_stats.as<uint8_t>(), c->m, (int)c->pairs.size(), c->n_strips, kind, dst);
     }
-    c->launches += 2;
+    c->launches += 3;
     LTG_CUDA_CHECK(cudaGetLastError());
     // Q4 pre-filter: the granules that hold one of the 28 rows above a stripe start of the reference's 16-lane layout (an F
     // that enters such a row with >= 132 was opened below a cell >= 148 at most 26 rows up)
@@ -331,6 +344,19 @@ int build_profiles(ltg_context* c)
         if (int e = c->d_bnd_gran.ensure(sizeof(int) * std::max<size_t>(1, list.size()))) return e;
         if (!list.empty()) LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_bnd_gran.p, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, c->stream));
         LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // `list` is host memory of this scope
+    }
+    // cost model of the fused carried-F recording: in strips that hold a stripe start every step ends with a screening test and
+    // a (rarely taken) branch, which costs the sweep its scheduling freedom across steps — measured ~25 % of such a strip's time
+    {
+        const int stripe = (c->m + 15) / 16, R = c->scan_r;
+        int with_start = 0;
+        for (int strip = 0; strip < c->n_strips; ++strip) {
+            bool any = false;
+            for (int k = 1; k < 16; ++k) if ((k * stripe) / (32 * R) == strip) any = true;
+            with_start += any ? 1 : 0;
+        }
+        c->frec_cost = 0.25 * with_start / std::max(1, c->n_strips);
+        c->frec_on = (c->frec_mode == 1);
     }
     c->profiles_dirty = false;
     return LTG_OK;
@@ -369,7 +395,8 @@ constexpr int kScanSharedWarps = 6;         // warps per CTA of the shared-profi
 // h_items (host copy of the item list) enables the shared-profile variant: the items are grouped by task pair, kScanSharedWarps to a
 // group, and a CTA keeps ONE copy of the pair's profiles for its six warps — what lifts the scan from 2 to 3 warps per scheduler.
 int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax_all, uint16_t* blkmax,
-                uint32_t* probe_out = nullptr, const int* task_jstar = nullptr, const std::vector<ScanItem>* h_items = nullptr)
+                uint32_t* probe_out = nullptr, const int* task_jstar = nullptr, const std::vector<ScanItem>* h_items = nullptr, uint16_t* frec = nullptr,
+                bool taint = false)
 {
     const int R = c->scan_r;
     int* counters = c->d_counters.as<int>();
@@ -381,10 +408,11 @@ int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_le
     a.counter = counters + kCntScan;
     a.order = nullptr; a.group_pair = nullptr; a.n_groups = 0;
     a.probe_out = probe_out; a.task_jstar = task_jstar; a.tasks_per_seg = (int)c->tasks.size(); a.stripe_len = (c->m + 15) / 16;
+    a.frec = frec;
     // shared-profile variant when the pair's profiles (all strips) and six warps' private parts fit twice into an SM
     const size_t prof_bytes = (size_t)c->n_strips * 5 * 32 * R * 4;
     const size_t smem_shared = prof_bytes + (size_t)kScanSharedWarps * (R == 32 ? scan_warp_smem_bytes_shared<32>(max_len) : scan_warp_smem_bytes_shared<16>(max_len));
-    if (c->scan_shared && !probe_out && h_items && n_items >= 4 * kScanSharedWarps && smem_shared <= 112 * 1024) {
+    if (c->scan_shared && !probe_out && !frec && !taint && h_items && n_items >= 4 * kScanSharedWarps && smem_shared <= 112 * 1024) {
         const int W = kScanSharedWarps, P = (int)c->pairs.size();
         std::vector<std::vector<int> > by_pair((size_t)P);
         for (int i = 0; i < n_items; ++i) by_pair[(*h_items)[i].pair].push_back(i);
@@ -421,13 +449,29 @@ int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_le
     if (smem > 227 * 1024) { set_error("segment length %d needs %zu bytes of shared memory per CTA", max_len, smem); return LTG_ERR_LIMIT; }
     if (int e = c->d_bnd.ensure((size_t)blocks * kScanWarps * max_len * sizeof(uint2))) return e;
     a.bnd = c->d_bnd.as<uint2>();
-    if (probe_out) {
+    if (taint) {
+        if (R == 32) {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_scan<32, kScanWarps, false, false, false, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+        } else {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<16, kScanWarps, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_scan<16, kScanWarps, false, false, false, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+        }
+    } else if (probe_out) {
         if (R == 32) {
             LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_scan<32, kScanWarps, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
         } else {
             LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<16, kScanWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_scan<16, kScanWarps, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+        }
+    } else if (frec) {
+        if (R == 32) {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_scan<32, kScanWarps, false, false, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
+        } else {
+            LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<16, kScanWarps, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_scan<16, kScanWarps, false, false, true><<<blocks, kScanWarps * 32, smem, c->stream>>>(a);
         }
     } else if (R == 32) {
         LTG_CUDA_CHECK(cudaFuncSetAttribute(k_scan<32, kScanWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -737,9 +781,18 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
         stats_max = c->d_stats_max.as<int>();
         LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));          // `sitems` is host memory of this scope
     }
+    // fused carried-F recording (see ltg_context::frec_mode): this batch's verdict on the Q4 quirk comes from the main sweep
+    const bool lit_forced = (lit_mode == kLitOnly) && !c->litonly_old;     // literal-only batch: the literal tasks are the requested ones
+    const bool use_frec = c->q4_probe && c->frec_on && lit_mode != kLitSkip && lit_mode != kLitOnly;
+    uint16_t* frec = nullptr;
+    if (use_frec) {
+        if (int e = c->d_frec.ensure((size_t)n_items * kFrecRows * blk_pitch * sizeof(uint16_t))) return e;
+        frec = c->d_frec.as<uint16_t>();
+        c->n_frec_batches += 1;
+    }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[4], c->stream));
     if (int e = launch_scan(c, c->d_items.as<ScanItem>(), n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax_all.as<uint32_t>(),
-                            c->d_blkmax.as<uint16_t>(), nullptr, nullptr, &items)) return e;
+                            c->d_blkmax.as<uint16_t>(), nullptr, nullptr, &items, frec)) return e;
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[5], c->stream));
 
     // peaks: statistics + count, literal re-runs, count of those, exclusive scan, write
@@ -748,7 +801,8 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     ea.colmax_all = c->d_colmax_all.as<uint32_t>(); ea.lit_colmax = nullptr; ea.task_litrow = c->d_task_litrow.as<int>();
     ea.items = c->d_items.as<ScanItem>(); ea.segs = c->d_segs.as<SegDesc>();
     ea.item_orig = nullptr; ea.probe = nullptr;
-    ea.bnd_gran = (c->q4_probe && c->n_bnd_gran > 0) ? c->d_bnd_gran.as<int>() : nullptr; ea.n_bnd_gran = c->n_bnd_gran;
+    ea.bnd_gran = (c->q4_probe && c->n_bnd_gran > 0 && !lit_forced) ? c->d_bnd_gran.as<int>() : nullptr; ea.n_bnd_gran = c->n_bnd_gran;
+    ea.frec = frec; ea.stripe_len = (c->m + 15) / 16; ea.taint_colmax = nullptr;
     ea.n_items = n_items; ea.max_len = max_len; ea.tasks_per_seg = T; ea.stats_max = stats_max; ea.stats_all = c->rna_plain ? 0 : 1; ea.mode = 0;
     ea.task_max = ti.max; ea.task_thr = ti.thr; ea.task_npeaks = ti.npk; ea.task_flags = ti.flags; ea.task_jstar = ti.jstar;
     ea.task_off = c->d_task_off.as<int>(); ea.pk_task = nullptr; ea.pk_pos = nullptr; ea.pk_score = nullptr;
@@ -756,6 +810,19 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     k_epilogue<<<epi_blocks, 128, 0, c->stream>>>(ea);
     c->launches += 1;
     LTG_CUDA_CHECK(cudaGetLastError());
+    if (lit_forced) {
+        // the verdict on these tasks was reached in their main batch (by the probe sweep or by the recording sweep, whose
+        // block granularity may flag a few tasks more): it is not taken again, the requested tasks ARE the literal ones
+        std::vector<unsigned char> want((size_t)n_tasks, 0);
+        for (int t : *only_tasks) want[(size_t)t] = 1;
+        if (int e = c->d_probe_orig.ensure((size_t)n_tasks)) return e;
+        LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_probe_orig.p, want.data(), (size_t)n_tasks, cudaMemcpyHostToDevice, c->stream));
+        k_force_literal<<<(n_tasks + 255) / 256, 256, 0, c->stream>>>(ti.flags, ti.npk, c->d_probe_orig.as<unsigned char>(), n_tasks);
+        c->launches += 1;
+        LTG_CUDA_CHECK(cudaGetLastError());
+        LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));          // `want` is host memory of this scope
+        c->h2d_bytes += n_tasks;
+    }
 
     // Q4 guard: tasks whose exact maximum could carry F >= 132 across a stripe boundary are re-run through
     // the literal striped emulation, their peaks come from the literal column maxima
@@ -764,7 +831,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
     c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
     // Q4 probe: a second sweep of the pairs that carry a flagged task finds the largest F carried into a stripe start of the
     // reference's layout; below 132 the signed compare cannot misfire and the task returns to the exact path (mode 3)
-    if (c->q4_probe && lit_mode != kLitSkip) {
+    if (c->q4_probe && lit_mode != kLitSkip && !lit_forced && (c->q4_taint || !use_frec)) {
         std::vector<ScanItem> pitems;
         std::vector<int> porig;
         for (int i = 0; i < n_items; ++i) {
@@ -779,19 +846,39 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
             if (int e = c->d_probe_out.ensure(sizeof(uint32_t) * (size_t)np)) return e;
             LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_probe_items.p, pitems.data(), sizeof(ScanItem) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
             LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_probe_orig.p, porig.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
-            if (int e = launch_scan(c, c->d_probe_items.as<ScanItem>(), np, max_len, c->d_prof_ssw.as<uint32_t>(), nullptr, nullptr,
-                                    c->d_probe_out.as<uint32_t>(), ti.jstar)) return e;
             EpiArgs pa = ea;
             pa.items = c->d_probe_items.as<ScanItem>(); pa.item_orig = c->d_probe_orig.as<int>(); pa.probe = c->d_probe_out.as<uint32_t>();
-            pa.n_items = np; pa.mode = 3;
+            pa.n_items = np;
+            if (c->q4_taint) {
+                // taint sweep: exact Smith-Waterman once more over these pairs, carrying one bit per value that says whether the
+                // quirk could have lowered it; a task whose recorded column maxima are all untainted returns to the exact path
+                if (int e = c->d_taint_colmax.ensure((size_t)np * max_len * 4)) return e;
+                if (int e = launch_scan(c, c->d_probe_items.as<ScanItem>(), np, max_len, c->d_prof_ssw2.as<uint32_t>(), c->d_taint_colmax.as<uint32_t>(),
+                                        nullptr, c->d_probe_out.as<uint32_t>(), ti.jstar, nullptr, nullptr, true)) return e;
+                pa.taint_colmax = c->d_taint_colmax.as<uint32_t>();
+                pa.mode = 4;
+            } else {
+                if (int e = launch_scan(c, c->d_probe_items.as<ScanItem>(), np, max_len, c->d_prof_ssw.as<uint32_t>(), nullptr, nullptr,
+                                        c->d_probe_out.as<uint32_t>(), ti.jstar)) return e;
+                pa.mode = 3;
+            }
             k_epilogue<<<(np * 32 + 127) / 128, 128, 0, c->stream>>>(pa);
             c->launches += 1;
             LTG_CUDA_CHECK(cudaGetLastError());
+            int lit_before = 0;
+            for (int t = 0; t < n_tasks; ++t) lit_before += (hti.flags[t] & kTaskLiteral) ? 1 : 0;
             LTG_CUDA_CHECK(cudaMemcpyAsync(hti.flags, ti.flags, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
             LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // (also: `pitems` / `porig` are host memory of this scope)
+            int lit_after = 0;
+            for (int t = 0; t < n_tasks; ++t) lit_after += (hti.flags[t] & kTaskLiteral) ? 1 : 0;
+            if (c->q4_taint) c->n_certified += lit_before - lit_after;
             c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
             c->h2d_bytes += (int64_t)(sizeof(ScanItem) + sizeof(int)) * np;
             c->n_probe_items += np;
+            // the probe swept np of n_items pairs again: beyond the cost of recording in the main sweep, later batches of this
+            // query record (kLitOnly batches and tiny ones say little about the query: at least 64 items)
+            // (the probe sweep itself runs at ~0.8 of the plain sweep's rate)
+            if (!c->q4_taint && c->frec_mode < 0 && n_items >= 64 && 1.25 * (double)np > std::max(c->frec_cost, 0.02) * (double)n_items) c->frec_on = true;
         }
     }
     // kLitOnly: were all requested tasks already swept by the side stream (their literal column maxima wait in d_side_colmax)?
@@ -1521,6 +1608,9 @@ int ltg_create(int device, ltg_context** out)
     // LTG_NO_SKIP=1 runs every window round of fastSIM's loop even when it provably repeats the previous result
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
+    if (const char* e = getenv("LTG_FREC")) c->frec_mode = atoi(e) != 0 ? 1 : 0;
+    if (const char* e = getenv("LTG_LITONLY_OLD")) c->litonly_old = atoi(e) != 0;
+    if (const char* e = getenv("LTG_Q4_TAINT")) c->q4_taint = atoi(e) != 0;
     if (const char* e = getenv("LTG_SCAN_SHARED")) c->scan_shared = atoi(e) != 0;
     // LTG_FLOORS=1: the first window sweep only tracks cells that reach the peak score (fewer slow-path trips of the tracker, more
     // re-planned sweeps; measured neutral on the headline workload, profiles/README.md)

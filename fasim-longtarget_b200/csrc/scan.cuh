@@ -138,9 +138,10 @@ __global__ void k_build_profiles(const uint8_t* __restrict__ rna_ssw, const uint
             int s;
             if (row >= m16) s = kGhost;
             else if (row >= m) s = 0;
-            else if (kind == 0) {
+            else if (kind == 0 || kind == 2) {
                 const int q = rna_ssw[row];
                 s = (q == d && d < 4) ? kMatch : kMismatch;
+                if (kind == 2) s *= 2;              // taint sweep (k_scan TAINT): values are 2 * score - taint bit
             } else {
                 const int q = rna_stats[row];       // 0 A,1 C,2 G,3 T,4 U,5 N
                 if (q == 5 || d == 4) s = -1;
@@ -176,12 +177,26 @@ struct ScanArgs {
     const int* group_pair;      // [group]
     int n_groups;
     // Q4 probe variant (k_scan<R, W, true>): no column maxima are written; per item the largest F value carried into a
-    // row that starts a stripe of the reference's 16-lane layout (rows k * stripe_len) within the recorded columns
+    // row that starts a stripe of the reference's 16-lane layout (rows k * stripe_len) within the recorded columns.
+    // Q4 taint variant (k_scan<R, W, false, false, false, true>, see taint_slow_step): `profiles` hold doubled scores, colmax_all
+    // receives 2 * maximum - taint bit per column, probe_out bit 0 / bit 16 = "gave up" for task 0 / 1
     uint32_t* probe_out;        // [item] packed (task 0 | task 1 << 16)
     const int* task_jstar;      // [seg * T + task] first column the reference does not record any more (or n)
     int tasks_per_seg;
     int stripe_len;             // ceil(m / 16)
+    // fused carried-F recording (k_scan<R, W, false, false, true>): the main sweep itself keeps, per stripe start of the
+    // reference's layout and per block of kBlkCols wavefront steps, the largest F carried into that row (two saturated bytes
+    // like blkmax), so no second sweep is needed to decide which tasks the Q4 quirk can touch
+    uint16_t* frec;             // [item][kFrecRows][blk_pitch]
 };
+constexpr int kFrecRows = 15;   // stripe starts k * stripe_len, k = 1..15
+// A lane of the scan (R consecutive rows from row0) that holds stripe starts records all of them in the row of the FIRST one:
+// index (k - 1) of that stripe start, or -1 when the lane holds none
+__host__ __device__ inline int frec_row_of_lane(int row0, int R, int stripe_len)
+{
+    const int kf = row0 <= 0 ? 1 : (row0 + stripe_len - 1) / stripe_len;
+    return (kf <= kFrecRows && kf * stripe_len < row0 + R) ? kf - 1 : -1;
+}
 
 // The column maxima are kept PER GRANULE of kGranRows / R lanes (kGranRows RNA rows; the running maximum that travels
 // along the lanes restarts at every granule head and the granule's last lane — its "tail" — holds the granule's maximum of
@@ -211,6 +226,62 @@ __host__ __device__ constexpr int scan_warp_smem_bytes_shared(int max_len)
     return 32 * 8 + (32 / (kGranRows / R)) * kCringPitch * 4 + ((max_len + 64 + 15) / 16) * 16;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Q4 certification by taint tracking (CPU prototype and soundness harness: tests/test_q4_theory_cpu.py
+// `certify(kernel_rule=True)`).  The sweep computes exact Smith-Waterman on values x = 2 * score - tau, tau = 1 meaning "the
+// reference's kernel (signed lazy-F test, sswNew.cpp:369) may hold a LOWER value here"; a maximum prefers the untainted side
+// on ties, adding even numbers keeps the bit, the zero floor is untainted.  The quirk can only drop contributions of an F chain
+// that entered a stripe start of the reference's layout with >= 132, from the row after the chain has passed through [132, 143]
+// (its value is <= 139 then): those contributions are tainted.  A chain that is itself tainted and >= 132 at a stripe start is
+// beyond the model ("give up").  A task whose recorded column maxima are all untainted has exactly the reference's maxima.
+//
+// Most steps of a lane cannot start or carry such a chain (screened before the cells, see LTG_SCAN_STEP): they run the plain
+// packed recurrence, in which the chain through a stripe start is simply the merged F.  taint_slow_step is the general form of
+// one lane-step: the F chain split into the part opened inside the stripe (fs) and the carried chain (fc, with its "started
+// >= 132" flag), per 16-bit half; H, E and the scores stay packed.  fcin / fcout: carried chain per half, bit 15 = flag.
+template <int R>
+__device__ __forceinline__ void taint_slow_step(uint32_t (&Hd)[R], uint32_t (&E)[R], const uint4 (&sc)[R / 4], uint32_t hdiag, uint32_t fin,
+                                                uint32_t fcin, uint32_t bmask, uint32_t live, uint32_t& cm, uint32_t& hlast, uint32_t& fout,
+                                                uint32_t& fcout, uint32_t& giveup)
+{
+    const uint32_t kOpen2 = 0xFFE0FFE0u, kExt2 = 0xFFF8FFF8u;
+    int fs[2] = {lo16(fin), hi16(fin)};
+    int fc[2] = {(int)(fcin & 0x7FFFu), (int)((fcin >> 16) & 0x7FFFu)};
+    int og[2] = {(int)((fcin >> 15) & 1u), (int)(fcin >> 31)};
+    uint32_t d = hdiag;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (bmask & (1u << r)) {                     // this row starts a stripe: the chain that crosses is the larger of the two
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int fend = fs[h], old = fc[h];
+                if (((fend + 1) >> 1) >= ((old + 1) >> 1)) { fc[h] = fend; og[h] = ((fend + 1) >> 1) >= kQ4CarryF; }
+                fs[h] = 0;
+                if ((fc[h] & 1) && ((fc[h] + 1) >> 1) >= kQ4CarryF && ((live >> h) & 1u)) giveup |= 1u << (16 * h);
+            }
+        }
+        int cb[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool cut = og[h] && ((fc[h] + 1) >> 1) <= 139;
+            cb[h] = cut ? ((fc[h] - 1) | 1) : fc[h];
+        }
+        const uint32_t sv = r % 4 == 0 ? sc[r / 4].x : r % 4 == 1 ? sc[r / 4].y : r % 4 == 2 ? sc[r / 4].z : sc[r / 4].w;
+        const uint32_t t = __viaddmax_s16x2_relu(d, sv, E[r]);
+        const uint32_t u = __vadd2(t, kOpen2);
+        E[r] = __viaddmax_s16x2(E[r], kExt2, u);
+        const uint32_t hh = __vmaxs2(__vmaxs2(t, pack16(fs[0], fs[1])), pack16(cb[0], cb[1]));
+        fs[0] = max(fs[0] - 8, lo16(u)); fs[1] = max(fs[1] - 8, hi16(u));
+        fc[0] = max(fc[0] - 8, 0); fc[1] = max(fc[1] - 8, 0);
+        og[0] &= (int)(fc[0] > 0); og[1] &= (int)(fc[1] > 0);
+        d = Hd[r]; Hd[r] = hh;
+        cm = __vmaxs2(cm, t);
+        hlast = hh;
+    }
+    fout = pack16(fs[0], fs[1]);
+    fcout = (uint32_t)fc[0] | ((uint32_t)og[0] << 15) | ((uint32_t)fc[1] << 16) | ((uint32_t)og[1] << 31);
+}
+
 // E update: fused VIADDMNMX (2 ALU-pipe slots) or VIADD on the FMA pipe + VIMNMX (1 ALU-pipe slot); the split form
 // trades one issue slot for one ALU-pipe slot (measured rates: profiles/int_simd_peak.json)
 #ifdef LTG_SCAN_SPLIT_E
@@ -221,7 +292,24 @@ __host__ __device__ constexpr int scan_warp_smem_bytes_shared(int max_len)
 #define LTG_E_UPDATE(EV, U) EV = __viaddmax_s16x2(EV, kNegExt, (U))
 #endif
 
-#define LTG_PROBE_F(RR) if (bmask & (1u << (RR))) fb = __vmaxs2(fb, f & vmask);
+// Carried F (PROBE and FREC variants): the F that enters a row which starts a stripe of the reference's layout.  Taking it out
+// of the cell loop row by row costs a branch (or 3 instructions) per row; instead every step is SCREENED after its cells with 4
+// instructions — an F >= 132 entering any row of this lane needs fin >= 132 or a cell >= 148 in this lane's part of the column,
+// and the running column maximum cm covers those cells — and only a step that passes (rare: never on random DNA) rebuilds
+// the lane's F chain from the column's H values, which sit in Hd[] after the step: F(r+1) = max(F(r) - 4, H(r) - 16)
+// (identical to the chain of the cell loop, F - 16 < F - 4).  ACC: accumulator, MASKED: apply vmask (column range) to a value.
+#define LTG_CARRIED_F(ACC, MASKED)                                                                              \
+            if (amask) {                                                                                        \
+                const uint32_t x_ = __viaddmax_s16x2(fin, 0x00100010u, cm);                                     \
+                const bool trig_ = bmask != 0 && __vmaxs2(x_, 0x00930093u) != 0x00930093u;                      \
+                if (__any_sync(0xffffffffu, trig_)) {                                                           \
+                    uint32_t g_ = fin;                                                                          \
+                    _Pragma("unroll") for (int r_ = 0; r_ < R; ++r_) {                                          \
+                        if (bmask & (1u << r_)) ACC = __vmaxs2(ACC, (MASKED) ? (g_ & vmask) : g_);              \
+                        g_ = __viaddmax_s16x2(g_, kNegExt, __vadd2(Hd[r_], kNegOpen));                          \
+                    }                                                                                           \
+                }                                                                                               \
+            }
 #define LTG_CELL(SV, RR)                                          \
     {                                                             \
         const uint32_t t_ = __viaddmax_s16x2_relu(d, (SV), E[RR]); \
@@ -232,17 +320,20 @@ __host__ __device__ constexpr int scan_warp_smem_bytes_shared(int max_len)
         d = Hd[RR];                                               \
         Hd[RR] = h_;                                              \
         tv[(RR) & 1] = t_;                                        \
-        if (!PROBE && ((RR) & 1)) cm = __vimax3_s16x2(cm, tv[0], tv[1]); \
+        if ((RR) & 1) cm = __vimax3_s16x2(cm, tv[0], tv[1]);        \
         hlast = h_;                                               \
     }
 
-template <int R, int WARPS, bool PROBE = false, bool SHARED = false>
+template <int R, int WARPS, bool PROBE = false, bool SHARED = false, bool FREC = false, bool TAINT = false>
 __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 {
     static_assert(R % 4 == 0, "R must be a multiple of 4");
     static_assert(!(PROBE && SHARED), "the probe sweep keeps per-warp profiles");
+    static_assert(!(FREC && (PROBE || SHARED)), "carried-F recording belongs to the plain main sweep");
+    static_assert(!(TAINT && (PROBE || SHARED || FREC)), "the taint sweep is a variant of its own");
     extern __shared__ uint4 smem_u4[];
     __shared__ int s_group;
+    __shared__ alignas(8) unsigned long long s_bar[WARPS];      // per warp: mbarrier of the strip-profile bulk copy
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr int PLANE = (R / 4) * 32;     // uint4 per base-code plane
     const int warp_bytes = SHARED ? scan_warp_smem_bytes_shared<R>(a.max_len) : scan_warp_smem_bytes<R>(a.max_len);
@@ -256,8 +347,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
     uint32_t* s_cring = reinterpret_cast<uint32_t*>(s_ring + 32);          // [granule of the strip][step & 63] granule maxima in flight
     uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_cring + kGranPerStrip * kCringPitch);
     uint2* bnd = a.bnd + (size_t)(blockIdx.x * WARPS + wib) * a.max_len;
-    const uint32_t kNegOpen = 0xFFF0FFF0u, kNegExt = 0xFFFCFFFCu;
+    const uint32_t kNegOpen = TAINT ? 0xFFE0FFE0u : 0xFFF0FFF0u, kNegExt = TAINT ? 0xFFF8FFF8u : 0xFFFCFFFCu;      // TAINT: doubled scores
     int cur_pair = -1;
+    // Staging of the strip profile (20 KB at R = 32), once per warp and strip: ONE bulk asynchronous copy (cp.async.bulk, the 1-D
+    // TMA path: SASS UBLKCP) that completes on the warp's own mbarrier, instead of 40 LDG.128 + STS.128 per lane.  The copy is
+    // ~0.1 % of a strip's time, so the two forms measure the same (7086 vs 7072 GCUPS, profiles/README.md; -DLTG_NO_BULK keeps
+    // the loop).  The wait loop leaves on a warp vote: with a per-lane exit the compiler treated the warp as possibly diverged
+    // for the rest of the kernel (BRA.DIV before every shuffle, +8 registers) and the kernel lost 4.5 %.
+    const uint32_t sa_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[wib]);
+    uint32_t bar_phase = 0;
+    (void)sa_bar; (void)bar_phase;
+#ifndef LTG_NO_BULK
+    if (!SHARED) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sa_bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+#endif
 
     for (;;) {
         int item = 0;
@@ -298,8 +406,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
         const bool gran_head = (lane & (kGranLanes - 1)) == 0, gran_tail = (lane & (kGranLanes - 1)) == kGranLanes - 1;
 
         uint32_t fb = 0;                                           // PROBE: running maximum of the carried F values
+        uint32_t giveup = 0;                                       // TAINT: bit 0 / bit 16 = the model gave up on task 0 / 1
         int jst0 = 0, jst1 = 0;
-        if (PROBE) {
+        if (PROBE || TAINT) {
             const PairDef pd = c_pairs[it.pair];
             // columns the reference processes: up to and including the one where it stops recording (Q2)
             jst0 = min(a.task_jstar[it.seg * a.tasks_per_seg + pd.task[0]] + 1, n);
@@ -309,7 +418,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
         for (int strip = 0; strip < a.n_strips; ++strip) {
             // PROBE: which of this lane's rows start a stripe of the reference's layout (row = k * stripe_len, k = 1..15)
             uint32_t bmask = 0, vmask = 0, amask = 0;
-            if (PROBE) {
+            uint32_t fr = 0;                                       // FREC: largest carried F of the block of steps in flight
+            uint16_t* frec_row = nullptr;
+            if (FREC) {
+                const int fk = frec_row_of_lane((strip * 32 + lane) * R, R, a.stripe_len);
+                if (fk >= 0) frec_row = a.frec + ((size_t)item * kFrecRows + fk) * a.blk_pitch;
+            }
+            if (PROBE || FREC || TAINT) {
                 const int row0 = (strip * 32 + lane) * R;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -321,8 +436,24 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             if (SHARED) s_prof = s_prof_all + (size_t)strip * (5 * PLANE);
             else {
                 const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
-                __syncwarp();
+                __syncwarp();                                      // every lane is done with the previous strip's profile
+#ifdef LTG_NO_BULK
                 for (int i = lane; i < 5 * PLANE; i += 32) s_prof[i] = gp[i];
+#else
+                if (lane == 0) {
+                    constexpr uint32_t kBytes = 5 * PLANE * 16;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sa_bar), "r"(kBytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 :: "r"((uint32_t)__cvta_generic_to_shared(s_prof)), "l"(gp), "r"(kBytes), "r"(sa_bar) : "memory");
+                }
+                for (;;) {                                         // (the exit is a vote: the warp leaves the loop converged)
+                    uint32_t done;
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(sa_bar), "r"(bar_phase) : "memory");
+                    if (__all_sync(0xffffffffu, done != 0)) break;
+                }
+                bar_phase ^= 1;
+#endif
                 __syncwarp();
             }
             const bool first = (strip == 0), last = (strip == a.n_strips - 1);
@@ -333,6 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 #pragma unroll
             for (int r = 0; r < R; ++r) { Hd[r] = 0; E[r] = 0; }
             uint32_t hout = 0, fout = 0, cmout = 0, hdiag = 0;
+            uint32_t fcout = 0, scr = 0;                          // TAINT: carried chain handed to the next lane; bound of this lane's column
             const int steps = n + 31;
             // Steps run in blocks of 32 (the ring of strip-boundary packets is refilled per block).  Shared memory is
             // addressed with explicit 32-bit shared addresses (one add per profile fetch instead of a generic-pointer
@@ -378,21 +510,39 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                     else asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hin), "=r"(fin) : "r"(sa_ring + (K) * 8)); \
                 }                                                                                               \
                 if (PROBE) { const int j_ = (S) - lane; vmask = (j_ < jst0 ? 0xFFFFu : 0u) | (j_ < jst1 ? 0xFFFF0000u : 0u); } \
+                if (FREC && GUARD) vmask = ((S) >= lane && (S) - lane < n) ? 0xFFFFFFFFu : 0u;                  \
                 uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;                                              \
                 uint32_t tv[2];                                                                                 \
-                _Pragma("unroll") for (int k = 0; k < R / 4; ++k) {                                             \
-                    if (PROBE && ((amask >> (4 * k)) & 0xFu)) {     /* warp-uniform: some lane has a stripe start here */ \
-                        LTG_PROBE_F(4 * k + 0) LTG_CELL(sc[k].x, 4 * k + 0)                                     \
-                        LTG_PROBE_F(4 * k + 1) LTG_CELL(sc[k].y, 4 * k + 1)                                     \
-                        LTG_PROBE_F(4 * k + 2) LTG_CELL(sc[k].z, 4 * k + 2)                                     \
-                        LTG_PROBE_F(4 * k + 3) LTG_CELL(sc[k].w, 4 * k + 3)                                     \
-                    } else {                                                                                    \
+                /* TAINT: a lane-step that may start or carry a chain of >= 132 through a stripe start takes the general form. \
+                   Without a chain coming in, that needs fin >= 132 or a cell >= 148 in this lane's part of the column; a cell  \
+                   is at most 5 above the previous column's H values, which scr (previous step: cm, fin, chain) and hdiag bound */ \
+                uint32_t fcin = 0, fcnew = 0;                                                                   \
+                bool slow_ = false;                                                                             \
+                if (TAINT) {                                                                                    \
+                    fcin = __shfl_up_sync(0xffffffffu, fcout, 1);                                               \
+                    if (lane == 0) fcin = 0;                                                                    \
+                    const uint32_t x_ = __viaddmax_s16x2(fin, 0x00160016u, __vimax3_s16x2(scr, hdiag, hdiag));  \
+                    slow_ = __any_sync(0xffffffffu, fcin != 0 || (bmask != 0 && __vmaxs2(x_, 0x011C011Cu) != 0x011C011Cu)); \
+                }                                                                                               \
+                if (TAINT && slow_) {                                                                           \
+                    const int j_ = (S) - lane;                                                                  \
+                    const uint32_t live_ = (j_ >= 0 && j_ < jst0 ? 1u : 0u) | (j_ >= 0 && j_ < jst1 ? 2u : 0u); \
+                    taint_slow_step<R>(Hd, E, sc, hdiag, fin, fcin, bmask, live_, cm, hlast, f, fcnew, giveup); \
+                } else {                                                                                        \
+                    _Pragma("unroll") for (int k = 0; k < R / 4; ++k) {                                         \
                         LTG_CELL(sc[k].x, 4 * k + 0)                                                            \
                         LTG_CELL(sc[k].y, 4 * k + 1)                                                            \
                         LTG_CELL(sc[k].z, 4 * k + 2)                                                            \
                         LTG_CELL(sc[k].w, 4 * k + 3)                                                            \
                     }                                                                                           \
                 }                                                                                               \
+                if (TAINT) {                                                                                    \
+                    scr = __vimax3_s16x2(cm, fin, fcin & 0x7FFF7FFFu);                                          \
+                    fcout = fcnew;                                                                              \
+                    if (lane == 31 && !last && (fcnew & 0x7FFF7FFFu) != 0) giveup |= 0x00010001u;   /* a chain would cross into the next strip */ \
+                }                                                                                               \
+                if (PROBE) LTG_CARRIED_F(fb, true)                                                              \
+                if (FREC) LTG_CARRIED_F(fr, GUARD)                                                              \
                 _Pragma("unroll") for (int k = 0; k < R / 4; ++k) sc[k] = scn[k];                               \
                 hdiag = hin;                                                                                    \
                 hout = hlast; fout = f; cmout = cm;                                                             \
@@ -413,9 +563,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             }
             // block maximum of the last kBlkCols steps: two saturated bytes (task 0 low)
 #define LTG_BLK_STORE(S)                                                                                        \
-            if (!PROBE) {                                                                                       \
+            if (!PROBE && !TAINT) {                                                                             \
                 if (gran_tail) blk_row[(S) / kBlkCols] = (uint16_t)__byte_perm(__vminu2(blk, 0x00FF00FFu), 0u, 0x4420); \
                 blk = 0;                                                                                        \
+                if (FREC) {                                                                                     \
+                    if (frec_row) frec_row[(S) / kBlkCols] = (uint16_t)__byte_perm(__vminu2(fr, 0x00FF00FFu), 0u, 0x4420); \
+                    fr = 0;                                                                                     \
+                }                                                                                               \
             }
 
             for (int s0 = 0; s0 < steps; s0 += 32) {
@@ -427,7 +581,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                     s_ring[lane] = pk;
                     __syncwarp();
                 }
-                if (s0 >= 32 && s0 + 33 < n) {
+                if (!TAINT && s0 >= 32 && s0 + 33 < n) {       // (TAINT branches per step anyway: one copy of the step is enough)
                     static_assert(kBlkCols == 16, "two blocks per 32 steps");
 #pragma unroll 4
                     for (int k = 0; k < 16; ++k) LTG_SCAN_STEP(false, s0 + k, k)
@@ -470,10 +624,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
             for (int o = 16; o; o >>= 1) fb = __vmaxs2(fb, __shfl_xor_sync(0xffffffffu, fb, o));
             if (lane == 0) a.probe_out[item] = fb;
         }
+        if (TAINT) {
+            giveup = __reduce_or_sync(0xffffffffu, giveup);
+            if (lane == 0) a.probe_out[item] = giveup;
+        }
     }
 }
 #undef LTG_CELL
-#undef LTG_PROBE_F
+#undef LTG_CARRIED_F
 #undef LTG_E_UPDATE
 
 // ---------------------------------------------------------------------------------------------
@@ -497,8 +655,11 @@ struct EpiArgs {
     const ScanItem* items;
     const int* bnd_gran;         // mode 0: granules that hold one of the 28 rows above a stripe start of the reference's layout
     int n_bnd_gran;              //         (nullptr: every task that reaches 148 is flagged)
+    const uint16_t* frec;        // mode 0: [item][kFrecRows][blk_pitch] carried-F block maxima recorded by the sweep itself (k_scan FREC), or
+    int stripe_len;              //         nullptr; with them the verdict is final (no granule pre-filter, no probe sweep)
     const int* item_orig;        // mode 3: [item] index of the item in the batch's full item list (rows of colmax_all)
-    const uint32_t* probe;       // mode 3: [item] packed carried-F maxima of the Q4 probe sweep
+    const uint32_t* probe;       // mode 3: [item] packed carried-F maxima of the Q4 probe sweep; mode 4: "gave up" bits of the taint sweep
+    const uint32_t* taint_colmax;// mode 4: [item][max_len] 2 * column maximum - taint bit (k_scan TAINT)
     const SegDesc* segs;
     int n_items;
     int max_len;
@@ -517,6 +678,7 @@ struct EpiArgs {
     int* pk_score;
 };
 constexpr int kTaskOverflow = 1, kTaskLiteral = 2, kTaskRange = 4;
+constexpr int kTaskSkip = 8;     // literal-only batches: a task that shares a pair with a requested one; it has no peaks in this batch
 
 __device__ inline void epi_flush(const EpiArgs& a, int lane, int& nbuf, int base, int task, int bpos, int bscore)
 {
@@ -536,7 +698,7 @@ __global__ void k_epilogue(const EpiArgs a)
     const ScanItem it = a.items[warp];
     const SegDesc sd = a.segs[it.seg];
     const int n = sd.len;
-    const int row = (a.mode == 3) ? a.item_orig[warp] : warp;
+    const int row = (a.mode == 3 || a.mode == 4) ? a.item_orig[warp] : warp;
     const uint16_t* blk = a.blkmax + (size_t)row * a.n_gran * a.blk_pitch;
     const uint32_t* cm_all = a.colmax_all + (size_t)row * a.max_len;
     const PairDef pd = c_pairs[it.pair];
@@ -563,7 +725,27 @@ __global__ void k_epilogue(const EpiArgs a)
             // Q4 can only fire where an F >= 132 enters a stripe start, i.e. below a cell >= 148 at most 26 rows up, in a column
             // the reference still processes: without such a cell in the granules that hold those rows the task stays exact
             bool q4 = mx >= kQ4Guard;
-            if (q4 && a.bnd_gran) {
+            if (q4 && a.frec) {
+                // the sweep recorded the largest F carried into every stripe start per block of 16 steps: the quirk needs one
+                // >= 132 in a column the reference still processes (blocks: the last one may reach up to 15 columns further,
+                // which can only flag more)
+                int carried = 0;
+                const int jend = min(jstar + 1, n);
+                const uint16_t* fbase = a.frec + (size_t)row * kFrecRows * a.blk_pitch;
+                for (int k = 1; k <= kFrecRows; ++k) {
+                    const int gl = (k * a.stripe_len) / a.scan_r;                      // lane (counted over all strips) that holds the stripe start
+                    if (frec_row_of_lane(gl * a.scan_r, a.scan_r, a.stripe_len) != k - 1) continue;    // recorded with an earlier stripe start of that lane
+                    const int tl = gl & 31;
+                    const uint16_t* rowp = fbase + (size_t)(k - 1) * a.blk_pitch;
+                    for (int b = blk_of(0, tl) + lane; b <= blk_of(jend - 1, tl); b += 32) {
+                        const int v = rowp[b];
+                        carried = max(carried, h ? (v >> 8) : (v & 0xff));
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) carried = max(carried, __shfl_xor_sync(0xffffffffu, carried, o));
+                q4 = carried >= kQ4CarryF;
+            } else if (q4 && a.bnd_gran) {
                 // (block maxima: upper bounds over 16-column blocks, saturated at 255 — coarser than per column, never smaller)
                 int near = 0;
                 const int jend = min(jstar + 1, n);
@@ -595,8 +777,24 @@ __global__ void k_epilogue(const EpiArgs a)
             if (lane == 0) a.task_flags[task] &= ~kTaskLiteral;
             thr = a.task_thr[task];
             jstar = a.task_jstar[task];
+        } else if (a.mode == 4) {
+            // Q4 taint verdict: every column maximum the reference records is untainted and the model never gave up, so the
+            // reference's column maxima are the exact ones (scan.cuh, taint_slow_step): back to the fast path
+            const bool is_lit = (a.task_flags[task] & kTaskLiteral) != 0;
+            const uint32_t gv = a.probe[warp];
+            const int jend = min(a.task_jstar[task] + 1, n);
+            const uint32_t* tc = a.taint_colmax + (size_t)warp * a.max_len;
+            int bad = 0;
+            for (int j = lane; j < jend; j += 32) bad |= (int)((h ? (tc[j] >> 16) : tc[j]) & 1u);
+            bad = __any_sync(0xffffffffu, bad != 0) ? 1 : 0;
+            // (doubled values must stay inside 16 bits: a task that scores >= 16000 is not judged)
+            if (!is_lit || bad || (h ? (gv >> 16) : (gv & 0xffffu)) != 0 || a.task_max[task] >= 16000) continue;
+            if (lane == 0) a.task_flags[task] &= ~kTaskLiteral;
+            thr = a.task_thr[task];
+            jstar = a.task_jstar[task];
         } else {
             const bool is_lit = (a.task_flags[task] & kTaskLiteral) != 0;
+            if (a.task_flags[task] & kTaskSkip) continue;
             if (a.mode == 1 && !is_lit) continue;
             thr = a.task_thr[task];
             jstar = is_lit ? n : a.task_jstar[task];     // literal maxima already carry the stop-recording zeros
@@ -640,6 +838,17 @@ __global__ void k_epilogue(const EpiArgs a)
         if (write) { if (nbuf) epi_flush(a, lane, nbuf, base + npk - nbuf, task, bpos, bscore); }
         else if (lane == 0) a.task_npeaks[task] = npk;
     }
+}
+
+// literal-only batches: the literal flag of every task is set from a list decided earlier (epilogue mode 0 of such a batch ran
+// without any filter, so every listed task carries the flag already); the unlisted ones are marked kTaskSkip: modes 1 and 2 of
+// the epilogue pass over them (their rows would be dropped on the host anyway), so they own no slot of the peak pool
+__global__ void k_force_literal(int* __restrict__ task_flags, int* __restrict__ task_npeaks, const unsigned char* __restrict__ want, int n_tasks)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    task_flags[t] = (task_flags[t] & ~kTaskLiteral) | (want[t] ? kTaskLiteral : kTaskSkip);
+    if (!want[t]) task_npeaks[t] = 0;        // (mode 0 counted the peaks of the unflagged ones)
 }
 
 // exclusive prefix sum of the per-task peak counts (one block; n is a few 10^4..10^5)

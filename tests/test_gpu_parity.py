@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 import fasim_b200 as fb
-from _harness import GOLDEN, TASKS, oracle, oracle_side, params_array, read_fasta, splitmix_bases
+from _harness import GOLDEN, TASKS, have_ref_shim, oracle, oracle_side, params_array, read_fasta, ref_side, splitmix_bases
 
 pytestmark = pytest.mark.gpu
 O = oracle_side()
@@ -187,10 +187,12 @@ def test_microsatellite_stress_vs_oracle(engine):
         engine.set_params(**kw)
         res = engine.scan_record(dna, "chrM", 1)
         rows = fb.result_rows(res)
-        lit = (res.contents.n_literal_tasks, res.contents.n_literal_windows)
+        lit = (res.contents.n_literal_tasks, res.contents.n_literal_windows, res.contents.n_q4_probed)
         engine.free(res)
         assert rows_as_oracle_text(rows) == oracle_text_rows(O.longtarget(rna, dna, **ekw)), kw
-        assert lit[0] > 0 and lit[1] > 0          # the literal (Q4) paths were exercised
+        # the Q4 paths were exercised: flagged pairs went through the taint sweep (which may certify every one of them, so
+        # literal TASKS are not guaranteed here; test_q4_probe_is_exact forces them), windows through the literal emulation
+        assert lit[2] > 0 and lit[1] > 0
         total += len(rows)
     assert total > 1000
     engine.set_params()
@@ -357,10 +359,13 @@ def test_cli_long_lncrnas_complex_flags(tmp_path, data_dir, name):
     assert got == open(os.path.join(GOLDEN, "%s_testDNA_complex__TFOsorted" % name)).read()
 
 
-@pytest.mark.parametrize("name", ["NEAT1", "MALAT1"])
-def test_cli_long_lncrnas_vs_meg3_regions(tmp_path, data_dir, name):
+@pytest.mark.parametrize("name,frec", [("NEAT1", None), ("MALAT1", None), ("NEAT1", "1"), ("MALAT1", "1"), ("MALAT1", "0")])
+def test_cli_long_lncrnas_vs_meg3_regions(tmp_path, data_dir, name, frec, monkeypatch):
     """BASELINE configs[2] on the second substitute DNA set: NEAT1 (22.8 knt) / MALAT1 (8.7 knt) against the first 12 MEG3
-    regions (multi-record file), complex flags; golden from the reference (tests/golden/make_golden_config3.py)."""
+    regions (multi-record file), complex flags; golden from the reference (tests/golden/make_golden_config3.py).  LTG_FREC: the
+    Q4 verdict from the carried-F blocks the main sweep records (1), from the probe sweep (0), or chosen per query (unset)."""
+    if frec is not None:
+        monkeypatch.setenv("LTG_FREC", frec)
     files = run_cli_files(tmp_path, "MEG3-12.fa", open(os.path.join(data_dir, "MEG3-DNAseq-first12.fa")).read(), name + ".fa",
                           open(os.path.join(data_dir, name + ".fa")).read(),
                           ["-i", "70", "-S", "1.0", "-ni", "25", "-pt", "-500", "-ds", "10", "-lg", "60"])
@@ -635,18 +640,24 @@ def test_scan_packed_equals_text(engine):
     assert got == want
     assert h2d_text - h2d > 0.7 * (hi - lo)                      # a quarter byte per base crossed PCIe, not one
     dev = torch.frombuffer(packed, dtype=torch.uint8).cuda()     # the packed store resident in HBM
-    parts, h2d_dev = [], 0
-    for r in range(3):
-        first, count, first_byte, n_bytes = fb.shard_segments(hi - lo, 3, r)
-        sb = [(max(a, first_byte) - first_byte, min(a + n, first_byte + n_bytes) - max(a, first_byte)) for a, n in blocks
-              if min(a + n, first_byte + n_bytes) > max(a, first_byte)]
-        res = engine.scan_packed(None, lo + first_byte, n_bytes, sb, "chrP", lo + 1, record_len=hi - lo, first_segment=first, n_segments=count,
-                                 device_ptr=dev.data_ptr())
-        parts.append(fb.result_rows(res))
-        h2d_dev += res.contents.h2d_bytes
-        engine.free(res)
-    assert fb.merge_shard_rows(parts) == want
-    assert h2d_dev < (hi - lo) // 2                              # descriptors and string jobs only: the bases were already on the device
+    h2d_shards = {}
+    for where in ("host", "device"):
+        parts, total = [], 0
+        for r in range(3):
+            first, count, first_byte, n_bytes = fb.shard_segments(hi - lo, 3, r)
+            sb = [(max(a, first_byte) - first_byte, min(a + n, first_byte + n_bytes) - max(a, first_byte)) for a, n in blocks
+                  if min(a + n, first_byte + n_bytes) > max(a, first_byte)]
+            res = engine.scan_packed(bytes(packed) if where == "host" else None, lo + first_byte, n_bytes, sb, "chrP", lo + 1, record_len=hi - lo,
+                                     first_segment=first, n_segments=count, device_ptr=dev.data_ptr() if where == "device" else None)
+            parts.append(fb.result_rows(res))
+            total += res.contents.h2d_bytes
+            engine.free(res)
+        assert fb.merge_shard_rows(parts) == want
+        h2d_shards[where] = total
+    # with the packed store resident in HBM only descriptors, job lists and string jobs cross PCIe: the same shards fed from host
+    # memory copy their packed bytes (a quarter byte per base, the shards overlap by a segment tail) on top of exactly that
+    saved = h2d_shards["host"] - h2d_shards["device"]
+    assert (hi - lo) // 4 <= saved <= (hi - lo) // 4 + 3 * (5000 // 4 + 8)
     engine.set_params()
 
 
@@ -888,21 +899,105 @@ def test_q4_probe_is_exact(engine):
         old_kernel = fb.Engine(0)
     finally:
         del os.environ["LTG_LIT_OLD"]
+    os.environ["LTG_FREC"] = "1"                 # the main sweep records the carried F itself (exact flags instead of the granule pre-filter)
+    try:
+        recording = fb.Engine(0)
+    finally:
+        del os.environ["LTG_FREC"]
+    os.environ["LTG_Q4_TAINT"] = "0"             # round 1's path: probe sweep (largest carried F) instead of the taint sweep
+    os.environ["LTG_FREC"] = "0"
+    try:
+        probing = fb.Engine(0)
+    finally:
+        del os.environ["LTG_Q4_TAINT"]
+        del os.environ["LTG_FREC"]
+    os.environ["LTG_Q4_TAINT"] = "0"             # ... and the recording sweep alone (no second sweep at all)
+    os.environ["LTG_FREC"] = "1"
+    try:
+        recording_only = fb.Engine(0)
+    finally:
+        del os.environ["LTG_Q4_TAINT"]
+        del os.environ["LTG_FREC"]
+    engines = (plain, engine, old_kernel, recording, probing, recording_only)
     try:
         outs = []
-        for eng in (plain, engine, old_kernel):
+        for eng in engines:
             eng.set_params(c_length=25)
             eng.set_query("lnc", rna)
             res = eng.scan_record(dna, "chr1", 1)
             outs.append((fb.result_rows(res), res.contents.n_literal_tasks, res.contents.n_q4_probed))
             eng.free(res)
-        assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 100
+        rows = outs[0][0]
+        assert len(rows) > 100
+        for o in outs[1:]:
+            assert o[0] == rows
         assert outs[0][2] == 0 and outs[1][2] > 0
-        assert 0 < outs[1][1] < outs[0][1]
         assert outs[2] == outs[1]
+        # literal tasks: all flagged (plain) > probe sweep >= taint sweep (it certifies most of what the probe leaves)
+        assert 0 < outs[4][1] < outs[0][1] and outs[1][1] < outs[4][1]
+        # recording sweep: exact per stripe start but per block of 16 steps instead of per column: a few more than the probe at most
+        assert outs[5][2] == 0 and outs[4][1] <= outs[5][1] <= outs[4][1] + max(8, outs[4][1] // 10)
+        # recording + taint: fewer pairs reach the taint sweep than with the granule pre-filter, same verdicts up to those few
+        assert 0 < outs[3][2] <= outs[1][2] and outs[3][1] <= outs[1][1] + max(8, outs[1][1] // 10)
     finally:
-        plain.close()
-        old_kernel.close()
+        for eng in engines:
+            if eng is not engine:
+                eng.close()
+        engine.set_params()
+
+
+def test_q4_taint_certification_on_device(engine):
+    """The taint sweep (k_scan TAINT) returns flagged tasks to the exact path only when their recorded column maxima are
+    provably the reference's.  Planted cases (insertions that start exactly at a stripe start, the constellation that makes the
+    Q4 quirk visible; tests/test_q4_theory_cpu.py) through the function-level seam: whatever the verdict, the column maxima must
+    equal the reference's; most flagged cases must be certified; every really different case must stay literal.  The verdicts are
+    also compared with the CPU prototype of the same rule (they may differ on taint ties, which both resolve soundly)."""
+    import random
+    from test_q4_theory_cpu import certify, exact_colmax_and_carried_f, make_case
+    S = ref_side() if have_ref_shim() else oracle_side()
+    inv = str.maketrans("GCTA", "ACGT")           # AntiMinus rule 8 maps A->G C->C G->T T->A (a bijection): raw DNA of a translated string
+    task = (-1, 1, 8)
+    rng = random.Random(5)
+    cases = [make_case(rng) for _ in range(160)]
+    # longer lncRNAs: several strips of the scan kernel (R = 32: 1024 rows per strip), stripe starts inside any lane
+    for _ in range(40):
+        m = rng.randrange(1100, 3300)
+        n = rng.randrange(100, 400)
+        L = (m + 15) // 16
+        rna = [rng.choice("ACGT") for _ in range(m)]
+        dna = [rng.choice("ACGT") for _ in range(n)]
+        for _ in range(rng.randrange(1, 4)):
+            b = L * rng.randrange(1, 16)
+            a = max(0, b - rng.randrange(28, 48))
+            gap = rng.randrange(2, 7)
+            frag = rna[a:b] + rna[b + gap:b + gap + rng.randrange(8, 30)]
+            frag = [c if rng.random() > 0.03 else rng.choice("ACGT") for c in frag]
+            at = rng.randrange(0, max(1, n - len(frag)))
+            dna[at:at + len(frag)] = frag
+        cases.append(("".join(rna), "".join(dna[:n])))
+    engine.set_params()
+    flagged = certified = different = agree = 0
+    for rna, dna_t in cases:
+        raw = dna_t.translate(inv)
+        assert S.task_strings(raw, *task)[0] == dna_t
+        engine.set_query("lnc", rna)
+        got = engine.probe_segment(raw, [task])[0]
+        ref = S.colmax(rna, dna_t)
+        assert (got["colmax"] == ref).all(), (rna, dna_t)
+        exact, fmax = exact_colmax_and_carried_f(rna, dna_t)
+        differs = not np.array_equal(exact, ref)
+        if fmax >= 132:
+            flagged += 1
+            certified += 0 if got["literal"] else 1
+            different += int(differs)
+            assert not (differs and not got["literal"]), (rna, dna_t)
+            agree += int(bool(got["literal"]) == (not certify(rna, dna_t, kernel_rule=True)))
+        else:
+            assert not differs
+    print("flagged %d, certified on the device %d, really different %d, same verdict as the CPU prototype %d" % (flagged, certified, different, agree))
+    assert flagged > 120 and different >= 5
+    assert certified >= flagged // 2
+    assert agree >= flagged - flagged // 10
 
 
 def test_error_behaviour(engine):
