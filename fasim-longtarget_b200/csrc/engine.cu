@@ -163,6 +163,11 @@ struct ltg_context {
     bool q4_taint = true;               // the flagged pairs are swept by the taint variant (certifies tasks) instead of the probe variant
                                         // (LTG_Q4_TAINT=0: probe); with it the recording sweep is only used on request (LTG_FREC=1)
     int64_t n_certified = 0;            // tasks the taint sweep returned to the exact path (diagnostics)
+    // Window sweeps that also watch for an F >= 132 entering a stripe start (k_win_dp Q4CHK: ~3 % more instructions): only the
+    // windows that saw one go through the literal emulation.  Switched on for a query once a batch sent more than 64 windows
+    // there (LTG_WIN_Q4CHK=0 never, 1 always); without it every window that scores >= 148 does.
+    int win_q4_mode = -1;               // -1 auto, 0 off, 1 on
+    bool win_q4_on = false;
     int frec_mode = -1;                 // -1 auto, 0 off, 1 on
     bool frec_on = false;               // current query: main sweeps record the carried F
     bool litonly_old = false;           // LTG_LITONLY_OLD=1 (diagnostics): literal-only batches take the Q4 verdict again instead of being told
@@ -357,6 +362,7 @@ int build_profiles(ltg_context* c)
         }
         c->frec_cost = 0.25 * with_start / std::max(1, c->n_strips);
         c->frec_on = (c->frec_mode == 1);
+        c->win_q4_on = (c->win_q4_mode == 1);
     }
     c->profiles_dirty = false;
     return LTG_OK;
@@ -579,6 +585,8 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.res64 = c->d_res64.as<unsigned long long>(); w.w_next = c->d_w[17].as<int>(); w.w_probe = c->d_w[18].as<int>();
     w.w_ws = c->d_w[12].as<int>(); w.fin_ws = c->d_w[13].as<int>(); w.w_shift = c->d_w[19].as<int>(); w.best_ws = c->d_w[20].as<int>();
     w.fin_shift = c->d_w[21].as<int>();
+    const bool q4chk = c->win_q4_on && forced_cut == nullptr;
+    w.w_q4 = q4chk ? c->d_w[22].as<int>() : nullptr;
     w.compat = (c->compat && forced_cut == nullptr) ? 1 : 0;
     w.sched = c->d_win_sched.as<WinSched>(); w.list = c->d_win_list.as<int>();
     w.res = c->d_res.as<int4>();
@@ -606,12 +614,17 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     };
     // the sweep itself, then the per-peak combination of its pieces
     auto sweep = [&](bool rev) {
-        if (rev) { if (c->rna_acgt) k_win_dp<true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false><<<dp_blocks, 128, 0, c->stream>>>(w); }
+        if (q4chk) {
+            if (rev) { if (c->rna_acgt) k_win_dp<true, true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false, true><<<dp_blocks, 128, 0, c->stream>>>(w); }
+            else { if (c->rna_acgt) k_win_dp<false, true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<false, false, true><<<dp_blocks, 128, 0, c->stream>>>(w); }
+        }
+        else if (rev) { if (c->rna_acgt) k_win_dp<true, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<true, false><<<dp_blocks, 128, 0, c->stream>>>(w); }
         else { if (c->rna_acgt) k_win_dp<false, true><<<dp_blocks, 128, 0, c->stream>>>(w); else k_win_dp<false, false><<<dp_blocks, 128, 0, c->stream>>>(w); }
         k_win_combine<<<pb, 256, 0, c->stream>>>(w);
         c->launches += 2;
     };
     for (int round = 0; round < 4; ++round) {
+        if (q4chk) LTG_CUDA_CHECK(cudaMemsetAsync(w.w_q4, 0, sizeof(int) * (size_t)n_peaks, c->stream));      // flags of this round's windows
         for (int retry = 0; retry < (w.gran_blk ? 2 : 1); ++retry) {
             schedule(round, retry);
             sweep(false);
@@ -630,6 +643,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
         LTG_CUDA_CHECK(cudaGetLastError());
     }
     // reverse pass over the chosen alignments
+    if (q4chk) LTG_CUDA_CHECK(cudaMemsetAsync(w.w_q4, 0, sizeof(int) * (size_t)n_peaks, c->stream));
     schedule(-1, 0);
     sweep(true);
     k_win_finish<<<pb, 256, 0, c->stream>>>(w);
@@ -1230,6 +1244,7 @@ int retire_batch(ltg_context* c, HostBatch& hb, RecordStats& st, std::vector<ltg
     const BatchScalars* bs = hb.scalars.as<BatchScalars>();
     st.window_cells += bs->window_cells;
     st.n_literal_windows += bs->lit_total;
+    if (c->win_q4_mode < 0 && bs->lit_total > 64) c->win_q4_on = true;        // later batches of this query check their windows
     for (int k = 0; k < 20; ++k) c->win_stats[k] += bs->win_stats[k];
     for (int k = 0; k < 4; ++k) c->win_stats[20 + k] += (unsigned long long)bs->trace_handed[k];
     for (int k = 0; k < 6; ++k) c->win_stats[24 + k] += bs->filter_stats[k];
@@ -1611,6 +1626,7 @@ int ltg_create(int device, ltg_context** out)
     if (const char* e = getenv("LTG_FREC")) c->frec_mode = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("LTG_LITONLY_OLD")) c->litonly_old = atoi(e) != 0;
     if (const char* e = getenv("LTG_Q4_TAINT")) c->q4_taint = atoi(e) != 0;
+    if (const char* e = getenv("LTG_WIN_Q4CHK")) c->win_q4_mode = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("LTG_SCAN_SHARED")) c->scan_shared = atoi(e) != 0;
     // LTG_FLOORS=1: the first window sweep only tracks cells that reach the peak score (fewer slow-path trips of the tracker, more
     // re-planned sweeps; measured neutral on the headline workload, profiles/README.md)

@@ -442,12 +442,14 @@ __global__ void k_lit_collect(const WinState w, int reverse, int round, LiteralJ
         // (no upper bound: with the Q4 quirk the reference's byte kernel can stay below 251 where exact SW reaches it and then
         //  keeps its own, lower result; the literal kernels detect a real overflow themselves and leave the exact result alone)
         if (v.x < kQ4Guard) return;
+        if (w.w_q4 && !(w.w_q4[i] & 1)) return;                // no F >= 132 entered a stripe start in any sweep of this window: exact = reference
         const int cut = w.w_len[i];
         J.kind = 1; J.ref_start = w.w_ws[i]; J.ref_len = cut; J.ref_dir = 0;
         J.read_start = 0; J.read_len = w.m; J.read_dir = 1; J.terminate = 255;
     } else {
         const int sw = w.fin_sw[i];
         if (sw < kQ4Guard || sw >= kOverflowU8) return;
+        if (w.w_q4 && !(w.w_q4[i] & 2)) return;
         J.kind = 2; J.ref_start = w.fin_ws[i]; J.ref_len = w.fin_re[i] + 1; J.ref_dir = 1;
         J.read_start = w.fin_qe[i]; J.read_len = w.fin_qe[i] + 1; J.read_dir = -1; J.terminate = sw & 0xff;
     }

@@ -81,6 +81,9 @@ struct WinState {
     int* w_done;       // 1: final alignment chosen
     int* w_next;       // next forward round this peak takes part in (rounds in between are provably no-ops, see k_win_probe)
     int* w_probe;      // 1: the round's result waits for its reverse probe; 2: fin_rb / fin_qb are final already
+    int* w_q4;         // k_win_dp<.., Q4CHK>: bit 0 / bit 1 = a forward / reverse sweep of the window in flight saw an F >= 132 enter a row
+                       // that starts a stripe of the reference's layout (the only place the Q4 quirk can act); nullptr: not checked, every
+                       // window that scores >= 148 goes through the literal emulation
     int* best_sw; int* best_cut; int* best_re; int* best_qe; int* best_ws;
     int* fin_sw; int* fin_cut; int* fin_re; int* fin_qe; int* fin_rb; int* fin_qb; int* fin_ws; int* fin_shift;
     int compat;        // 1: window loop of the older variant (fastSim.h:194-226): no start clamp, accept on equality only, no best candidate
@@ -375,7 +378,13 @@ __device__ __forceinline__ int half_s16(uint32_t v, int h)
 }
 
 // TAB: score lookup with one PRMT per cell pair (needs an lncRNA made of A/C/G/T/U only); otherwise XNOR + VIADDMNMX.
-template <bool REV, bool TAB>
+// Q4CHK: the sweep also watches the vertical gap state (E[] here; the reference's vF) where it crosses into a row that starts a
+// stripe of the reference's 16-lane layout of THIS alignment call (forward: the whole lncRNA, stripe = ceil(m / 16) rows; reverse:
+// the reversed prefix that ends at the forward end row).  Without a value >= 132 there the reference's signed lazy-F test behaves
+// like an unsigned one for every cell the result depends on (they all lie inside the swept rows, whose derivations never leave
+// them; cells outside can only be LOWER in the reference, and were below the result already), so the exact result is the
+// reference's and the window needs no literal emulation.
+template <bool REV, bool TAB, bool Q4CHK = false>
 __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
 {
     constexpr int R = kWinR;
@@ -491,6 +500,19 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
             if (s < ln1) { const uint32_t q = w.rna_ssw[sbase[1] + sdir[1] * s]; c1 = q < 4 ? q * 16 : 64u; }
             return c0 | (c1 << 16);
         };
+        // Q4CHK: step at which this lane's row of half h is the LAST row of a stripe (E[] after that step enters the stripe start)
+        int nq[2] = {0x7fffffff, 0x7fffffff}, ql[2] = {1, 1}, q4seen = 0;
+        if (Q4CHK) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (wi[h] < 0) continue;
+                const int L = REV ? (w.fin_qe[wi[h]] + 16) / 16 : (w.m + 15) / 16;
+                const int b = REV ? 0 : sbase[h];                  // index, in the read the reference aligns, of stream position 0
+                nq[h] = lig + (2 * L - 1 - (b % L)) % L;           // first position t with (b + t + 1) % L == 0
+                ql[h] = L;
+            }
+        }
+        int nqmin = min(nq[0], nq[1]);
         uint32_t xnext = fetch(0);
 #pragma unroll 2
         for (int s = 0; s < nsteps; ++s) {
@@ -521,6 +543,18 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
             for (int r = 1; r + 1 < R; r += 2) ms = __vimax3_s16x2(ms, t[r], t[r + 1]);
             if ((R & 1) == 0) ms = __vmaxs2(ms, t[R - 1]);
             if (!REV) runmax = __vmaxs2(runmax, ms);
+            if (Q4CHK && s == nqmin) {
+                uint32_t e = E[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) e = __vmaxs2(e, E[r]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (s != nq[h]) continue;
+                    if (s - lig + 1 < slen[h] && half_s16(e, h) >= kQ4CarryF) q4seen |= 1 << h;      // (the stripe start itself is streamed)
+                    nq[h] += ql[h];
+                }
+                nqmin = min(nq[0], nq[1]);
+            }
             if (__vmaxs2(trigm1, ms) != trigm1) {
                 const int row = s - lig;
 #pragma unroll
@@ -539,6 +573,10 @@ __global__ void __launch_bounds__(128) k_win_dp(const WinState w)
             }
             hdiag = hin;
             hout = hlast; fout = f; xout = xin;
+        }
+        if (Q4CHK && q4seen) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) if ((q4seen >> h) & 1) atomicOr(&w.w_q4[wi[h]], REV ? 2 : 1);
         }
         // group reduction: highest value, then smallest column (lower lanes own smaller columns)
 #pragma unroll

@@ -359,13 +359,16 @@ def test_cli_long_lncrnas_complex_flags(tmp_path, data_dir, name):
     assert got == open(os.path.join(GOLDEN, "%s_testDNA_complex__TFOsorted" % name)).read()
 
 
-@pytest.mark.parametrize("name,frec", [("NEAT1", None), ("MALAT1", None), ("NEAT1", "1"), ("MALAT1", "1"), ("MALAT1", "0")])
-def test_cli_long_lncrnas_vs_meg3_regions(tmp_path, data_dir, name, frec, monkeypatch):
+@pytest.mark.parametrize("name,frec,winchk", [("NEAT1", None, None), ("MALAT1", None, None), ("NEAT1", "1", None), ("MALAT1", "1", "0"),
+                                              ("MALAT1", "0", "1"), ("NEAT1", None, "1"), ("NEAT1", None, "0")])
+def test_cli_long_lncrnas_vs_meg3_regions(tmp_path, data_dir, name, frec, winchk, monkeypatch):
     """BASELINE configs[2] on the second substitute DNA set: NEAT1 (22.8 knt) / MALAT1 (8.7 knt) against the first 12 MEG3
     regions (multi-record file), complex flags; golden from the reference (tests/golden/make_golden_config3.py).  LTG_FREC: the
     Q4 verdict from the carried-F blocks the main sweep records (1), from the probe sweep (0), or chosen per query (unset)."""
     if frec is not None:
         monkeypatch.setenv("LTG_FREC", frec)
+    if winchk is not None:               # window sweeps that watch the stripe starts (only flagged windows are emulated literally): forced / off
+        monkeypatch.setenv("LTG_WIN_Q4CHK", winchk)
     files = run_cli_files(tmp_path, "MEG3-12.fa", open(os.path.join(data_dir, "MEG3-DNAseq-first12.fa")).read(), name + ".fa",
                           open(os.path.join(data_dir, name + ".fa")).read(),
                           ["-i", "70", "-S", "1.0", "-ni", "25", "-pt", "-500", "-ds", "10", "-lg", "60"])
@@ -918,15 +921,27 @@ def test_q4_probe_is_exact(engine):
     finally:
         del os.environ["LTG_Q4_TAINT"]
         del os.environ["LTG_FREC"]
-    engines = (plain, engine, old_kernel, recording, probing, recording_only)
+    os.environ["LTG_WIN_Q4CHK"] = "1"            # window sweeps watch the stripe starts: only the windows that saw an F >= 132 there are emulated
     try:
-        outs = []
+        win_checked = fb.Engine(0)
+    finally:
+        del os.environ["LTG_WIN_Q4CHK"]
+    os.environ["LTG_WIN_Q4CHK"] = "0"
+    try:
+        win_unchecked = fb.Engine(0)
+    finally:
+        del os.environ["LTG_WIN_Q4CHK"]
+    engines = (plain, engine, old_kernel, recording, probing, recording_only, win_checked, win_unchecked)
+    try:
+        outs, lit_windows = [], []
         for eng in engines:
             eng.set_params(c_length=25)
             eng.set_query("lnc", rna)
             res = eng.scan_record(dna, "chr1", 1)
             outs.append((fb.result_rows(res), res.contents.n_literal_tasks, res.contents.n_q4_probed))
+            lit_windows.append(res.contents.n_literal_windows)
             eng.free(res)
+        assert 0 < lit_windows[6] < lit_windows[7] // 2 and lit_windows[7] > 100
         rows = outs[0][0]
         assert len(rows) > 100
         for o in outs[1:]:
