@@ -156,19 +156,19 @@ struct ltg_context {
     int batch_segments = kBatchSegments;                  // segments per device batch (LTG_BATCH_SEGMENTS)
     int lit_rows_per_chunk = 24, lit_min_chunks = 0;      // tuning of the column-parallel literal kernel (LTG_LIT_ROWS / LTG_LIT_CH)
     int64_t n_probe_items = 0;          // pairs swept a second time by the Q4 probe (diagnostics)
-    // Fused carried-F recording (k_scan FREC): the main sweep records what the probe sweep would find.  It costs the main sweep
-    // frec_cost (fraction of its instructions, from the stripe geometry of the lncRNA) for EVERY item, the probe costs one more
-    // sweep of the pairs that carry a flagged task: a context starts with the probe and switches a query to the fused form
-    // once a batch had to probe a larger share of its pairs than that (LTG_FREC=0 never, 1 always).
+    // Stripe-start screen in the main sweep (k_scan FREC, 3 instructions per step, measured 4.9 % of the sweep): a pre-filter with
+    // the resolution of one lane next to the granule pre-filter.  On the example lncRNAs it spares only 12-15 % of the pairs the
+    // second (taint / probe) sweep (their high-scoring regions span many lanes), which does not pay for it: off unless LTG_FREC=1
+    // (-1 = switch a query to it once a batch had to sweep more than 4 % of its pairs again).
+    int frec_mode = 0;                  // -1 auto, 0 off, 1 on
     bool q4_taint = true;               // the flagged pairs are swept by the taint variant (certifies tasks) instead of the probe variant
-                                        // (LTG_Q4_TAINT=0: probe); with it the recording sweep is only used on request (LTG_FREC=1)
+                                        // (LTG_Q4_TAINT=0: probe)
     int64_t n_certified = 0;            // tasks the taint sweep returned to the exact path (diagnostics)
     // Window sweeps that also watch for an F >= 132 entering a stripe start (k_win_dp Q4CHK: ~3 % more instructions): only the
     // windows that saw one go through the literal emulation.  Switched on for a query once a batch sent more than 64 windows
     // there (LTG_WIN_Q4CHK=0 never, 1 always); without it every window that scores >= 148 does.
     int win_q4_mode = -1;               // -1 auto, 0 off, 1 on
     bool win_q4_on = false;
-    int frec_mode = -1;                 // -1 auto, 0 off, 1 on
     bool frec_on = false;               // current query: main sweeps record the carried F
     bool litonly_old = false;           // LTG_LITONLY_OLD=1 (diagnostics): literal-only batches take the Q4 verdict again instead of being told
     double frec_cost = 0.0;
@@ -350,17 +350,8 @@ int build_profiles(ltg_context* c)
         if (!list.empty()) LTG_CUDA_CHECK(cudaMemcpyAsync(c->d_bnd_gran.p, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, c->stream));
         LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // `list` is host memory of this scope
     }
-    // cost model of the fused carried-F recording: in strips that hold a stripe start every step ends with a screening test and
-    // a (rarely taken) branch, which costs the sweep its scheduling freedom across steps — measured ~25 % of such a strip's time
     {
-        const int stripe = (c->m + 15) / 16, R = c->scan_r;
-        int with_start = 0;
-        for (int strip = 0; strip < c->n_strips; ++strip) {
-            bool any = false;
-            for (int k = 1; k < 16; ++k) if ((k * stripe) / (32 * R) == strip) any = true;
-            with_start += any ? 1 : 0;
-        }
-        c->frec_cost = 0.25 * with_start / std::max(1, c->n_strips);
+        c->frec_cost = 0.015;
         c->frec_on = (c->frec_mode == 1);
         c->win_q4_on = (c->win_q4_mode == 1);
     }
@@ -889,10 +880,9 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
             c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
             c->h2d_bytes += (int64_t)(sizeof(ScanItem) + sizeof(int)) * np;
             c->n_probe_items += np;
-            // the probe swept np of n_items pairs again: beyond the cost of recording in the main sweep, later batches of this
-            // query record (kLitOnly batches and tiny ones say little about the query: at least 64 items)
-            // (the probe sweep itself runs at ~0.8 of the plain sweep's rate)
-            if (!c->q4_taint && c->frec_mode < 0 && n_items >= 64 && 1.25 * (double)np > std::max(c->frec_cost, 0.02) * (double)n_items) c->frec_on = true;
+            // np of n_items pairs were swept again: when that is more than a few percent, later batches of this query record the
+            // stripe-start screen in the main sweep (kLitOnly batches and tiny ones say little about the query: at least 64 items)
+            if (c->frec_mode < 0 && !use_frec && n_items >= 64 && (double)np > 0.04 * (double)n_items) c->frec_on = true;
         }
     }
     // kLitOnly: were all requested tasks already swept by the side stream (their literal column maxima wait in d_side_colmax)?
@@ -1623,7 +1613,7 @@ int ltg_create(int device, ltg_context** out)
     // LTG_NO_SKIP=1 runs every window round of fastSIM's loop even when it provably repeats the previous result
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
-    if (const char* e = getenv("LTG_FREC")) c->frec_mode = atoi(e) != 0 ? 1 : 0;
+    if (const char* e = getenv("LTG_FREC")) c->frec_mode = atoi(e) < 0 ? -1 : (atoi(e) != 0 ? 1 : 0);
     if (const char* e = getenv("LTG_LITONLY_OLD")) c->litonly_old = atoi(e) != 0;
     if (const char* e = getenv("LTG_Q4_TAINT")) c->q4_taint = atoi(e) != 0;
     if (const char* e = getenv("LTG_WIN_Q4CHK")) c->win_q4_mode = atoi(e) != 0 ? 1 : 0;

@@ -184,9 +184,10 @@ struct ScanArgs {
     const int* task_jstar;      // [seg * T + task] first column the reference does not record any more (or n)
     int tasks_per_seg;
     int stripe_len;             // ceil(m / 16)
-    // fused carried-F recording (k_scan<R, W, false, false, true>): the main sweep itself keeps, per stripe start of the
-    // reference's layout and per block of kBlkCols wavefront steps, the largest F carried into that row (two saturated bytes
-    // like blkmax), so no second sweep is needed to decide which tasks the Q4 quirk can touch
+    // Stripe-start screen recorded by the main sweep (k_scan<R, W, false, false, true>): per stripe start of the reference's
+    // layout and per block of kBlkCols wavefront steps, max(fin + 16, largest cell of the lane that holds the stripe start) as two
+    // saturated bytes like blkmax.  An F >= 132 can only enter that stripe start in a column where this reaches 148: a pre-filter
+    // with the resolution of one lane (R rows) instead of the granules around the stripe start, for 3 instructions per step
     uint16_t* frec;             // [item][kFrecRows][blk_pitch]
 };
 constexpr int kFrecRows = 15;   // stripe starts k * stripe_len, k = 1..15
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
         for (int strip = 0; strip < a.n_strips; ++strip) {
             // PROBE: which of this lane's rows start a stripe of the reference's layout (row = k * stripe_len, k = 1..15)
             uint32_t bmask = 0, vmask = 0, amask = 0;
-            uint32_t fr = 0;                                       // FREC: largest carried F of the block of steps in flight
+            uint32_t fr = 0;                                       // FREC: screen value (see LTG_SCAN_STEP) of the block of steps in flight
             uint16_t* frec_row = nullptr;
             if (FREC) {
                 const int fk = frec_row_of_lane((strip * 32 + lane) * R, R, a.stripe_len);
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 }
                 amask = __reduce_or_sync(0xffffffffu, bmask);
             }
+            const uint32_t bm_all = bmask ? 0xFFFFFFFFu : 0u;     // FREC: only lanes that hold a stripe start record
             if (SHARED) s_prof = s_prof_all + (size_t)strip * (5 * PLANE);
             else {
                 const uint4* gp = reinterpret_cast<const uint4*>(a.profiles) + ((size_t)it.pair * a.n_strips + strip) * (5 * PLANE);
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                 }                                                                                               \
                 if (PROBE) { const int j_ = (S) - lane; vmask = (j_ < jst0 ? 0xFFFFu : 0u) | (j_ < jst1 ? 0xFFFF0000u : 0u); } \
                 if (FREC && GUARD) vmask = ((S) >= lane && (S) - lane < n) ? 0xFFFFFFFFu : 0u;                  \
-                uint32_t d = hdiag, f = fin, cm = cmin, hlast = 0;                                              \
+                uint32_t d = hdiag, f = fin, cm = FREC ? 0u : cmin, hlast = 0;   /* FREC: the lane's own maximum first */ \
                 uint32_t tv[2];                                                                                 \
                 /* TAINT: a lane-step that may start or carry a chain of >= 132 through a stripe start takes the general form. \
                    Without a chain coming in, that needs fin >= 132 or a cell >= 148 in this lane's part of the column; a cell  \
@@ -542,7 +544,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
                     if (lane == 31 && !last && (fcnew & 0x7FFF7FFFu) != 0) giveup |= 0x00010001u;   /* a chain would cross into the next strip */ \
                 }                                                                                               \
                 if (PROBE) LTG_CARRIED_F(fb, true)                                                              \
-                if (FREC) LTG_CARRIED_F(fr, GUARD)                                                              \
+                if (FREC) {     /* branch-free screen: an F >= 132 entering a row of this lane needs fin >= 132 or a cell >= 148 here */ \
+                    const uint32_t x_ = __viaddmax_s16x2(fin, 0x00100010u, cm) & bm_all;                        \
+                    fr = __vmaxs2(fr, (GUARD) ? (x_ & vmask) : x_);                                             \
+                    cm = __vmaxs2(cm, cmin);                                                                    \
+                }                                                                                               \
                 _Pragma("unroll") for (int k = 0; k < R / 4; ++k) sc[k] = scn[k];                               \
                 hdiag = hin;                                                                                    \
                 hout = hlast; fout = f; cmout = cm;                                                             \
@@ -726,9 +732,9 @@ __global__ void k_epilogue(const EpiArgs a)
             // the reference still processes: without such a cell in the granules that hold those rows the task stays exact
             bool q4 = mx >= kQ4Guard;
             if (q4 && a.frec) {
-                // the sweep recorded the largest F carried into every stripe start per block of 16 steps: the quirk needs one
-                // >= 132 in a column the reference still processes (blocks: the last one may reach up to 15 columns further,
-                // which can only flag more)
+                // the sweep recorded, per stripe start and block of 16 steps, max(fin + 16, cells of the lane that holds the stripe
+                // start): the quirk needs 148 there in a column the reference still processes (blocks: the last one may reach up
+                // to 15 columns further, which can only flag more)
                 int carried = 0;
                 const int jend = min(jstar + 1, n);
                 const uint16_t* fbase = a.frec + (size_t)row * kFrecRows * a.blk_pitch;
@@ -744,8 +750,9 @@ __global__ void k_epilogue(const EpiArgs a)
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) carried = max(carried, __shfl_xor_sync(0xffffffffu, carried, o));
-                q4 = carried >= kQ4CarryF;
-            } else if (q4 && a.bnd_gran) {
+                q4 = carried >= kQ4Guard;
+            }
+            if (q4 && a.bnd_gran) {
                 // (block maxima: upper bounds over 16-column blocks, saturated at 255 — coarser than per column, never smaller)
                 int near = 0;
                 const int jend = min(jstar + 1, n);

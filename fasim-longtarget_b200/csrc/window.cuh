@@ -191,7 +191,9 @@ __global__ void k_win_plan(const WinState w, int round, int retry)
         const int lo_col = ws, pos = ws + len - 1;
         const int grp = (threadIdx.x & 31) & ~7;       // first lane of this peak's 8 threads
         int pending = 0;        // largest bound among the non-qualifying granules after the last qualifying one
-        for (int k0 = 0; k0 < w.n_gran; k0 += 8) {
+        // (after round 0 most peaks are finished: a warp whose four peaks have nothing to scan skips the walk altogether)
+        const int n_walk = __any_sync(0xffffffffu, scan) ? w.n_gran : 0;
+        for (int k0 = 0; k0 < n_walk; k0 += 8) {
             // thread `sub` reads the bound of granule k0 + sub: the maximum of the (skewed) 16-column blocks that cover the window
             int mine_b = 0;
             if (scan && k0 + sub < w.n_gran) {

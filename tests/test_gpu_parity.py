@@ -902,7 +902,7 @@ def test_q4_probe_is_exact(engine):
         old_kernel = fb.Engine(0)
     finally:
         del os.environ["LTG_LIT_OLD"]
-    os.environ["LTG_FREC"] = "1"                 # the main sweep records the carried F itself (exact flags instead of the granule pre-filter)
+    os.environ["LTG_FREC"] = "1"                 # the main sweep records a stripe-start screen (lane resolution) next to the granule pre-filter
     try:
         recording = fb.Engine(0)
     finally:
@@ -914,7 +914,7 @@ def test_q4_probe_is_exact(engine):
     finally:
         del os.environ["LTG_Q4_TAINT"]
         del os.environ["LTG_FREC"]
-    os.environ["LTG_Q4_TAINT"] = "0"             # ... and the recording sweep alone (no second sweep at all)
+    os.environ["LTG_Q4_TAINT"] = "0"             # ... and the screen alone (no second sweep at all)
     os.environ["LTG_FREC"] = "1"
     try:
         recording_only = fb.Engine(0)
@@ -950,10 +950,10 @@ def test_q4_probe_is_exact(engine):
         assert outs[2] == outs[1]
         # literal tasks: all flagged (plain) > probe sweep >= taint sweep (it certifies most of what the probe leaves)
         assert 0 < outs[4][1] < outs[0][1] and outs[1][1] < outs[4][1]
-        # recording sweep: exact per stripe start but per block of 16 steps instead of per column: a few more than the probe at most
-        assert outs[5][2] == 0 and outs[4][1] <= outs[5][1] <= outs[4][1] + max(8, outs[4][1] // 10)
-        # recording + taint: fewer pairs reach the taint sweep than with the granule pre-filter, same verdicts up to those few
-        assert 0 < outs[3][2] <= outs[1][2] and outs[3][1] <= outs[1][1] + max(8, outs[1][1] // 10)
+        # stripe-start screen recorded by the main sweep, alone: no second sweep; coarser than the probe, finer than no filter
+        assert outs[5][2] == 0 and outs[4][1] <= outs[5][1] < outs[0][1]
+        # screen + taint: fewer pairs reach the taint sweep than with the granule pre-filter alone, and no more literal tasks
+        assert 0 < outs[3][2] < outs[1][2] and outs[3][1] <= outs[1][1]
     finally:
         for eng in engines:
             if eng is not engine:
