@@ -576,7 +576,7 @@ int run_windows(ltg_context* c, int n_peaks, int T, const int* forced_cut, const
     w.res64 = c->d_res64.as<unsigned long long>(); w.w_next = c->d_w[17].as<int>(); w.w_probe = c->d_w[18].as<int>();
     w.w_ws = c->d_w[12].as<int>(); w.fin_ws = c->d_w[13].as<int>(); w.w_shift = c->d_w[19].as<int>(); w.best_ws = c->d_w[20].as<int>();
     w.fin_shift = c->d_w[21].as<int>();
-    const bool q4chk = c->win_q4_on && forced_cut == nullptr;
+    const bool q4chk = c->win_q4_on;
     w.w_q4 = q4chk ? c->d_w[22].as<int>() : nullptr;
     w.compat = (c->compat && forced_cut == nullptr) ? 1 : 0;
     w.sched = c->d_win_sched.as<WinSched>(); w.list = c->d_win_list.as<int>();

@@ -192,7 +192,7 @@ def test_microsatellite_stress_vs_oracle(engine):
         assert rows_as_oracle_text(rows) == oracle_text_rows(O.longtarget(rna, dna, **ekw)), kw
         # the Q4 paths were exercised: flagged pairs went through the taint sweep (which may certify every one of them, so
         # literal TASKS are not guaranteed here; test_q4_probe_is_exact forces them), windows through the literal emulation
-        assert lit[2] > 0 and lit[1] > 0
+        assert lit[2] > 0 and (lit[1] > 0 or os.environ.get("LTG_WIN_Q4CHK") == "1")
         total += len(rows)
     assert total > 1000
     engine.set_params()
@@ -959,6 +959,48 @@ def test_q4_probe_is_exact(engine):
             if eng is not engine:
                 eng.close()
         engine.set_params()
+
+
+def test_window_q4_check_on_device(golden):
+    """Window sweeps that watch the stripe starts (k_win_dp Q4CHK, forced on): only windows that saw an F >= 132 enter a stripe
+    start of their alignment call are emulated literally.  Planted windows (insertions that start at a stripe start, the
+    constellation that makes the Q4 quirk visible in Aligner::Align; tests/test_q4_theory_cpu.py) through the function-level
+    seam: score and the four coordinates must equal the reference's in every case, including the ones where the reference
+    really deviates from exact Smith-Waterman — those must have been flagged — and the constructed reproducer."""
+    import random
+    from test_q4_theory_cpu import exact_align, make_case
+    S = ref_side() if have_ref_shim() else oracle_side()
+    os.environ["LTG_WIN_Q4CHK"] = "1"
+    try:
+        eng = fb.Engine(0)
+    finally:
+        del os.environ["LTG_WIN_Q4CHK"]
+    try:
+        eng.set_params()
+        q = golden["q4"]
+        eng.set_query("q4", q["rna"])
+        (o5, cig), = eng.Align([q["dna"]])
+        assert [list(o5), cig] == [q["align"][0], [c for c in q["align"][1] if c >> 4]] and o5[0] == 181
+        rng = random.Random(77)
+        n_cases = n_high = n_diverged = 0
+        for _ in range(500):
+            rna, win = make_case(rng)
+            win = win[:196]
+            ex = exact_align(rna, win)
+            if ex is None:
+                continue
+            want_exact, fmax = ex
+            ref5, ref_cig = S.align(rna, win)
+            eng.set_query("lnc", rna)
+            (got5, got_cig), = eng.Align([win])
+            assert tuple(got5) == tuple(ref5), (rna, win, got5, ref5, fmax)
+            n_cases += 1
+            n_high += int(want_exact[0] >= 148)
+            n_diverged += int(tuple(ref5) != tuple(want_exact))
+        print("windows %d, reach 148: %d, reference differs from exact SW: %d" % (n_cases, n_high, n_diverged))
+        assert n_cases > 300 and n_high > 100 and n_diverged >= 5
+    finally:
+        eng.close()
 
 
 def test_q4_taint_certification_on_device(engine):
