@@ -163,16 +163,12 @@ struct ltg_context {
     int frec_mode = 0;                  // -1 auto, 0 off, 1 on
     bool q4_taint = true;               // the flagged pairs are swept by the taint variant (certifies tasks) instead of the probe variant
                                         // (LTG_Q4_TAINT=0: probe)
-    int64_t n_certified = 0;            // tasks the taint sweep returned to the exact path (diagnostics)
     // Window sweeps that also watch for an F >= 132 entering a stripe start (k_win_dp Q4CHK: ~3 % more instructions): only the
     // windows that saw one go through the literal emulation.  Switched on for a query once a batch sent more than 64 windows
     // there (LTG_WIN_Q4CHK=0 never, 1 always); without it every window that scores >= 148 does.
     int win_q4_mode = -1;               // -1 auto, 0 off, 1 on
     bool win_q4_on = false;
     bool frec_on = false;               // current query: main sweeps record the carried F
-    bool litonly_old = false;           // LTG_LITONLY_OLD=1 (diagnostics): literal-only batches take the Q4 verdict again instead of being told
-    double frec_cost = 0.0;
-    int64_t n_frec_batches = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, lit_stream = nullptr;
     cudaEvent_t lit_event = nullptr;
     ltg_params params;
@@ -351,7 +347,6 @@ int build_profiles(ltg_context* c)
         LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // `list` is host memory of this scope
     }
     {
-        c->frec_cost = 0.015;
         c->frec_on = (c->frec_mode == 1);
         c->win_q4_on = (c->win_q4_mode == 1);
     }
@@ -787,13 +782,12 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
         LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));          // `sitems` is host memory of this scope
     }
     // fused carried-F recording (see ltg_context::frec_mode): this batch's verdict on the Q4 quirk comes from the main sweep
-    const bool lit_forced = (lit_mode == kLitOnly) && !c->litonly_old;     // literal-only batch: the literal tasks are the requested ones
+    const bool lit_forced = (lit_mode == kLitOnly);     // literal-only batch: the literal tasks are the requested ones
     const bool use_frec = c->q4_probe && c->frec_on && lit_mode != kLitSkip && lit_mode != kLitOnly;
     uint16_t* frec = nullptr;
     if (use_frec) {
         if (int e = c->d_frec.ensure((size_t)n_items * kFrecRows * blk_pitch * sizeof(uint16_t))) return e;
         frec = c->d_frec.as<uint16_t>();
-        c->n_frec_batches += 1;
     }
     LTG_CUDA_CHECK(cudaEventRecord(hb.ev[4], c->stream));
     if (int e = launch_scan(c, c->d_items.as<ScanItem>(), n_items, max_len, c->d_prof_ssw.as<uint32_t>(), c->d_colmax_all.as<uint32_t>(),
@@ -870,13 +864,8 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
             k_epilogue<<<(np * 32 + 127) / 128, 128, 0, c->stream>>>(pa);
             c->launches += 1;
             LTG_CUDA_CHECK(cudaGetLastError());
-            int lit_before = 0;
-            for (int t = 0; t < n_tasks; ++t) lit_before += (hti.flags[t] & kTaskLiteral) ? 1 : 0;
             LTG_CUDA_CHECK(cudaMemcpyAsync(hti.flags, ti.flags, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, c->stream));
             LTG_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // (also: `pitems` / `porig` are host memory of this scope)
-            int lit_after = 0;
-            for (int t = 0; t < n_tasks; ++t) lit_after += (hti.flags[t] & kTaskLiteral) ? 1 : 0;
-            if (c->q4_taint) c->n_certified += lit_before - lit_after;
             c->d2h_bytes += sizeof(int) * (int64_t)n_tasks;
             c->h2d_bytes += (int64_t)(sizeof(ScanItem) + sizeof(int)) * np;
             c->n_probe_items += np;
@@ -1614,7 +1603,6 @@ int ltg_create(int device, ltg_context** out)
     if (const char* e = getenv("LTG_NO_SKIP")) c->skip_rounds = atoi(e) == 0;
     if (const char* e = getenv("LTG_NO_Q4PROBE")) c->q4_probe = atoi(e) == 0;
     if (const char* e = getenv("LTG_FREC")) c->frec_mode = atoi(e) < 0 ? -1 : (atoi(e) != 0 ? 1 : 0);
-    if (const char* e = getenv("LTG_LITONLY_OLD")) c->litonly_old = atoi(e) != 0;
     if (const char* e = getenv("LTG_Q4_TAINT")) c->q4_taint = atoi(e) != 0;
     if (const char* e = getenv("LTG_WIN_Q4CHK")) c->win_q4_mode = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("LTG_SCAN_SHARED")) c->scan_shared = atoi(e) != 0;
