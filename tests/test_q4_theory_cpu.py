@@ -392,3 +392,73 @@ def test_taint_certification_of_window_alignments_is_sound():
         certified += int(ok); different += int(differs)
     assert flagged > 150 and certified > flagged // 2 and different >= 5
     print("windows flagged %d, certified %d, really different %d" % (flagged, certified, different))
+
+
+# ---------------------------------------------------------------------------------------------- the kernels' screening bounds
+def _exact_planes(rna, dna):
+    """Exact affine SW on the padded lncRNA: T (cell value without the vertical-gap source), H, and F entering every row."""
+    m, n = len(rna), len(dna)
+    L = (m + 15) // 16
+    m16 = 16 * L
+    code = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 0}
+    d = np.array([code.get(c, 4) for c in dna])
+    idx = np.arange(n)
+    Tm = np.zeros((m16, n), dtype=np.int64)
+    Hm = np.zeros((m16, n), dtype=np.int64)
+    Fin = np.zeros((m16, n), dtype=np.int64)
+    H = np.zeros(n, dtype=np.int64)
+    T = np.zeros(n, dtype=np.int64)
+    F = np.zeros(n, dtype=np.int64)
+    for i in range(m16):
+        if i > 0:
+            F = np.maximum(F - EXT, T - OPEN)
+        Fin[i] = F
+        if i < m:
+            r = code.get(rna[i], 4)
+            s = np.where((d == r) & (d < 4), MATCH, MISMATCH) if r < 4 else np.full(n, MISMATCH)
+        else:
+            s = np.zeros(n, dtype=np.int64)
+        diag = np.concatenate(([0], H[:-1]))
+        t0 = np.maximum(diag + s, 0)
+        pm = np.maximum.accumulate(t0 + EXT * idx)
+        E = np.maximum(np.concatenate(([0], pm[:-1] - OPEN - EXT * (idx[1:] - 1))), 0)
+        T = np.maximum(t0, E)
+        H = np.maximum(T, F)
+        Tm[i] = T
+        Hm[i] = H
+    return L, m16, Tm, Hm, Fin
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_kernel_screens_never_miss_a_carried_f(R):
+    """What the device kernels rely on (scan.cuh), on the exact DP of the planted cases, for lanes of R consecutive rows:
+    an F >= 132 can enter a stripe-start row of a lane in column j only if
+      (post-cell screen: probe sweep, stripe-start screen)  fin + 16 >= 148 or the lane's own cells of column j reach 148, and
+      (pre-cell screen: taint sweep)  fin >= 132 or one of {the lane's cells of column j - 1, fin of column j - 1, the H diagonally
+      above the lane} reaches 143,
+    where fin is the F entering the lane's first row.  (Window sweeps need no screen: they look at the vertical gap state itself.)"""
+    rng = random.Random(19)
+    events = 0
+    for _ in range(120):
+        rna, dna = make_case(rng)
+        L, m16, Tm, Hm, Fin = _exact_planes(rna, dna)
+        n = len(dna)
+        for k in range(1, 16):
+            row = k * L
+            if row >= m16:
+                break
+            hot = np.nonzero(Fin[row] >= 132)[0]
+            if len(hot) == 0:
+                continue
+            lo = (row // R) * R                               # first row of the lane that holds the stripe start
+            hi = min(lo + R, m16)
+            fin = Fin[lo]
+            own = Tm[lo:hi].max(axis=0)                       # the lane's cells (values before the vertical-gap source)
+            hd = Hm[lo - 1] if lo > 0 else np.zeros(n, dtype=np.int64)
+            for j in hot:
+                events += 1
+                assert fin[j] + 16 >= 148 or Tm[lo:row, j].max(initial=0) >= 148, (rna, dna, k, j)
+                assert fin[j] + 16 >= 148 or own[j] >= 148
+                prev = max(own[j - 1], fin[j - 1], hd[j - 1]) if j > 0 else 0
+                assert fin[j] >= 132 or prev >= 143, (rna, dna, k, j, fin[j], prev)
+    assert events > 200
