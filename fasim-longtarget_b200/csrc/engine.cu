@@ -388,7 +388,7 @@ constexpr int kScanSharedWarps = 6;         // warps per CTA of the shared-profi
 // group, and a CTA keeps ONE copy of the pair's profiles for its six warps — what lifts the scan from 2 to 3 warps per scheduler.
 int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_len, const uint32_t* prof, uint32_t* colmax_all, uint16_t* blkmax,
                 uint32_t* probe_out = nullptr, const int* task_jstar = nullptr, const std::vector<ScanItem>* h_items = nullptr, uint16_t* frec = nullptr,
-                bool taint = false)
+                bool taint = false, const int* task_flags = nullptr)
 {
     const int R = c->scan_r;
     int* counters = c->d_counters.as<int>();
@@ -400,7 +400,7 @@ int launch_scan(ltg_context* c, const ScanItem* d_items, int n_items, int max_le
     a.counter = counters + kCntScan;
     a.order = nullptr; a.group_pair = nullptr; a.n_groups = 0;
     a.probe_out = probe_out; a.task_jstar = task_jstar; a.tasks_per_seg = (int)c->tasks.size(); a.stripe_len = (c->m + 15) / 16;
-    a.frec = frec;
+    a.frec = frec; a.task_flags = task_flags;
     // shared-profile variant when the pair's profiles (all strips) and six warps' private parts fit twice into an SM
     const size_t prof_bytes = (size_t)c->n_strips * 5 * 32 * R * 4;
     const size_t smem_shared = prof_bytes + (size_t)kScanSharedWarps * (R == 32 ? scan_warp_smem_bytes_shared<32>(max_len) : scan_warp_smem_bytes_shared<16>(max_len));
@@ -853,7 +853,7 @@ int run_batch_device(ltg_context* c, const std::vector<HostSeg>& segs, HostBatch
                 // quirk could have lowered it; a task whose recorded column maxima are all untainted returns to the exact path
                 if (int e = c->d_taint_colmax.ensure((size_t)np * max_len * 4)) return e;
                 if (int e = launch_scan(c, c->d_probe_items.as<ScanItem>(), np, max_len, c->d_prof_ssw2.as<uint32_t>(), c->d_taint_colmax.as<uint32_t>(),
-                                        nullptr, c->d_probe_out.as<uint32_t>(), ti.jstar, nullptr, nullptr, true)) return e;
+                                        nullptr, c->d_probe_out.as<uint32_t>(), ti.jstar, nullptr, nullptr, true, ti.flags)) return e;
                 pa.taint_colmax = c->d_taint_colmax.as<uint32_t>();
                 pa.mode = 4;
             } else {

@@ -181,6 +181,7 @@ struct ScanArgs {
     // Q4 taint variant (k_scan<R, W, false, false, false, true>, see taint_slow_step): `profiles` hold doubled scores, colmax_all
     // receives 2 * maximum - taint bit per column, probe_out bit 0 / bit 16 = "gave up" for task 0 / 1
     uint32_t* probe_out;        // [item] packed (task 0 | task 1 << 16)
+    const int* task_flags;      // taint variant: [seg * T + task] flags of epilogue mode 0 (which tasks of a pair are flagged)
     const int* task_jstar;      // [seg * T + task] first column the reference does not record any more (or n)
     int tasks_per_seg;
     int stripe_len;             // ceil(m / 16)
@@ -393,14 +394,29 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
         }
         const ScanItem it = a.items[item];
         const SegDesc sd = a.segs[it.seg];
-        const int n = sd.len;
+        const int n_full = sd.len;
+        int n = n_full;                                            // columns this sweep works on
         const bool rev = c_pairs[it.pair].reversed != 0;
         const uint8_t* gcodes = a.codes + sd.start;
+        int jst0 = 0, jst1 = 0;
+        if (PROBE || TAINT) {
+            const PairDef pd = c_pairs[it.pair];
+            // columns the reference processes: up to and including the one where it stops recording (Q2)
+            jst0 = min(a.task_jstar[it.seg * a.tasks_per_seg + pd.task[0]] + 1, n_full);
+            jst1 = min(a.task_jstar[it.seg * a.tasks_per_seg + pd.task[1]] + 1, n_full);
+            if (TAINT) {
+                // the verdict only reads the columns a FLAGGED task still records: the sweep ends there (tasks that overflow
+                // early, the common case on repeat-rich DNA, need a fraction of the segment)
+                const int* tf = a.task_flags + it.seg * a.tasks_per_seg;
+                const int need = max((tf[pd.task[0]] & 2 /* kTaskLiteral */) ? jst0 : 0, (tf[pd.task[1]] & 2) ? jst1 : 0);
+                n = max(1, min(n_full, need));
+            }
+        }
         __syncwarp();
         // stage base codes with 32 neutral ('N' plane) columns on both sides
         for (int i = lane; i < n + 64; i += 32) {
             const int j = i - 32;
-            s_codes[i] = (j < 0 || j >= n) ? (uint8_t)kBaseOther : gcodes[rev ? (n - 1 - j) : j];
+            s_codes[i] = (j < 0 || j >= n) ? (uint8_t)kBaseOther : gcodes[rev ? (n_full - 1 - j) : j];
         }
         uint32_t* cm_all = a.colmax_all + (size_t)item * a.max_len;
         uint16_t* blk_item = a.blkmax + (size_t)item * a.n_strips * kGranPerStrip * a.blk_pitch;
@@ -408,13 +424,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const ScanArgs a)
 
         uint32_t fb = 0;                                           // PROBE: running maximum of the carried F values
         uint32_t giveup = 0;                                       // TAINT: bit 0 / bit 16 = the model gave up on task 0 / 1
-        int jst0 = 0, jst1 = 0;
-        if (PROBE || TAINT) {
-            const PairDef pd = c_pairs[it.pair];
-            // columns the reference processes: up to and including the one where it stops recording (Q2)
-            jst0 = min(a.task_jstar[it.seg * a.tasks_per_seg + pd.task[0]] + 1, n);
-            jst1 = min(a.task_jstar[it.seg * a.tasks_per_seg + pd.task[1]] + 1, n);
-        }
 
         for (int strip = 0; strip < a.n_strips; ++strip) {
             // PROBE: which of this lane's rows start a stripe of the reference's layout (row = k * stripe_len, k = 1..15)
